@@ -1,0 +1,21 @@
+# Builds librover_fe.so (C ABI, include/rover_fe.h) for sm_100a.  nvcc cross-compiles without a GPU.
+NVCC ?= /usr/local/cuda/bin/nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+CSRC := rover_slam_b200/csrc
+NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Iinclude -I$(CSRC) --expt-relaxed-constexpr
+OBJ := $(CSRC)/rover_fe.o $(CSRC)/sp_kernels.o $(CSRC)/lg_kernels.o $(CSRC)/tensormap.o $(CSRC)/weights.o
+LIB := rover_slam_b200/librover_fe.so
+
+all: $(LIB)
+
+$(CSRC)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/rover_fe.h
+	$(NVCC) $(NVCCFLAGS) -Xptxas -v -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; exit 1)
+
+$(CSRC)/%.o: $(CSRC)/%.cc $(wildcard $(CSRC)/*.h)
+	$(NVCC) $(NVCCFLAGS) -x cu -c $< -o $@
+
+$(LIB): $(OBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart
+
+clean:
+	rm -f $(OBJ) $(LIB) $(CSRC)/*.ptxas.log

@@ -1,0 +1,106 @@
+/* rover_fe.h -- C ABI of the B200-native Rover-SLAM feature front end (SuperPoint extract + LightGlue match).
+ *
+ * This is the drop-in boundary for the reference's ONNXRuntime calls.  Each entry point names the
+ * reference interface it replaces (paths relative to the Rover-SLAM repository):
+ *
+ *   rfe_create / rfe_destroy   <- SuperPointOnnxRunner::InitOrtEnv      src/Extractors/superpoint_onnx.cc:4-66
+ *                                 LightGlueDecoupleOnnxRunner::InitOrtEnv src/Matchers/lightglue_onnx.cpp:4-98
+ *   rfe_sp_extract_u8          <- NormalizeImage                         src/Matchers/transform.cpp:3-17
+ *                                 + SuperPointOnnxRunner::Extractor_Inference   superpoint_onnx.cc:88-162
+ *                                 + the tensor unpacking of Extractor_PostProcess superpoint_onnx.cc:165-255
+ *   rfe_lg_match               <- LightGlueDecoupleOnnxRunner::Matcher_PreProcess lightglue_onnx.cpp:140-159
+ *                                 + Matcher_Inference                    lightglue_onnx.cpp:162-240 / 241-330
+ *                                 + the score>thresh filter of Matcher_PostProcess_fused lightglue_onnx.cpp:437-453
+ *   rfe_get_timer_ms           <- SuperPointOnnxRunner::GetTimer         superpoint_onnx.cc:268-277
+ *
+ * Conventions (same as the reference's runners): return codes, never exceptions (EXIT_SUCCESS == RFE_OK);
+ * plain pointers and sizes; caller owns every output buffer; one rfe_ctx per thread (a ctx is NOT
+ * re-entrant, several ctxs may share a GPU).  All arithmetic runs on the GPU; there is no CPU fallback:
+ * rfe_create fails when no sm_100 device is present.
+ *
+ * Outputs follow the ONNX graphs' conventions exactly: keypoints are integer pixel centres (x, y) in
+ * row-major (y, then x) order; descriptors are unit-norm 256-vectors in keypoint order; matches are
+ * (index into set 0, index into set 1) pairs ascending in the first index.
+ */
+#ifndef ROVER_FE_H_
+#define ROVER_FE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFE_OK 0
+#define RFE_ERR_INVALID 1   /* bad argument (null pointer, size not a multiple of 8, batch too large ...) */
+#define RFE_ERR_CUDA 2      /* CUDA runtime / driver error; see rfe_last_error() */
+#define RFE_ERR_IO 3        /* weight blob missing or malformed */
+#define RFE_ERR_CAPACITY 4  /* more keypoints than the ctx / caller capacity; outputs hold the first `cap` */
+#define RFE_ERR_NO_DEVICE 5 /* no sm_100 GPU */
+
+#define RFE_DESC_DIM 256
+
+typedef struct rfe_ctx rfe_ctx;
+
+typedef struct rfe_config {
+  int device;               /* CUDA device ordinal */
+  void* stream;             /* cudaStream_t to enqueue on; NULL = the ctx creates its own stream */
+  const char* weights_path; /* RFW1 blob; NULL = $ROVER_FE_WEIGHTS, else "weights/rover_fe.rfw" */
+  int max_batch;            /* images per rfe_sp_* call            (0 = 8) */
+  int max_height;           /* largest image height, multiple of 8 (0 = 480) */
+  int max_width;            /* largest image width, multiple of 8  (0 = 768) */
+  int max_keypoints;        /* per-image keypoint capacity         (0 = 4096) */
+} rfe_config;
+
+int rfe_create(const rfe_config* cfg, rfe_ctx** out);
+void rfe_destroy(rfe_ctx* ctx);
+/* Thread-local text of the last failure on this thread. */
+const char* rfe_last_error(void);
+/* Block until everything enqueued on the ctx stream has finished. */
+int rfe_sync(rfe_ctx* ctx);
+
+/* ---- SuperPoint ------------------------------------------------------------------------------- */
+/* Host in / host out.  gray: batch images of h x w uint8 (CV_8UC1), row pitch stride_bytes, image pitch
+ * h*stride_bytes.  For image b, counts[b] = N_b keypoints and the first min(N_b, cap) rows of
+ * kpts_xy[b*cap ...], scores[b*cap ...], desc[b*cap*256 ...] are written.  scores/desc may be NULL.
+ * h, w multiples of 8 (the graph reshapes to [h/8, w/8, 8, 8]).  Returns RFE_ERR_CAPACITY if any N_b > cap. */
+int rfe_sp_extract_u8(rfe_ctx* ctx, const uint8_t* gray, int h, int w, int stride_bytes, int batch,
+                      int32_t* kpts_xy, float* scores, float* desc, int32_t* counts, int cap);
+
+/* Device in / device-resident out (asynchronous on the ctx stream).  d_gray: device pointer, layout as
+ * above.  Features stay in the ctx ("slots" 0..batch-1) for rfe_lg_match_slots / rfe_sp_read_slot. */
+int rfe_sp_extract_device(rfe_ctx* ctx, const uint8_t* d_gray, int h, int w, int stride_bytes, int batch);
+/* Copy slot b's features to the host (synchronises).  Any output pointer may be NULL. */
+int rfe_sp_read_slot(rfe_ctx* ctx, int slot, int32_t* kpts_xy, float* scores, float* desc, int32_t* count, int cap);
+
+/* ---- LightGlue -------------------------------------------------------------------------------- */
+/* Host in / host out.  kpts*_px: [n][2] pixel coordinates (x, y); desc*: [n][256].  Keypoints are
+ * normalised as the reference does, (kpt - (norm_w/2, norm_h/2)) / (max(norm_w, norm_h)/2).
+ * Writes k pairs with mscore > match_thresh (the ONNX graph already drops mscore <= 0.1):
+ * matches[2*i], matches[2*i+1], mscores[i]; capacity of both arrays: n0 entries. */
+int rfe_lg_match(rfe_ctx* ctx, const float* kpts0_px, int n0, const float* kpts1_px, int n1, const float* desc0,
+                 const float* desc1, int norm_h, int norm_w, float match_thresh, int32_t* matches, float* mscores,
+                 int* k);
+
+/* Match two feature slots left on the device by rfe_sp_extract_device (asynchronous); the result
+ * stays on the device in result slot `rslot` (0 .. max_batch-1). */
+int rfe_lg_match_slots(rfe_ctx* ctx, int slot0, int slot1, int norm_h, int norm_w, float match_thresh, int rslot);
+/* Copy a match result to the host (synchronises). */
+int rfe_lg_read_result(rfe_ctx* ctx, int rslot, int32_t* matches, float* mscores, int* k, int cap);
+
+/* ---- timers / introspection --------------------------------------------------------------------- */
+/* Accumulated GPU milliseconds (CUDA events) of "extractor" / "matcher" calls, like the reference's GetTimer. */
+double rfe_get_timer_ms(rfe_ctx* ctx, const char* name);
+/* Number of kernels the library has launched on this ctx so far. */
+long long rfe_kernel_launches(rfe_ctx* ctx);
+/* Test hook: copy a named intermediate device tensor of the last call to the host (fp32 or raw bytes).
+ * Returns the byte size of the tensor through *bytes; copies min(*bytes, capacity). */
+int rfe_debug_read(rfe_ctx* ctx, const char* name, void* dst, size_t capacity, size_t* bytes);
+/* Test hook: run one split-fp16 tensor-core GEMM D = A[M,K] * B[N,K]^T (+bias) on host fp32 data. */
+int rfe_debug_gemm(rfe_ctx* ctx, const float* a, const float* b, const float* bias, float* d, int m, int n, int kdim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROVER_FE_H_ */

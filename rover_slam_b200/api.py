@@ -1,0 +1,188 @@
+"""ctypes binding of include/rover_fe.h (the same stub a reference-side Python harness would use)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+DESC_DIM = 256
+
+RFE_OK, RFE_ERR_INVALID, RFE_ERR_CUDA, RFE_ERR_IO, RFE_ERR_CAPACITY, RFE_ERR_NO_DEVICE = range(6)
+
+
+class RoverFeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"rover_fe error {code}: {msg}")
+        self.code = code
+
+
+def lib_path() -> str:
+    return os.environ.get("ROVER_FE_LIB", os.path.join(_HERE, "librover_fe.so"))
+
+
+class _Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("stream", C.c_void_p), ("weights_path", C.c_char_p),
+                ("max_batch", C.c_int), ("max_height", C.c_int), ("max_width", C.c_int),
+                ("max_keypoints", C.c_int)]
+
+
+_lib = None
+
+
+def exported_symbols() -> list:
+    """Every function include/rover_fe.h declares (parsed from the header)."""
+    with open(os.path.join(ROOT, "include", "rover_fe.h")) as f:
+        src = f.read()
+    return sorted(set(re.findall(r"\b(rfe_[a-z0-9_]+)\s*\(", src)))
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise RoverFeError(-1, f"{p} not found: build it with `make` (python -c 'import __graft_entry__ as g; g.build()'); "
+                               "there is no CPU fallback")
+    lib = C.CDLL(p)
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    P = C.POINTER
+    lib.rfe_create.argtypes = [P(_Config), P(vp)]
+    lib.rfe_destroy.argtypes = [vp]
+    lib.rfe_destroy.restype = None
+    lib.rfe_last_error.restype = C.c_char_p
+    lib.rfe_sync.argtypes = [vp]
+    lib.rfe_sp_extract_u8.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp, vp, vp, ci]
+    lib.rfe_sp_extract_device.argtypes = [vp, vp, ci, ci, ci, ci]
+    lib.rfe_sp_read_slot.argtypes = [vp, ci, vp, vp, vp, vp, ci]
+    lib.rfe_lg_match.argtypes = [vp, vp, ci, vp, ci, vp, vp, ci, ci, cf, vp, vp, vp]
+    lib.rfe_lg_match_slots.argtypes = [vp, ci, ci, ci, ci, cf, ci]
+    lib.rfe_lg_read_result.argtypes = [vp, ci, vp, vp, vp, ci]
+    lib.rfe_get_timer_ms.argtypes = [vp, C.c_char_p]
+    lib.rfe_get_timer_ms.restype = C.c_double
+    lib.rfe_kernel_launches.argtypes = [vp]
+    lib.rfe_kernel_launches.restype = C.c_longlong
+    lib.rfe_debug_read.argtypes = [vp, C.c_char_p, vp, C.c_size_t, P(C.c_size_t)]
+    lib.rfe_debug_gemm.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class FrontEnd:
+    """One rfe_ctx.  Mirrors what the reference's SuperPointOnnxRunner + LightGlueDecoupleOnnxRunner pair does."""
+
+    def __init__(self, device: int = 0, stream: int | None = None, weights: str | None = None, max_batch: int = 8,
+                 max_height: int = 480, max_width: int = 768, max_keypoints: int = 4096):
+        self.lib = load_library()
+        weights = weights or os.environ.get("ROVER_FE_WEIGHTS") or os.path.join(ROOT, "weights", "rover_fe.rfw")
+        cfg = _Config(device, stream, weights.encode(), max_batch, max_height, max_width, max_keypoints)
+        h = C.c_void_p()
+        self.ctx = None
+        self._check(self.lib.rfe_create(C.byref(cfg), C.byref(h)))
+        self.ctx = h
+        self.cap = max_keypoints
+        self.max_batch = max_batch
+
+    def _check(self, code, allow=()):
+        if code != RFE_OK and code not in allow:
+            raise RoverFeError(code, (self.lib.rfe_last_error() or b"").decode())
+        return code
+
+    def close(self):
+        if self.ctx is not None:
+            self.lib.rfe_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._check(self.lib.rfe_sync(self.ctx))
+
+    # ---- SuperPoint -----------------------------------------------------------------------------
+    def extract(self, images: np.ndarray, want_desc: bool = True):
+        """images: uint8 [H,W] or [B,H,W] (host).  Returns a list of (kpts int32 [N,2] xy, scores [N], desc [N,256])."""
+        imgs = np.ascontiguousarray(images if images.ndim == 3 else images[None], dtype=np.uint8)
+        b, h, w = imgs.shape
+        cap = self.cap
+        kp = np.empty((b, cap, 2), np.int32)
+        sc = np.empty((b, cap), np.float32)
+        de = np.empty((b, cap, DESC_DIM), np.float32) if want_desc else None
+        cnt = np.zeros(b, np.int32)
+        self._check(self.lib.rfe_sp_extract_u8(self.ctx, _ptr(imgs), h, w, w, b, _ptr(kp), _ptr(sc), _ptr(de), _ptr(cnt), cap))
+        return [(kp[i, :cnt[i]].copy(), sc[i, :cnt[i]].copy(), de[i, :cnt[i]].copy() if want_desc else None)
+                for i in range(b)]
+
+    def extract_device(self, d_ptr: int, h: int, w: int, stride: int, batch: int):
+        self._check(self.lib.rfe_sp_extract_device(self.ctx, C.c_void_p(d_ptr), h, w, stride, batch))
+
+    def read_slot(self, slot: int, want_desc: bool = True):
+        cap = self.cap
+        kp = np.empty((cap, 2), np.int32)
+        sc = np.empty(cap, np.float32)
+        de = np.empty((cap, DESC_DIM), np.float32) if want_desc else None
+        n = C.c_int(0)
+        self._check(self.lib.rfe_sp_read_slot(self.ctx, slot, _ptr(kp), _ptr(sc), _ptr(de), C.byref(n), cap))
+        n = n.value
+        return kp[:n].copy(), sc[:n].copy(), de[:n].copy() if want_desc else None
+
+    # ---- LightGlue -------------------------------------------------------------------------------
+    def match(self, kpts0, kpts1, desc0, desc1, norm_h: int, norm_w: int, thresh: float = 0.0):
+        """Pixel keypoints [N,2] (x,y), descriptors [N,256].  Returns (matches int32 [K,2], mscores [K])."""
+        k0 = np.ascontiguousarray(kpts0, np.float32).reshape(-1, 2)
+        k1 = np.ascontiguousarray(kpts1, np.float32).reshape(-1, 2)
+        d0 = np.ascontiguousarray(desc0, np.float32).reshape(-1, DESC_DIM)
+        d1 = np.ascontiguousarray(desc1, np.float32).reshape(-1, DESC_DIM)
+        n0, n1 = len(k0), len(k1)
+        m = np.empty((max(n0, 1), 2), np.int32)
+        s = np.empty(max(n0, 1), np.float32)
+        k = C.c_int(0)
+        self._check(self.lib.rfe_lg_match(self.ctx, _ptr(k0), n0, _ptr(k1), n1, _ptr(d0), _ptr(d1), norm_h, norm_w,
+                                          thresh, _ptr(m), _ptr(s), C.byref(k)))
+        return m[:k.value].copy(), s[:k.value].copy()
+
+    def match_slots(self, slot0: int, slot1: int, norm_h: int, norm_w: int, thresh: float = 0.0, rslot: int = 0):
+        self._check(self.lib.rfe_lg_match_slots(self.ctx, slot0, slot1, norm_h, norm_w, thresh, rslot))
+
+    def read_result(self, rslot: int = 0):
+        m = np.empty((self.cap, 2), np.int32)
+        s = np.empty(self.cap, np.float32)
+        k = C.c_int(0)
+        self._check(self.lib.rfe_lg_read_result(self.ctx, rslot, _ptr(m), _ptr(s), C.byref(k), self.cap))
+        return m[:k.value].copy(), s[:k.value].copy()
+
+    # ---- introspection -----------------------------------------------------------------------------
+    def timer_ms(self, name: str) -> float:
+        return float(self.lib.rfe_get_timer_ms(self.ctx, name.encode()))
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.rfe_kernel_launches(self.ctx))
+
+    def debug_read(self, name: str, shape=None) -> np.ndarray:
+        nb = C.c_size_t(0)
+        self._check(self.lib.rfe_debug_read(self.ctx, name.encode(), None, 0, C.byref(nb)))
+        out = np.empty(nb.value // 4, np.float32)
+        if nb.value:
+            self._check(self.lib.rfe_debug_read(self.ctx, name.encode(), _ptr(out), nb.value, C.byref(nb)))
+        return out.reshape(shape) if shape is not None else out
+
+    def debug_gemm(self, a: np.ndarray, b: np.ndarray, bias: np.ndarray | None = None) -> np.ndarray:
+        a = np.ascontiguousarray(a, np.float32)
+        b = np.ascontiguousarray(b, np.float32)
+        m, k = a.shape
+        n = b.shape[0]
+        d = np.empty((m, n), np.float32)
+        bias = None if bias is None else np.ascontiguousarray(bias, np.float32)
+        self._check(self.lib.rfe_debug_gemm(self.ctx, _ptr(a), _ptr(b), _ptr(bias), _ptr(d), m, n, k))
+        return d

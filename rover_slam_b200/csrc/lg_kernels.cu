@@ -1,0 +1,407 @@
+// LightGlue kernels that are not tensor-core contractions: keypoint normalisation + Fourier positional
+// encoding, rotary embedding + head split, row softmax, LayerNorm+GELU, matchability, dual log-softmax
+// statistics, row/column arg-max, mutual check + ordered compaction.
+// Reference: onnxmodel/lightglue_sim.onnx as run by src/Matchers/lightglue_onnx.cpp:210-214 (SURVEY.md
+// Appendix B), keypoint normalisation from src/Matchers/transform.cpp:19-32.
+#include "kernels.h"
+
+namespace rfe {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- posenc: cs/sn [N][32] (nodes 0-17) ---------------------------------------------------------------
+__global__ void posenc_kernel(const float* __restrict__ kpts_px, int n, float shift_x, float shift_y, float scale,
+                              const float* __restrict__ wr /*[32][2]*/, float* __restrict__ cs,
+                              float* __restrict__ sn) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 32) return;
+  const int k = i >> 5, j = i & 31;
+  const float x = (kpts_px[2 * k] - shift_x) / scale;
+  const float y = (kpts_px[2 * k + 1] - shift_y) / scale;
+  const float p = x * wr[2 * j] + y * wr[2 * j + 1];
+  cs[i] = cosf(p);
+  sn[i] = sinf(p);
+}
+void launch_posenc(cudaStream_t s, const float* kpts_px, int n, int norm_h, int norm_w, const float* wr, float* cs,
+                   float* sn) {
+  if (n == 0) return;
+  const float sx = static_cast<float>(norm_w) / 2.0f, sy = static_cast<float>(norm_h) / 2.0f;
+  const float sc = static_cast<float>(norm_w > norm_h ? norm_w : norm_h) / 2.0f;
+  posenc_kernel<<<(n * 32 + 255) / 256, 256, 0, s>>>(kpts_px, n, sx, sy, sc, wr, cs, sn);
+}
+
+// ---- int keypoints -> float pixels (device-resident hand-off from SuperPoint) ---------------------------
+__global__ void kpts_to_float_kernel(const int* __restrict__ k, int n, float* __restrict__ o) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * n) o[i] = static_cast<float>(k[i]);
+}
+void launch_kpts_to_float(cudaStream_t s, const int* k, int n, float* o) {
+  if (n) kpts_to_float_kernel<<<(2 * n + 255) / 256, 256, 0, s>>>(k, n, o);
+}
+
+// ---- fp32 [rows][cols] -> fp32 copy + split-fp16 (row pitches may differ) -------------------------------
+__global__ void split_rows_kernel(const float* __restrict__ src, int rows, int cols, int ld_src, float* __restrict__ dst,
+                                  int ld_dst, __half* __restrict__ hi, __half* __restrict__ lo, int ld_h) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(rows) * cols) return;
+  const int r = i / cols, c = i - static_cast<size_t>(r) * cols;
+  const float v = src[static_cast<size_t>(r) * ld_src + c];
+  if (dst) dst[static_cast<size_t>(r) * ld_dst + c] = v;
+  __half h, l;
+  split_f32(v, h, l);
+  hi[static_cast<size_t>(r) * ld_h + c] = h;
+  lo[static_cast<size_t>(r) * ld_h + c] = l;
+}
+void launch_split_rows(cudaStream_t s, const float* src, int rows, int cols, int ld_src, float* dst, int ld_dst,
+                       __half* hi, __half* lo, int ld_h) {
+  const size_t n = static_cast<size_t>(rows) * cols;
+  if (n == 0) return;
+  split_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(src, rows, cols, ld_src, dst, ld_dst, hi, lo,
+                                                                          ld_h);
+}
+
+// ---- rotary + scale + head split (nodes 20-51) ----------------------------------------------------------
+// qkv fp32 [N][768] with columns [q(256) | k(256) | v(256)], each head-major (h*64+d).
+// Q, K -> split-fp16 head-major [4][N][64]; V -> split-fp16 transposed [256][ldv].
+__global__ void rope_split_kernel(const float* __restrict__ qkv, int n, const float* __restrict__ cs,
+                                  const float* __restrict__ sn, float scale, __half* __restrict__ q_hi,
+                                  __half* __restrict__ q_lo, __half* __restrict__ k_hi, __half* __restrict__ k_lo,
+                                  __half* __restrict__ vt_hi, __half* __restrict__ vt_lo, int ldv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over n * 128 pairs (h, f) f in 0..31
+  if (i >= n * 128) return;
+  const int row = i >> 7, pr = i & 127;
+  const int f = pr & 31;
+  const float c = cs[row * 32 + f], s = sn[row * 32 + f];
+  const float* base = qkv + static_cast<size_t>(row) * 768 + pr * 2;
+  const size_t o = static_cast<size_t>(pr >> 5) * n * 64 + static_cast<size_t>(row) * 64 + (pr & 31) * 2;
+  {
+    const float a = base[0], b = base[1];
+    const float r0 = (a * c + (-b) * s) * scale, r1 = (b * c + a * s) * scale;
+    __half h, l;
+    split_f32(r0, h, l); q_hi[o] = h; q_lo[o] = l;
+    split_f32(r1, h, l); q_hi[o + 1] = h; q_lo[o + 1] = l;
+  }
+  {
+    const float a = base[256], b = base[257];
+    const float r0 = (a * c + (-b) * s) * scale, r1 = (b * c + a * s) * scale;
+    __half h, l;
+    split_f32(r0, h, l); k_hi[o] = h; k_lo[o] = l;
+    split_f32(r1, h, l); k_hi[o + 1] = h; k_lo[o + 1] = l;
+  }
+  {
+    __half h, l;
+    split_f32(base[512], h, l);
+    vt_hi[static_cast<size_t>(pr * 2) * ldv + row] = h; vt_lo[static_cast<size_t>(pr * 2) * ldv + row] = l;
+    split_f32(base[513], h, l);
+    vt_hi[static_cast<size_t>(pr * 2 + 1) * ldv + row] = h; vt_lo[static_cast<size_t>(pr * 2 + 1) * ldv + row] = l;
+  }
+}
+void launch_rope_split(cudaStream_t s, const float* qkv, int n, const float* cs, const float* sn, float scale,
+                       __half* q_hi, __half* q_lo, __half* k_hi, __half* k_lo, __half* vt_hi, __half* vt_lo, int ldv) {
+  if (n == 0) return;
+  rope_split_kernel<<<(n * 128 + 255) / 256, 256, 0, s>>>(qkv, n, cs, sn, scale, q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo,
+                                                           ldv);
+}
+
+// ---- row softmax -> split-fp16 (one warp per row) ------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_split_kernel(const float* __restrict__ S, int rows_total, int cols,
+                                                            int ld_s, __half* __restrict__ p_hi,
+                                                            __half* __restrict__ p_lo, int ld_p) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= rows_total) return;
+  const float* r = S + static_cast<size_t>(wid) * ld_s;
+  float mx = -INFINITY;
+  for (int j = lane; j < cols; j += 32) mx = fmaxf(mx, r[j]);
+  mx = warp_max(mx);
+  float sum = 0.0f;
+  for (int j = lane; j < cols; j += 32) sum += expf(r[j] - mx);
+  sum = warp_sum(sum);
+  __half* oh = p_hi + static_cast<size_t>(wid) * ld_p;
+  __half* ol = p_lo + static_cast<size_t>(wid) * ld_p;
+  for (int j = lane; j < cols; j += 32) {
+    const float p = expf(r[j] - mx) / sum;
+    __half h, l;
+    split_f32(p, h, l);
+    oh[j] = h;
+    ol[j] = l;
+  }
+}
+void launch_softmax_split(cudaStream_t s, const float* S, int rows_total, int cols, int ld_s, __half* p_hi, __half* p_lo,
+                          int ld_p) {
+  if (rows_total == 0) return;
+  softmax_split_kernel<<<(rows_total * 32 + 255) / 256, 256, 0, s>>>(S, rows_total, cols, ld_s, p_hi, p_lo, ld_p);
+}
+
+// ---- LayerNorm(512, eps 1e-5) + exact GELU -> split-fp16 (one warp per row; nodes 62-67) --------------------
+__global__ void __launch_bounds__(256) ln_gelu_split_kernel(const float* __restrict__ x, int rows,
+                                                            const float* __restrict__ g, const float* __restrict__ b,
+                                                            __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= rows) return;
+  const float* r = x + static_cast<size_t>(wid) * 512;
+  float v[16];
+  float s = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    v[j] = r[j * 32 + lane];
+    s += v[j];
+  }
+  const float mean = warp_sum(s) * (1.0f / 512.0f);
+  float q = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float d = v[j] - mean;
+    q += d * d;
+  }
+  const float var = warp_sum(q) * (1.0f / 512.0f);
+  const float rstd = 1.0f / sqrtf(var + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int c = j * 32 + lane;
+    const float y = (v[j] - mean) * rstd * g[c] + b[c];
+    const float ge = (y * (erff(y / 1.4142135381698608f) + 1.0f)) * 0.5f;
+    __half h, l;
+    split_f32(ge, h, l);
+    hi[static_cast<size_t>(wid) * 512 + c] = h;
+    lo[static_cast<size_t>(wid) * 512 + c] = l;
+  }
+}
+void launch_ln_gelu_split(cudaStream_t s, const float* x, int rows, const float* g, const float* b, __half* hi,
+                          __half* lo) {
+  if (rows == 0) return;
+  ln_gelu_split_kernel<<<(rows * 32 + 255) / 256, 256, 0, s>>>(x, rows, g, b, hi, lo);
+}
+
+// ---- matchability: log(sigmoid(x . w + b)) (nodes 1488-1495), one warp per row --------------------------------
+__global__ void __launch_bounds__(256) matchability_kernel(const float* __restrict__ x, int rows,
+                                                           const float* __restrict__ w, const float* __restrict__ b,
+                                                           float* __restrict__ out) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= rows) return;
+  const float* r = x + static_cast<size_t>(wid) * 256;
+  float s = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s = fmaf(r[j * 32 + lane], w[j * 32 + lane], s);
+  s = warp_sum(s);
+  if (lane == 0) {
+    const float z = b[0] + s;
+    out[wid] = logf(1.0f / (1.0f + expf(-z)));
+  }
+}
+void launch_matchability(cudaStream_t s, const float* x, int rows, const float* w, const float* b, float* out) {
+  if (rows == 0) return;
+  matchability_kernel<<<(rows * 32 + 255) / 256, 256, 0, s>>>(x, rows, w, b, out);
+}
+
+// ---- dual log-softmax statistics ------------------------------------------------------------------------------
+// row_stat[i] = (max_j sim[i][j], log sum_j exp(sim - max))   one warp per row
+__global__ void __launch_bounds__(256) row_lse_kernel(const float* __restrict__ sim, int n0, int n1, int ld,
+                                                      float* __restrict__ rmax, float* __restrict__ rlog) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= n0) return;
+  const float* r = sim + static_cast<size_t>(wid) * ld;
+  float mx = -INFINITY;
+  for (int j = lane; j < n1; j += 32) mx = fmaxf(mx, r[j]);
+  mx = warp_max(mx);
+  float sum = 0.0f;
+  for (int j = lane; j < n1; j += 32) sum += expf(r[j] - mx);
+  sum = warp_sum(sum);
+  if (lane == 0) {
+    rmax[wid] = mx;
+    rlog[wid] = logf(sum);
+  }
+}
+// column statistics: block = 32 columns x 32 row-lanes; two passes over the rows (max, then sum)
+__global__ void __launch_bounds__(1024) col_lse_kernel(const float* __restrict__ sim, int n0, int n1, int ld,
+                                                       float* __restrict__ cmax, float* __restrict__ clog) {
+  __shared__ float red[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  float mx = -INFINITY;
+  if (j < n1)
+    for (int i = ty; i < n0; i += 32) mx = fmaxf(mx, sim[static_cast<size_t>(i) * ld + j]);
+  red[ty][tx] = mx;
+  __syncthreads();
+  if (ty == 0) {
+    float m = red[0][tx];
+    for (int k = 1; k < 32; ++k) m = fmaxf(m, red[k][tx]);
+    red[0][tx] = m;
+  }
+  __syncthreads();
+  mx = red[0][tx];
+  __syncthreads();
+  float sum = 0.0f;
+  if (j < n1)
+    for (int i = ty; i < n0; i += 32) sum += expf(sim[static_cast<size_t>(i) * ld + j] - mx);
+  red[ty][tx] = sum;
+  __syncthreads();
+  if (ty == 0 && j < n1) {
+    float sacc = 0.0f;
+    for (int k = 0; k < 32; ++k) sacc += red[k][tx];
+    cmax[j] = mx;
+    clog[j] = logf(sacc);
+  }
+}
+void launch_lse(cudaStream_t s, const float* sim, int n0, int n1, int ld, float* rmax, float* rlog, float* cmax,
+                float* clog) {
+  if (n0 == 0 || n1 == 0) return;
+  row_lse_kernel<<<(n0 * 32 + 255) / 256, 256, 0, s>>>(sim, n0, n1, ld, rmax, rlog);
+  col_lse_kernel<<<(n1 + 31) / 32, 1024, 0, s>>>(sim, n0, n1, ld, cmax, clog);
+}
+
+// S[i][j] = ((sim - rmax_i) - rlog_i) + ((sim - cmax_j) - clog_j) + (ls0_i + ls1_j)         (nodes 1497-1501)
+__device__ __forceinline__ float assign_score(float v, float rm, float rl, float cm, float cl, float a0, float a1) {
+  return (((v - rm) - rl) + ((v - cm) - cl)) + (a0 + a1);
+}
+
+// row arg-max (TopK k=1 axis 2; ties -> lowest index), one warp per row
+__global__ void __launch_bounds__(256) row_argmax_kernel(const float* __restrict__ sim, int n0, int n1, int ld,
+                                                         const float* __restrict__ rmax, const float* __restrict__ rlog,
+                                                         const float* __restrict__ cmax, const float* __restrict__ clog,
+                                                         const float* __restrict__ ls0, const float* __restrict__ ls1,
+                                                         float* __restrict__ max0, int* __restrict__ m0,
+                                                         float* __restrict__ S_dbg) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= n0) return;
+  const float* r = sim + static_cast<size_t>(wid) * ld;
+  const float rm = rmax[wid], rl = rlog[wid], a0 = ls0[wid];
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = lane; j < n1; j += 32) {
+    const float sc = assign_score(r[j], rm, rl, cmax[j], clog[j], a0, ls1[j]);
+    if (S_dbg) S_dbg[static_cast<size_t>(wid) * n1 + j] = sc;
+    if (sc > best) {
+      best = sc;
+      bi = j;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) {
+      best = ob;
+      bi = oi;
+    }
+  }
+  if (lane == 0) {
+    max0[wid] = best;
+    m0[wid] = bi;
+  }
+}
+// column arg-max (TopK k=1 axis 1), block = 32 columns x 32 row-lanes
+__global__ void __launch_bounds__(1024) col_argmax_kernel(const float* __restrict__ sim, int n0, int n1, int ld,
+                                                          const float* __restrict__ rmax, const float* __restrict__ rlog,
+                                                          const float* __restrict__ cmax, const float* __restrict__ clog,
+                                                          const float* __restrict__ ls0, const float* __restrict__ ls1,
+                                                          int* __restrict__ m1) {
+  __shared__ float rb[32][33];
+  __shared__ int ri[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  if (j < n1) {
+    const float cm = cmax[j], cl = clog[j], a1 = ls1[j];
+    for (int i = ty; i < n0; i += 32) {
+      const float sc = assign_score(sim[static_cast<size_t>(i) * ld + j], rmax[i], rlog[i], cm, cl, ls0[i], a1);
+      if (sc > best) {
+        best = sc;
+        bi = i;
+      }
+    }
+  }
+  rb[ty][tx] = best;
+  ri[ty][tx] = bi;
+  __syncthreads();
+  if (ty == 0 && j < n1) {
+    for (int k = 1; k < 32; ++k) {
+      const float ob = rb[k][tx];
+      const int oi = ri[k][tx];
+      if (ob > best || (ob == best && oi < bi)) {
+        best = ob;
+        bi = oi;
+      }
+    }
+    m1[j] = bi;
+  }
+}
+void launch_argmax(cudaStream_t s, const float* sim, int n0, int n1, int ld, const float* rmax, const float* rlog,
+                   const float* cmax, const float* clog, const float* ls0, const float* ls1, float* max0, int* m0,
+                   int* m1, float* S_dbg) {
+  if (n0 == 0 || n1 == 0) return;
+  row_argmax_kernel<<<(n0 * 32 + 255) / 256, 256, 0, s>>>(sim, n0, n1, ld, rmax, rlog, cmax, clog, ls0, ls1, max0, m0,
+                                                           S_dbg);
+  col_argmax_kernel<<<(n1 + 31) / 32, 1024, 0, s>>>(sim, n0, n1, ld, rmax, rlog, cmax, clog, ls0, ls1, m1);
+}
+
+// ---- mutual check + exp + filter + ordered compaction (nodes 1504-1525 + lightglue_onnx.cpp:437-453) -----------
+__global__ void __launch_bounds__(1024) match_compact_kernel(const float* __restrict__ max0, const int* __restrict__ m0,
+                                                             const int* __restrict__ m1, int n0, float filter,
+                                                             float thresh, int* __restrict__ matches,
+                                                             float* __restrict__ mscores, int* __restrict__ count) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n0; base += 1024) {
+    const int i = base + threadIdx.x;
+    float ms = 0.0f;
+    int j = 0;
+    if (i < n0) {
+      j = m0[i];
+      const bool mutual = (m1[j] == i);
+      ms = mutual ? expf(max0[i]) : 0.0f;
+    }
+    const int keep = (i < n0 && ms > filter && ms > thresh) ? 1 : 0;
+    int incl = keep;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      int ws = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, ws, o);
+        if (lane >= o) ws += t;
+      }
+      warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    const int pos = carry + (w ? warp_sums[w - 1] : 0) + incl - keep;
+    if (keep) {
+      matches[2 * pos] = i;
+      matches[2 * pos + 1] = j;
+      mscores[pos] = ms;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = pos + keep;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = carry;
+}
+void launch_match_compact(cudaStream_t s, const float* max0, const int* m0, const int* m1, int n0, float filter,
+                          float thresh, int* matches, float* mscores, int* count) {
+  match_compact_kernel<<<1, 1024, 0, s>>>(max0, m0, m1, n0, filter, thresh, matches, mscores, count);
+}
+
+}  // namespace rfe

@@ -1,0 +1,991 @@
+// rover_fe: context, weight upload, the SuperPoint / LightGlue launch sequences and the C ABI (include/rover_fe.h).
+// Everything here is host orchestration; the arithmetic lives in umma_kernel.cuh, sp_kernels.cu, lg_kernels.cu.
+#include "rover_fe.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "tensormap.h"
+#include "umma_kernel.cuh"
+#include "weights.h"
+
+using namespace rfe;
+
+namespace {
+
+constexpr float kAttnScale = 0.3535533845424652f;   // 64^-1/4 (lightglue_sim.onnx /inner_attn/Sqrt_1)
+constexpr float kDetThreshold = 0.0005f;            // superpoint.onnx /Constant_116
+constexpr float kFilterThreshold = 0.10000000149011612f;   // lightglue_sim.onnx /Constant_6
+constexpr int kLayers = 9;
+
+struct SplitBuf {   // device split-fp16 tensor
+  __half* hi = nullptr;
+  __half* lo = nullptr;
+};
+struct SplitW {     // device split-fp16 weight [n][k] (K contiguous) + fp32 bias
+  SplitBuf w;
+  float* bias = nullptr;
+  int n = 0, k = 0;
+};
+struct LgLayer {
+  SplitW wqkv, out_proj, s_ffn0, s_ffn3, to_qk, to_v, to_out, c_ffn0, c_ffn3;
+  float *s_ln_w = nullptr, *s_ln_b = nullptr, *c_ln_w = nullptr, *c_ln_b = nullptr;
+};
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+}  // namespace
+
+struct rfe_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int max_batch = 8, max_h = 480, max_w = 768, cap = 4096;
+  std::vector<void*> allocs;
+  long long launches = 0;
+  double timer_extract_ms = 0.0, timer_match_ms = 0.0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // ---- weights ----
+  float *conv1a_w = nullptr, *conv1a_b = nullptr;
+  SplitW c1b, c2a, c2b, c3a, c3b, c4a, c4b, cPa, cPb, cDa, cDb;
+  float* posenc_w = nullptr;
+  LgLayer layers[kLayers];
+  SplitW final_proj;
+  float *match_w = nullptr, *match_b = nullptr;
+
+  // ---- SuperPoint buffers (sized for max_batch x max_h x max_w) ----
+  uint8_t* img = nullptr;
+  SplitBuf a1a, a1, a2a, a2, a3a, a3, a4a, feat, pa, da;
+  float *heat = nullptr, *nmsmap = nullptr, *dense = nullptr;
+  int *row_cnt = nullptr, *row_off = nullptr;
+  int* kp_counts = nullptr;     // [max_batch]
+  int* kpts = nullptr;          // [max_batch][cap][2]
+  float* kp_scores = nullptr;   // [max_batch][cap]
+  float* desc = nullptr;        // [max_batch][cap][256]
+  int last_batch = 0, last_h = 0, last_w = 0;
+  int* h_counts = nullptr;      // pinned [max_batch]
+
+  // ---- LightGlue buffers (sized for 2*cap rows) ----
+  int lg_rows = 0, lg_ld = 0;   // row capacity (2*cap+8), padded key count
+  float *in_kpts = nullptr, *in_desc = nullptr;   // staging for the host API: [2*cap][2], [2*cap][256]
+  float *cs = nullptr, *sn = nullptr;             // [rows][32]
+  float* x = nullptr;                             // [rows][256]
+  SplitBuf cat;                                   // [rows][512]
+  float* qkv = nullptr;                           // [rows][768]
+  SplitBuf q, k, vt;                              // q,k: [4][rows][64]; vt: [256][lg_ldv]
+  int lg_ldv = 0;
+  float* S = nullptr;                             // [4][cap][lg_ld]
+  SplitBuf P;                                     // [4][cap][lg_ld]
+  SplitBuf attn;                                  // [rows][256]
+  float* hid = nullptr;                           // [rows][512]
+  SplitBuf hs;                                    // [rows][512]
+  SplitBuf md;                                    // [rows][256]
+  float* sim = nullptr;                           // [cap][lg_ld]
+  float *rmax = nullptr, *rlog = nullptr, *cmax = nullptr, *clog = nullptr, *ls = nullptr, *max0 = nullptr;
+  int *m0 = nullptr, *m1 = nullptr;
+  float* S_dbg = nullptr;
+  int dbg_n0 = 0, dbg_n1 = 0, dbg_n0p = 0;
+  // match results: [max_batch] slots
+  int* res_matches = nullptr;   // [slots][cap][2]
+  float* res_scores = nullptr;  // [slots][cap]
+  int* res_count = nullptr;     // [slots]
+
+  // debug scratch
+  float* dbg = nullptr;
+  size_t dbg_bytes = 0;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// allocation / upload helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+int dev_alloc(rfe_ctx* c, T** p, size_t count) {
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, count * sizeof(T) + 256);
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    return RFE_ERR_CUDA;
+  }
+  cudaMemset(d, 0, count * sizeof(T) + 256);
+  c->allocs.push_back(d);
+  *p = static_cast<T*>(d);
+  return RFE_OK;
+}
+int split_alloc(rfe_ctx* c, SplitBuf* b, size_t count) {
+  int r = dev_alloc(c, &b->hi, count);
+  if (r) return r;
+  return dev_alloc(c, &b->lo, count);
+}
+int upload_f32(rfe_ctx* c, float** dst, const float* src, size_t n) {
+  int r = dev_alloc(c, dst, n);
+  if (r) return r;
+  RFE_CUDA_CHECK(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+  return RFE_OK;
+}
+// rows of `src` ([n][k] fp32) are taken in the order perm[] (or identity) and stored split
+int upload_split(rfe_ctx* c, SplitW* w, const float* src, const float* bias, int n, int k, const int* perm = nullptr) {
+  std::vector<__half> hi(static_cast<size_t>(n) * k), lo(static_cast<size_t>(n) * k);
+  std::vector<float> b(n);
+  for (int i = 0; i < n; ++i) {
+    const int si = perm ? perm[i] : i;
+    for (int j = 0; j < k; ++j) split_f32(src[static_cast<size_t>(si) * k + j], hi[static_cast<size_t>(i) * k + j],
+                                          lo[static_cast<size_t>(i) * k + j]);
+    b[i] = bias ? bias[si] : 0.0f;
+  }
+  int r = split_alloc(c, &w->w, hi.size());
+  if (r) return r;
+  RFE_CUDA_CHECK(cudaMemcpy(w->w.hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
+  RFE_CUDA_CHECK(cudaMemcpy(w->w.lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+  if (bias) {
+    r = upload_f32(c, &w->bias, b.data(), n);
+    if (r) return r;
+  }
+  w->n = n;
+  w->k = k;
+  return RFE_OK;
+}
+
+int load_linear(rfe_ctx* c, const WeightBlob& blob, const std::string& name, SplitW* w, const int* perm = nullptr) {
+  const HostTensor* t = blob.find(name + ".w");
+  const HostTensor* b = blob.find(name + ".b");
+  if (!t || t->dims.size() < 2) {
+    set_error("weight '%s.w' missing from blob", name.c_str());
+    return RFE_ERR_IO;
+  }
+  const int n = t->dims[0];
+  const int k = static_cast<int>(t->size() / n);
+  return upload_split(c, w, t->data, b ? b->data : nullptr, n, k, perm);
+}
+int load_vec(rfe_ctx* c, const WeightBlob& blob, const std::string& name, float** dst) {
+  const HostTensor* t = blob.find(name);
+  if (!t) {
+    set_error("weight '%s' missing from blob", name.c_str());
+    return RFE_ERR_IO;
+  }
+  return upload_f32(c, dst, t->data, t->size());
+}
+
+int load_weights(rfe_ctx* c, const char* path) {
+  WeightBlob blob;
+  if (blob.load(path)) return RFE_ERR_IO;
+  int r;
+  if ((r = load_vec(c, blob, "sp.conv1a.w", &c->conv1a_w))) return r;
+  if ((r = load_vec(c, blob, "sp.conv1a.b", &c->conv1a_b))) return r;
+  struct { const char* n; SplitW* w; } convs[] = {
+      {"sp.conv1b", &c->c1b}, {"sp.conv2a", &c->c2a}, {"sp.conv2b", &c->c2b}, {"sp.conv3a", &c->c3a},
+      {"sp.conv3b", &c->c3b}, {"sp.conv4a", &c->c4a}, {"sp.conv4b", &c->c4b}, {"sp.convPa", &c->cPa},
+      {"sp.convPb", &c->cPb}, {"sp.convDa", &c->cDa}, {"sp.convDb", &c->cDb}};
+  for (auto& e : convs)
+    if ((r = load_linear(c, blob, e.n, e.w))) return r;   // OHWI flattens to [Cout][9*Cin]
+  if ((r = load_vec(c, blob, "lg.posenc.w", &c->posenc_w))) return r;
+  // Wqkv rows: ONNX column c = h*192 + d*3 + t  ->  ours t*256 + h*64 + d
+  std::vector<int> perm(768);
+  for (int t = 0; t < 3; ++t)
+    for (int h = 0; h < 4; ++h)
+      for (int d = 0; d < 64; ++d) perm[t * 256 + h * 64 + d] = h * 192 + d * 3 + t;
+  for (int i = 0; i < kLayers; ++i) {
+    LgLayer& L = c->layers[i];
+    const std::string p = "lg.l" + std::to_string(i);
+    if ((r = load_linear(c, blob, p + ".self.wqkv", &L.wqkv, perm.data()))) return r;
+    if ((r = load_linear(c, blob, p + ".self.out_proj", &L.out_proj))) return r;
+    if ((r = load_linear(c, blob, p + ".self.ffn0", &L.s_ffn0))) return r;
+    if ((r = load_linear(c, blob, p + ".self.ffn3", &L.s_ffn3))) return r;
+    if ((r = load_linear(c, blob, p + ".cross.to_qk", &L.to_qk))) return r;
+    if ((r = load_linear(c, blob, p + ".cross.to_v", &L.to_v))) return r;
+    if ((r = load_linear(c, blob, p + ".cross.to_out", &L.to_out))) return r;
+    if ((r = load_linear(c, blob, p + ".cross.ffn0", &L.c_ffn0))) return r;
+    if ((r = load_linear(c, blob, p + ".cross.ffn3", &L.c_ffn3))) return r;
+    if ((r = load_vec(c, blob, p + ".self.ln.w", &L.s_ln_w))) return r;
+    if ((r = load_vec(c, blob, p + ".self.ln.b", &L.s_ln_b))) return r;
+    if ((r = load_vec(c, blob, p + ".cross.ln.w", &L.c_ln_w))) return r;
+    if ((r = load_vec(c, blob, p + ".cross.ln.b", &L.c_ln_b))) return r;
+  }
+  if ((r = load_linear(c, blob, "lg.final_proj", &c->final_proj))) return r;
+  if ((r = load_vec(c, blob, "lg.matchability.w", &c->match_w))) return r;
+  if ((r = load_vec(c, blob, "lg.matchability.b", &c->match_b))) return r;
+  return RFE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor-core launches
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int AMODE, int EPI>
+int launch_umma(rfe_ctx* c, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                const CUtensorMap& b_lo, const UmmaParams& p, dim3 grid) {
+  static bool configured[64] = {};
+  auto kern = umma_kernel<BLOCK_N, AMODE, EPI>;
+  if (!configured[c->device & 63]) {
+    RFE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, umma_smem_bytes(BLOCK_N)));
+    configured[c->device & 63] = true;
+  }
+  kern<<<grid, kUmmaThreads, umma_smem_bytes(BLOCK_N), c->stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+  c->launches++;
+  RFE_CUDA_CHECK(cudaGetLastError());
+  return RFE_OK;
+}
+
+struct Operand {          // K-major split-fp16 matrix [batch][rows][k], row pitch ld, batch pitch bstride (elements)
+  const __half* hi;
+  const __half* lo;
+  int rows, k;
+  long long ld, bstride;
+  int batch;
+};
+
+int make_operand_maps(const Operand& o, int box_rows, CUtensorMap* mh, CUtensorMap* ml) {
+  const uint64_t dims[3] = {static_cast<uint64_t>(o.k), static_cast<uint64_t>(o.rows), static_cast<uint64_t>(o.batch)};
+  const long long bs = o.batch > 1 ? o.bstride : static_cast<long long>(o.rows) * o.ld;
+  const uint64_t strides[2] = {static_cast<uint64_t>(o.ld) * 2, static_cast<uint64_t>(bs) * 2};
+  const uint32_t box[3] = {64, static_cast<uint32_t>(box_rows), 1};
+  if (make_tmap_f16_sw128(mh, o.hi, 3, dims, strides, box)) return RFE_ERR_CUDA;
+  if (make_tmap_f16_sw128(ml, o.lo, 3, dims, strides, box)) return RFE_ERR_CUDA;
+  return RFE_OK;
+}
+
+UmmaParams default_params() {
+  UmmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.scale = 1.0f;
+  return p;
+}
+
+// D = A * B^T with the LINEAR epilogue.  p carries the epilogue; M/N/K are filled here.
+int gemm_linear(rfe_ctx* c, const Operand& A, const Operand& B, UmmaParams p, int block_n) {
+  if (A.rows == 0 || B.rows == 0) return RFE_OK;
+  CUtensorMap ah, al, bh, bl;
+  int r;
+  if ((r = make_operand_maps(A, kBlockM, &ah, &al))) return r;
+  if ((r = make_operand_maps(B, block_n, &bh, &bl))) return r;
+  p.num_k_steps = (A.k + 63) / 64;
+  p.M = A.rows;
+  p.N = B.rows;
+  p.a_batched = A.batch > 1;
+  p.b_batched = B.batch > 1;
+  const int z = A.batch > B.batch ? A.batch : B.batch;
+  dim3 grid((A.rows + kBlockM - 1) / kBlockM, (B.rows + block_n - 1) / block_n, z);
+  if (block_n == 64) return launch_umma<64, A_GEMM, EPI_LINEAR>(c, ah, al, bh, bl, p, grid);
+  return launch_umma<128, A_GEMM, EPI_LINEAR>(c, ah, al, bh, bl, p, grid);
+}
+
+// 3x3 conv (pad 1) + bias + ReLU (+ 2x2 max-pool), NHWC split-fp16 in/out.
+int conv3x3(rfe_ctx* c, const SplitBuf& in, int B, int H, int W, int Cin, const SplitW& w, const SplitBuf& out,
+            bool pool) {
+  const uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                            static_cast<uint64_t>(B)};
+  const uint64_t strides[3] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(W) * Cin * 2,
+                               static_cast<uint64_t>(H) * W * Cin * 2};
+  const uint32_t box[4] = {64, 16, 8, 1};
+  CUtensorMap ah, al, bh, bl;
+  if (make_tmap_f16_sw128(&ah, in.hi, 4, dims, strides, box)) return RFE_ERR_CUDA;
+  if (make_tmap_f16_sw128(&al, in.lo, 4, dims, strides, box)) return RFE_ERR_CUDA;
+  const int block_n = w.n == 64 ? 64 : 128;
+  Operand Bop{w.w.hi, w.w.lo, w.n, w.k, w.k, 0, 1};
+  int r;
+  if ((r = make_operand_maps(Bop, block_n, &bh, &bl))) return r;
+  UmmaParams p = default_params();
+  p.num_k_steps = 9 * Cin / 64;
+  p.cin_chunks = Cin / 64;
+  p.N = w.n;
+  p.H = H;
+  p.W = W;
+  p.tiles_x = (W + 15) / 16;
+  p.tiles_y = (H + 7) / 8;
+  p.bias = w.bias;
+  p.out_hi = out.hi;
+  p.out_lo = out.lo;
+  p.pool = pool ? 1 : 0;
+  p.relu = 1;
+  dim3 grid(p.tiles_x * p.tiles_y * B, w.n / block_n, 1);
+  if (block_n == 64) return launch_umma<64, A_CONV3, EPI_CONV>(c, ah, al, bh, bl, p, grid);
+  return launch_umma<128, A_CONV3, EPI_CONV>(c, ah, al, bh, bl, p, grid);
+}
+
+// ------------------------------------------------------------------------------------------------
+// SuperPoint: device in -> device-resident features
+// ------------------------------------------------------------------------------------------------
+int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B) {
+  cudaStream_t s = c->stream;
+  int r;
+  launch_conv1a(s, d_gray, stride, h, w, B, c->conv1a_w, c->conv1a_b, c->a1a.hi, c->a1a.lo);
+  c->launches++;
+  if ((r = conv3x3(c, c->a1a, B, h, w, 64, c->c1b, c->a1, true))) return r;
+  if ((r = conv3x3(c, c->a1, B, h / 2, w / 2, 64, c->c2a, c->a2a, false))) return r;
+  if ((r = conv3x3(c, c->a2a, B, h / 2, w / 2, 64, c->c2b, c->a2, true))) return r;
+  if ((r = conv3x3(c, c->a2, B, h / 4, w / 4, 64, c->c3a, c->a3a, false))) return r;
+  if ((r = conv3x3(c, c->a3a, B, h / 4, w / 4, 128, c->c3b, c->a3, true))) return r;
+  const int hc = h / 8, wc = w / 8;
+  if ((r = conv3x3(c, c->a3, B, hc, wc, 128, c->c4a, c->a4a, false))) return r;
+  if ((r = conv3x3(c, c->a4a, B, hc, wc, 128, c->c4b, c->feat, false))) return r;
+  if ((r = conv3x3(c, c->feat, B, hc, wc, 128, c->cPa, c->pa, false))) return r;
+  if ((r = conv3x3(c, c->feat, B, hc, wc, 128, c->cDa, c->da, false))) return r;
+  const int npix = B * hc * wc;
+  {   // detector head: 1x1 conv 256->65 + softmax + depth-to-space
+    Operand A{c->pa.hi, c->pa.lo, npix, 256, 256, 0, 1};
+    Operand Bw{c->cPb.w.hi, c->cPb.w.lo, 65, 256, 256, 0, 1};
+    CUtensorMap ah, al, bh, bl;
+    if ((r = make_operand_maps(A, kBlockM, &ah, &al))) return r;
+    if ((r = make_operand_maps(Bw, 80, &bh, &bl))) return r;
+    UmmaParams p = default_params();
+    p.num_k_steps = 4;
+    p.M = npix;
+    p.N = 65;
+    p.H = hc;
+    p.W = wc;
+    p.bias = c->cPb.bias;
+    p.out_f32 = c->heat;
+    if ((r = launch_umma<80, A_GEMM, EPI_DET>(c, ah, al, bh, bl, p, dim3((npix + 127) / 128, 1, 1)))) return r;
+  }
+  {   // descriptor head: 1x1 conv 256->256 + L2 norm
+    Operand A{c->da.hi, c->da.lo, npix, 256, 256, 0, 1};
+    Operand Bw{c->cDb.w.hi, c->cDb.w.lo, 256, 256, 256, 0, 1};
+    CUtensorMap ah, al, bh, bl;
+    if ((r = make_operand_maps(A, kBlockM, &ah, &al))) return r;
+    if ((r = make_operand_maps(Bw, 256, &bh, &bl))) return r;
+    UmmaParams p = default_params();
+    p.num_k_steps = 4;
+    p.M = npix;
+    p.N = 256;
+    p.bias = c->cDb.bias;
+    p.out_f32 = c->dense;
+    p.ld_f32 = 256;
+    if ((r = launch_umma<256, A_GEMM, EPI_DESC>(c, ah, al, bh, bl, p, dim3((npix + 127) / 128, 1, 1)))) return r;
+  }
+  launch_nms(s, c->heat, c->nmsmap, B, h, w);
+  launch_select(s, c->nmsmap, B, h, w, kDetThreshold, c->cap, c->row_cnt, c->row_off, c->kp_counts, c->kpts,
+                c->kp_scores);
+  launch_desc_sample(s, c->dense, hc, wc, B, c->kpts, c->kp_counts, c->cap, c->desc);
+  c->launches += 5;
+  RFE_CUDA_CHECK(cudaGetLastError());
+  c->last_batch = B;
+  c->last_h = h;
+  c->last_w = w;
+  return RFE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LightGlue: device-resident inputs (pixel keypoints fp32 [n][2], descriptors fp32 [n][256])
+// Rows of image 0 live at [0, n0), rows of image 1 at [n0p, n0p + n1) with n0p = round_up(n0, 8).
+// ------------------------------------------------------------------------------------------------
+int ffn_block(rfe_ctx* c, int rows, const SplitW& ffn0, const float* ln_w, const float* ln_b, const SplitW& ffn3) {
+  int r;
+  {   // hid = cat @ ffn0^T + b
+    Operand A{c->cat.hi, c->cat.lo, rows, 512, 512, 0, 1};
+    Operand B{ffn0.w.hi, ffn0.w.lo, 512, 512, 512, 0, 1};
+    UmmaParams p = default_params();
+    p.bias = ffn0.bias;
+    p.out_f32 = c->hid;
+    p.ld_f32 = 512;
+    if ((r = gemm_linear(c, A, B, p, 128))) return r;
+  }
+  launch_ln_gelu_split(c->stream, c->hid, rows, ln_w, ln_b, c->hs.hi, c->hs.lo);
+  c->launches++;
+  {   // x = x + hs @ ffn3^T + b ; refresh split(x) in cat[:, 0:256]
+    Operand A{c->hs.hi, c->hs.lo, rows, 512, 512, 0, 1};
+    Operand B{ffn3.w.hi, ffn3.w.lo, 256, 512, 512, 0, 1};
+    UmmaParams p = default_params();
+    p.bias = ffn3.bias;
+    p.residual = c->x;
+    p.ld_res = 256;
+    p.out_f32 = c->x;
+    p.ld_f32 = 256;
+    p.out_hi = c->cat.hi;
+    p.out_lo = c->cat.lo;
+    p.ld_h = 512;
+    if ((r = gemm_linear(c, A, B, p, 128))) return r;
+  }
+  return RFE_OK;
+}
+
+// softmax(Qa Kb^T) Vb for 4 heads; Q rows [qa, qa+nq), K/V rows/cols [kb, kb+nk); result -> attn rows [qa, ...)
+int attention(rfe_ctx* c, const SplitBuf& Q, const SplitBuf& K, int rows_total, int qa, int nq, int kb, int nk) {
+  if (nq == 0 || nk == 0) return RFE_OK;
+  int r;
+  const long long hs = static_cast<long long>(rows_total) * 64;
+  const int ld = round_up(nk, 8);
+  {
+    Operand A{Q.hi + static_cast<size_t>(qa) * 64, Q.lo + static_cast<size_t>(qa) * 64, nq, 64, 64, hs, 4};
+    Operand B{K.hi + static_cast<size_t>(kb) * 64, K.lo + static_cast<size_t>(kb) * 64, nk, 64, 64, hs, 4};
+    UmmaParams p = default_params();
+    p.out_f32 = c->S;
+    p.ld_f32 = ld;
+    p.bstride_f32 = static_cast<long long>(nq) * ld;
+    if ((r = gemm_linear(c, A, B, p, 128))) return r;
+  }
+  launch_softmax_split(c->stream, c->S, 4 * nq, nk, ld, c->P.hi, c->P.lo, ld);
+  c->launches++;
+  {
+    Operand A{c->P.hi, c->P.lo, nq, nk, ld, static_cast<long long>(nq) * ld, 4};
+    Operand B{c->vt.hi + kb, c->vt.lo + kb, 64, nk, c->lg_ldv, 64LL * c->lg_ldv, 4};
+    UmmaParams p = default_params();
+    p.out_hi = c->attn.hi + static_cast<size_t>(qa) * 256;
+    p.out_lo = c->attn.lo + static_cast<size_t>(qa) * 256;
+    p.ld_h = 256;
+    p.bstride_h = 64;
+    if ((r = gemm_linear(c, A, B, p, 64))) return r;
+  }
+  return RFE_OK;
+}
+
+int lg_run(rfe_ctx* c, const float* d_kpts0, int n0, const float* d_kpts1, int n1, const float* d_desc0,
+           const float* d_desc1, int norm_h, int norm_w, float thresh, int rslot) {
+  cudaStream_t s = c->stream;
+  int* count = c->res_count + rslot;
+  if (n0 == 0 || n1 == 0) {
+    RFE_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int), s));
+    return RFE_OK;
+  }
+  const int n0p = round_up(n0, 8);
+  const int rows = n0p + n1;
+  int r;
+  launch_posenc(s, d_kpts0, n0, norm_h, norm_w, c->posenc_w, c->cs, c->sn);
+  launch_posenc(s, d_kpts1, n1, norm_h, norm_w, c->posenc_w, c->cs + static_cast<size_t>(n0p) * 32,
+                c->sn + static_cast<size_t>(n0p) * 32);
+  launch_split_rows(s, d_desc0, n0, 256, 256, c->x, 256, c->cat.hi, c->cat.lo, 512);
+  launch_split_rows(s, d_desc1, n1, 256, 256, c->x + static_cast<size_t>(n0p) * 256, 256,
+                    c->cat.hi + static_cast<size_t>(n0p) * 512, c->cat.lo + static_cast<size_t>(n0p) * 512, 512);
+  c->launches += 4;
+  const long long hs = static_cast<long long>(rows) * 64;
+  for (int i = 0; i < kLayers; ++i) {
+    const LgLayer& L = c->layers[i];
+    // ---------------- self attention ----------------
+    {
+      Operand A{c->cat.hi, c->cat.lo, rows, 256, 512, 0, 1};
+      Operand B{L.wqkv.w.hi, L.wqkv.w.lo, 768, 256, 256, 0, 1};
+      UmmaParams p = default_params();
+      p.bias = L.wqkv.bias;
+      p.out_f32 = c->qkv;
+      p.ld_f32 = 768;
+      if ((r = gemm_linear(c, A, B, p, 128))) return r;
+    }
+    launch_rope_split(s, c->qkv, rows, c->cs, c->sn, kAttnScale, c->q.hi, c->q.lo, c->k.hi, c->k.lo, c->vt.hi,
+                      c->vt.lo, c->lg_ldv);
+    c->launches++;
+    if ((r = attention(c, c->q, c->k, rows, 0, n0, 0, n0))) return r;
+    if ((r = attention(c, c->q, c->k, rows, n0p, n1, n0p, n1))) return r;
+    {
+      Operand A{c->attn.hi, c->attn.lo, rows, 256, 256, 0, 1};
+      Operand B{L.out_proj.w.hi, L.out_proj.w.lo, 256, 256, 256, 0, 1};
+      UmmaParams p = default_params();
+      p.bias = L.out_proj.bias;
+      p.out_hi = c->cat.hi + 256;
+      p.out_lo = c->cat.lo + 256;
+      p.ld_h = 512;
+      if ((r = gemm_linear(c, A, B, p, 128))) return r;
+    }
+    if ((r = ffn_block(c, rows, L.s_ffn0, L.s_ln_w, L.s_ln_b, L.s_ffn3))) return r;
+    // ---------------- cross attention ----------------
+    {
+      Operand A{c->cat.hi, c->cat.lo, rows, 256, 512, 0, 1};
+      Operand B{L.to_qk.w.hi, L.to_qk.w.lo, 256, 256, 256, 0, 1};
+      UmmaParams p = default_params();
+      p.bias = L.to_qk.bias;
+      p.scale = kAttnScale;
+      p.out_hi = c->q.hi;
+      p.out_lo = c->q.lo;
+      p.head_major = 1;
+      p.head_stride = hs;
+      if ((r = gemm_linear(c, A, B, p, 128))) return r;
+    }
+    {
+      Operand A{c->cat.hi, c->cat.lo, rows, 256, 512, 0, 1};
+      Operand B{L.to_v.w.hi, L.to_v.w.lo, 256, 256, 256, 0, 1};
+      UmmaParams p = default_params();
+      p.bias = L.to_v.bias;
+      p.out_hi = c->vt.hi;
+      p.out_lo = c->vt.lo;
+      p.transpose_h = 1;
+      p.ld_h = c->lg_ldv;
+      if ((r = gemm_linear(c, A, B, p, 128))) return r;
+    }
+    if ((r = attention(c, c->q, c->q, rows, 0, n0, n0p, n1))) return r;
+    if ((r = attention(c, c->q, c->q, rows, n0p, n1, 0, n0))) return r;
+    {
+      Operand A{c->attn.hi, c->attn.lo, rows, 256, 256, 0, 1};
+      Operand B{L.to_out.w.hi, L.to_out.w.lo, 256, 256, 256, 0, 1};
+      UmmaParams p = default_params();
+      p.bias = L.to_out.bias;
+      p.out_hi = c->cat.hi + 256;
+      p.out_lo = c->cat.lo + 256;
+      p.ld_h = 512;
+      if ((r = gemm_linear(c, A, B, p, 128))) return r;
+    }
+    if ((r = ffn_block(c, rows, L.c_ffn0, L.c_ln_w, L.c_ln_b, L.c_ffn3))) return r;
+  }
+  // ---------------- assignment ----------------
+  {
+    Operand A{c->cat.hi, c->cat.lo, rows, 256, 512, 0, 1};
+    Operand B{c->final_proj.w.hi, c->final_proj.w.lo, 256, 256, 256, 0, 1};
+    UmmaParams p = default_params();
+    p.bias = c->final_proj.bias;
+    p.scale = 0.25f;
+    p.out_hi = c->md.hi;
+    p.out_lo = c->md.lo;
+    p.ld_h = 256;
+    if ((r = gemm_linear(c, A, B, p, 128))) return r;
+  }
+  const int ld = round_up(n1, 8);
+  {
+    Operand A{c->md.hi, c->md.lo, n0, 256, 256, 0, 1};
+    Operand B{c->md.hi + static_cast<size_t>(n0p) * 256, c->md.lo + static_cast<size_t>(n0p) * 256, n1, 256, 256, 0, 1};
+    UmmaParams p = default_params();
+    p.out_f32 = c->sim;
+    p.ld_f32 = ld;
+    if ((r = gemm_linear(c, A, B, p, 128))) return r;
+  }
+  launch_matchability(s, c->x, rows, c->match_w, c->match_b, c->ls);
+  launch_lse(s, c->sim, n0, n1, ld, c->rmax, c->rlog, c->cmax, c->clog);
+  launch_argmax(s, c->sim, n0, n1, ld, c->rmax, c->rlog, c->cmax, c->clog, c->ls, c->ls + n0p, c->max0, c->m0, c->m1,
+                c->S_dbg);
+  launch_match_compact(s, c->max0, c->m0, c->m1, n0, kFilterThreshold, thresh,
+                       c->res_matches + static_cast<size_t>(rslot) * c->cap * 2,
+                       c->res_scores + static_cast<size_t>(rslot) * c->cap, count);
+  c->launches += 6;
+  c->dbg_n0 = n0;
+  c->dbg_n1 = n1;
+  c->dbg_n0p = n0p;
+  RFE_CUDA_CHECK(cudaGetLastError());
+  return RFE_OK;
+}
+
+int check_ctx(rfe_ctx* c) {
+  if (!c) {
+    set_error("null ctx");
+    return RFE_ERR_INVALID;
+  }
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) {
+    set_error("cudaSetDevice(%d): %s", c->device, cudaGetErrorString(e));
+    return RFE_ERR_CUDA;
+  }
+  return RFE_OK;
+}
+
+// combine a split tensor into fp32 on the device (debug only)
+__global__ void combine_split_kernel(const __half* hi, const __half* lo, float* out, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __half2float(hi[i]) + __half2float(lo[i]) * RFE_SPLIT_INV;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* rfe_last_error(void) { return get_error(); }
+
+int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
+  if (!cfg || !out) {
+    set_error("rfe_create: null argument");
+    return RFE_ERR_INVALID;
+  }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: the rover_fe front end has no CPU fallback");
+    return RFE_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  RFE_CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library contains sm_100a code only", cfg->device, prop.major, prop.minor);
+    return RFE_ERR_NO_DEVICE;
+  }
+  RFE_CUDA_CHECK(cudaSetDevice(cfg->device));
+  rfe_ctx* c = new rfe_ctx();
+  c->device = cfg->device;
+  c->max_batch = cfg->max_batch > 0 ? cfg->max_batch : 8;
+  c->max_h = cfg->max_height > 0 ? cfg->max_height : 480;
+  c->max_w = cfg->max_width > 0 ? cfg->max_width : 768;
+  c->cap = cfg->max_keypoints > 0 ? cfg->max_keypoints : 4096;
+  if (c->max_h % 8 || c->max_w % 8) {
+    set_error("max_height/max_width must be multiples of 8");
+    delete c;
+    return RFE_ERR_INVALID;
+  }
+  if (cfg->stream) {
+    c->stream = static_cast<cudaStream_t>(cfg->stream);
+  } else {
+    RFE_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  RFE_CUDA_CHECK(cudaEventCreate(&c->ev0));
+  RFE_CUDA_CHECK(cudaEventCreate(&c->ev1));
+  const char* path = cfg->weights_path;
+  if (!path) path = getenv("ROVER_FE_WEIGHTS");
+  if (!path) path = "weights/rover_fe.rfw";
+  int r = load_weights(c, path);
+  if (r) {
+    rfe_destroy(c);
+    return r;
+  }
+  if (nms_prepare()) {
+    set_error("cudaFuncSetAttribute(nms) failed");
+    rfe_destroy(c);
+    return RFE_ERR_CUDA;
+  }
+  // ---- SuperPoint buffers ----
+  const size_t B = c->max_batch, H = c->max_h, W = c->max_w, cap = c->cap;
+  const size_t full = B * H * W, half_ = full / 4, quarter = full / 16, coarse = full / 64;
+#define A_(expr) if ((r = (expr))) { rfe_destroy(c); return r; }
+  A_(dev_alloc(c, &c->img, full));
+  A_(split_alloc(c, &c->a1a, full * 64));
+  A_(split_alloc(c, &c->a1, half_ * 64));
+  A_(split_alloc(c, &c->a2a, half_ * 64));
+  A_(split_alloc(c, &c->a2, quarter * 64));
+  A_(split_alloc(c, &c->a3a, quarter * 128));
+  A_(split_alloc(c, &c->a3, coarse * 128));
+  A_(split_alloc(c, &c->a4a, coarse * 128));
+  A_(split_alloc(c, &c->feat, coarse * 128));
+  A_(split_alloc(c, &c->pa, coarse * 256));
+  A_(split_alloc(c, &c->da, coarse * 256));
+  A_(dev_alloc(c, &c->heat, full));
+  A_(dev_alloc(c, &c->nmsmap, full));
+  A_(dev_alloc(c, &c->dense, coarse * 256));
+  A_(dev_alloc(c, &c->row_cnt, B * H));
+  A_(dev_alloc(c, &c->row_off, B * H));
+  A_(dev_alloc(c, &c->kp_counts, B));
+  A_(dev_alloc(c, &c->kpts, B * cap * 2));
+  A_(dev_alloc(c, &c->kp_scores, B * cap));
+  A_(dev_alloc(c, &c->desc, B * cap * 256));
+  RFE_CUDA_CHECK(cudaMallocHost(&c->h_counts, sizeof(int) * (B + 1)));
+  // ---- LightGlue buffers ----
+  c->lg_rows = 2 * c->cap + 8;
+  c->lg_ld = round_up(c->cap, 8);
+  c->lg_ldv = round_up(c->lg_rows, 8);
+  const size_t R = c->lg_rows, LD = c->lg_ld;
+  A_(dev_alloc(c, &c->in_kpts, R * 2));
+  A_(dev_alloc(c, &c->in_desc, R * 256));
+  A_(dev_alloc(c, &c->cs, R * 32));
+  A_(dev_alloc(c, &c->sn, R * 32));
+  A_(dev_alloc(c, &c->x, R * 256));
+  A_(split_alloc(c, &c->cat, R * 512));
+  A_(dev_alloc(c, &c->qkv, R * 768));
+  A_(split_alloc(c, &c->q, R * 256));
+  A_(split_alloc(c, &c->k, R * 256));
+  A_(split_alloc(c, &c->vt, 256 * static_cast<size_t>(c->lg_ldv)));
+  A_(dev_alloc(c, &c->S, 4 * cap * LD));
+  A_(split_alloc(c, &c->P, 4 * cap * LD));
+  A_(split_alloc(c, &c->attn, R * 256));
+  A_(dev_alloc(c, &c->hid, R * 512));
+  A_(split_alloc(c, &c->hs, R * 512));
+  A_(split_alloc(c, &c->md, R * 256));
+  A_(dev_alloc(c, &c->sim, cap * LD));
+  A_(dev_alloc(c, &c->rmax, cap));
+  A_(dev_alloc(c, &c->rlog, cap));
+  A_(dev_alloc(c, &c->cmax, cap));
+  A_(dev_alloc(c, &c->clog, cap));
+  A_(dev_alloc(c, &c->ls, R));
+  A_(dev_alloc(c, &c->max0, cap));
+  A_(dev_alloc(c, &c->m0, cap));
+  A_(dev_alloc(c, &c->m1, cap));
+  A_(dev_alloc(c, &c->res_matches, B * cap * 2));
+  A_(dev_alloc(c, &c->res_scores, B * cap));
+  A_(dev_alloc(c, &c->res_count, B));
+#undef A_
+  RFE_CUDA_CHECK(cudaDeviceSynchronize());
+  *out = c;
+  return RFE_OK;
+}
+
+void rfe_destroy(rfe_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (void* p : c->allocs) cudaFree(p);
+  if (c->h_counts) cudaFreeHost(c->h_counts);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int rfe_sync(rfe_ctx* c) {
+  int r = check_ctx(c);
+  if (r) return r;
+  RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return RFE_OK;
+}
+
+static int check_image_args(rfe_ctx* c, int h, int w, int stride, int batch) {
+  if (h <= 0 || w <= 0 || h % 8 || w % 8 || h > c->max_h || w > c->max_w || stride < w || batch <= 0 ||
+      batch > c->max_batch || static_cast<size_t>(batch) * h * stride > static_cast<size_t>(c->max_batch) * c->max_h * c->max_w) {
+    set_error("invalid image arguments h=%d w=%d stride=%d batch=%d (limits %dx%d x%d; h,w multiples of 8)", h, w,
+              stride, batch, c->max_h, c->max_w, c->max_batch);
+    return RFE_ERR_INVALID;
+  }
+  return RFE_OK;
+}
+
+int rfe_sp_extract_device(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int batch) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (!d_gray) {
+    set_error("null image");
+    return RFE_ERR_INVALID;
+  }
+  if ((r = check_image_args(c, h, w, stride, batch))) return r;
+  return sp_run(c, d_gray, h, w, stride, batch);
+}
+
+int rfe_sp_read_slot(rfe_ctx* c, int slot, int32_t* kpts_xy, float* scores, float* desc, int32_t* count, int cap) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (slot < 0 || slot >= c->last_batch) {
+    set_error("slot %d out of range (last batch %d)", slot, c->last_batch);
+    return RFE_ERR_INVALID;
+  }
+  RFE_CUDA_CHECK(cudaMemcpyAsync(c->h_counts, c->kp_counts + slot, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  const int n = c->h_counts[0];
+  if (count) *count = n;
+  int m = n < c->cap ? n : c->cap;
+  if (cap < m) m = cap;
+  if (m > 0) {
+    if (kpts_xy) RFE_CUDA_CHECK(cudaMemcpyAsync(kpts_xy, c->kpts + static_cast<size_t>(slot) * c->cap * 2, sizeof(int) * 2 * m, cudaMemcpyDeviceToHost, c->stream));
+    if (scores) RFE_CUDA_CHECK(cudaMemcpyAsync(scores, c->kp_scores + static_cast<size_t>(slot) * c->cap, sizeof(float) * m, cudaMemcpyDeviceToHost, c->stream));
+    if (desc) RFE_CUDA_CHECK(cudaMemcpyAsync(desc, c->desc + static_cast<size_t>(slot) * c->cap * 256, sizeof(float) * 256 * m, cudaMemcpyDeviceToHost, c->stream));
+    RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  }
+  if (n > c->cap || n > cap) {
+    set_error("image slot %d has %d keypoints, capacity %d", slot, n, cap < c->cap ? cap : c->cap);
+    return RFE_ERR_CAPACITY;
+  }
+  return RFE_OK;
+}
+
+int rfe_sp_extract_u8(rfe_ctx* c, const uint8_t* gray, int h, int w, int stride, int batch, int32_t* kpts_xy,
+                      float* scores, float* desc, int32_t* counts, int cap) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (!gray || !kpts_xy || !counts || cap <= 0) {
+    set_error("rfe_sp_extract_u8: null/invalid argument");
+    return RFE_ERR_INVALID;
+  }
+  if ((r = check_image_args(c, h, w, stride, batch))) return r;
+  cudaStream_t s = c->stream;
+  RFE_CUDA_CHECK(cudaEventRecord(c->ev0, s));
+  RFE_CUDA_CHECK(cudaMemcpyAsync(c->img, gray, static_cast<size_t>(batch) * h * stride, cudaMemcpyHostToDevice, s));
+  if ((r = sp_run(c, c->img, h, w, stride, batch))) return r;
+  RFE_CUDA_CHECK(cudaMemcpyAsync(c->h_counts, c->kp_counts, sizeof(int) * batch, cudaMemcpyDeviceToHost, s));
+  RFE_CUDA_CHECK(cudaStreamSynchronize(s));
+  int rc = RFE_OK;
+  for (int b = 0; b < batch; ++b) {
+    const int n = c->h_counts[b];
+    counts[b] = n;
+    int m = n < c->cap ? n : c->cap;
+    if (cap < m) m = cap;
+    if (n > c->cap || n > cap) {
+      set_error("image %d has %d keypoints, capacity %d", b, n, cap < c->cap ? cap : c->cap);
+      rc = RFE_ERR_CAPACITY;
+    }
+    if (m == 0) continue;
+    RFE_CUDA_CHECK(cudaMemcpyAsync(kpts_xy + static_cast<size_t>(b) * cap * 2, c->kpts + static_cast<size_t>(b) * c->cap * 2, sizeof(int) * 2 * m, cudaMemcpyDeviceToHost, s));
+    if (scores) RFE_CUDA_CHECK(cudaMemcpyAsync(scores + static_cast<size_t>(b) * cap, c->kp_scores + static_cast<size_t>(b) * c->cap, sizeof(float) * m, cudaMemcpyDeviceToHost, s));
+    if (desc) RFE_CUDA_CHECK(cudaMemcpyAsync(desc + static_cast<size_t>(b) * cap * 256, c->desc + static_cast<size_t>(b) * c->cap * 256, sizeof(float) * 256 * m, cudaMemcpyDeviceToHost, s));
+  }
+  RFE_CUDA_CHECK(cudaEventRecord(c->ev1, s));
+  RFE_CUDA_CHECK(cudaStreamSynchronize(s));
+  float ms = 0.0f;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  c->timer_extract_ms += ms;
+  return rc;
+}
+
+int rfe_lg_match_slots(rfe_ctx* c, int slot0, int slot1, int norm_h, int norm_w, float thresh, int rslot) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (slot0 < 0 || slot1 < 0 || slot0 >= c->last_batch || slot1 >= c->last_batch || rslot < 0 || rslot >= c->max_batch) {
+    set_error("rfe_lg_match_slots: slot out of range");
+    return RFE_ERR_INVALID;
+  }
+  // keypoint counts are needed on the host to size the launches
+  RFE_CUDA_CHECK(cudaMemcpyAsync(c->h_counts, c->kp_counts, sizeof(int) * c->last_batch, cudaMemcpyDeviceToHost, c->stream));
+  RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  const int n0 = c->h_counts[slot0] < c->cap ? c->h_counts[slot0] : c->cap;
+  const int n1 = c->h_counts[slot1] < c->cap ? c->h_counts[slot1] : c->cap;
+  const int n0p = round_up(n0, 8);
+  launch_kpts_to_float(c->stream, c->kpts + static_cast<size_t>(slot0) * c->cap * 2, n0, c->in_kpts);
+  launch_kpts_to_float(c->stream, c->kpts + static_cast<size_t>(slot1) * c->cap * 2, n1, c->in_kpts + static_cast<size_t>(n0p) * 2);
+  c->launches += 2;
+  return lg_run(c, c->in_kpts, n0, c->in_kpts + static_cast<size_t>(n0p) * 2, n1,
+                c->desc + static_cast<size_t>(slot0) * c->cap * 256, c->desc + static_cast<size_t>(slot1) * c->cap * 256,
+                norm_h, norm_w, thresh, rslot);
+}
+
+int rfe_lg_read_result(rfe_ctx* c, int rslot, int32_t* matches, float* mscores, int* k, int cap) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (rslot < 0 || rslot >= c->max_batch || !k) {
+    set_error("rfe_lg_read_result: invalid argument");
+    return RFE_ERR_INVALID;
+  }
+  RFE_CUDA_CHECK(cudaMemcpyAsync(c->h_counts, c->res_count + rslot, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  const int n = c->h_counts[0];
+  *k = n;
+  const int m = n < cap ? n : cap;
+  if (m > 0) {
+    if (matches) RFE_CUDA_CHECK(cudaMemcpyAsync(matches, c->res_matches + static_cast<size_t>(rslot) * c->cap * 2, sizeof(int) * 2 * m, cudaMemcpyDeviceToHost, c->stream));
+    if (mscores) RFE_CUDA_CHECK(cudaMemcpyAsync(mscores, c->res_scores + static_cast<size_t>(rslot) * c->cap, sizeof(float) * m, cudaMemcpyDeviceToHost, c->stream));
+    RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  }
+  if (n > cap) {
+    set_error("%d matches, capacity %d", n, cap);
+    return RFE_ERR_CAPACITY;
+  }
+  return RFE_OK;
+}
+
+int rfe_lg_match(rfe_ctx* c, const float* kpts0, int n0, const float* kpts1, int n1, const float* desc0,
+                 const float* desc1, int norm_h, int norm_w, float thresh, int32_t* matches, float* mscores, int* k) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (!k || n0 < 0 || n1 < 0 || (n0 > 0 && (!kpts0 || !desc0)) || (n1 > 0 && (!kpts1 || !desc1)) || norm_h <= 0 || norm_w <= 0) {
+    set_error("rfe_lg_match: null/invalid argument");
+    return RFE_ERR_INVALID;
+  }
+  if (n0 > c->cap || n1 > c->cap) {
+    set_error("rfe_lg_match: %d/%d keypoints exceed the ctx capacity %d", n0, n1, c->cap);
+    return RFE_ERR_CAPACITY;
+  }
+  *k = 0;
+  if (n0 == 0 || n1 == 0) return RFE_OK;
+  cudaStream_t s = c->stream;
+  const int n0p = round_up(n0, 8);
+  RFE_CUDA_CHECK(cudaEventRecord(c->ev0, s));
+  RFE_CUDA_CHECK(cudaMemcpyAsync(c->in_kpts, kpts0, sizeof(float) * 2 * n0, cudaMemcpyHostToDevice, s));
+  RFE_CUDA_CHECK(cudaMemcpyAsync(c->in_kpts + static_cast<size_t>(n0p) * 2, kpts1, sizeof(float) * 2 * n1, cudaMemcpyHostToDevice, s));
+  RFE_CUDA_CHECK(cudaMemcpyAsync(c->in_desc, desc0, sizeof(float) * 256 * n0, cudaMemcpyHostToDevice, s));
+  RFE_CUDA_CHECK(cudaMemcpyAsync(c->in_desc + static_cast<size_t>(n0p) * 256, desc1, sizeof(float) * 256 * n1, cudaMemcpyHostToDevice, s));
+  if ((r = lg_run(c, c->in_kpts, n0, c->in_kpts + static_cast<size_t>(n0p) * 2, n1, c->in_desc,
+                  c->in_desc + static_cast<size_t>(n0p) * 256, norm_h, norm_w, thresh, 0)))
+    return r;
+  r = rfe_lg_read_result(c, 0, matches, mscores, k, n0);
+  cudaEventRecord(c->ev1, s);
+  cudaStreamSynchronize(s);
+  float ms = 0.0f;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  c->timer_match_ms += ms;
+  return r;
+}
+
+double rfe_get_timer_ms(rfe_ctx* c, const char* name) {
+  if (!c || !name) return 0.0;
+  if (!strcmp(name, "extractor")) return c->timer_extract_ms;
+  if (!strcmp(name, "matcher")) return c->timer_match_ms;
+  return 0.0;
+}
+
+long long rfe_kernel_launches(rfe_ctx* c) { return c ? c->launches : 0; }
+
+int rfe_debug_read(rfe_ctx* c, const char* name, void* dst, size_t capacity, size_t* bytes) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (!name || !bytes) {
+    set_error("rfe_debug_read: null argument");
+    return RFE_ERR_INVALID;
+  }
+  const size_t B = c->last_batch, H = c->last_h, W = c->last_w;
+  const SplitBuf* sb = nullptr;
+  const float* fb = nullptr;
+  size_t n = 0;
+  const std::string s(name);
+  if (s == "sp.a1a") { sb = &c->a1a; n = B * H * W * 64; }
+  else if (s == "sp.pool1") { sb = &c->a1; n = B * H * W / 4 * 64; }
+  else if (s == "sp.a2a") { sb = &c->a2a; n = B * H * W / 4 * 64; }
+  else if (s == "sp.pool2") { sb = &c->a2; n = B * H * W / 16 * 64; }
+  else if (s == "sp.a3a") { sb = &c->a3a; n = B * H * W / 16 * 128; }
+  else if (s == "sp.pool3") { sb = &c->a3; n = B * H * W / 64 * 128; }
+  else if (s == "sp.a4a") { sb = &c->a4a; n = B * H * W / 64 * 128; }
+  else if (s == "sp.feat") { sb = &c->feat; n = B * H * W / 64 * 128; }
+  else if (s == "sp.pa") { sb = &c->pa; n = B * H * W / 64 * 256; }
+  else if (s == "sp.da") { sb = &c->da; n = B * H * W / 64 * 256; }
+  else if (s == "sp.heat") { fb = c->heat; n = B * H * W; }
+  else if (s == "sp.nms") { fb = c->nmsmap; n = B * H * W; }
+  else if (s == "sp.dense") { fb = c->dense; n = B * H * W / 64 * 256; }
+  else if (s == "lg.x") { fb = c->x; n = static_cast<size_t>(c->dbg_n0p + c->dbg_n1) * 256; }
+  else if (s == "lg.sim") { fb = c->sim; n = static_cast<size_t>(c->dbg_n0) * round_up(c->dbg_n1, 8); }
+  else if (s == "lg.S") {
+    if (!c->S_dbg) {   // first request arms the capture; the NEXT match fills it
+      if ((r = dev_alloc(c, &c->S_dbg, static_cast<size_t>(c->cap) * c->cap))) return r;
+      *bytes = 0;
+      return RFE_OK;
+    }
+    fb = c->S_dbg;
+    n = static_cast<size_t>(c->dbg_n0) * c->dbg_n1;
+  } else {
+    set_error("rfe_debug_read: unknown tensor '%s'", name);
+    return RFE_ERR_INVALID;
+  }
+  *bytes = n * sizeof(float);
+  if (n == 0 || !dst) return RFE_OK;
+  if (sb) {
+    if (c->dbg_bytes < n * sizeof(float)) {
+      if ((r = dev_alloc(c, &c->dbg, n))) return r;
+      c->dbg_bytes = n * sizeof(float);
+    }
+    combine_split_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(sb->hi, sb->lo, c->dbg, n);
+    fb = c->dbg;
+  }
+  const size_t cp = *bytes < capacity ? *bytes : capacity;
+  RFE_CUDA_CHECK(cudaMemcpyAsync(dst, fb, cp, cudaMemcpyDeviceToHost, c->stream));
+  RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return RFE_OK;
+}
+
+int rfe_debug_gemm(rfe_ctx* c, const float* a, const float* b, const float* bias, float* d, int m, int n, int kdim) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (!a || !b || !d || m <= 0 || n <= 0 || kdim <= 0 || kdim % 8) {
+    set_error("rfe_debug_gemm: invalid argument (K must be a multiple of 8)");
+    return RFE_ERR_INVALID;
+  }
+  std::vector<__half> ah(static_cast<size_t>(m) * kdim), al(ah.size()), bh(static_cast<size_t>(n) * kdim), bl(bh.size());
+  for (size_t i = 0; i < ah.size(); ++i) split_f32(a[i], ah[i], al[i]);
+  for (size_t i = 0; i < bh.size(); ++i) split_f32(b[i], bh[i], bl[i]);
+  __half *dah, *dal, *dbh, *dbl;
+  float *dd, *dbias = nullptr;
+  RFE_CUDA_CHECK(cudaMalloc(&dah, ah.size() * 2));
+  RFE_CUDA_CHECK(cudaMalloc(&dal, ah.size() * 2));
+  RFE_CUDA_CHECK(cudaMalloc(&dbh, bh.size() * 2));
+  RFE_CUDA_CHECK(cudaMalloc(&dbl, bh.size() * 2));
+  RFE_CUDA_CHECK(cudaMalloc(&dd, static_cast<size_t>(m) * n * 4));
+  RFE_CUDA_CHECK(cudaMemcpy(dah, ah.data(), ah.size() * 2, cudaMemcpyHostToDevice));
+  RFE_CUDA_CHECK(cudaMemcpy(dal, al.data(), al.size() * 2, cudaMemcpyHostToDevice));
+  RFE_CUDA_CHECK(cudaMemcpy(dbh, bh.data(), bh.size() * 2, cudaMemcpyHostToDevice));
+  RFE_CUDA_CHECK(cudaMemcpy(dbl, bl.data(), bl.size() * 2, cudaMemcpyHostToDevice));
+  if (bias) {
+    RFE_CUDA_CHECK(cudaMalloc(&dbias, n * 4));
+    RFE_CUDA_CHECK(cudaMemcpy(dbias, bias, n * 4, cudaMemcpyHostToDevice));
+  }
+  Operand A{dah, dal, m, kdim, kdim, 0, 1};
+  Operand Bo{dbh, dbl, n, kdim, kdim, 0, 1};
+  UmmaParams p = default_params();
+  p.bias = dbias;
+  p.out_f32 = dd;
+  p.ld_f32 = n;
+  r = gemm_linear(c, A, Bo, p, n <= 64 ? 64 : 128);
+  if (!r) {
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+      set_error("debug gemm failed: %s", cudaGetErrorString(e));
+      r = RFE_ERR_CUDA;
+    } else {
+      cudaMemcpy(d, dd, static_cast<size_t>(m) * n * 4, cudaMemcpyDeviceToHost);
+    }
+  }
+  cudaFree(dah); cudaFree(dal); cudaFree(dbh); cudaFree(dbl); cudaFree(dd);
+  if (dbias) cudaFree(dbias);
+  return r;
+}
+
+}  // extern "C"

@@ -1,0 +1,352 @@
+// SuperPoint kernels that are not tensor-core contractions:
+//   conv1a (u8 -> 1/255 -> 3x3 conv 1->64 + ReLU, fp32 CUDA cores; K = 9 is too small for an MMA and the
+//           weights reach +-197 so it is kept in exact fp32),
+//   the 2-iteration 9x9 NMS + border + threshold (graph nodes 58-363),
+//   the ordered (row-major) keypoint compaction (NonZero semantics, nodes 360-398),
+//   the bilinear descriptor sampling + L2 normalisation (nodes 414-485).
+// Reference: onnxmodel/superpoint.onnx as run by src/Extractors/superpoint_onnx.cc:133-136; SURVEY.md Appendix A.
+#include "kernels.h"
+
+namespace rfe {
+
+// ------------------------------------------------------------------------------------------------
+// conv1a: one thread = one pixel x 8 output channels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv1a_kernel(const uint8_t* __restrict__ img, int stride, int H, int W, int B,
+                                                     const float* __restrict__ w /*[64][9]*/,
+                                                     const float* __restrict__ bias, __half* __restrict__ out_hi,
+                                                     __half* __restrict__ out_lo) {
+  __shared__ float sw[64 * 9];
+  __shared__ float sb[64];
+  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t npix = static_cast<size_t>(B) * H * W;
+  const size_t pix = gid >> 3;
+  if (pix >= npix) return;
+  const int cg = gid & 7;
+  const int x = pix % W;
+  const int y = (pix / W) % H;
+  const int b = pix / (static_cast<size_t>(W) * H);
+  const uint8_t* im = img + static_cast<size_t>(b) * H * stride;
+  float in[9];
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int yy = y + dy - 1, xx = x + dx - 1;
+      float v = 0.0f;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+        v = static_cast<float>(im[static_cast<size_t>(yy) * stride + xx]) * 0.003921568859368563f;  // transform.cpp:8
+      in[dy * 3 + dx] = v;
+    }
+  __align__(16) __half hi[8];
+  __align__(16) __half lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg * 8 + j;
+    float acc = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc = fmaf(in[t], sw[c * 9 + t], acc);
+    acc = fmaxf(acc + sb[c], 0.0f);
+    split_f32(acc, hi[j], lo[j]);
+  }
+  const size_t o = pix * 64 + cg * 8;
+  *reinterpret_cast<uint4*>(out_hi + o) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<const uint4*>(lo);
+}
+
+void launch_conv1a(cudaStream_t s, const uint8_t* img, int stride, int H, int W, int B, const float* w,
+                   const float* bias, __half* out_hi, __half* out_lo) {
+  const size_t threads = static_cast<size_t>(B) * H * W * 8;
+  conv1a_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(img, stride, H, W, B, w, bias, out_hi,
+                                                                             out_lo);
+}
+
+// ------------------------------------------------------------------------------------------------
+// NMS: fused tile kernel.  Tile 64x32 outputs, halo 20 = 5 chained 9x9 max-pools.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int NT_W = 64, NT_H = 32, NHALO = 20, NR = 4;
+constexpr int RW = NT_W + 2 * NHALO;  // 104
+constexpr int RH = NT_H + 2 * NHALO;  // 72
+constexpr int NMS_THREADS = 512;
+
+// dst(y,x) = max over the 9x9 window of src, for (y,x) in the region shrunk by `e_out` from the full
+// halo region; src must be valid on the region shrunk by e_out - 4.  tmp is scratch.
+__device__ __forceinline__ void pool9(const float* src, float* tmp, float* dst, int e_out) {
+  const int ex = e_out, ey = e_out - NR;  // horizontal pass rows: [ey, RH-ey), cols [ex, RW-ex)
+  const int w = RW - 2 * ex, h = RH - 2 * ey;
+  for (int i = threadIdx.x; i < w * h; i += NMS_THREADS) {
+    const int y = ey + i / w, x = ex + i % w;
+    const float* r = src + y * RW + x;
+    float m = r[-4];
+#pragma unroll
+    for (int d = -3; d <= 4; ++d) m = fmaxf(m, r[d]);
+    tmp[y * RW + x] = m;
+  }
+  __syncthreads();
+  const int h2 = RH - 2 * e_out;
+  for (int i = threadIdx.x; i < w * h2; i += NMS_THREADS) {
+    const int y = e_out + i / w, x = ex + i % w;
+    const float* r = tmp + y * RW + x;
+    float m = r[-4 * RW];
+#pragma unroll
+    for (int d = -3; d <= 4; ++d) m = fmaxf(m, r[d * RW]);
+    dst[y * RW + x] = m;
+  }
+  __syncthreads();
+}
+}  // namespace
+
+__global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const float* __restrict__ heat, float* __restrict__ out,
+                                                            int H, int W) {
+  extern __shared__ float sm[];
+  float* S = sm;                 // scores, -inf outside the image
+  float* T = S + RW * RH;        // scratch (row pass)
+  float* P = T + RW * RH;        // pool result
+  float* MX = P + RW * RH;       // max_mask as 0/1 (0 outside the image)
+  float* SS = MX + RW * RH;      // supp_scores (-inf outside the image)
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * NT_W - NHALO, y0 = blockIdx.y * NT_H - NHALO;
+  const float* hb = heat + static_cast<size_t>(b) * H * W;
+  const float NEG = -INFINITY;
+  for (int i = threadIdx.x; i < RW * RH; i += NMS_THREADS) {
+    const int y = y0 + i / RW, x = x0 + i % RW;
+    const bool in = (y >= 0 && y < H && x >= 0 && x < W);
+    S[i] = in ? hb[static_cast<size_t>(y) * W + x] : NEG;
+    MX[i] = 0.0f;
+  }
+  __syncthreads();
+  // max_mask = scores == max_pool(scores)                                   (nodes 59-62)
+  pool9(S, T, P, 4);
+  for (int i = threadIdx.x; i < RW * RH; i += NMS_THREADS) {
+    const int ry = i / RW, rx = i % RW;
+    if (ry >= 4 && ry < RH - 4 && rx >= 4 && rx < RW - 4) {
+      const bool in = S[i] != NEG;
+      MX[i] = (in && S[i] == P[i]) ? 1.0f : 0.0f;
+    }
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int it = 0; it < 2; ++it) {                                           // nodes 63-84
+    const int e = 8 + it * 8;   // supp valid on shrink e; new mask valid on shrink e+4
+    pool9(MX, T, P, e);         // P = max_pool(max_mask) ; supp_mask = P > 0
+    for (int i = threadIdx.x; i < RW * RH; i += NMS_THREADS) {
+      const int ry = i / RW, rx = i % RW;
+      if (ry >= e && ry < RH - e && rx >= e && rx < RW - e) {
+        const bool in = S[i] != NEG;
+        SS[i] = in ? (P[i] > 0.0f ? 0.0f : S[i]) : NEG;      // where(supp, 0, scores)
+        T[i] = P[i];                                           // keep supp for the update below
+      }
+    }
+    __syncthreads();
+    // stash supp (T gets clobbered by pool9's row pass) into P's place: reuse MX update in two steps
+    // 1) copy supp flags into the sign of a side buffer: we use P after pooling SS, so save supp first.
+    for (int i = threadIdx.x; i < RW * RH; i += NMS_THREADS) {
+      const int ry = i / RW, rx = i % RW;
+      if (ry >= e && ry < RH - e && rx >= e && rx < RW - e) {
+        // encode supp into MX: 2.0 = (mask 0, supp), 3.0 = (mask 1, supp); mask value stays recoverable
+        if (T[i] > 0.0f) MX[i] += 2.0f;
+      }
+    }
+    __syncthreads();
+    pool9(SS, T, P, e + 4);     // P = max_pool(supp_scores)
+    for (int i = threadIdx.x; i < RW * RH; i += NMS_THREADS) {
+      const int ry = i / RW, rx = i % RW;
+      if (ry >= e && ry < RH - e && rx >= e && rx < RW - e) {
+        float m = MX[i];
+        const bool supp = m >= 2.0f;
+        if (supp) m -= 2.0f;
+        const bool inner = (ry >= e + 4 && ry < RH - e - 4 && rx >= e + 4 && rx < RW - e - 4);
+        if (inner) {
+          const bool in = S[i] != NEG;
+          const bool new_max = in && (SS[i] == P[i]);
+          if (new_max && !supp) m = 1.0f;
+        }
+        MX[i] = m;
+      }
+    }
+    __syncthreads();
+  }
+  // scores = where(max_mask, scores, 0); borders -> -1                       (nodes 84-359)
+  float* ob = out + static_cast<size_t>(b) * H * W;
+  for (int i = threadIdx.x; i < NT_W * NT_H; i += NMS_THREADS) {
+    const int ty = i / NT_W, tx = i % NT_W;
+    const int y = blockIdx.y * NT_H + ty, x = blockIdx.x * NT_W + tx;
+    if (y < H && x < W) {
+      const int r = (ty + NHALO) * RW + tx + NHALO;
+      float v = MX[r] == 1.0f ? S[r] : 0.0f;
+      if (y < 4 || x < 4 || y >= H - 4 || x >= W - 4) v = -1.0f;
+      ob[static_cast<size_t>(y) * W + x] = v;
+    }
+  }
+}
+
+int nms_smem_bytes() { return 5 * RW * RH * static_cast<int>(sizeof(float)); }
+
+void launch_nms(cudaStream_t s, const float* heat, float* out, int B, int H, int W) {
+  dim3 grid((W + NT_W - 1) / NT_W, (H + NT_H - 1) / NT_H, B);
+  nms_kernel<<<grid, NMS_THREADS, nms_smem_bytes(), s>>>(heat, out, H, W);
+}
+
+int nms_prepare() {
+  return cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nms_smem_bytes()) == cudaSuccess
+             ? 0
+             : 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ordered compaction: idx = nonzero(s > 0.0005) in row-major order.
+//   pass 1: one warp per image row counts; pass 2: one block per image scans the row counts;
+//   pass 3: one warp per row writes (x, y), score at its offset.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kp_count_kernel(const float* __restrict__ nms, int H, int W, int B,
+                                                       int* __restrict__ row_cnt, float thr) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= B * H) return;
+  const float* r = nms + static_cast<size_t>(wid) * W;
+  int c = 0;
+  for (int x = lane; x < W; x += 32) c += (r[x] > thr) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) row_cnt[wid] = c;
+}
+
+__global__ void __launch_bounds__(1024) kp_scan_kernel(const int* __restrict__ row_cnt, int H, int* __restrict__ row_off,
+                                                       int* __restrict__ counts) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < H; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < H ? row_cnt[b * H + i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      int ws = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, ws, o);
+        if (lane >= o) ws += t;
+      }
+      warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    const int prefix = carry + (w ? warp_sums[w - 1] : 0) + incl - v;
+    if (i < H) row_off[b * H + i] = prefix;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = prefix + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counts[b] = carry;
+}
+
+__global__ void __launch_bounds__(256) kp_write_kernel(const float* __restrict__ nms, int H, int W, int B,
+                                                       const int* __restrict__ row_off, float thr, int cap,
+                                                       int* __restrict__ kpts, float* __restrict__ scores) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= B * H) return;
+  const int b = wid / H, y = wid - b * H;
+  const float* r = nms + static_cast<size_t>(wid) * W;
+  int off = row_off[wid];
+  for (int x0 = 0; x0 < W; x0 += 32) {
+    const int x = x0 + lane;
+    const float v = x < W ? r[x] : 0.0f;
+    const bool keep = v > thr;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int idx = off + __popc(m & ((1u << lane) - 1));
+      if (idx < cap) {
+        kpts[(static_cast<size_t>(b) * cap + idx) * 2 + 0] = x;
+        kpts[(static_cast<size_t>(b) * cap + idx) * 2 + 1] = y;
+        scores[static_cast<size_t>(b) * cap + idx] = v;
+      }
+    }
+    off += __popc(m);
+  }
+}
+
+void launch_select(cudaStream_t s, const float* nms, int B, int H, int W, float thr, int cap, int* row_cnt,
+                   int* row_off, int* counts, int* kpts, float* scores) {
+  const int warps = B * H;
+  const int blocks = (warps * 32 + 255) / 256;
+  kp_count_kernel<<<blocks, 256, 0, s>>>(nms, H, W, B, row_cnt, thr);
+  kp_scan_kernel<<<B, 1024, 0, s>>>(row_cnt, H, row_off, counts);
+  kp_write_kernel<<<blocks, 256, 0, s>>>(nms, H, W, B, row_off, thr, cap, kpts, scores);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Descriptor sampling: one warp per keypoint, lane = 8 channels.
+// grid = 2 * ((kp - 4 + 0.5) / (8*dim - 4 - 0.5)) - 1 ; grid_sample(bilinear, zeros, align_corners=True) ; L2 norm.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) desc_sample_kernel(const float* __restrict__ dense /*[B][h][w][256]*/, int h,
+                                                          int w, int B, const int* __restrict__ kpts,
+                                                          const int* __restrict__ counts, int cap,
+                                                          float* __restrict__ desc /*[B][cap][256]*/) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= B * cap) return;
+  const int b = wid / cap, i = wid - b * cap;
+  const int n = min(counts[b], cap);
+  if (i >= n) return;
+  const float kx = static_cast<float>(kpts[(static_cast<size_t>(b) * cap + i) * 2 + 0]) - 4.0f + 0.5f;
+  const float ky = static_cast<float>(kpts[(static_cast<size_t>(b) * cap + i) * 2 + 1]) - 4.0f + 0.5f;
+  const float gx = (kx / (static_cast<float>(w * 8) - 4.0f - 0.5f)) * 2.0f - 1.0f;
+  const float gy = (ky / (static_cast<float>(h * 8) - 4.0f - 0.5f)) * 2.0f - 1.0f;
+  // align_corners=True un-normalisation: ((g + 1) / 2) * (size - 1)
+  const float ix = ((gx + 1.0f) / 2.0f) * static_cast<float>(w - 1);
+  const float iy = ((gy + 1.0f) / 2.0f) * static_cast<float>(h - 1);
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+  const int x1 = x0 + 1, y1 = y0 + 1;
+  const float w_nw = (static_cast<float>(x1) - ix) * (static_cast<float>(y1) - iy);
+  const float w_ne = (ix - static_cast<float>(x0)) * (static_cast<float>(y1) - iy);
+  const float w_sw = (static_cast<float>(x1) - ix) * (iy - static_cast<float>(y0));
+  const float w_se = (ix - static_cast<float>(x0)) * (iy - static_cast<float>(y0));
+  const float* db = dense + static_cast<size_t>(b) * h * w * 256 + lane * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+  auto corner = [&](int yy, int xx, float wt) {
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+      const float4* p = reinterpret_cast<const float4*>(db + (static_cast<size_t>(yy) * w + xx) * 256);
+      const float4 a = __ldg(p), c = __ldg(p + 1);
+      acc[0] += a.x * wt; acc[1] += a.y * wt; acc[2] += a.z * wt; acc[3] += a.w * wt;
+      acc[4] += c.x * wt; acc[5] += c.y * wt; acc[6] += c.z * wt; acc[7] += c.w * wt;
+    }
+  };
+  corner(y0, x0, w_nw);
+  corner(y0, x1, w_ne);
+  corner(y1, x0, w_sw);
+  corner(y1, x1, w_se);
+  float ss = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ss += acc[j] * acc[j];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+  float4* o = reinterpret_cast<float4*>(desc + (static_cast<size_t>(b) * cap + i) * 256 + lane * 8);
+  o[0] = make_float4(acc[0] / nrm, acc[1] / nrm, acc[2] / nrm, acc[3] / nrm);
+  o[1] = make_float4(acc[4] / nrm, acc[5] / nrm, acc[6] / nrm, acc[7] / nrm);
+}
+
+void launch_desc_sample(cudaStream_t s, const float* dense, int h, int w, int B, const int* kpts, const int* counts,
+                        int cap, float* desc) {
+  const int warps = B * cap;
+  desc_sample_kernel<<<(warps * 32 + 255) / 256, 256, 0, s>>>(dense, h, w, B, kpts, counts, cap, desc);
+}
+
+}  // namespace rfe

@@ -1,0 +1,364 @@
+// The one tensor-core kernel of the library: a TMA-fed, tcgen05 (UMMA) split-fp16 contraction
+//     D[M x N] = A[M x K] * B[N x K]^T        (fp32-equivalent, see common.cuh)
+// with the A tile fetched either as a plain GEMM tile (rows x K) or as the implicit-GEMM tile of a
+// 3x3 convolution over an NHWC activation tensor (9 shifted TMA boxes, zero-filled out of bounds =
+// the conv's zero padding), and a fused epilogue per use (bias/ReLU/2x2 max-pool/split-fp16 store for
+// the SuperPoint conv stack; softmax-65 + 8x8 depth-to-space for the detector head; channel L2-norm for
+// the descriptor head; bias/scale/residual/transpose variants for LightGlue's linears and attention).
+//
+// CTA = 192 threads: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer
+// (one elected lane), warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31).
+// Pipeline: NUM_STAGES smem stages {A_hi, A_lo, B_hi, B_lo}, full/empty mbarriers, one tmem_full barrier.
+// Replaces (reference): every Conv/MatMul node that ONNXRuntime executes for superpoint.onnx /
+// lightglue_sim.onnx (src/Extractors/superpoint_onnx.cc:133-136, src/Matchers/lightglue_onnx.cpp:210-214).
+#pragma once
+
+#include "common.cuh"
+
+namespace rfe {
+
+enum AMode { A_GEMM = 0, A_CONV3 = 1 };
+enum Epi {
+  EPI_LINEAR = 0,    // (acc + bias) * scale (+ residual) -> fp32 and/or split-fp16, optional transposed split store
+  EPI_CONV = 1,      // bias + ReLU (+ 2x2 max-pool) -> split-fp16 NHWC
+  EPI_DET = 2,       // bias + softmax over 65 + drop dustbin + 8x8 depth-to-space -> fp32 heat-map
+  EPI_DESC = 3,      // bias + L2 normalise over N=256 -> fp32 NHWC
+};
+
+struct UmmaParams {
+  // problem
+  int num_k_steps;     // K / 64 (K tail is zero-filled by TMA)
+  int cin_chunks;      // conv: Cin / 64
+  int M;               // GEMM: valid rows per batch;  conv: unused
+  int N;               // valid output columns
+  int H, W;            // conv: spatial size of the conv output (before pooling); DET/DESC: coarse h, w
+  int tiles_x, tiles_y;  // conv: 16x8 pixel tiles per image
+  int a_batched, b_batched;  // GEMM: use blockIdx.z as the A / B tensor-map batch coordinate
+  // epilogue
+  const float* bias;       // [N] or null
+  const float* residual;   // fp32 [M][ld_res] or null
+  float* out_f32;          // fp32 [M][ld_f32] or null
+  __half* out_hi;          // split-fp16 [M][ld_h] (or [N][ld_h] when transpose_h) or null
+  __half* out_lo;
+  long long bstride_f32, bstride_h, bstride_res;   // per blockIdx.z element strides
+  int ld_f32, ld_h, ld_res;
+  int transpose_h;
+  int head_major;          // split store as [n/64][M][64] (attention heads), head_stride elements apart
+  long long head_stride;
+  int relu;
+  int pool;
+  float scale;
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                  // fp16 elements = one 128-byte swizzle row
+constexpr int kStageABytes = kBlockM * 128;  // one of A_hi / A_lo
+constexpr int kUmmaThreads = 192;
+
+__host__ __device__ constexpr int umma_stage_bytes(int block_n) { return 2 * kStageABytes + 2 * block_n * 128; }
+__host__ __device__ constexpr int umma_num_stages(int block_n) {
+  return (200 * 1024 / umma_stage_bytes(block_n)) > 6 ? 6 : (200 * 1024 / umma_stage_bytes(block_n));
+}
+__host__ __device__ constexpr int umma_smem_bytes(int block_n) {
+  return umma_num_stages(block_n) * umma_stage_bytes(block_n) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+__host__ __device__ constexpr int umma_tmem_cols(int block_n) {
+  return 2 * block_n <= 32 ? 32 : 2 * block_n <= 64 ? 64 : 2 * block_n <= 128 ? 128 : 2 * block_n <= 256 ? 256 : 512;
+}
+
+#ifdef __CUDACC__
+
+template <int BLOCK_N, int AMODE, int EPI>
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+            const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+            const UmmaParams p) {
+  constexpr int STAGES = umma_num_stages(BLOCK_N);
+  constexpr int STAGE_BYTES = umma_stage_bytes(BLOCK_N);
+  constexpr int STAGE_B = BLOCK_N * 128;
+  constexpr int TMEM_COLS = umma_tmem_cols(BLOCK_N);
+  constexpr int ACC1_COL = TMEM_COLS / 2;
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
+  static_assert(STAGES >= 2, "need at least two stages");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates --------------------------------------------------------------------------
+  const int n0 = blockIdx.y * BLOCK_N;
+  int m0 = 0, img = 0, x0 = 0, y0 = 0;
+  if constexpr (AMODE == A_CONV3) {
+    int t = blockIdx.x;
+    const int tx = t % p.tiles_x;
+    t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    img = t / p.tiles_y;
+    x0 = tx * 16;
+    y0 = ty * 8;
+  } else {
+    m0 = blockIdx.x * kBlockM;
+  }
+
+  // ---- one-time setup ------------------------------------------------------------------------------
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi);
+    tma_prefetch_desc(&tmA_lo);
+    tma_prefetch_desc(&tmB_hi);
+    tma_prefetch_desc(&tmB_lo);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====================================================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ks = 0; ks < p.num_k_steps; ++ks) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+        if constexpr (AMODE == A_CONV3) {
+          const int tap = ks / p.cin_chunks;
+          const int cc = ks - tap * p.cin_chunks;
+          const int dy = tap / 3, dx = tap - dy * 3;
+          tma_load_4d(st, &tmA_hi, &full_bar[stage], cc * 64, x0 + dx - 1, y0 + dy - 1, img);
+          tma_load_4d(st + kStageABytes, &tmA_lo, &full_bar[stage], cc * 64, x0 + dx - 1, y0 + dy - 1, img);
+        } else {
+          const int zb = p.a_batched ? blockIdx.z : 0;
+          tma_load_3d(st, &tmA_hi, &full_bar[stage], ks * 64, m0, zb);
+          tma_load_3d(st + kStageABytes, &tmA_lo, &full_bar[stage], ks * 64, m0, zb);
+        }
+        const int zb = p.b_batched ? blockIdx.z : 0;
+        tma_load_3d(st + 2 * kStageABytes, &tmB_hi, &full_bar[stage], ks * 64, n0, zb);
+        tma_load_3d(st + 2 * kStageABytes + STAGE_B, &tmB_lo, &full_bar[stage], ks * 64, n0, zb);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer ===========================================================================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
+      const uint32_t acc0 = tmem_base;
+      const uint32_t acc1 = tmem_base + ACC1_COL;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ks = 0; ks < p.num_k_steps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t a_lo = a_hi + kStageABytes;
+        const uint32_t b_hi = a_hi + 2 * kStageABytes;
+        const uint32_t b_lo = b_hi + STAGE_B;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t da_hi = make_sw128_kmajor_desc(a_hi + k * 32);
+          const uint64_t da_lo = make_sw128_kmajor_desc(a_lo + k * 32);
+          const uint64_t db_hi = make_sw128_kmajor_desc(b_hi + k * 32);
+          const uint64_t db_lo = make_sw128_kmajor_desc(b_lo + k * 32);
+          const uint32_t acc = (ks > 0 || k > 0) ? 1u : 0u;
+          umma_f16(acc0, da_hi, db_hi, idesc, acc);
+          umma_f16(acc1, da_hi, db_lo, idesc, acc);
+          umma_f16(acc1, da_lo, db_hi, idesc, 1u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ===== epilogue warps ===========================================================================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;                // row of the 128-row tile
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t t1 = t0 + ACC1_COL;
+
+    auto load16 = [&](int col, float (&v)[16]) {
+      uint32_t r0[16], r1[16];
+      tmem_ld16(t0 + col, r0);
+      tmem_ld16(t1 + col, r1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]) * RFE_SPLIT_INV;
+    };
+
+    if constexpr (EPI == EPI_CONV) {
+      const int ry = row >> 4, rx = row & 15;
+      const int y = y0 + ry, x = x0 + rx;
+      const bool valid = (y < p.H) && (x < p.W);
+      const int Ho = p.pool ? p.H >> 1 : p.H, Wo = p.pool ? p.W >> 1 : p.W;
+      const int yo = p.pool ? y >> 1 : y, xo = p.pool ? x >> 1 : x;
+      const bool writer = valid && (!p.pool || (((rx | ry) & 1) == 0));
+      const size_t pix = (static_cast<size_t>(img) * Ho + yo) * Wo + xo;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 16) {
+        float v[16];
+        load16(c, v);
+        __align__(16) __half hi[16];
+        __align__(16) __half lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float t = v[j] + __ldg(p.bias + n0 + c + j);
+          t = fmaxf(t, 0.0f);
+          if (p.pool) {
+            t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
+            t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 16));
+          }
+          split_f32(t, hi[j], lo[j]);
+        }
+        if (writer) {
+          const size_t o = pix * p.N + n0 + c;
+          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
+          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
+          dh[0] = reinterpret_cast<const uint4*>(hi)[0];
+          dh[1] = reinterpret_cast<const uint4*>(hi)[1];
+          dl[0] = reinterpret_cast<const uint4*>(lo)[0];
+          dl[1] = reinterpret_cast<const uint4*>(lo)[1];
+        }
+      }
+    } else if constexpr (EPI == EPI_DET) {
+      // row = coarse pixel; 65 logits -> softmax -> first 64 -> 8x8 block of the heat-map
+      static_assert(EPI != EPI_DET || BLOCK_N == 80, "detector head uses N = 80 (65 padded)");
+      const int m = m0 + row;
+      const bool valid = m < p.M;
+      float e[80];
+#pragma unroll
+      for (int c = 0; c < 80; c += 16) {
+        float v[16];
+        load16(c, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) e[c + j] = v[j];
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 65; ++j) {
+        e[j] += __ldg(p.bias + j);
+        mx = fmaxf(mx, e[j]);
+      }
+      float sum = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 65; ++j) {
+        e[j] = expf(e[j] - mx);
+        sum += e[j];
+      }
+      if (valid) {
+        const int hw = p.H * p.W;
+        const int b = m / hw;
+        const int r = m - b * hw;
+        const int cy = r / p.W, cx = r - cy * p.W;
+        float* base = p.out_f32 + (static_cast<size_t>(b) * p.H * 8 + cy * 8) * (p.W * 8) + cx * 8;
+#pragma unroll
+        for (int dy = 0; dy < 8; ++dy) {
+          float4 a = make_float4(e[dy * 8 + 0] / sum, e[dy * 8 + 1] / sum, e[dy * 8 + 2] / sum, e[dy * 8 + 3] / sum);
+          float4 c4 = make_float4(e[dy * 8 + 4] / sum, e[dy * 8 + 5] / sum, e[dy * 8 + 6] / sum, e[dy * 8 + 7] / sum);
+          float4* d = reinterpret_cast<float4*>(base + static_cast<size_t>(dy) * p.W * 8);
+          d[0] = a;
+          d[1] = c4;
+        }
+      }
+    } else if constexpr (EPI == EPI_DESC) {
+      const int m = m0 + row;
+      const bool valid = m < p.M;
+      float ss = 0.0f;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 16) {
+        float v[16];
+        load16(c, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float t = v[j] + __ldg(p.bias + n0 + c + j);
+          ss += t * t;
+        }
+      }
+      const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 16) {
+        float v[16];
+        load16(c, v);
+        if (valid) {
+          float4* d = reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(m) * p.ld_f32 + n0 + c);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            d[j >> 2] = make_float4((v[j] + __ldg(p.bias + n0 + c + j)) / nrm,
+                                    (v[j + 1] + __ldg(p.bias + n0 + c + j + 1)) / nrm,
+                                    (v[j + 2] + __ldg(p.bias + n0 + c + j + 2)) / nrm,
+                                    (v[j + 3] + __ldg(p.bias + n0 + c + j + 3)) / nrm);
+          }
+        }
+      }
+    } else {  // EPI_LINEAR
+      const int m = m0 + row;
+      const bool valid = m < p.M;
+      const size_t z = blockIdx.z;
+      float* of = p.out_f32 ? p.out_f32 + z * p.bstride_f32 : nullptr;
+      __half* oh = p.out_hi ? p.out_hi + z * p.bstride_h : nullptr;
+      __half* ol = p.out_lo ? p.out_lo + z * p.bstride_h : nullptr;
+      const float* res = p.residual ? p.residual + z * p.bstride_res : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 16) {
+        float v[16];
+        load16(c, v);
+        if (!valid) continue;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = n0 + c + j;
+          if (n < p.N) {
+            float t = v[j];
+            if (p.bias) t += __ldg(p.bias + n);
+            t *= p.scale;
+            if (res) t += res[static_cast<size_t>(m) * p.ld_res + n];
+            if (p.relu) t = fmaxf(t, 0.0f);
+            if (of) of[static_cast<size_t>(m) * p.ld_f32 + n] = t;
+            if (oh) {
+              __half h, l;
+              split_f32(t, h, l);
+              const size_t o = p.transpose_h ? static_cast<size_t>(n) * p.ld_h + m
+                             : p.head_major ? static_cast<size_t>(n >> 6) * p.head_stride + static_cast<size_t>(m) * 64 + (n & 63)
+                                            : static_cast<size_t>(m) * p.ld_h + n;
+              oh[o] = h;
+              ol[o] = l;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace rfe
