@@ -19,3 +19,21 @@ $(LIB): $(OBJ)
 
 clean:
 	rm -f $(OBJ) $(LIB) $(CSRC)/*.ptxas.log
+
+# ---- host C++ class surface (SPextractor / SPmatcher / runners) on top of the C ABI -------------------------
+HOST := rover_slam_b200/host
+HOSTSRC := $(HOST)/src/transform.cpp $(HOST)/src/superpoint_onnx.cc $(HOST)/src/lightglue_onnx.cpp \
+           $(HOST)/src/SPextractor.cc $(HOST)/src/SPmatcher_onnx.cc
+HOSTFLAGS := -O2 -std=c++14 -fPIC -Wall -Iinclude -I$(HOST)/include -I$(HOST)/shim -DROVER_FE_OPENCV_SHIM -DROVER_FE_STANDALONE
+HOSTLIB := rover_slam_b200/librover_slam_frontend.so
+HOSTDRV := rover_slam_b200/host_driver
+
+host: $(HOSTLIB) $(HOSTDRV)
+
+$(HOSTLIB): $(HOSTSRC) $(wildcard $(HOST)/include/*/*.h) $(LIB)
+	g++ $(HOSTFLAGS) -shared -o $@ $(HOSTSRC) -Lrover_slam_b200 -lrover_fe -Wl,-rpath,'$$ORIGIN'
+
+$(HOSTDRV): $(HOST)/test/host_driver.cpp $(HOSTLIB)
+	g++ $(HOSTFLAGS) -o $@ $< -Lrover_slam_b200 -lrover_slam_frontend -lrover_fe -Wl,-rpath,'$$ORIGIN'
+
+all: host

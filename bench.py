@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec (SuperPoint extract + LightGlue match) on 640x480 synthetic frame pairs.
+
+A "step" = one batch of PAIRS 640x480 frame pairs: both frames of every pair are extracted (one batched
+SuperPoint launch sequence over 2*PAIRS frames), then every pair is matched.  frames/s = 2*PAIRS*steps / time.
+  value : inputs already resident in HBM, features handed from the extractor to the matcher on the device
+          (rfe_sp_extract_device + rfe_lg_match_slots), device-timed with CUDA events, max over ranks.
+  e2e   : the same work through the reference-facing host API (rfe_sp_extract_u8 / rfe_lg_match: host images in,
+          host keypoints+descriptors out, host features in, host matches out), copies inside the timed region.
+  --impl reference : the reference's CPU path for the same workload -- its two ONNX graphs restated on torch-CPU
+          (oracle/, stand-in for ONNXRuntime-CPU which is not installable here), all host threads, one pair per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 480, 640
+CONV1B_FLOPS_PER_FRAME = 2 * 9 * 64 * 64 * H * W          # 22.65 GFLOP
+SP_FLOPS_PER_FRAME = 52.10e9
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1440.2), d.get("hbm_gbs", 6572.5), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+def make_pairs(n_pairs, seed0):
+    from oracle import synth   # input generator only (numpy); not the checker
+    rng = np.random.RandomState(seed0)
+    frames = np.empty((n_pairs, 2, H, W), np.uint8)
+    for p in range(n_pairs):
+        dx, dy = rng.randint(-16, 17, size=2)
+        a, b = synth.frame_pair(seed0 * 1000 + 2 * p, H, W, shift=(int(dx), int(dy)))
+        frames[p, 0], frames[p, 1] = a, b
+    return frames
+
+
+def cpu_pair_seconds(frames_pair, threads):
+    """Reference CPU path for one pair: 2 extracts + 1 match (torch-CPU restatement of the two ONNX graphs)."""
+    import torch
+    from oracle import lightglue_ref, superpoint_ref
+    torch.set_num_threads(threads)
+    sp = cpu_pair_seconds.sp = getattr(cpu_pair_seconds, "sp", None) or superpoint_ref.SuperPointRef()
+    lg = cpu_pair_seconds.lg = getattr(cpu_pair_seconds, "lg", None) or lightglue_ref.LightGlueRef()
+    t = time.perf_counter()
+    with torch.no_grad():
+        ka, _, da = sp(frames_pair[0])
+        kb, _, db = sp(frames_pair[1])
+        m, _ = lg(lightglue_ref.normalize_keypoints(ka.numpy(), H, W), lightglue_ref.normalize_keypoints(kb.numpy(), H, W), da, db)
+    return time.perf_counter() - t, len(m)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    frames = make_pairs(1, 7)
+    for _ in range(args.warmup):
+        cpu_pair_seconds(frames[0], threads)
+    t = 0.0
+    for _ in range(args.steps):
+        dt, _ = cpu_pair_seconds(frames[0], threads)
+        t += dt
+    fps = 2 * args.steps / t
+    line = {"metric": "frames/sec (extract+match) on 640x480", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * t / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "640x480 synthetic frame pairs: SuperPoint on both frames + LightGlue per pair",
+                       "pairs_per_step": 1, "reference_kind": "torch-CPU restatement of superpoint.onnx / lightglue_sim.onnx "
+                       "(ONNXRuntime is not installable offline)"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                             "sample": f"{args.steps} steps x 1 pair (2 extracts + 1 match)"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=4, help="frame pairs per step per GPU")
+    ap.add_argument("--cpu-pairs", type=int, default=2, help="pairs timed for cpu_baseline (rank 0, N=1)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from rover_slam_b200 import FrontEnd     # raises loudly when librover_fe.so is missing
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    P = args.pairs
+    B = 2 * P
+    stream = torch.cuda.current_stream()
+    fe = FrontEnd(device=local, stream=stream.cuda_stream, max_batch=B, max_height=H, max_width=W, max_keypoints=4096)
+
+    # ---- input: rank 0 makes the synthetic stream, NCCL scatters one shard per rank (the path's only collective) ----
+    n_sets = 4                                  # distinct step inputs, cycled
+    if rank == 0:
+        allf = torch.from_numpy(make_pairs(n_sets * P * world, 1)).reshape(world, n_sets, B, H, W)
+    shard = torch.empty((n_sets, B, H, W), dtype=torch.uint8, device=dev)
+    if world > 1:
+        dist.scatter(shard, [allf[r].to(dev) for r in range(world)] if rank == 0 else None, src=0)
+    else:
+        shard.copy_(allf[0])
+    host_sets = shard.cpu().pin_memory()
+
+    def step_device(i):
+        fe.extract_device(shard[i % n_sets].data_ptr(), H, W, W, B)
+        for p in range(P):
+            fe.match_slots(2 * p, 2 * p + 1, H, W, 0.0, p)
+
+    h2d = d2h = 0
+
+    def step_host(i):
+        nonlocal h2d, d2h
+        imgs = host_sets[i % n_sets].numpy()
+        feats = fe.extract(imgs)
+        h2d += imgs.nbytes
+        for k, s, d in feats:
+            d2h += k.nbytes + s.nbytes + d.nbytes + 4
+        for p in range(P):
+            (k0, _, d0), (k1, _, d1) = feats[2 * p], feats[2 * p + 1]
+            m, ms = fe.match(k0, k1, d0, d1, H, W)
+            h2d += 2 * 4 * (len(k0) + len(k1)) + d0.nbytes + d1.nbytes
+            d2h += m.nbytes + ms.nbytes + 4
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ("value") ----
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    fe.profile(True)
+    launches0 = fe.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step_device(i)
+    e1.record(stream)
+    barrier()
+    launches = fe.kernel_launches() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    conv1b_ms, conv1b_n = fe.profile_read("sp.conv1b", reset=False)
+    all_ms, all_n = fe.profile_read(None, reset=True)
+    fe.profile(False)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    nmatch = [len(fe.read_result(p)[0]) for p in range(P)]
+    frames_total = 2 * P * args.steps * world
+    value = frames_total / (ms_total / 1e3)
+
+    # ---- end to end through the host API ("e2e") ----
+    for i in range(2):
+        step_host(i)
+    h2d = d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    e_steps = max(3, args.steps // 2)
+    for i in range(e_steps):
+        step_host(i)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = 2 * P * e_steps * world / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    tf_peak, hbm_peak, peak_src = peaks()
+    per_launch_ms = conv1b_ms / max(conv1b_n, 1)
+    achieved = CONV1B_FLOPS_PER_FRAME * B / (per_launch_ms / 1e3) / 1e12 if conv1b_n else 0.0
+    line = {
+        "metric": "frames/sec (extract+match) on 640x480", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16x2-split (fp32-equivalent), f32 accumulate", "data": "synthetic",
+        "config": {"workload": "BASELINE config 5 shape: 640x480 synthetic frame pairs, SuperPoint on both frames + one LightGlue match per pair",
+                   "pairs_per_step_per_gpu": P, "frames_per_step_per_gpu": B, "keypoints_per_frame": "about 2000 (no top-K, threshold 0.0005)",
+                   "parallelism": f"dp{world} (independent pairs per GPU; NCCL only scatters the input shards)",
+                   "l2": "per-step activation working set about 2.5 GB >> 126 MB L2; 4 distinct input sets cycled",
+                   "matches_last_step": nmatch},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d // e_steps, "d2h_bytes_per_step": d2h // e_steps,
+                "steps": e_steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "umma_kernel<64,A_CONV3,EPI_CONV> (sp.conv1b: 3x3 conv 64->64 + ReLU + 2x2 pool)",
+                     "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak if tf_peak else None,
+                     "traffic": None, "peak_source": peak_src, "launch_ms": per_launch_ms, "launches_timed": conv1b_n,
+                     "algorithmic_flops_per_launch": CONV1B_FLOPS_PER_FRAME * B,
+                     "executed_mma_flops_per_launch": 3 * CONV1B_FLOPS_PER_FRAME * B,
+                     "share_of_step": conv1b_ms / all_ms if all_ms else None,
+                     "note": "split-fp16 runs 3 MMAs per algorithmic MAC: frac <= 1/3 by construction"},
+    }
+    if world == 1:
+        threads = os.cpu_count() or 1
+        cpu_frames = make_pairs(args.cpu_pairs, 7)
+        cpu_pair_seconds(cpu_frames[0], threads)          # warm-up
+        tt = 0.0
+        for p in range(args.cpu_pairs):
+            dt, _ = cpu_pair_seconds(cpu_frames[p], threads)
+            tt += dt
+        line["cpu_baseline"] = {"value": 2 * args.cpu_pairs / tt, "unit": "frames/s", "cores": threads, "kind": "port",
+                                "sample": f"{args.cpu_pairs} pairs (2 extracts + 1 match each) of the same synthetic stream, after 1 warm-up pair"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

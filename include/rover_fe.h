@@ -94,6 +94,11 @@ int rfe_lg_read_result(rfe_ctx* ctx, int rslot, int32_t* matches, float* mscores
 double rfe_get_timer_ms(rfe_ctx* ctx, const char* name);
 /* Number of kernels the library has launched on this ctx so far. */
 long long rfe_kernel_launches(rfe_ctx* ctx);
+/* Per-kernel timing with CUDA events on the ctx stream (off by default).  Tags: "sp.conv1b", "sp.conv2a", ...,
+ * "sp.convPb_softmax", "sp.convDb_l2norm", "lg.wqkv", "lg.attn_qk", "lg.attn_pv", "lg.ffn0", "lg.sim", ...
+ * rfe_profile_read sums the launches whose tag starts with `prefix` (NULL = all); synchronises. */
+int rfe_profile(rfe_ctx* ctx, int enable);
+int rfe_profile_read(rfe_ctx* ctx, const char* prefix, double* total_ms, long long* launches, int reset);
 /* Test hook: copy a named intermediate device tensor of the last call to the host (fp32 or raw bytes).
  * Returns the byte size of the tensor through *bytes; copies min(*bytes, capacity). */
 int rfe_debug_read(rfe_ctx* ctx, const char* name, void* dst, size_t capacity, size_t* bytes);

@@ -66,6 +66,8 @@ def load_library():
     lib.rfe_get_timer_ms.restype = C.c_double
     lib.rfe_kernel_launches.argtypes = [vp]
     lib.rfe_kernel_launches.restype = C.c_longlong
+    lib.rfe_profile.argtypes = [vp, ci]
+    lib.rfe_profile_read.argtypes = [vp, C.c_char_p, P(C.c_double), P(C.c_longlong), ci]
     lib.rfe_debug_read.argtypes = [vp, C.c_char_p, vp, C.c_size_t, P(C.c_size_t)]
     lib.rfe_debug_gemm.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci]
     _lib = lib
@@ -168,6 +170,16 @@ class FrontEnd:
 
     def kernel_launches(self) -> int:
         return int(self.lib.rfe_kernel_launches(self.ctx))
+
+    def profile(self, enable: bool = True):
+        self._check(self.lib.rfe_profile(self.ctx, 1 if enable else 0))
+
+    def profile_read(self, prefix: str | None = None, reset: bool = False):
+        """(total_ms, launches) of the profiled kernels whose tag starts with `prefix`."""
+        ms, n = C.c_double(0), C.c_longlong(0)
+        self._check(self.lib.rfe_profile_read(self.ctx, None if prefix is None else prefix.encode(), C.byref(ms),
+                                              C.byref(n), 1 if reset else 0))
+        return ms.value, n.value
 
     def debug_read(self, name: str, shape=None) -> np.ndarray:
         nb = C.c_size_t(0)

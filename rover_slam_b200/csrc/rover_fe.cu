@@ -95,6 +95,12 @@ struct rfe_ctx {
   float* res_scores = nullptr;  // [slots][cap]
   int* res_count = nullptr;     // [slots]
 
+  // optional per-kernel CUDA-event profiling (rfe_profile)
+  struct ProfRec { std::string tag; cudaEvent_t a, b; };
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pool;
+
   // debug scratch
   float* dbg = nullptr;
   size_t dbg_bytes = 0;
@@ -216,8 +222,30 @@ int load_weights(rfe_ctx* c, const char* path) {
 // ------------------------------------------------------------------------------------------------
 // tensor-core launches
 // ------------------------------------------------------------------------------------------------
+struct ProfScope {   // records a CUDA event pair around one launch when profiling is on
+  rfe_ctx* c;
+  cudaEvent_t b = nullptr;
+  ProfScope(rfe_ctx* ctx, const char* tag) : c(ctx) {
+    if (!c->profiling || c->prof.size() >= 8192) return;
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!c->prof_pool.empty()) {
+      ev = c->prof_pool.back();
+      c->prof_pool.pop_back();
+    } else {
+      cudaEventCreate(&ev.first);
+      cudaEventCreate(&ev.second);
+    }
+    cudaEventRecord(ev.first, c->stream);
+    b = ev.second;
+    c->prof.push_back({tag, ev.first, ev.second});
+  }
+  ~ProfScope() {
+    if (b) cudaEventRecord(b, c->stream);
+  }
+};
+
 template <int BLOCK_N, int AMODE, int EPI>
-int launch_umma(rfe_ctx* c, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+int launch_umma(rfe_ctx* c, const char* tag, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                 const CUtensorMap& b_lo, const UmmaParams& p, dim3 grid) {
   static bool configured[64] = {};
   auto kern = umma_kernel<BLOCK_N, AMODE, EPI>;
@@ -225,6 +253,7 @@ int launch_umma(rfe_ctx* c, const CUtensorMap& a_hi, const CUtensorMap& a_lo, co
     RFE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, umma_smem_bytes(BLOCK_N)));
     configured[c->device & 63] = true;
   }
+  ProfScope ps(c, tag);
   kern<<<grid, kUmmaThreads, umma_smem_bytes(BLOCK_N), c->stream>>>(a_hi, a_lo, b_hi, b_lo, p);
   c->launches++;
   RFE_CUDA_CHECK(cudaGetLastError());
@@ -257,7 +286,7 @@ UmmaParams default_params() {
 }
 
 // D = A * B^T with the LINEAR epilogue.  p carries the epilogue; M/N/K are filled here.
-int gemm_linear(rfe_ctx* c, const Operand& A, const Operand& B, UmmaParams p, int block_n) {
+int gemm_linear(rfe_ctx* c, const char* tag, const Operand& A, const Operand& B, UmmaParams p, int block_n) {
   if (A.rows == 0 || B.rows == 0) return RFE_OK;
   CUtensorMap ah, al, bh, bl;
   int r;
@@ -270,12 +299,12 @@ int gemm_linear(rfe_ctx* c, const Operand& A, const Operand& B, UmmaParams p, in
   p.b_batched = B.batch > 1;
   const int z = A.batch > B.batch ? A.batch : B.batch;
   dim3 grid((A.rows + kBlockM - 1) / kBlockM, (B.rows + block_n - 1) / block_n, z);
-  if (block_n == 64) return launch_umma<64, A_GEMM, EPI_LINEAR>(c, ah, al, bh, bl, p, grid);
-  return launch_umma<128, A_GEMM, EPI_LINEAR>(c, ah, al, bh, bl, p, grid);
+  if (block_n == 64) return launch_umma<64, A_GEMM, EPI_LINEAR>(c, tag, ah, al, bh, bl, p, grid);
+  return launch_umma<128, A_GEMM, EPI_LINEAR>(c, tag, ah, al, bh, bl, p, grid);
 }
 
 // 3x3 conv (pad 1) + bias + ReLU (+ 2x2 max-pool), NHWC split-fp16 in/out.
-int conv3x3(rfe_ctx* c, const SplitBuf& in, int B, int H, int W, int Cin, const SplitW& w, const SplitBuf& out,
+int conv3x3(rfe_ctx* c, const char* tag, const SplitBuf& in, int B, int H, int W, int Cin, const SplitW& w, const SplitBuf& out,
             bool pool) {
   const uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
                             static_cast<uint64_t>(B)};
@@ -303,8 +332,8 @@ int conv3x3(rfe_ctx* c, const SplitBuf& in, int B, int H, int W, int Cin, const 
   p.pool = pool ? 1 : 0;
   p.relu = 1;
   dim3 grid(p.tiles_x * p.tiles_y * B, w.n / block_n, 1);
-  if (block_n == 64) return launch_umma<64, A_CONV3, EPI_CONV>(c, ah, al, bh, bl, p, grid);
-  return launch_umma<128, A_CONV3, EPI_CONV>(c, ah, al, bh, bl, p, grid);
+  if (block_n == 64) return launch_umma<64, A_CONV3, EPI_CONV>(c, tag, ah, al, bh, bl, p, grid);
+  return launch_umma<128, A_CONV3, EPI_CONV>(c, tag, ah, al, bh, bl, p, grid);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -315,16 +344,16 @@ int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B) {
   int r;
   launch_conv1a(s, d_gray, stride, h, w, B, c->conv1a_w, c->conv1a_b, c->a1a.hi, c->a1a.lo);
   c->launches++;
-  if ((r = conv3x3(c, c->a1a, B, h, w, 64, c->c1b, c->a1, true))) return r;
-  if ((r = conv3x3(c, c->a1, B, h / 2, w / 2, 64, c->c2a, c->a2a, false))) return r;
-  if ((r = conv3x3(c, c->a2a, B, h / 2, w / 2, 64, c->c2b, c->a2, true))) return r;
-  if ((r = conv3x3(c, c->a2, B, h / 4, w / 4, 64, c->c3a, c->a3a, false))) return r;
-  if ((r = conv3x3(c, c->a3a, B, h / 4, w / 4, 128, c->c3b, c->a3, true))) return r;
+  if ((r = conv3x3(c, "sp.conv1b", c->a1a, B, h, w, 64, c->c1b, c->a1, true))) return r;
+  if ((r = conv3x3(c, "sp.conv2a", c->a1, B, h / 2, w / 2, 64, c->c2a, c->a2a, false))) return r;
+  if ((r = conv3x3(c, "sp.conv2b", c->a2a, B, h / 2, w / 2, 64, c->c2b, c->a2, true))) return r;
+  if ((r = conv3x3(c, "sp.conv3a", c->a2, B, h / 4, w / 4, 64, c->c3a, c->a3a, false))) return r;
+  if ((r = conv3x3(c, "sp.conv3b", c->a3a, B, h / 4, w / 4, 128, c->c3b, c->a3, true))) return r;
   const int hc = h / 8, wc = w / 8;
-  if ((r = conv3x3(c, c->a3, B, hc, wc, 128, c->c4a, c->a4a, false))) return r;
-  if ((r = conv3x3(c, c->a4a, B, hc, wc, 128, c->c4b, c->feat, false))) return r;
-  if ((r = conv3x3(c, c->feat, B, hc, wc, 128, c->cPa, c->pa, false))) return r;
-  if ((r = conv3x3(c, c->feat, B, hc, wc, 128, c->cDa, c->da, false))) return r;
+  if ((r = conv3x3(c, "sp.conv4a", c->a3, B, hc, wc, 128, c->c4a, c->a4a, false))) return r;
+  if ((r = conv3x3(c, "sp.conv4b", c->a4a, B, hc, wc, 128, c->c4b, c->feat, false))) return r;
+  if ((r = conv3x3(c, "sp.convPa", c->feat, B, hc, wc, 128, c->cPa, c->pa, false))) return r;
+  if ((r = conv3x3(c, "sp.convDa", c->feat, B, hc, wc, 128, c->cDa, c->da, false))) return r;
   const int npix = B * hc * wc;
   {   // detector head: 1x1 conv 256->65 + softmax + depth-to-space
     Operand A{c->pa.hi, c->pa.lo, npix, 256, 256, 0, 1};
@@ -340,7 +369,7 @@ int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B) {
     p.W = wc;
     p.bias = c->cPb.bias;
     p.out_f32 = c->heat;
-    if ((r = launch_umma<80, A_GEMM, EPI_DET>(c, ah, al, bh, bl, p, dim3((npix + 127) / 128, 1, 1)))) return r;
+    if ((r = launch_umma<80, A_GEMM, EPI_DET>(c, "sp.convPb_softmax", ah, al, bh, bl, p, dim3((npix + 127) / 128, 1, 1)))) return r;
   }
   {   // descriptor head: 1x1 conv 256->256 + L2 norm
     Operand A{c->da.hi, c->da.lo, npix, 256, 256, 0, 1};
@@ -355,7 +384,7 @@ int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B) {
     p.bias = c->cDb.bias;
     p.out_f32 = c->dense;
     p.ld_f32 = 256;
-    if ((r = launch_umma<256, A_GEMM, EPI_DESC>(c, ah, al, bh, bl, p, dim3((npix + 127) / 128, 1, 1)))) return r;
+    if ((r = launch_umma<256, A_GEMM, EPI_DESC>(c, "sp.convDb_l2norm", ah, al, bh, bl, p, dim3((npix + 127) / 128, 1, 1)))) return r;
   }
   launch_nms(s, c->heat, c->nmsmap, B, h, w);
   launch_select(s, c->nmsmap, B, h, w, kDetThreshold, c->cap, c->row_cnt, c->row_off, c->kp_counts, c->kpts,
@@ -382,7 +411,7 @@ int ffn_block(rfe_ctx* c, int rows, const SplitW& ffn0, const float* ln_w, const
     p.bias = ffn0.bias;
     p.out_f32 = c->hid;
     p.ld_f32 = 512;
-    if ((r = gemm_linear(c, A, B, p, 128))) return r;
+    if ((r = gemm_linear(c, "lg.ffn0", A, B, p, 128))) return r;
   }
   launch_ln_gelu_split(c->stream, c->hid, rows, ln_w, ln_b, c->hs.hi, c->hs.lo);
   c->launches++;
@@ -398,7 +427,7 @@ int ffn_block(rfe_ctx* c, int rows, const SplitW& ffn0, const float* ln_w, const
     p.out_hi = c->cat.hi;
     p.out_lo = c->cat.lo;
     p.ld_h = 512;
-    if ((r = gemm_linear(c, A, B, p, 128))) return r;
+    if ((r = gemm_linear(c, "lg.ffn3", A, B, p, 128))) return r;
   }
   return RFE_OK;
 }
@@ -416,7 +445,7 @@ int attention(rfe_ctx* c, const SplitBuf& Q, const SplitBuf& K, int rows_total, 
     p.out_f32 = c->S;
     p.ld_f32 = ld;
     p.bstride_f32 = static_cast<long long>(nq) * ld;
-    if ((r = gemm_linear(c, A, B, p, 128))) return r;
+    if ((r = gemm_linear(c, "lg.attn_qk", A, B, p, 128))) return r;
   }
   launch_softmax_split(c->stream, c->S, 4 * nq, nk, ld, c->P.hi, c->P.lo, ld);
   c->launches++;
@@ -428,7 +457,7 @@ int attention(rfe_ctx* c, const SplitBuf& Q, const SplitBuf& K, int rows_total, 
     p.out_lo = c->attn.lo + static_cast<size_t>(qa) * 256;
     p.ld_h = 256;
     p.bstride_h = 64;
-    if ((r = gemm_linear(c, A, B, p, 64))) return r;
+    if ((r = gemm_linear(c, "lg.attn_pv", A, B, p, 64))) return r;
   }
   return RFE_OK;
 }
@@ -462,7 +491,7 @@ int lg_run(rfe_ctx* c, const float* d_kpts0, int n0, const float* d_kpts1, int n
       p.bias = L.wqkv.bias;
       p.out_f32 = c->qkv;
       p.ld_f32 = 768;
-      if ((r = gemm_linear(c, A, B, p, 128))) return r;
+      if ((r = gemm_linear(c, "lg.wqkv", A, B, p, 128))) return r;
     }
     launch_rope_split(s, c->qkv, rows, c->cs, c->sn, kAttnScale, c->q.hi, c->q.lo, c->k.hi, c->k.lo, c->vt.hi,
                       c->vt.lo, c->lg_ldv);
@@ -477,7 +506,7 @@ int lg_run(rfe_ctx* c, const float* d_kpts0, int n0, const float* d_kpts1, int n
       p.out_hi = c->cat.hi + 256;
       p.out_lo = c->cat.lo + 256;
       p.ld_h = 512;
-      if ((r = gemm_linear(c, A, B, p, 128))) return r;
+      if ((r = gemm_linear(c, "lg.out_proj", A, B, p, 128))) return r;
     }
     if ((r = ffn_block(c, rows, L.s_ffn0, L.s_ln_w, L.s_ln_b, L.s_ffn3))) return r;
     // ---------------- cross attention ----------------
@@ -491,7 +520,7 @@ int lg_run(rfe_ctx* c, const float* d_kpts0, int n0, const float* d_kpts1, int n
       p.out_lo = c->q.lo;
       p.head_major = 1;
       p.head_stride = hs;
-      if ((r = gemm_linear(c, A, B, p, 128))) return r;
+      if ((r = gemm_linear(c, "lg.to_qk", A, B, p, 128))) return r;
     }
     {
       Operand A{c->cat.hi, c->cat.lo, rows, 256, 512, 0, 1};
@@ -502,7 +531,7 @@ int lg_run(rfe_ctx* c, const float* d_kpts0, int n0, const float* d_kpts1, int n
       p.out_lo = c->vt.lo;
       p.transpose_h = 1;
       p.ld_h = c->lg_ldv;
-      if ((r = gemm_linear(c, A, B, p, 128))) return r;
+      if ((r = gemm_linear(c, "lg.to_v", A, B, p, 128))) return r;
     }
     if ((r = attention(c, c->q, c->q, rows, 0, n0, n0p, n1))) return r;
     if ((r = attention(c, c->q, c->q, rows, n0p, n1, 0, n0))) return r;
@@ -514,7 +543,7 @@ int lg_run(rfe_ctx* c, const float* d_kpts0, int n0, const float* d_kpts1, int n
       p.out_hi = c->cat.hi + 256;
       p.out_lo = c->cat.lo + 256;
       p.ld_h = 512;
-      if ((r = gemm_linear(c, A, B, p, 128))) return r;
+      if ((r = gemm_linear(c, "lg.to_out", A, B, p, 128))) return r;
     }
     if ((r = ffn_block(c, rows, L.c_ffn0, L.c_ln_w, L.c_ln_b, L.c_ffn3))) return r;
   }
@@ -528,7 +557,7 @@ int lg_run(rfe_ctx* c, const float* d_kpts0, int n0, const float* d_kpts1, int n
     p.out_hi = c->md.hi;
     p.out_lo = c->md.lo;
     p.ld_h = 256;
-    if ((r = gemm_linear(c, A, B, p, 128))) return r;
+    if ((r = gemm_linear(c, "lg.final_proj", A, B, p, 128))) return r;
   }
   const int ld = round_up(n1, 8);
   {
@@ -537,7 +566,7 @@ int lg_run(rfe_ctx* c, const float* d_kpts0, int n0, const float* d_kpts1, int n
     UmmaParams p = default_params();
     p.out_f32 = c->sim;
     p.ld_f32 = ld;
-    if ((r = gemm_linear(c, A, B, p, 128))) return r;
+    if ((r = gemm_linear(c, "lg.sim", A, B, p, 128))) return r;
   }
   launch_matchability(s, c->x, rows, c->match_w, c->match_b, c->ls);
   launch_lse(s, c->sim, n0, n1, ld, c->rmax, c->rlog, c->cmax, c->clog);
@@ -887,6 +916,37 @@ double rfe_get_timer_ms(rfe_ctx* c, const char* name) {
 
 long long rfe_kernel_launches(rfe_ctx* c) { return c ? c->launches : 0; }
 
+int rfe_profile(rfe_ctx* c, int enable) {
+  int r = check_ctx(c);
+  if (r) return r;
+  c->profiling = enable != 0;
+  return RFE_OK;
+}
+
+int rfe_profile_read(rfe_ctx* c, const char* prefix, double* total_ms, long long* launches, int reset) {
+  int r = check_ctx(c);
+  if (r) return r;
+  RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  double ms = 0.0;
+  long long n = 0;
+  const size_t pl = prefix ? strlen(prefix) : 0;
+  for (auto& rec : c->prof) {
+    if (pl && rec.tag.compare(0, pl, prefix) != 0) continue;
+    float t = 0.0f;
+    if (cudaEventElapsedTime(&t, rec.a, rec.b) == cudaSuccess) {
+      ms += t;
+      ++n;
+    }
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = n;
+  if (reset) {
+    for (auto& rec : c->prof) c->prof_pool.push_back({rec.a, rec.b});
+    c->prof.clear();
+  }
+  return RFE_OK;
+}
+
 int rfe_debug_read(rfe_ctx* c, const char* name, void* dst, size_t capacity, size_t* bytes) {
   int r = check_ctx(c);
   if (r) return r;
@@ -973,7 +1033,7 @@ int rfe_debug_gemm(rfe_ctx* c, const float* a, const float* b, const float* bias
   p.bias = dbias;
   p.out_f32 = dd;
   p.ld_f32 = n;
-  r = gemm_linear(c, A, Bo, p, n <= 64 ? 64 : 128);
+  r = gemm_linear(c, "debug.gemm", A, Bo, p, n <= 64 ? 64 : 128);
   if (!r) {
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) {

@@ -62,8 +62,16 @@ __host__ __device__ constexpr int umma_num_stages(int block_n) {
 __host__ __device__ constexpr int umma_smem_bytes(int block_n) {
   return umma_num_stages(block_n) * umma_stage_bytes(block_n) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
-__host__ __device__ constexpr int umma_tmem_cols(int block_n) {
-  return 2 * block_n <= 32 ? 32 : 2 * block_n <= 64 ? 64 : 2 * block_n <= 128 ? 128 : 2 * block_n <= 256 ? 256 : 512;
+// Number of hi*hi accumulators.  The tensor core adds each K=16 partial sum into the fp32 accumulator with
+// truncation, so the error grows linearly with the number of accumulation steps (measured: 1.1e-4 abs at K=512 on
+// sums of magnitude 80).  The 3x3 convs (36-72 K-steps) therefore rotate over one accumulator per kernel row and
+// the epilogue adds the three in round-to-nearest fp32.
+__host__ __device__ constexpr int umma_num_acc0(int amode) { return amode == 1 ? 3 : 1; }
+__host__ __device__ constexpr int umma_tmem_cols_n(int cols) {
+  return cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+}
+__host__ __device__ constexpr int umma_tmem_cols(int block_n, int amode) {
+  return umma_tmem_cols_n((umma_num_acc0(amode) + 1) * block_n);
 }
 
 #ifdef __CUDACC__
@@ -76,8 +84,11 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
   constexpr int STAGES = umma_num_stages(BLOCK_N);
   constexpr int STAGE_BYTES = umma_stage_bytes(BLOCK_N);
   constexpr int STAGE_B = BLOCK_N * 128;
-  constexpr int TMEM_COLS = umma_tmem_cols(BLOCK_N);
-  constexpr int ACC1_COL = TMEM_COLS / 2;
+  constexpr int NACC0 = umma_num_acc0(AMODE);
+  constexpr int TMEM_COLS = umma_tmem_cols(BLOCK_N, AMODE);
+  constexpr int ACC_STRIDE = TMEM_COLS / (NACC0 + 1);        // column pitch between accumulators
+  constexpr int ACC1_COL = NACC0 * ACC_STRIDE;
+  static_assert(ACC_STRIDE >= BLOCK_N && (NACC0 + 1) * ACC_STRIDE <= 512, "TMEM budget");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
   static_assert(STAGES >= 2, "need at least two stages");
 
@@ -161,7 +172,6 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     // ===== MMA issuer ===========================================================================
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
-      const uint32_t acc0 = tmem_base;
       const uint32_t acc1 = tmem_base + ACC1_COL;
       int stage = 0;
       uint32_t phase = 0;
@@ -172,6 +182,14 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
         const uint32_t a_lo = a_hi + kStageABytes;
         const uint32_t b_hi = a_hi + 2 * kStageABytes;
         const uint32_t b_lo = b_hi + STAGE_B;
+        uint32_t acc0 = tmem_base;
+        bool first0 = (ks == 0);
+        if constexpr (AMODE == A_CONV3) {       // one hi*hi accumulator per kernel row dy
+          const int tap = ks / p.cin_chunks;
+          const int dy = tap / 3;
+          acc0 = tmem_base + dy * ACC_STRIDE;
+          first0 = (ks == dy * 3 * p.cin_chunks);
+        }
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
           const uint64_t da_hi = make_sw128_kmajor_desc(a_hi + k * 32);
@@ -179,7 +197,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
           const uint64_t db_hi = make_sw128_kmajor_desc(b_hi + k * 32);
           const uint64_t db_lo = make_sw128_kmajor_desc(b_lo + k * 32);
           const uint32_t acc = (ks > 0 || k > 0) ? 1u : 0u;
-          umma_f16(acc0, da_hi, db_hi, idesc, acc);
+          umma_f16(acc0, da_hi, db_hi, idesc, (first0 && k == 0) ? 0u : 1u);
           umma_f16(acc1, da_hi, db_lo, idesc, acc);
           umma_f16(acc1, da_lo, db_hi, idesc, 1u);
         }
@@ -204,9 +222,20 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       uint32_t r0[16], r1[16];
       tmem_ld16(t0 + col, r0);
       tmem_ld16(t1 + col, r1);
-      tmem_ld_wait();
+      if constexpr (NACC0 == 3) {
+        uint32_t ra[16], rb[16];
+        tmem_ld16(t0 + ACC_STRIDE + col, ra);
+        tmem_ld16(t0 + 2 * ACC_STRIDE + col, rb);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]) * RFE_SPLIT_INV;
+        for (int j = 0; j < 16; ++j)
+          v[j] = ((__uint_as_float(r0[j]) + __uint_as_float(ra[j])) + __uint_as_float(rb[j])) +
+                 __uint_as_float(r1[j]) * RFE_SPLIT_INV;
+      } else {
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]) * RFE_SPLIT_INV;
+      }
     };
 
     if constexpr (EPI == EPI_CONV) {

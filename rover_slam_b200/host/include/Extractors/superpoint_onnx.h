@@ -1,0 +1,46 @@
+// SuperPointOnnxRunner without ONNXRuntime: same class name and ORT-free members as the reference's
+// include/Extractors/superpoint_onnx.h:10-68; the Ort::Value carriers are replaced by a POD result struct and
+// the session by an rfe_ctx (include/rover_fe.h).  All arithmetic runs in librover_fe.so on the GPU.
+#pragma once
+#include <opencv2/opencv.hpp>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "Matchers/Configuration.h"
+#include "Matchers/transform.h"
+#include "rover_fe.h"
+
+struct SuperPointResult {              // what the three ONNX outputs carried (superpoint_onnx.cc:150)
+  std::vector<int32_t> keypoints;      // [N][2] (x, y)
+  std::vector<float> scores;           // [N]
+  std::vector<float> descriptors;      // [N][256]
+  int count = 0;
+};
+
+class SuperPointOnnxRunner {
+ public:
+  const unsigned int num_threads;
+  float matchThresh = 0.0f;
+  long long extractor_timer = 0;       // milliseconds, like the reference (superpoint_onnx.cc:138-140)
+  long long matcher_timer = 0;
+  float lastmatch = 0;
+  std::vector<float> scales = {1.0f, 1.0f};
+  std::vector<SuperPointResult> extractor_outputtensors;
+
+  explicit SuperPointOnnxRunner(unsigned int num_threads = 1);
+  ~SuperPointOnnxRunner();
+
+  int InitOrtEnv(Configuration cfg);                                               // superpoint_onnx.cc:4-66
+  int Extractor_Inference(Configuration cfg, const cv::Mat& image);                // superpoint_onnx.cc:88-162 (CV_32F [0,1] or CV_8UC1)
+  void Extractor_PostProcess(Configuration cfg, SuperPointResult tensor, std::vector<cv::KeyPoint>& vKeyPoints,
+                             cv::Mat& Descriptors);                                // superpoint_onnx.cc:165-255
+  float GetMatchThresh();
+  void SetMatchThresh(float thresh);
+  double GetTimer(std::string name);                                               // superpoint_onnx.cc:268-277
+  rfe_ctx* context() { return ctx_; }
+
+ private:
+  rfe_ctx* ctx_ = nullptr;
+  int cap_ = 8192;
+};

@@ -1,0 +1,74 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds, loads and exports every symbol the header
+declares; argument checking fails loudly; there is no CPU fallback."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+
+from rover_slam_b200 import api
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(api.lib_path()):
+        subprocess.run(["make", "-j8", "-C", ROOT], check=True)
+    return api.load_library()
+
+
+def test_header_symbols_exported(lib):
+    syms = api.exported_symbols()
+    assert {"rfe_create", "rfe_destroy", "rfe_sp_extract_u8", "rfe_lg_match", "rfe_last_error"} <= set(syms)
+    for s in syms:
+        assert getattr(lib, s) is not None
+
+
+def test_library_has_blackwell_tensor_core_code():
+    out = subprocess.run(["cuobjdump", "-sass", api.lib_path()], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in out, "tcgen05.mma missing from SASS"
+    assert "UTMALDG" in out, "TMA loads missing from SASS"
+    assert "LDTM" in out, "tcgen05.ld missing from SASS"
+    assert "sm_100a" in out
+
+
+def test_no_device_fails_loudly(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(api.RoverFeError) as e:
+        api.FrontEnd()
+    assert e.value.code == api.RFE_ERR_NO_DEVICE
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_null_arguments(lib):
+    assert lib.rfe_create(None, None) == api.RFE_ERR_INVALID
+    assert b"null" in lib.rfe_last_error()
+    assert lib.rfe_sync(None) == api.RFE_ERR_INVALID
+    lib.rfe_destroy(None)   # no-op
+
+
+def test_product_does_not_import_oracle():
+    """The product path (package + csrc) must never reference oracle/."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "rover_slam_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h", ".cpp", ".hpp")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in src.replace("the CPU oracle", ""), f"{f} mentions oracle"
+
+
+def test_weight_blob_matches_reference_when_mounted():
+    ref = "/root/reference/onnxmodel/superpoint.onnx"
+    if not os.path.exists(ref):
+        pytest.skip("reference not mounted")
+    import numpy as np
+    from oracle import onnx_reader, weights
+    blob = weights.load()
+    g = onnx_reader.load(ref)
+    w = g.initializers["conv3b.weight"]
+    assert np.array_equal(blob["sp.conv3b.w"], w.transpose(0, 2, 3, 1))
+    g2 = onnx_reader.load("/root/reference/onnxmodel/lightglue_sim.onnx")
+    assert np.array_equal(blob["lg.l4.cross.to_v.b"], g2.initializers["transformers.4.cross_attn.to_v.bias"])
+    assert blob["lg.l0.self.wqkv.w"].shape == (768, 256)

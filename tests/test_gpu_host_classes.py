@@ -1,0 +1,61 @@
+"""GPU test of the reference-facing C++ class surface (ORB_SLAM3::SPextractor / SPmatcher and the two runner
+classes) built on the C ABI: the host_driver binary follows the reference's call pattern
+(Frame.cc:544-559 -> SPextractor::operator(); Tracking.cc:3465 -> SPmatcher::MatchingPoints_onnx) and its
+results must equal the C-ABI path bit for bit and the oracle within tolerance."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import lightglue_ref, synth
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_spextractor_spmatcher_classes():
+    from rover_slam_b200 import FrontEnd
+    drv = os.path.join(ROOT, "rover_slam_b200", "host_driver")
+    if not os.path.exists(drv):
+        subprocess.run(["make", "-C", ROOT, "host"], check=True)
+    h, w = 240, 320
+    a, b = synth.frame_pair(31, h, w, shift=(7, -4))
+    with tempfile.TemporaryDirectory() as td:
+        a.tofile(os.path.join(td, "a.raw"))
+        b.tofile(os.path.join(td, "b.raw"))
+        out = os.path.join(td, "out.bin")
+        env = dict(os.environ, ROVER_FE_WEIGHTS=os.path.join(ROOT, "weights", "rover_fe.rfw"))
+        r = subprocess.run([drv, str(h), str(w), os.path.join(td, "a.raw"), os.path.join(td, "b.raw"), out],
+                           capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        raw = np.fromfile(out, dtype=np.uint8)
+    hdr = raw[:24].view(np.int32)
+    na, nb, nmulti, m_frame, m_kp = (int(v) for v in hdr[:5])
+    off = 24
+    feats = []
+    for n in (na, nb):
+        kp = raw[off:off + n * 12].view(np.float32).reshape(n, 3); off += n * 12
+        de = raw[off:off + n * 1024].view(np.float32).reshape(n, 256); off += n * 1024
+        feats.append((kp, de))
+    vn_frame = raw[off:off + na * 4].view(np.int32); off += na * 4
+    vn_kp = raw[off:off + na * 4].view(np.int32)
+    assert nmulti == 0                                   # nLevels != 1 extracts nothing, like the reference
+    fe = FrontEnd(max_batch=2, max_height=h, max_width=w)
+    ref = fe.extract(np.stack([a, b]))
+    for (kp, de), (k, s, d) in zip(feats, ref):
+        assert np.array_equal(kp[:, :2], k.astype(np.float32))
+        assert np.array_equal(kp[:, 2], s)               # response = score (the reference's scores[2*i] bug waived)
+        assert np.array_equal(de, d)
+    # Frame overload normalises with the image size; the KeyPoint overload with the hard-coded 300 x 400
+    for vn, cnt, (nh, nw) in ((vn_frame, m_frame, (h, w)), (vn_kp, m_kp, (300, 400))):
+        m, ms = fe.match(ref[0][0], ref[1][0], ref[0][2], ref[1][2], nh, nw)
+        exp, c = lightglue_ref.scatter_matches(m, ms, na, 0.0)
+        assert c == cnt and np.array_equal(exp, vn)
+    rm, rms = lightglue_ref.LightGlueRef()(lightglue_ref.normalize_keypoints(ref[0][0], h, w),
+                                           lightglue_ref.normalize_keypoints(ref[1][0], h, w), ref[0][2], ref[1][2])
+    m, ms = fe.match(ref[0][0], ref[1][0], ref[0][2], ref[1][2], h, w)
+    parity.compare_matches(rm.numpy(), rms.numpy(), m, ms)
+    fe.close()

@@ -1,0 +1,193 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against the CPU oracle
+and the committed golden vectors.  Tolerances: tests/parity.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lightglue_ref, superpoint_ref, synth
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fe():
+    from rover_slam_b200 import FrontEnd
+    f = FrontEnd(max_batch=8, max_height=480, max_width=752, max_keypoints=4096)
+    yield f
+    f.close()
+
+
+@pytest.fixture(scope="module")
+def sp():
+    return superpoint_ref.SuperPointRef()
+
+
+@pytest.fixture(scope="module")
+def lg():
+    return lightglue_ref.LightGlueRef()
+
+
+# ---- the tensor-core building block -------------------------------------------------------------------
+@pytest.mark.parametrize("m,n,k", [(128, 64, 64), (128, 128, 512), (300, 200, 512), (77, 768, 256), (1, 8, 8),
+                                   (2049, 65, 256)])
+def test_split_fp16_gemm_is_fp32_equivalent(fe, m, n, k):
+    rng = np.random.RandomState(m + n + k)
+    a = (rng.randn(m, k) * 3).astype(np.float32)
+    b = rng.randn(n, k).astype(np.float32)
+    bias = rng.randn(n).astype(np.float32)
+    d = fe.debug_gemm(a, b, bias)
+    ref64 = a.astype(np.float64) @ b.astype(np.float64).T + bias
+    ref32 = a @ b.T + bias
+    err = np.abs(d - ref64).max()
+    err32 = np.abs(ref32 - ref64).max()
+    scale = np.abs(ref64).max()
+    assert err <= max(4 * err32, 2e-6 * scale), (err, err32)
+
+
+# ---- SuperPoint -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["sp_640x480_seed0", "sp_752x480_seed100_a"])
+def test_superpoint_vs_golden(fe, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    (k, s, d), = fe.extract(g["image"])
+    r = parity.compare_keypoints(g["keypoints"], g["scores"], k, s)
+    h, w = g["image"].shape
+    heat = fe.debug_read("sp.heat").reshape(-1, h, w)[0]
+    assert np.abs(heat[g["heat_rows"]] - g["heat"]).max() <= parity.HEAT_ATOL
+    # descriptors of the golden subset that is common
+    pos = {int(i): j for j, i in enumerate(r["ref_idx"])}
+    rows = [(gi, r["tst_idx"][pos[int(ri)]]) for gi, ri in enumerate(g["desc_rows"]) if int(ri) in pos]
+    gi, ti = np.array(rows).T
+    parity.compare_descriptors(g["desc"][gi], d[ti])
+    dense = fe.debug_read("sp.dense").reshape(h // 8, w // 8, 256)
+    assert np.abs(np.transpose(dense, (2, 0, 1))[:, ::8, ::8] - g["dense_desc_px"]).max() <= parity.DESC_ATOL
+
+
+def test_superpoint_batch8_vs_oracle(fe, sp):
+    """BASELINE config 2: batch of 8 synthetic 640x480 frames."""
+    imgs = np.stack([synth.frame(s, 480, 640) for s in range(8)])
+    feats = fe.extract(imgs)
+    for i in range(8):
+        rk, rs, rd = sp(imgs[i])
+        k, s, d = feats[i]
+        r = parity.compare_keypoints(rk.numpy(), rs.numpy(), k, s)
+        parity.compare_descriptors(rd.numpy()[r["ref_idx"]], d[r["tst_idx"]])
+        assert np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-5)
+
+
+def test_superpoint_intermediates(fe, sp):
+    img = synth.frame(21, 96, 160)
+    fe.extract(img)
+    taps = {}
+    sp(img, taps)
+    for name, key, c, div, tol in [("sp.a1a", "relu1a", 64, 1, 2e-4), ("sp.pool1", "pool1", 64, 2, 2e-4),
+                                   ("sp.pool2", "pool2", 64, 4, 2e-4), ("sp.pool3", "pool3", 128, 8, 2e-4),
+                                   ("sp.feat", "feat", 128, 8, 2e-4)]:
+        got = np.transpose(fe.debug_read(name).reshape(96 // div, 160 // div, c), (2, 0, 1))
+        ref = taps[key][0].numpy()
+        assert np.abs(got - ref).max() <= tol * max(1.0, np.abs(ref).max()), name
+
+
+def test_nms_kernel_exact_on_own_heatmap(fe):
+    """NMS + border + threshold + ordering are integer/comparison work: bit-exact given the same heat-map."""
+    img = synth.frame(5, 240, 320)
+    (k, s, _), = fe.extract(img, want_desc=False)
+    heat = torch.from_numpy(fe.debug_read("sp.heat").reshape(1, 240, 320))
+    nmsed = superpoint_ref.SuperPointRef.nms(heat)
+    rk, rs, post = superpoint_ref.SuperPointRef.select(nmsed)
+    assert np.array_equal(fe.debug_read("sp.nms").reshape(240, 320), post[0].numpy())
+    assert np.array_equal(rk.numpy(), k)
+    assert np.array_equal(rs.numpy(), s)
+
+
+@pytest.mark.parametrize("hw", [(8, 8), (16, 24), (64, 96), (480, 752)])
+def test_superpoint_sizes_and_blank(fe, sp, hw):
+    h, w = hw
+    for img in (np.zeros((h, w), np.uint8), synth.frame(9, h, w) if min(h, w) >= 16 else np.full((h, w), 200, np.uint8)):
+        (k, s, d), = fe.extract(img)
+        rk, rs, rd = sp(img)
+        r = parity.compare_keypoints(rk.numpy(), rs.numpy(), k, s)
+        if len(r["ref_idx"]):
+            parity.compare_descriptors(rd.numpy()[r["ref_idx"]], d[r["tst_idx"]])
+
+
+def test_superpoint_rejects_bad_sizes(fe):
+    from rover_slam_b200 import RoverFeError
+    with pytest.raises(RoverFeError):
+        fe.extract(np.zeros((100, 100), np.uint8))       # not multiples of 8
+    with pytest.raises(RoverFeError):
+        fe.extract(np.zeros((9, 480, 640), np.uint8))    # batch > max_batch
+
+
+# ---- LightGlue --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [256, 512])
+def test_lightglue_vs_golden_synth(fe, golden_dir, n):
+    g = np.load(os.path.join(golden_dir, f"lg_synth_n{n}.npz"))
+    k0, k1, d0, d1, perm = synth.lightglue_inputs(n, 200 + n)
+    m, ms = fe.match(k0, k1, d0, d1, 480, 640)
+    r = parity.compare_matches(g["matches"], g["mscores"], m, ms)
+    assert r["common"] >= len(g["matches"]) - 2
+
+
+@pytest.mark.parametrize("n0,n1", [(1024, 1024), (300, 777), (5, 1000), (1, 1), (2048, 2048)])
+def test_lightglue_vs_oracle_ragged(fe, lg, n0, n1):
+    """BASELINE config 4 (N sweep) + ragged sizes."""
+    n = max(n0, n1)
+    k0, k1, d0, d1, perm = synth.lightglue_inputs(n, 300 + n)
+    k0, d0, k1, d1 = k0[:n0], d0[:n0], k1[:n1], d1[:n1]
+    m, ms = fe.match(k0, k1, d0, d1, 480, 640)
+    rm, rms = lg(lightglue_ref.normalize_keypoints(k0, 480, 640), lightglue_ref.normalize_keypoints(k1, 480, 640), d0, d1)
+    parity.compare_matches(rm.numpy(), rms.numpy(), m, ms)
+
+
+def test_lightglue_empty_inputs(fe):
+    k0, k1, d0, d1, _ = synth.lightglue_inputs(16, 1)
+    m, ms = fe.match(k0[:0], k1, d0[:0], d1, 480, 640)
+    assert m.shape == (0, 2) and ms.shape == (0,)
+    m, ms = fe.match(k0, k1[:0], d0, d1[:0], 480, 640)
+    assert m.shape == (0, 2)
+
+
+def test_lightglue_threshold_and_normalisation(fe, lg):
+    k0, k1, d0, d1, _ = synth.lightglue_inputs(256, 9)
+    m_all, s_all = fe.match(k0, k1, d0, d1, 480, 640, thresh=0.0)
+    m_hi, s_hi = fe.match(k0, k1, d0, d1, 480, 640, thresh=0.5)
+    assert (s_hi > 0.5).all() and len(m_hi) <= len(m_all)
+    keep = s_all > 0.5
+    assert np.array_equal(m_all[keep], m_hi)
+    # the three non-Frame overloads of the reference hard-code rows=300, cols=400 (SPmatcher.cc:360-361)
+    m3, s3 = fe.match(k0, k1, d0, d1, 300, 400)
+    rm, rms = lg(lightglue_ref.normalize_keypoints(k0, 300, 400), lightglue_ref.normalize_keypoints(k1, 300, 400), d0, d1)
+    parity.compare_matches(rm.numpy(), rms.numpy(), m3, s3)
+
+
+# ---- end to end (BASELINE config 3) ------------------------------------------------------------------------
+def test_pair_end_to_end_752x480(fe, golden_dir, sp, lg):
+    ga = np.load(os.path.join(golden_dir, "sp_752x480_seed100_a.npz"))
+    gb = np.load(os.path.join(golden_dir, "sp_752x480_seed100_b.npz"))
+    g = np.load(os.path.join(golden_dir, "lg_752x480_seed100.npz"))
+    imgs = np.stack([ga["image"], gb["image"]])
+    feats = fe.extract(imgs)
+    ra = parity.compare_keypoints(ga["keypoints"], ga["scores"], feats[0][0], feats[0][1])
+    rb = parity.compare_keypoints(gb["keypoints"], gb["scores"], feats[1][0], feats[1][1])
+    m, ms = fe.match(feats[0][0], feats[1][0], feats[0][2], feats[1][2], 480, 752)
+    if len(ra["only_ref"]) + len(ra["only_tst"]) + len(rb["only_ref"]) + len(rb["only_tst"]) == 0:
+        parity.compare_matches(g["matches"], g["mscores"], m, ms)      # identical features -> golden matches
+    # in every case: identical to the oracle run on OUR features
+    rm, rms = lg(lightglue_ref.normalize_keypoints(feats[0][0], 480, 752),
+                 lightglue_ref.normalize_keypoints(feats[1][0], 480, 752), feats[0][2], feats[1][2])
+    parity.compare_matches(rm.numpy(), rms.numpy(), m, ms)
+    disp = feats[1][0][m[:, 1]] - feats[0][0][m[:, 0]]
+    assert tuple(np.median(disp, 0)) == (12.0, 7.0)
+    # device-resident hand-off gives the same answer as the host round trip
+    fe.match_slots(0, 1, 480, 752)
+    m2, ms2 = fe.read_result(0)
+    assert np.array_equal(m, m2) and np.array_equal(ms, ms2)
+
+
+def test_gpu_path_launches_kernels(fe):
+    before = fe.kernel_launches()
+    fe.extract(synth.frame(1, 64, 64))
+    assert fe.kernel_launches() - before >= 15
