@@ -257,7 +257,7 @@ def main():
                      "share_of_step": conv1b_ms / all_ms if all_ms else None,
                      "note": "split-fp16 runs 3 MMAs per algorithmic MAC: frac <= 1/3 by construction"},
     }
-    if world == 1:
+    if world == 1 and args.cpu_pairs > 0:
         threads = os.cpu_count() or 1
         cpu_frames = make_pairs(args.cpu_pairs, 7)
         cpu_pair_seconds(cpu_frames[0], threads)          # warm-up

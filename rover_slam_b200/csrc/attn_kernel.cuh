@@ -1,0 +1,281 @@
+// Fused multi-head attention for LightGlue's self and cross blocks, split-fp16 on tcgen05:
+//     O[q] = softmax_k( Q[q] . K[k] ) V[k]          4 heads x 64 dims, Q and K pre-scaled by 64^-1/4
+// (lightglue_sim.onnx /inner_attn: Mul, Mul_1, MatMul, Softmax, MatMul_1 -- e.g. layer 0 self nodes 50-54,
+//  cross nodes 141-151; run by the reference at src/Matchers/lightglue_onnx.cpp:210-214).
+// The N x N score matrix never leaves the SM: one CTA owns a 128-query tile of one (image, head) and walks the
+// key tiles twice -- pass 1 finds the exact row maximum (the reference's softmax subtracts exactly that), pass 2
+// recomputes the scores, exponentiates, accumulates the row sum and feeds P = exp(S - max) straight back to the
+// tensor core from shared memory for O += P V.  The epilogue divides by the row sum.
+//
+// CTA = 320 threads: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2..9 softmax/epilogue
+// (warp w and w+4 share TMEM lane quarter w%4 and split each 64-key tile's columns 32/32).
+// TMEM: 2 x (S_hh, S_x) score buffers of 64 columns + (O_hh, O_x) 2 x 64 = 384 columns.
+#pragma once
+
+#include "common.cuh"
+
+namespace rfe {
+
+struct AttnParams {
+  int nq[2], nk[2];          // per problem (blockIdx.z): query rows, key rows
+  int q_row0[2], k_row0[2];  // row offsets of the problems inside the head-major Q / K tensors and the V^T columns
+  __half* out_hi;            // split-fp16 [rows][256]
+  __half* out_lo;
+};
+
+constexpr int kAttnThreads = 320;
+constexpr int kAttnStages = 3;
+constexpr int kAttnKeyTile = 64;
+constexpr int kAttnStageBytes = 4 * 8192;                       // K_hi, K_lo, Vt_hi, Vt_lo  (64 rows x 128 B each)
+constexpr int kAttnQBytes = 2 * 16384;                          // Q_hi, Q_lo (128 rows x 128 B)
+constexpr int kAttnPBytes = 2 * 16384;                          // P_hi, P_lo (128 rows x 128 B)
+constexpr int kAttnSmemBytes = kAttnQBytes + kAttnPBytes + kAttnStages * kAttnStageBytes + 1024 + 4096;
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// tensor maps: Q and K: 3-D (64, rows_total, 4 heads), box (64, 128) resp. (64, 64); V^T: 3-D (cols_total, 64, 4), box (64, 64)
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ CUtensorMap tmQ_lo,
+            const __grid_constant__ CUtensorMap tmK_hi, const __grid_constant__ CUtensorMap tmK_lo,
+            const __grid_constant__ CUtensorMap tmV_hi, const __grid_constant__ CUtensorMap tmV_lo, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // Q_hi | Q_lo
+  uint8_t* sP = smem + kAttnQBytes;                     // P_hi | P_lo
+  uint8_t* sKV = sP + kAttnPBytes;                      // stages
+  uint8_t* tail = sKV + kAttnStages * kAttnStageBytes;
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* kv_full = q_full + 1;
+  uint64_t* kv_empty = kv_full + kAttnStages;
+  uint64_t* s_full = kv_empty + kAttnStages;            // [2]
+  uint64_t* s_empty = s_full + 2;                       // [2]
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* p_empty = p_full + 1;
+  uint64_t* o_full = p_empty + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 1);
+  float* stat = reinterpret_cast<float*>(tail + 256);   // [2][128] partial row max, then partial row sum
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int z = blockIdx.z;
+  const int head = blockIdx.y;
+  const int nq = p.nq[z], nk = p.nk[z];
+  const int m0 = blockIdx.x * 128;
+  if (m0 >= nq) return;                                 // uniform per CTA
+  const int T = (nk + kAttnKeyTile - 1) / kAttnKeyTile;
+  const int qrow = p.q_row0[z] + m0, krow = p.k_row0[z];
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ_hi); tma_prefetch_desc(&tmQ_lo); tma_prefetch_desc(&tmK_hi);
+    tma_prefetch_desc(&tmK_lo); tma_prefetch_desc(&tmV_hi); tma_prefetch_desc(&tmV_lo);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kAttnStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 8); }
+    mbar_init(p_full, 8);
+    mbar_init(p_empty, 1);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  // TMEM columns: S buffer b: hh at b*128, x at b*128+64 ; O: hh at 256, x at 320
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, kAttnQBytes);
+      tma_load_3d(sQ, &tmQ_hi, q_full, 0, qrow, head);
+      tma_load_3d(sQ + 16384, &tmQ_lo, q_full, 0, qrow, head);
+      for (int g = 0; g < 2 * T; ++g) {
+        const int t = g < T ? g : g - T;
+        const bool with_v = g >= T;
+        const int st = g % kAttnStages;
+        mbar_wait(&kv_empty[st], ((g / kAttnStages) & 1) ^ 1);
+        uint8_t* sb = sKV + st * kAttnStageBytes;
+        mbar_expect_tx(&kv_full[st], with_v ? kAttnStageBytes : kAttnStageBytes / 2);
+        tma_load_3d(sb, &tmK_hi, &kv_full[st], 0, krow + t * kAttnKeyTile, head);
+        tma_load_3d(sb + 8192, &tmK_lo, &kv_full[st], 0, krow + t * kAttnKeyTile, head);
+        if (with_v) {
+          tma_load_3d(sb + 16384, &tmV_hi, &kv_full[st], krow + t * kAttnKeyTile, 0, head);
+          tma_load_3d(sb + 24576, &tmV_lo, &kv_full[st], krow + t * kAttnKeyTile, 0, head);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_f16(128, 64);
+      const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + 16384;
+      const uint32_t p_hi = smem_u32(sP), p_lo = p_hi + 16384;
+      const uint32_t o_hh = tmem_base + 256, o_x = tmem_base + 320;
+      mbar_wait(q_full, 0);
+      auto issue_s = [&](int g) {
+        const int st = g % kAttnStages, b = g & 1;
+        mbar_wait(&kv_full[st], (g / kAttnStages) & 1);
+        mbar_wait(&s_empty[b], ((g >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t k_hi = smem_u32(sKV + st * kAttnStageBytes), k_lo = k_hi + 8192;
+        const uint32_t s_hh = tmem_base + b * 128, s_x = s_hh + 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t dq_hi = make_sw128_kmajor_desc(q_hi + k * 32), dq_lo = make_sw128_kmajor_desc(q_lo + k * 32);
+          const uint64_t dk_hi = make_sw128_kmajor_desc(k_hi + k * 32), dk_lo = make_sw128_kmajor_desc(k_lo + k * 32);
+          umma_f16(s_hh, dq_hi, dk_hi, idesc, k > 0);
+          umma_f16(s_x, dq_hi, dk_lo, idesc, k > 0);
+          umma_f16(s_x, dq_lo, dk_hi, idesc, 1u);
+        }
+        umma_commit(&s_full[b]);
+      };
+      auto issue_pv = [&](int g, int t) {   // consumes P of tile t and the V^T half of stage g%ST
+        const int st = g % kAttnStages;
+        mbar_wait(p_full, t & 1);
+        tc_fence_after();
+        const uint32_t v_hi = smem_u32(sKV + st * kAttnStageBytes) + 16384, v_lo = v_hi + 8192;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t dp_hi = make_sw128_kmajor_desc(p_hi + k * 32), dp_lo = make_sw128_kmajor_desc(p_lo + k * 32);
+          const uint64_t dv_hi = make_sw128_kmajor_desc(v_hi + k * 32), dv_lo = make_sw128_kmajor_desc(v_lo + k * 32);
+          const uint32_t acc = (t > 0 || k > 0) ? 1u : 0u;
+          umma_f16(o_hh, dp_hi, dv_hi, idesc, acc);
+          umma_f16(o_x, dp_hi, dv_lo, idesc, acc);
+          umma_f16(o_x, dp_lo, dv_hi, idesc, 1u);
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(p_empty);
+      };
+      // pass 1: scores only; the K stage is free as soon as its MMAs retire
+      for (int g = 0; g < T; ++g) {
+        issue_s(g);
+        umma_commit(&kv_empty[g % kAttnStages]);
+      }
+      // pass 2: S(t) is issued before PV(t-1) so the softmax of tile t-1 overlaps the score MMAs of tile t
+      for (int t = 0; t < T; ++t) {
+        issue_s(T + t);
+        if (t > 0) issue_pv(T + t - 1, t - 1);
+      }
+      issue_pv(2 * T - 1, T - 1);
+      umma_commit(o_full);
+    }
+  } else {
+    // ===== softmax / epilogue warps =========================================================================
+    const int sw = warp - 2;                 // 0..7
+    const int q = warp & 3;                  // TMEM lane quarter
+    const int hw = sw >> 2;                  // which 32-column half of every 64-key tile (warps 2..5 -> 0, 6..9 -> 1)
+    const int row = q * 32 + lane;
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float NEG = -INFINITY;
+
+    auto load_scores = [&](int g, float (&s)[32]) {
+      const int b = g & 1;
+      mbar_wait(&s_full[b], (g >> 1) & 1);
+      tc_fence_after();
+      uint32_t a0[16], a1[16], x0[16], x1[16];
+      const uint32_t base = tlane + b * 128 + hw * 32;
+      tmem_ld16(base, a0);
+      tmem_ld16(base + 16, a1);
+      tmem_ld16(base + 64, x0);
+      tmem_ld16(base + 80, x1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[b]);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        s[j] = __uint_as_float(a0[j]) + __uint_as_float(x0[j]) * RFE_SPLIT_INV;
+        s[16 + j] = __uint_as_float(a1[j]) + __uint_as_float(x1[j]) * RFE_SPLIT_INV;
+      }
+    };
+
+    // ---- pass 1: exact row maximum ----
+    float mx = NEG;
+    for (int g = 0; g < T; ++g) {
+      float s[32];
+      load_scores(g, s);
+      const int c0 = g * kAttnKeyTile + hw * 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c0 + j < nk) mx = fmaxf(mx, s[j]);
+    }
+    stat[hw * 128 + row] = mx;
+    named_bar_sync(1, 256);
+    mx = fmaxf(stat[row], stat[128 + row]);
+    named_bar_sync(1, 256);
+
+    // ---- pass 2: P = exp(S - max) -> smem (K-major, 128-byte swizzle), row sum ----
+    float l = 0.0f;
+    uint8_t* prow_hi = sP + row * 128;
+    uint8_t* prow_lo = prow_hi + 16384;
+    for (int t = 0; t < T; ++t) {
+      float s[32];
+      load_scores(T + t, s);
+      const int c0 = t * kAttnKeyTile + hw * 32;
+      __align__(16) __half ph[32];
+      __align__(16) __half pl[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float e = (c0 + j < nk) ? expf(s[j] - mx) : 0.0f;
+        l += e;
+        split_f32(e, ph[j], pl[j]);
+      }
+      mbar_wait(p_empty, (t & 1) ^ 1);       // PV(t-1) has consumed the previous P tile
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const int sc = ((hw * 4 + ch) ^ (row & 7)) << 4;
+        *reinterpret_cast<uint4*>(prow_hi + sc) = reinterpret_cast<const uint4*>(ph)[ch];
+        *reinterpret_cast<uint4*>(prow_lo + sc) = reinterpret_cast<const uint4*>(pl)[ch];
+      }
+      fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    stat[hw * 128 + row] = l;
+    named_bar_sync(1, 256);
+    l = stat[row] + stat[128 + row];
+
+    // ---- epilogue: O / l -> split-fp16 [rows][256] ----
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    {
+      uint32_t a0[16], a1[16], x0[16], x1[16];
+      const uint32_t base = tlane + 256 + hw * 32;
+      tmem_ld16(base, a0);
+      tmem_ld16(base + 16, a1);
+      tmem_ld16(base + 64, x0);
+      tmem_ld16(base + 80, x1);
+      tmem_ld_wait();
+      __align__(16) __half oh[32];
+      __align__(16) __half ol[32];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        split_f32((__uint_as_float(a0[j]) + __uint_as_float(x0[j]) * RFE_SPLIT_INV) / l, oh[j], ol[j]);
+        split_f32((__uint_as_float(a1[j]) + __uint_as_float(x1[j]) * RFE_SPLIT_INV) / l, oh[16 + j], ol[16 + j]);
+      }
+      if (m0 + row < nq) {
+        const size_t o = static_cast<size_t>(qrow + row) * 256 + head * 64 + hw * 32;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          reinterpret_cast<uint4*>(p.out_hi + o)[ch] = reinterpret_cast<const uint4*>(oh)[ch];
+          reinterpret_cast<uint4*>(p.out_lo + o)[ch] = reinterpret_cast<const uint4*>(ol)[ch];
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace rfe

@@ -10,6 +10,7 @@
 
 #include "kernels.h"
 #include "tensormap.h"
+#include "attn_kernel.cuh"
 #include "umma_kernel.cuh"
 #include "weights.h"
 
@@ -90,6 +91,7 @@ struct rfe_ctx {
   int *m0 = nullptr, *m1 = nullptr;
   float* S_dbg = nullptr;
   int dbg_n0 = 0, dbg_n1 = 0, dbg_n0p = 0;
+  bool unfused_attn = false;    // RFE_UNFUSED_ATTN=1: bring-up cross-check path (GEMM -> softmax -> GEMM through HBM)
   // match results: [max_batch] slots
   int* res_matches = nullptr;   // [slots][cap][2]
   float* res_scores = nullptr;  // [slots][cap]
@@ -462,6 +464,43 @@ int attention(rfe_ctx* c, const SplitBuf& Q, const SplitBuf& K, int rows_total, 
   return RFE_OK;
 }
 
+// Fused attention over both problems of a block (self: image0/image0 + image1/image1; cross: 0->1 + 1->0).
+int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitBuf& K, int rows_total, const int qa[2],
+                    const int nq[2], const int kb[2], const int nk[2]) {
+  static bool configured[64] = {};
+  if (!configured[c->device & 63]) {
+    RFE_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    configured[c->device & 63] = true;
+  }
+  CUtensorMap qh, ql, kh, kl, vh, vl;
+  const uint64_t dq[3] = {64, static_cast<uint64_t>(rows_total), 4};
+  const uint64_t sq[2] = {128, static_cast<uint64_t>(rows_total) * 128};
+  const uint32_t boxq[3] = {64, 128, 1}, boxk[3] = {64, 64, 1};
+  if (make_tmap_f16_sw128(&qh, Q.hi, 3, dq, sq, boxq) || make_tmap_f16_sw128(&ql, Q.lo, 3, dq, sq, boxq) ||
+      make_tmap_f16_sw128(&kh, K.hi, 3, dq, sq, boxk) || make_tmap_f16_sw128(&kl, K.lo, 3, dq, sq, boxk))
+    return RFE_ERR_CUDA;
+  const uint64_t dv[3] = {static_cast<uint64_t>(rows_total), 64, 4};
+  const uint64_t sv[2] = {static_cast<uint64_t>(c->lg_ldv) * 2, 64ULL * c->lg_ldv * 2};
+  if (make_tmap_f16_sw128(&vh, c->vt.hi, 3, dv, sv, boxk) || make_tmap_f16_sw128(&vl, c->vt.lo, 3, dv, sv, boxk))
+    return RFE_ERR_CUDA;
+  AttnParams p;
+  for (int i = 0; i < 2; ++i) {
+    p.nq[i] = nq[i];
+    p.nk[i] = nk[i];
+    p.q_row0[i] = qa[i];
+    p.k_row0[i] = kb[i];
+  }
+  p.out_hi = c->attn.hi;
+  p.out_lo = c->attn.lo;
+  const int mq = nq[0] > nq[1] ? nq[0] : nq[1];
+  dim3 grid((mq + 127) / 128, 4, 2);
+  ProfScope ps(c, tag);
+  attn_kernel<<<grid, kAttnThreads, kAttnSmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
+  c->launches++;
+  RFE_CUDA_CHECK(cudaGetLastError());
+  return RFE_OK;
+}
+
 int lg_run(rfe_ctx* c, const float* d_kpts0, int n0, const float* d_kpts1, int n1, const float* d_desc0,
            const float* d_desc1, int norm_h, int norm_w, float thresh, int rslot) {
   cudaStream_t s = c->stream;
@@ -496,8 +535,13 @@ int lg_run(rfe_ctx* c, const float* d_kpts0, int n0, const float* d_kpts1, int n
     launch_rope_split(s, c->qkv, rows, c->cs, c->sn, kAttnScale, c->q.hi, c->q.lo, c->k.hi, c->k.lo, c->vt.hi,
                       c->vt.lo, c->lg_ldv);
     c->launches++;
-    if ((r = attention(c, c->q, c->k, rows, 0, n0, 0, n0))) return r;
-    if ((r = attention(c, c->q, c->k, rows, n0p, n1, n0p, n1))) return r;
+    if (c->unfused_attn) {
+      if ((r = attention(c, c->q, c->k, rows, 0, n0, 0, n0))) return r;
+      if ((r = attention(c, c->q, c->k, rows, n0p, n1, n0p, n1))) return r;
+    } else {
+      const int qa[2] = {0, n0p}, nq[2] = {n0, n1};
+      if ((r = attention_fused(c, "lg.attn_self", c->q, c->k, rows, qa, nq, qa, nq))) return r;
+    }
     {
       Operand A{c->attn.hi, c->attn.lo, rows, 256, 256, 0, 1};
       Operand B{L.out_proj.w.hi, L.out_proj.w.lo, 256, 256, 256, 0, 1};
@@ -533,8 +577,13 @@ int lg_run(rfe_ctx* c, const float* d_kpts0, int n0, const float* d_kpts1, int n
       p.ld_h = c->lg_ldv;
       if ((r = gemm_linear(c, "lg.to_v", A, B, p, 128))) return r;
     }
-    if ((r = attention(c, c->q, c->q, rows, 0, n0, n0p, n1))) return r;
-    if ((r = attention(c, c->q, c->q, rows, n0p, n1, 0, n0))) return r;
+    if (c->unfused_attn) {
+      if ((r = attention(c, c->q, c->q, rows, 0, n0, n0p, n1))) return r;
+      if ((r = attention(c, c->q, c->q, rows, n0p, n1, 0, n0))) return r;
+    } else {
+      const int qa[2] = {0, n0p}, nq[2] = {n0, n1}, kb[2] = {n0p, 0}, nk[2] = {n1, n0};
+      if ((r = attention_fused(c, "lg.attn_cross", c->q, c->q, rows, qa, nq, kb, nk))) return r;
+    }
     {
       Operand A{c->attn.hi, c->attn.lo, rows, 256, 256, 0, 1};
       Operand B{L.to_out.w.hi, L.to_out.w.lo, 256, 256, 256, 0, 1};
@@ -648,6 +697,7 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   }
   RFE_CUDA_CHECK(cudaEventCreate(&c->ev0));
   RFE_CUDA_CHECK(cudaEventCreate(&c->ev1));
+  c->unfused_attn = getenv("RFE_UNFUSED_ATTN") && atoi(getenv("RFE_UNFUSED_ATTN")) != 0;
   const char* path = cfg->weights_path;
   if (!path) path = getenv("ROVER_FE_WEIGHTS");
   if (!path) path = "weights/rover_fe.rfw";

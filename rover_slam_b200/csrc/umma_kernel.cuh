@@ -350,11 +350,65 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       __half* oh = p.out_hi ? p.out_hi + z * p.bstride_h : nullptr;
       __half* ol = p.out_lo ? p.out_lo + z * p.bstride_h : nullptr;
       const float* res = p.residual ? p.residual + z * p.bstride_res : nullptr;
+      const bool vec_ok = ((p.ld_f32 & 3) == 0) && ((p.ld_h & 7) == 0) && ((p.ld_res & 3) == 0);
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 16) {
         float v[16];
         load16(c, v);
         if (!valid) continue;
+        const int nb = n0 + c;
+        if (nb >= p.N) continue;
+        if (nb + 16 <= p.N && vec_ok) {
+          // ---- full 16-column chunk: vectorised path ----
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= p.scale;
+          if (res) {
+            const float4* r4 = reinterpret_cast<const float4*>(res + static_cast<size_t>(m) * p.ld_res + nb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 t4 = r4[j];
+              v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+          }
+          if (of) {
+            float4* o4 = reinterpret_cast<float4*>(of + static_cast<size_t>(m) * p.ld_f32 + nb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (oh) {
+            __align__(16) __half hh[16];
+            __align__(16) __half ll[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split_f32(v[j], hh[j], ll[j]);
+            if (p.transpose_h) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                oh[static_cast<size_t>(nb + j) * p.ld_h + m] = hh[j];
+                ol[static_cast<size_t>(nb + j) * p.ld_h + m] = ll[j];
+              }
+            } else {
+              const size_t o = p.head_major ? static_cast<size_t>(nb >> 6) * p.head_stride + static_cast<size_t>(m) * 64 + (nb & 63)
+                                            : static_cast<size_t>(m) * p.ld_h + nb;
+              reinterpret_cast<uint4*>(oh + o)[0] = reinterpret_cast<const uint4*>(hh)[0];
+              reinterpret_cast<uint4*>(oh + o)[1] = reinterpret_cast<const uint4*>(hh)[1];
+              reinterpret_cast<uint4*>(ol + o)[0] = reinterpret_cast<const uint4*>(ll)[0];
+              reinterpret_cast<uint4*>(ol + o)[1] = reinterpret_cast<const uint4*>(ll)[1];
+            }
+          }
+          continue;
+        }
+        // ---- ragged tail: scalar path ----
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int n = n0 + c + j;
