@@ -158,10 +158,11 @@ def main():
         shard.copy_(allf[0])
     host_sets = shard.cpu().pin_memory()
 
+    slots_a, slots_b = list(range(0, B, 2)), list(range(1, B, 2))
+
     def step_device(i):
         fe.extract_device(shard[i % n_sets].data_ptr(), H, W, W, B)
-        for p in range(P):
-            fe.match_slots(2 * p, 2 * p + 1, H, W, 0.0, p)
+        fe.match_slots_batch(slots_a, slots_b, H, W, 0.0)
 
     h2d = d2h = 0
 

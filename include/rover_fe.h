@@ -86,6 +86,11 @@ int rfe_lg_match(rfe_ctx* ctx, const float* kpts0_px, int n0, const float* kpts1
 /* Match two feature slots left on the device by rfe_sp_extract_device (asynchronous); the result
  * stays on the device in result slot `rslot` (0 .. max_batch-1). */
 int rfe_lg_match_slots(rfe_ctx* ctx, int slot0, int slot1, int norm_h, int norm_w, float match_thresh, int rslot);
+/* Match n_pairs (<= max_batch) independent pairs of feature slots in ONE pass: every LightGlue linear layer runs as a
+ * single GEMM over the rows of all pairs and attention as one fused launch over 2*n_pairs problems.  Pair i's result
+ * goes to result slot i.  Asynchronous apart from one small device->host read of the keypoint counts. */
+int rfe_lg_match_slots_batch(rfe_ctx* ctx, int n_pairs, const int* slot0, const int* slot1, int norm_h, int norm_w,
+                             float match_thresh);
 /* Copy a match result to the host (synchronises). */
 int rfe_lg_read_result(rfe_ctx* ctx, int rslot, int32_t* matches, float* mscores, int* k, int cap);
 

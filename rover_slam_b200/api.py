@@ -61,6 +61,7 @@ def load_library():
     lib.rfe_sp_read_slot.argtypes = [vp, ci, vp, vp, vp, vp, ci]
     lib.rfe_lg_match.argtypes = [vp, vp, ci, vp, ci, vp, vp, ci, ci, cf, vp, vp, vp]
     lib.rfe_lg_match_slots.argtypes = [vp, ci, ci, ci, ci, cf, ci]
+    lib.rfe_lg_match_slots_batch.argtypes = [vp, ci, vp, vp, ci, ci, cf]
     lib.rfe_lg_read_result.argtypes = [vp, ci, vp, vp, vp, ci]
     lib.rfe_get_timer_ms.argtypes = [vp, C.c_char_p]
     lib.rfe_get_timer_ms.restype = C.c_double
@@ -129,6 +130,16 @@ class FrontEnd:
     def extract_device(self, d_ptr: int, h: int, w: int, stride: int, batch: int):
         self._check(self.lib.rfe_sp_extract_device(self.ctx, C.c_void_p(d_ptr), h, w, stride, batch))
 
+    def extract_device_from_host(self, images: np.ndarray):
+        """Upload with torch (plumbing only) and run the device-resident extractor; features stay in the slots."""
+        import torch
+        imgs = np.ascontiguousarray(images, dtype=np.uint8)
+        b, h, w = imgs.shape
+        self._dev_imgs = torch.from_numpy(imgs).cuda()
+        torch.cuda.synchronize()
+        self.extract_device(self._dev_imgs.data_ptr(), h, w, w, b)
+        self.sync()
+
     def read_slot(self, slot: int, want_desc: bool = True):
         cap = self.cap
         kp = np.empty((cap, 2), np.int32)
@@ -156,6 +167,11 @@ class FrontEnd:
 
     def match_slots(self, slot0: int, slot1: int, norm_h: int, norm_w: int, thresh: float = 0.0, rslot: int = 0):
         self._check(self.lib.rfe_lg_match_slots(self.ctx, slot0, slot1, norm_h, norm_w, thresh, rslot))
+
+    def match_slots_batch(self, slots0, slots1, norm_h: int, norm_w: int, thresh: float = 0.0):
+        s0 = np.ascontiguousarray(slots0, np.int32)
+        s1 = np.ascontiguousarray(slots1, np.int32)
+        self._check(self.lib.rfe_lg_match_slots_batch(self.ctx, len(s0), _ptr(s0), _ptr(s1), norm_h, norm_w, thresh))
 
     def read_result(self, rslot: int = 0):
         m = np.empty((self.cap, 2), np.int32)

@@ -16,9 +16,11 @@
 
 namespace rfe {
 
+constexpr int kAttnMaxProblems = 32;   // 16 pairs x 2 directions per launch
+
 struct AttnParams {
-  int nq[2], nk[2];          // per problem (blockIdx.z): query rows, key rows
-  int q_row0[2], k_row0[2];  // row offsets of the problems inside the head-major Q / K tensors and the V^T columns
+  int nq[kAttnMaxProblems], nk[kAttnMaxProblems];          // per problem (blockIdx.z): query rows, key rows
+  int q_row0[kAttnMaxProblems], k_row0[kAttnMaxProblems];  // row offsets inside the head-major Q / K tensors and the V^T columns
   __half* out_hi;            // split-fp16 [rows][256]
   __half* out_lo;
 };

@@ -22,6 +22,7 @@ constexpr float kAttnScale = 0.3535533845424652f;   // 64^-1/4 (lightglue_sim.on
 constexpr float kDetThreshold = 0.0005f;            // superpoint.onnx /Constant_116
 constexpr float kFilterThreshold = 0.10000000149011612f;   // lightglue_sim.onnx /Constant_6
 constexpr int kLayers = 9;
+constexpr int kMaxPairs = rfe::kAttnMaxProblems / 2;
 
 struct SplitBuf {   // device split-fp16 tensor
   __half* hi = nullptr;
@@ -72,7 +73,7 @@ struct rfe_ctx {
   int* h_counts = nullptr;      // pinned [max_batch]
 
   // ---- LightGlue buffers (sized for 2*cap rows) ----
-  int lg_rows = 0, lg_ld = 0;   // row capacity (2*cap+8), padded key count
+  int lg_rows = 0, lg_ld = 0, lg_pairs = 1;   // row capacity, padded key count, pairs per batched match
   float *in_kpts = nullptr, *in_desc = nullptr;   // staging for the host API: [2*cap][2], [2*cap][256]
   float *cs = nullptr, *sn = nullptr;             // [rows][32]
   float* x = nullptr;                             // [rows][256]
@@ -80,8 +81,6 @@ struct rfe_ctx {
   float* qkv = nullptr;                           // [rows][768]
   SplitBuf q, k, vt;                              // q,k: [4][rows][64]; vt: [256][lg_ldv]
   int lg_ldv = 0;
-  float* S = nullptr;                             // [4][cap][lg_ld]
-  SplitBuf P;                                     // [4][cap][lg_ld]
   SplitBuf attn;                                  // [rows][256]
   float* hid = nullptr;                           // [rows][512]
   SplitBuf hs;                                    // [rows][512]
@@ -90,8 +89,7 @@ struct rfe_ctx {
   float *rmax = nullptr, *rlog = nullptr, *cmax = nullptr, *clog = nullptr, *ls = nullptr, *max0 = nullptr;
   int *m0 = nullptr, *m1 = nullptr;
   float* S_dbg = nullptr;
-  int dbg_n0 = 0, dbg_n1 = 0, dbg_n0p = 0;
-  bool unfused_attn = false;    // RFE_UNFUSED_ATTN=1: bring-up cross-check path (GEMM -> softmax -> GEMM through HBM)
+  int dbg_n0 = 0, dbg_n1 = 0, dbg_off0 = 0, dbg_off1 = 0;
   // match results: [max_batch] slots
   int* res_matches = nullptr;   // [slots][cap][2]
   float* res_scores = nullptr;  // [slots][cap]
@@ -434,39 +432,9 @@ int ffn_block(rfe_ctx* c, int rows, const SplitW& ffn0, const float* ln_w, const
   return RFE_OK;
 }
 
-// softmax(Qa Kb^T) Vb for 4 heads; Q rows [qa, qa+nq), K/V rows/cols [kb, kb+nk); result -> attn rows [qa, ...)
-int attention(rfe_ctx* c, const SplitBuf& Q, const SplitBuf& K, int rows_total, int qa, int nq, int kb, int nk) {
-  if (nq == 0 || nk == 0) return RFE_OK;
-  int r;
-  const long long hs = static_cast<long long>(rows_total) * 64;
-  const int ld = round_up(nk, 8);
-  {
-    Operand A{Q.hi + static_cast<size_t>(qa) * 64, Q.lo + static_cast<size_t>(qa) * 64, nq, 64, 64, hs, 4};
-    Operand B{K.hi + static_cast<size_t>(kb) * 64, K.lo + static_cast<size_t>(kb) * 64, nk, 64, 64, hs, 4};
-    UmmaParams p = default_params();
-    p.out_f32 = c->S;
-    p.ld_f32 = ld;
-    p.bstride_f32 = static_cast<long long>(nq) * ld;
-    if ((r = gemm_linear(c, "lg.attn_qk", A, B, p, 128))) return r;
-  }
-  launch_softmax_split(c->stream, c->S, 4 * nq, nk, ld, c->P.hi, c->P.lo, ld);
-  c->launches++;
-  {
-    Operand A{c->P.hi, c->P.lo, nq, nk, ld, static_cast<long long>(nq) * ld, 4};
-    Operand B{c->vt.hi + kb, c->vt.lo + kb, 64, nk, c->lg_ldv, 64LL * c->lg_ldv, 4};
-    UmmaParams p = default_params();
-    p.out_hi = c->attn.hi + static_cast<size_t>(qa) * 256;
-    p.out_lo = c->attn.lo + static_cast<size_t>(qa) * 256;
-    p.ld_h = 256;
-    p.bstride_h = 64;
-    if ((r = gemm_linear(c, "lg.attn_pv", A, B, p, 64))) return r;
-  }
-  return RFE_OK;
-}
-
-// Fused attention over both problems of a block (self: image0/image0 + image1/image1; cross: 0->1 + 1->0).
-int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitBuf& K, int rows_total, const int qa[2],
-                    const int nq[2], const int kb[2], const int nk[2]) {
+// Fused attention over all problems of a block (self: every image against itself; cross: both directions of every pair).
+int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitBuf& K, int rows_total,
+                    const AttnParams& problems, int nprob, int max_nq) {
   static bool configured[64] = {};
   if (!configured[c->device & 63]) {
     RFE_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
@@ -483,17 +451,10 @@ int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitB
   const uint64_t sv[2] = {static_cast<uint64_t>(c->lg_ldv) * 2, 64ULL * c->lg_ldv * 2};
   if (make_tmap_f16_sw128(&vh, c->vt.hi, 3, dv, sv, boxk) || make_tmap_f16_sw128(&vl, c->vt.lo, 3, dv, sv, boxk))
     return RFE_ERR_CUDA;
-  AttnParams p;
-  for (int i = 0; i < 2; ++i) {
-    p.nq[i] = nq[i];
-    p.nk[i] = nk[i];
-    p.q_row0[i] = qa[i];
-    p.k_row0[i] = kb[i];
-  }
+  AttnParams p = problems;
   p.out_hi = c->attn.hi;
   p.out_lo = c->attn.lo;
-  const int mq = nq[0] > nq[1] ? nq[0] : nq[1];
-  dim3 grid((mq + 127) / 128, 4, 2);
+  dim3 grid((max_nq + 127) / 128, 4, nprob);
   ProfScope ps(c, tag);
   attn_kernel<<<grid, kAttnThreads, kAttnSmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
   c->launches++;
@@ -501,24 +462,66 @@ int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitB
   return RFE_OK;
 }
 
-int lg_run(rfe_ctx* c, const float* d_kpts0, int n0, const float* d_kpts1, int n1, const float* d_desc0,
-           const float* d_desc1, int norm_h, int norm_w, float thresh, int rslot) {
+struct PairDesc {      // one LightGlue problem: device-resident pixel keypoints [n][2] and descriptors [n][256]
+  const float* kpts0;
+  const float* kpts1;
+  const float* desc0;
+  const float* desc1;
+  int n0, n1;
+  int rslot;
+};
+
+// Match `np` independent pairs in one pass.  All images' rows are concatenated (each image starts at a multiple of
+// 8 rows), so every linear layer is ONE GEMM over all pairs; attention runs as 2*np problems of one fused launch.
+int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm_w, float thresh) {
   cudaStream_t s = c->stream;
-  int* count = c->res_count + rslot;
-  if (n0 == 0 || n1 == 0) {
-    RFE_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int), s));
-    return RFE_OK;
-  }
-  const int n0p = round_up(n0, 8);
-  const int rows = n0p + n1;
   int r;
-  launch_posenc(s, d_kpts0, n0, norm_h, norm_w, c->posenc_w, c->cs, c->sn);
-  launch_posenc(s, d_kpts1, n1, norm_h, norm_w, c->posenc_w, c->cs + static_cast<size_t>(n0p) * 32,
-                c->sn + static_cast<size_t>(n0p) * 32);
-  launch_split_rows(s, d_desc0, n0, 256, 256, c->x, 256, c->cat.hi, c->cat.lo, 512);
-  launch_split_rows(s, d_desc1, n1, 256, 256, c->x + static_cast<size_t>(n0p) * 256, 256,
-                    c->cat.hi + static_cast<size_t>(n0p) * 512, c->cat.lo + static_cast<size_t>(n0p) * 512, 512);
-  c->launches += 4;
+  PairDesc pairs[kMaxPairs];
+  int off0[kMaxPairs], off1[kMaxPairs];
+  int np = 0, rows = 0;
+  for (int i = 0; i < np_in; ++i) {
+    const PairDesc& pd = pairs_in[i];
+    if (pd.n0 == 0 || pd.n1 == 0) {       // the reference would run ORT on empty tensors; the answer is "no matches"
+      RFE_CUDA_CHECK(cudaMemsetAsync(c->res_count + pd.rslot, 0, sizeof(int), s));
+      continue;
+    }
+    pairs[np] = pd;
+    off0[np] = rows;
+    rows += round_up(pd.n0, 8);
+    off1[np] = rows;
+    rows += round_up(pd.n1, 8);
+    ++np;
+  }
+  if (np == 0) return RFE_OK;
+  if (rows > c->lg_rows) {
+    set_error("LightGlue batch needs %d rows, ctx capacity %d", rows, c->lg_rows);
+    return RFE_ERR_CAPACITY;
+  }
+  for (int i = 0; i < np; ++i) {
+    const PairDesc& pd = pairs[i];
+    launch_posenc(s, pd.kpts0, pd.n0, norm_h, norm_w, c->posenc_w, c->cs + static_cast<size_t>(off0[i]) * 32,
+                  c->sn + static_cast<size_t>(off0[i]) * 32);
+    launch_posenc(s, pd.kpts1, pd.n1, norm_h, norm_w, c->posenc_w, c->cs + static_cast<size_t>(off1[i]) * 32,
+                  c->sn + static_cast<size_t>(off1[i]) * 32);
+    launch_split_rows(s, pd.desc0, pd.n0, 256, 256, c->x + static_cast<size_t>(off0[i]) * 256, 256,
+                      c->cat.hi + static_cast<size_t>(off0[i]) * 512, c->cat.lo + static_cast<size_t>(off0[i]) * 512, 512);
+    launch_split_rows(s, pd.desc1, pd.n1, 256, 256, c->x + static_cast<size_t>(off1[i]) * 256, 256,
+                      c->cat.hi + static_cast<size_t>(off1[i]) * 512, c->cat.lo + static_cast<size_t>(off1[i]) * 512, 512);
+    c->launches += 4;
+  }
+  AttnParams self_p, cross_p;
+  memset(&self_p, 0, sizeof(self_p));
+  memset(&cross_p, 0, sizeof(cross_p));
+  int max_n = 0;
+  for (int i = 0; i < np; ++i) {
+    const int n0 = pairs[i].n0, n1 = pairs[i].n1;
+    max_n = n0 > max_n ? n0 : max_n;
+    max_n = n1 > max_n ? n1 : max_n;
+    self_p.nq[2 * i] = n0;      self_p.nk[2 * i] = n0;      self_p.q_row0[2 * i] = off0[i];      self_p.k_row0[2 * i] = off0[i];
+    self_p.nq[2 * i + 1] = n1;  self_p.nk[2 * i + 1] = n1;  self_p.q_row0[2 * i + 1] = off1[i];  self_p.k_row0[2 * i + 1] = off1[i];
+    cross_p.nq[2 * i] = n0;     cross_p.nk[2 * i] = n1;     cross_p.q_row0[2 * i] = off0[i];     cross_p.k_row0[2 * i] = off1[i];
+    cross_p.nq[2 * i + 1] = n1; cross_p.nk[2 * i + 1] = n0; cross_p.q_row0[2 * i + 1] = off1[i]; cross_p.k_row0[2 * i + 1] = off0[i];
+  }
   const long long hs = static_cast<long long>(rows) * 64;
   for (int i = 0; i < kLayers; ++i) {
     const LgLayer& L = c->layers[i];
@@ -535,13 +538,7 @@ int lg_run(rfe_ctx* c, const float* d_kpts0, int n0, const float* d_kpts1, int n
     launch_rope_split(s, c->qkv, rows, c->cs, c->sn, kAttnScale, c->q.hi, c->q.lo, c->k.hi, c->k.lo, c->vt.hi,
                       c->vt.lo, c->lg_ldv);
     c->launches++;
-    if (c->unfused_attn) {
-      if ((r = attention(c, c->q, c->k, rows, 0, n0, 0, n0))) return r;
-      if ((r = attention(c, c->q, c->k, rows, n0p, n1, n0p, n1))) return r;
-    } else {
-      const int qa[2] = {0, n0p}, nq[2] = {n0, n1};
-      if ((r = attention_fused(c, "lg.attn_self", c->q, c->k, rows, qa, nq, qa, nq))) return r;
-    }
+    if ((r = attention_fused(c, "lg.attn_self", c->q, c->k, rows, self_p, 2 * np, max_n))) return r;
     {
       Operand A{c->attn.hi, c->attn.lo, rows, 256, 256, 0, 1};
       Operand B{L.out_proj.w.hi, L.out_proj.w.lo, 256, 256, 256, 0, 1};
@@ -550,7 +547,7 @@ int lg_run(rfe_ctx* c, const float* d_kpts0, int n0, const float* d_kpts1, int n
       p.out_hi = c->cat.hi + 256;
       p.out_lo = c->cat.lo + 256;
       p.ld_h = 512;
-      if ((r = gemm_linear(c, "lg.out_proj", A, B, p, 128))) return r;
+      if ((r = gemm_linear(c, "lg.out_proj", A, B, p, 64))) return r;
     }
     if ((r = ffn_block(c, rows, L.s_ffn0, L.s_ln_w, L.s_ln_b, L.s_ffn3))) return r;
     // ---------------- cross attention ----------------
@@ -564,7 +561,7 @@ int lg_run(rfe_ctx* c, const float* d_kpts0, int n0, const float* d_kpts1, int n
       p.out_lo = c->q.lo;
       p.head_major = 1;
       p.head_stride = hs;
-      if ((r = gemm_linear(c, "lg.to_qk", A, B, p, 128))) return r;
+      if ((r = gemm_linear(c, "lg.to_qk", A, B, p, 64))) return r;
     }
     {
       Operand A{c->cat.hi, c->cat.lo, rows, 256, 512, 0, 1};
@@ -575,15 +572,9 @@ int lg_run(rfe_ctx* c, const float* d_kpts0, int n0, const float* d_kpts1, int n
       p.out_lo = c->vt.lo;
       p.transpose_h = 1;
       p.ld_h = c->lg_ldv;
-      if ((r = gemm_linear(c, "lg.to_v", A, B, p, 128))) return r;
+      if ((r = gemm_linear(c, "lg.to_v", A, B, p, 64))) return r;
     }
-    if (c->unfused_attn) {
-      if ((r = attention(c, c->q, c->q, rows, 0, n0, n0p, n1))) return r;
-      if ((r = attention(c, c->q, c->q, rows, n0p, n1, 0, n0))) return r;
-    } else {
-      const int qa[2] = {0, n0p}, nq[2] = {n0, n1}, kb[2] = {n0p, 0}, nk[2] = {n1, n0};
-      if ((r = attention_fused(c, "lg.attn_cross", c->q, c->q, rows, qa, nq, kb, nk))) return r;
-    }
+    if ((r = attention_fused(c, "lg.attn_cross", c->q, c->q, rows, cross_p, 2 * np, max_n))) return r;
     {
       Operand A{c->attn.hi, c->attn.lo, rows, 256, 256, 0, 1};
       Operand B{L.to_out.w.hi, L.to_out.w.lo, 256, 256, 256, 0, 1};
@@ -592,7 +583,7 @@ int lg_run(rfe_ctx* c, const float* d_kpts0, int n0, const float* d_kpts1, int n
       p.out_hi = c->cat.hi + 256;
       p.out_lo = c->cat.lo + 256;
       p.ld_h = 512;
-      if ((r = gemm_linear(c, "lg.to_out", A, B, p, 128))) return r;
+      if ((r = gemm_linear(c, "lg.to_out", A, B, p, 64))) return r;
     }
     if ((r = ffn_block(c, rows, L.c_ffn0, L.c_ln_w, L.c_ln_b, L.c_ffn3))) return r;
   }
@@ -606,28 +597,33 @@ int lg_run(rfe_ctx* c, const float* d_kpts0, int n0, const float* d_kpts1, int n
     p.out_hi = c->md.hi;
     p.out_lo = c->md.lo;
     p.ld_h = 256;
-    if ((r = gemm_linear(c, "lg.final_proj", A, B, p, 128))) return r;
-  }
-  const int ld = round_up(n1, 8);
-  {
-    Operand A{c->md.hi, c->md.lo, n0, 256, 256, 0, 1};
-    Operand B{c->md.hi + static_cast<size_t>(n0p) * 256, c->md.lo + static_cast<size_t>(n0p) * 256, n1, 256, 256, 0, 1};
-    UmmaParams p = default_params();
-    p.out_f32 = c->sim;
-    p.ld_f32 = ld;
-    if ((r = gemm_linear(c, "lg.sim", A, B, p, 128))) return r;
+    if ((r = gemm_linear(c, "lg.final_proj", A, B, p, 64))) return r;
   }
   launch_matchability(s, c->x, rows, c->match_w, c->match_b, c->ls);
-  launch_lse(s, c->sim, n0, n1, ld, c->rmax, c->rlog, c->cmax, c->clog);
-  launch_argmax(s, c->sim, n0, n1, ld, c->rmax, c->rlog, c->cmax, c->clog, c->ls, c->ls + n0p, c->max0, c->m0, c->m1,
-                c->S_dbg);
-  launch_match_compact(s, c->max0, c->m0, c->m1, n0, kFilterThreshold, thresh,
-                       c->res_matches + static_cast<size_t>(rslot) * c->cap * 2,
-                       c->res_scores + static_cast<size_t>(rslot) * c->cap, count);
-  c->launches += 6;
-  c->dbg_n0 = n0;
-  c->dbg_n1 = n1;
-  c->dbg_n0p = n0p;
+  c->launches++;
+  for (int i = 0; i < np; ++i) {
+    const int n0 = pairs[i].n0, n1 = pairs[i].n1, rslot = pairs[i].rslot;
+    const int ld = round_up(n1, 8);
+    {
+      Operand A{c->md.hi + static_cast<size_t>(off0[i]) * 256, c->md.lo + static_cast<size_t>(off0[i]) * 256, n0, 256, 256, 0, 1};
+      Operand B{c->md.hi + static_cast<size_t>(off1[i]) * 256, c->md.lo + static_cast<size_t>(off1[i]) * 256, n1, 256, 256, 0, 1};
+      UmmaParams p = default_params();
+      p.out_f32 = c->sim;
+      p.ld_f32 = ld;
+      if ((r = gemm_linear(c, "lg.sim", A, B, p, 128))) return r;
+    }
+    launch_lse(s, c->sim, n0, n1, ld, c->rmax, c->rlog, c->cmax, c->clog);
+    launch_argmax(s, c->sim, n0, n1, ld, c->rmax, c->rlog, c->cmax, c->clog, c->ls + off0[i], c->ls + off1[i], c->max0,
+                  c->m0, c->m1, c->S_dbg);
+    launch_match_compact(s, c->max0, c->m0, c->m1, n0, kFilterThreshold, thresh,
+                         c->res_matches + static_cast<size_t>(rslot) * c->cap * 2,
+                         c->res_scores + static_cast<size_t>(rslot) * c->cap, c->res_count + rslot);
+    c->launches += 5;
+    c->dbg_n0 = n0;
+    c->dbg_n1 = n1;
+    c->dbg_off0 = off0[i];
+    c->dbg_off1 = off1[i];
+  }
   RFE_CUDA_CHECK(cudaGetLastError());
   return RFE_OK;
 }
@@ -697,7 +693,6 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   }
   RFE_CUDA_CHECK(cudaEventCreate(&c->ev0));
   RFE_CUDA_CHECK(cudaEventCreate(&c->ev1));
-  c->unfused_attn = getenv("RFE_UNFUSED_ATTN") && atoi(getenv("RFE_UNFUSED_ATTN")) != 0;
   const char* path = cfg->weights_path;
   if (!path) path = getenv("ROVER_FE_WEIGHTS");
   if (!path) path = "weights/rover_fe.rfw";
@@ -737,7 +732,8 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   A_(dev_alloc(c, &c->desc, B * cap * 256));
   RFE_CUDA_CHECK(cudaMallocHost(&c->h_counts, sizeof(int) * (B + 1)));
   // ---- LightGlue buffers ----
-  c->lg_rows = 2 * c->cap + 8;
+  c->lg_pairs = c->max_batch < kMaxPairs ? c->max_batch : kMaxPairs;   // pairs per rfe_lg_match_slots_batch
+  c->lg_rows = 2 * c->lg_pairs * (c->cap + 8);
   c->lg_ld = round_up(c->cap, 8);
   c->lg_ldv = round_up(c->lg_rows, 8);
   const size_t R = c->lg_rows, LD = c->lg_ld;
@@ -751,8 +747,6 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   A_(split_alloc(c, &c->q, R * 256));
   A_(split_alloc(c, &c->k, R * 256));
   A_(split_alloc(c, &c->vt, 256 * static_cast<size_t>(c->lg_ldv)));
-  A_(dev_alloc(c, &c->S, 4 * cap * LD));
-  A_(split_alloc(c, &c->P, 4 * cap * LD));
   A_(split_alloc(c, &c->attn, R * 256));
   A_(dev_alloc(c, &c->hid, R * 512));
   A_(split_alloc(c, &c->hs, R * 512));
@@ -879,6 +873,41 @@ int rfe_sp_extract_u8(rfe_ctx* c, const uint8_t* gray, int h, int w, int stride,
   return rc;
 }
 
+int rfe_lg_match_slots_batch(rfe_ctx* c, int n_pairs, const int* slot0, const int* slot1, int norm_h, int norm_w,
+                             float thresh) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (n_pairs <= 0 || n_pairs > c->lg_pairs || !slot0 || !slot1 || norm_h <= 0 || norm_w <= 0) {
+    set_error("rfe_lg_match_slots_batch: invalid argument (at most %d pairs per call)", c->lg_pairs);
+    return RFE_ERR_INVALID;
+  }
+  for (int i = 0; i < n_pairs; ++i)
+    if (slot0[i] < 0 || slot1[i] < 0 || slot0[i] >= c->last_batch || slot1[i] >= c->last_batch) {
+      set_error("rfe_lg_match_slots_batch: slot out of range");
+      return RFE_ERR_INVALID;
+    }
+  // the keypoint counts are needed on the host to lay out the rows and size the launches
+  RFE_CUDA_CHECK(cudaMemcpyAsync(c->h_counts, c->kp_counts, sizeof(int) * c->last_batch, cudaMemcpyDeviceToHost, c->stream));
+  RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  PairDesc pd[kMaxPairs];
+  size_t koff = 0;
+  for (int i = 0; i < n_pairs; ++i) {
+    const int s0 = slot0[i], s1 = slot1[i];
+    const int n0 = c->h_counts[s0] < c->cap ? c->h_counts[s0] : c->cap;
+    const int n1 = c->h_counts[s1] < c->cap ? c->h_counts[s1] : c->cap;
+    float* k0 = c->in_kpts + koff * 2;
+    koff += round_up(n0, 8);
+    float* k1 = c->in_kpts + koff * 2;
+    koff += round_up(n1, 8);
+    launch_kpts_to_float(c->stream, c->kpts + static_cast<size_t>(s0) * c->cap * 2, n0, k0);
+    launch_kpts_to_float(c->stream, c->kpts + static_cast<size_t>(s1) * c->cap * 2, n1, k1);
+    c->launches += 2;
+    pd[i] = PairDesc{k0, k1, c->desc + static_cast<size_t>(s0) * c->cap * 256, c->desc + static_cast<size_t>(s1) * c->cap * 256,
+                     n0, n1, i};
+  }
+  return lg_run(c, pd, n_pairs, norm_h, norm_w, thresh);
+}
+
 int rfe_lg_match_slots(rfe_ctx* c, int slot0, int slot1, int norm_h, int norm_w, float thresh, int rslot) {
   int r = check_ctx(c);
   if (r) return r;
@@ -886,7 +915,6 @@ int rfe_lg_match_slots(rfe_ctx* c, int slot0, int slot1, int norm_h, int norm_w,
     set_error("rfe_lg_match_slots: slot out of range");
     return RFE_ERR_INVALID;
   }
-  // keypoint counts are needed on the host to size the launches
   RFE_CUDA_CHECK(cudaMemcpyAsync(c->h_counts, c->kp_counts, sizeof(int) * c->last_batch, cudaMemcpyDeviceToHost, c->stream));
   RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   const int n0 = c->h_counts[slot0] < c->cap ? c->h_counts[slot0] : c->cap;
@@ -895,9 +923,9 @@ int rfe_lg_match_slots(rfe_ctx* c, int slot0, int slot1, int norm_h, int norm_w,
   launch_kpts_to_float(c->stream, c->kpts + static_cast<size_t>(slot0) * c->cap * 2, n0, c->in_kpts);
   launch_kpts_to_float(c->stream, c->kpts + static_cast<size_t>(slot1) * c->cap * 2, n1, c->in_kpts + static_cast<size_t>(n0p) * 2);
   c->launches += 2;
-  return lg_run(c, c->in_kpts, n0, c->in_kpts + static_cast<size_t>(n0p) * 2, n1,
-                c->desc + static_cast<size_t>(slot0) * c->cap * 256, c->desc + static_cast<size_t>(slot1) * c->cap * 256,
-                norm_h, norm_w, thresh, rslot);
+  PairDesc pd{c->in_kpts, c->in_kpts + static_cast<size_t>(n0p) * 2, c->desc + static_cast<size_t>(slot0) * c->cap * 256,
+              c->desc + static_cast<size_t>(slot1) * c->cap * 256, n0, n1, rslot};
+  return lg_run(c, &pd, 1, norm_h, norm_w, thresh);
 }
 
 int rfe_lg_read_result(rfe_ctx* c, int rslot, int32_t* matches, float* mscores, int* k, int cap) {
@@ -945,9 +973,9 @@ int rfe_lg_match(rfe_ctx* c, const float* kpts0, int n0, const float* kpts1, int
   RFE_CUDA_CHECK(cudaMemcpyAsync(c->in_kpts + static_cast<size_t>(n0p) * 2, kpts1, sizeof(float) * 2 * n1, cudaMemcpyHostToDevice, s));
   RFE_CUDA_CHECK(cudaMemcpyAsync(c->in_desc, desc0, sizeof(float) * 256 * n0, cudaMemcpyHostToDevice, s));
   RFE_CUDA_CHECK(cudaMemcpyAsync(c->in_desc + static_cast<size_t>(n0p) * 256, desc1, sizeof(float) * 256 * n1, cudaMemcpyHostToDevice, s));
-  if ((r = lg_run(c, c->in_kpts, n0, c->in_kpts + static_cast<size_t>(n0p) * 2, n1, c->in_desc,
-                  c->in_desc + static_cast<size_t>(n0p) * 256, norm_h, norm_w, thresh, 0)))
-    return r;
+  PairDesc pd{c->in_kpts, c->in_kpts + static_cast<size_t>(n0p) * 2, c->in_desc, c->in_desc + static_cast<size_t>(n0p) * 256,
+              n0, n1, 0};
+  if ((r = lg_run(c, &pd, 1, norm_h, norm_w, thresh))) return r;
   r = rfe_lg_read_result(c, 0, matches, mscores, k, n0);
   cudaEventRecord(c->ev1, s);
   cudaStreamSynchronize(s);
@@ -1022,7 +1050,7 @@ int rfe_debug_read(rfe_ctx* c, const char* name, void* dst, size_t capacity, siz
   else if (s == "sp.heat") { fb = c->heat; n = B * H * W; }
   else if (s == "sp.nms") { fb = c->nmsmap; n = B * H * W; }
   else if (s == "sp.dense") { fb = c->dense; n = B * H * W / 64 * 256; }
-  else if (s == "lg.x") { fb = c->x; n = static_cast<size_t>(c->dbg_n0p + c->dbg_n1) * 256; }
+  else if (s == "lg.x") { fb = c->x; n = static_cast<size_t>(c->dbg_off1 + c->dbg_n1) * 256; }
   else if (s == "lg.sim") { fb = c->sim; n = static_cast<size_t>(c->dbg_n0) * round_up(c->dbg_n1, 8); }
   else if (s == "lg.S") {
     if (!c->S_dbg) {   // first request arms the capture; the NEXT match fills it

@@ -12,56 +12,64 @@ namespace rfe {
 // ------------------------------------------------------------------------------------------------
 // conv1a: one thread = one pixel x 8 output channels
 // ------------------------------------------------------------------------------------------------
+// thread = (pixel slot, 8-channel group); the 72 weights of the group live in registers and the thread walks
+// kConv1aIters pixels, so a warp stores 4 pixels x 128 B = 512 contiguous bytes per plane per iteration.
+constexpr int kConv1aIters = 16;
 __global__ void __launch_bounds__(256) conv1a_kernel(const uint8_t* __restrict__ img, int stride, int H, int W, int B,
                                                      const float* __restrict__ w /*[64][9]*/,
                                                      const float* __restrict__ bias, __half* __restrict__ out_hi,
                                                      __half* __restrict__ out_lo) {
-  __shared__ float sw[64 * 9];
-  __shared__ float sb[64];
-  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
-  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t npix = static_cast<size_t>(B) * H * W;
-  const size_t pix = gid >> 3;
-  if (pix >= npix) return;
-  const int cg = gid & 7;
-  const int x = pix % W;
-  const int y = (pix / W) % H;
-  const int b = pix / (static_cast<size_t>(W) * H);
-  const uint8_t* im = img + static_cast<size_t>(b) * H * stride;
-  float in[9];
-#pragma unroll
-  for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const int yy = y + dy - 1, xx = x + dx - 1;
-      float v = 0.0f;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-        v = static_cast<float>(im[static_cast<size_t>(yy) * stride + xx]) * 0.003921568859368563f;  // transform.cpp:8
-      in[dy * 3 + dx] = v;
-    }
-  __align__(16) __half hi[8];
-  __align__(16) __half lo[8];
+  const int cg = threadIdx.x & 7;
+  float wr[8][9], br[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int c = cg * 8 + j;
-    float acc = 0.0f;
+    br[j] = __ldg(bias + cg * 8 + j);
 #pragma unroll
-    for (int t = 0; t < 9; ++t) acc = fmaf(in[t], sw[c * 9 + t], acc);
-    acc = fmaxf(acc + sb[c], 0.0f);
-    split_f32(acc, hi[j], lo[j]);
+    for (int t = 0; t < 9; ++t) wr[j][t] = __ldg(w + (cg * 8 + j) * 9 + t);
   }
-  const size_t o = pix * 64 + cg * 8;
-  *reinterpret_cast<uint4*>(out_hi + o) = *reinterpret_cast<const uint4*>(hi);
-  *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<const uint4*>(lo);
+  const size_t npix = static_cast<size_t>(B) * H * W;
+  const size_t base = static_cast<size_t>(blockIdx.x) * (32 * kConv1aIters) + (threadIdx.x >> 3);
+#pragma unroll 1
+  for (int it = 0; it < kConv1aIters; ++it) {
+    const size_t pix = base + static_cast<size_t>(it) * 32;
+    if (pix >= npix) return;
+    const int x = pix % W;
+    const int y = (pix / W) % H;
+    const int b = pix / (static_cast<size_t>(W) * H);
+    const uint8_t* im = img + static_cast<size_t>(b) * H * stride;
+    float in[9];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int yy = y + dy - 1, xx = x + dx - 1;
+        float v = 0.0f;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+          v = static_cast<float>(__ldg(im + static_cast<size_t>(yy) * stride + xx)) * 0.003921568859368563f;  // transform.cpp:8
+        in[dy * 3 + dx] = v;
+      }
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc = fmaf(in[t], wr[j][t], acc);
+      acc = fmaxf(acc + br[j], 0.0f);
+      split_f32(acc, hi[j], lo[j]);
+    }
+    const size_t o = pix * 64 + cg * 8;
+    *reinterpret_cast<uint4*>(out_hi + o) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<const uint4*>(lo);
+  }
 }
 
 void launch_conv1a(cudaStream_t s, const uint8_t* img, int stride, int H, int W, int B, const float* w,
                    const float* bias, __half* out_hi, __half* out_lo) {
-  const size_t threads = static_cast<size_t>(B) * H * W * 8;
-  conv1a_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(img, stride, H, W, B, w, bias, out_hi,
-                                                                             out_lo);
+  const size_t npix = static_cast<size_t>(B) * H * W;
+  const size_t per_block = 32 * kConv1aIters;
+  conv1a_kernel<<<static_cast<unsigned>((npix + per_block - 1) / per_block), 256, 0, s>>>(img, stride, H, W, B, w, bias,
+                                                                                        out_hi, out_lo);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,6 +1,6 @@
 // Host-side driver used by tests/test_gpu_host_classes.py: exercises the reference's call pattern
 // (Frame::ExtractKeyPoints -> SPextractor::operator(); Tracking -> SPmatcher::MatchingPoints_onnx) through the
-// C++ class surface and dumps the results for comparison with the C-ABI / oracle path.
+// C++ class surface and dumps the results for comparison with the C-ABI path by the Python test.
 //   host_driver <h> <w> <imgA.raw> <imgB.raw> <out.bin>
 #include <stdio.h>
 #include <stdlib.h>

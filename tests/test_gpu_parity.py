@@ -187,6 +187,22 @@ def test_pair_end_to_end_752x480(fe, golden_dir, sp, lg):
     assert np.array_equal(m, m2) and np.array_equal(ms, ms2)
 
 
+def test_batched_matching_equals_single(fe):
+    """rfe_lg_match_slots_batch (all pairs in one pass) == one rfe_lg_match_slots per pair, bit for bit."""
+    imgs = np.stack([f for s in (40, 41, 42) for f in synth.frame_pair(s, 240, 320, shift=(5 + s % 3, -2))])
+    h, w = 240, 320
+    fe.extract_device_from_host(imgs)
+    single = []
+    for p in range(3):
+        fe.match_slots(2 * p, 2 * p + 1, h, w, 0.0, p)
+        single.append(fe.read_result(p))
+    fe.match_slots_batch([0, 2, 4], [1, 3, 5], h, w)
+    for p in range(3):
+        m, ms = fe.read_result(p)
+        assert np.array_equal(m, single[p][0]) and np.array_equal(ms, single[p][1])
+        assert len(m) > 50
+
+
 def test_gpu_path_launches_kernels(fe):
     before = fe.kernel_launches()
     fe.extract(synth.frame(1, 64, 64))
