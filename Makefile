@@ -3,7 +3,7 @@ NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 CSRC := rover_slam_b200/csrc
 NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Iinclude -I$(CSRC) --expt-relaxed-constexpr
-OBJ := $(CSRC)/rover_fe.o $(CSRC)/sp_kernels.o $(CSRC)/lg_kernels.o $(CSRC)/tensormap.o $(CSRC)/weights.o
+OBJ := $(CSRC)/rover_fe.o $(CSRC)/sp_kernels.o $(CSRC)/lg_kernels.o $(CSRC)/probe_kernels.o $(CSRC)/tensormap.o $(CSRC)/weights.o
 LIB := rover_slam_b200/librover_fe.so
 
 all: $(LIB)

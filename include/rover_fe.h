@@ -91,6 +91,14 @@ int rfe_lg_match_slots(rfe_ctx* ctx, int slot0, int slot1, int norm_h, int norm_
  * goes to result slot i.  Asynchronous apart from one small device->host read of the keypoint counts. */
 int rfe_lg_match_slots_batch(rfe_ctx* ctx, int n_pairs, const int* slot0, const int* slot1, int norm_h, int norm_w,
                              float match_thresh);
+/* The whole hot path in one call, host in / host out: n_pairs pairs of images (pair p = images 2p and 2p+1 of `gray`,
+ * layout as rfe_sp_extract_u8), SuperPoint on all 2*n_pairs images, LightGlue on every pair (keypoints normalised with
+ * the image size, i.e. the semantics of MatchingPoints_onnx(Frame&, Frame&, ...), SPmatcher.cc:457-542).  Descriptors
+ * never leave the GPU.  Outputs: kp_counts[2*n_pairs], kpts_xy[2*n_pairs][cap][2] (may be NULL),
+ * match_counts[n_pairs], matches[n_pairs][cap][2], mscores[n_pairs][cap] (may be NULL). */
+int rfe_match_pairs_u8(rfe_ctx* ctx, const uint8_t* gray, int h, int w, int stride_bytes, int n_pairs, float match_thresh,
+                       int32_t* kpts_xy, int32_t* kp_counts, int32_t* matches, float* mscores, int32_t* match_counts,
+                       int cap);
 /* Copy a match result to the host (synchronises). */
 int rfe_lg_read_result(rfe_ctx* ctx, int rslot, int32_t* matches, float* mscores, int* k, int cap);
 
@@ -109,6 +117,9 @@ int rfe_profile_read(rfe_ctx* ctx, const char* prefix, double* total_ms, long lo
 int rfe_debug_read(rfe_ctx* ctx, const char* name, void* dst, size_t capacity, size_t* bytes);
 /* Test hook: run one split-fp16 tensor-core GEMM D = A[M,K] * B[N,K]^T (+bias) on host fp32 data. */
 int rfe_debug_gemm(rfe_ctx* ctx, const float* a, const float* b, const float* bias, float* d, int m, int n, int kdim);
+
+/* Test hook: tcgen05 hardware probes used to pin down descriptor semantics (see csrc/probe_kernels.cu). */
+int rfe_debug_probe(rfe_ctx* ctx, int which, const float* a, const float* b, float* out);
 
 #ifdef __cplusplus
 }

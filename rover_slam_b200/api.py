@@ -62,6 +62,7 @@ def load_library():
     lib.rfe_lg_match.argtypes = [vp, vp, ci, vp, ci, vp, vp, ci, ci, cf, vp, vp, vp]
     lib.rfe_lg_match_slots.argtypes = [vp, ci, ci, ci, ci, cf, ci]
     lib.rfe_lg_match_slots_batch.argtypes = [vp, ci, vp, vp, ci, ci, cf]
+    lib.rfe_match_pairs_u8.argtypes = [vp, vp, ci, ci, ci, ci, cf, vp, vp, vp, vp, vp, ci]
     lib.rfe_lg_read_result.argtypes = [vp, ci, vp, vp, vp, ci]
     lib.rfe_get_timer_ms.argtypes = [vp, C.c_char_p]
     lib.rfe_get_timer_ms.restype = C.c_double
@@ -71,6 +72,7 @@ def load_library():
     lib.rfe_profile_read.argtypes = [vp, C.c_char_p, P(C.c_double), P(C.c_longlong), ci]
     lib.rfe_debug_read.argtypes = [vp, C.c_char_p, vp, C.c_size_t, P(C.c_size_t)]
     lib.rfe_debug_gemm.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci]
+    lib.rfe_debug_probe.argtypes = [vp, ci, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -173,6 +175,21 @@ class FrontEnd:
         s1 = np.ascontiguousarray(slots1, np.int32)
         self._check(self.lib.rfe_lg_match_slots_batch(self.ctx, len(s0), _ptr(s0), _ptr(s1), norm_h, norm_w, thresh))
 
+    def match_pairs(self, images: np.ndarray, thresh: float = 0.0, want_kpts: bool = True):
+        """images: uint8 [2*P, H, W] host array, pair p = images 2p, 2p+1.  One call = extract all + match all.
+        Returns (list of keypoint arrays [N,2] per image, list of (matches [K,2], mscores [K]) per pair)."""
+        imgs = np.ascontiguousarray(images, dtype=np.uint8)
+        b, h, w = imgs.shape
+        npairs, cap = b // 2, self.cap
+        if not hasattr(self, "_mp_buf") or self._mp_buf[0].shape[0] != b:
+            self._mp_buf = (np.empty((b, cap, 2), np.int32), np.zeros(b, np.int32), np.empty((npairs, cap, 2), np.int32),
+                            np.empty((npairs, cap), np.float32), np.zeros(npairs, np.int32))
+        kp, kc, m, ms, mc = self._mp_buf
+        self._check(self.lib.rfe_match_pairs_u8(self.ctx, _ptr(imgs), h, w, w, npairs, thresh, _ptr(kp) if want_kpts else None,
+                                                _ptr(kc), _ptr(m), _ptr(ms), _ptr(mc), cap))
+        kpts = [kp[i, :kc[i]] for i in range(b)] if want_kpts else None
+        return kpts, [(m[i, :mc[i]], ms[i, :mc[i]]) for i in range(npairs)]
+
     def read_result(self, rslot: int = 0):
         m = np.empty((self.cap, 2), np.int32)
         s = np.empty(self.cap, np.float32)
@@ -204,6 +221,13 @@ class FrontEnd:
         if nb.value:
             self._check(self.lib.rfe_debug_read(self.ctx, name.encode(), _ptr(out), nb.value, C.byref(nb)))
         return out.reshape(shape) if shape is not None else out
+
+    def debug_probe_shift(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, np.float32).reshape(136, 64)
+        b = np.ascontiguousarray(b, np.float32).reshape(64, 64)
+        out = np.empty((9, 3, 128, 64), np.float32)
+        self._check(self.lib.rfe_debug_probe(self.ctx, 0, _ptr(a), _ptr(b), _ptr(out)))
+        return out
 
     def debug_gemm(self, a: np.ndarray, b: np.ndarray, bias: np.ndarray | None = None) -> np.ndarray:
         a = np.ascontiguousarray(a, np.float32)

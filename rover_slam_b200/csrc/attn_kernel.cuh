@@ -35,6 +35,12 @@ constexpr int kAttnSmemBytes = kAttnQBytes + kAttnPBytes + kAttnStages * kAttnSt
 
 #ifdef __CUDACC__
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -201,9 +207,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       float s[32];
       load_scores(g, s);
       const int c0 = g * kAttnKeyTile + hw * 32;
+      if (c0 + 32 <= nk) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c0 + j < nk) mx = fmaxf(mx, s[j]);
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, s[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < nk) mx = fmaxf(mx, s[j]);
+      }
     }
     stat[hw * 128 + row] = mx;
     named_bar_sync(1, 256);
@@ -218,13 +229,24 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       float s[32];
       load_scores(T + t, s);
       const int c0 = t * kAttnKeyTile + hw * 32;
-      __align__(16) __half ph[32];
-      __align__(16) __half pl[32];
+      __align__(16) __half2 ph[16];
+      __align__(16) __half2 pl[16];
+      const bool full = (c0 + 32 <= nk);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float e = (c0 + j < nk) ? expf(s[j] - mx) : 0.0f;
-        l += e;
-        split_f32(e, ph[j], pl[j]);
+      for (int j = 0; j < 32; j += 2) {
+        // exp(s - max) through the SFU: ex2.approx((s - max) * log2 e); relative error <= 2^-22 + |s-max| * 2^-23,
+        // the same order as the 22-bit split-fp16 operand that carries P into the tensor core
+        float e0 = fast_exp2((s[j] - mx) * 1.4426950408889634f);
+        float e1 = fast_exp2((s[j + 1] - mx) * 1.4426950408889634f);
+        if (!full) {
+          if (c0 + j >= nk) e0 = 0.0f;
+          if (c0 + j + 1 >= nk) e1 = 0.0f;
+        }
+        l += e0 + e1;
+        const __half2 h2 = __floats2half2_rn(e0, e1);
+        const float2 hf = __half22float2(h2);
+        ph[j >> 1] = h2;
+        pl[j >> 1] = __floats2half2_rn((e0 - hf.x) * RFE_SPLIT_SCALE, (e1 - hf.y) * RFE_SPLIT_SCALE);
       }
       mbar_wait(p_empty, (t & 1) ^ 1);       // PV(t-1) has consumed the previous P tile
 #pragma unroll
@@ -254,10 +276,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       tmem_ld_wait();
       __align__(16) __half oh[32];
       __align__(16) __half ol[32];
+      const float inv_l = 1.0f / l;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        split_f32((__uint_as_float(a0[j]) + __uint_as_float(x0[j]) * RFE_SPLIT_INV) / l, oh[j], ol[j]);
-        split_f32((__uint_as_float(a1[j]) + __uint_as_float(x1[j]) * RFE_SPLIT_INV) / l, oh[16 + j], ol[16 + j]);
+        split_f32((__uint_as_float(a0[j]) + __uint_as_float(x0[j]) * RFE_SPLIT_INV) * inv_l, oh[j], ol[j]);
+        split_f32((__uint_as_float(a1[j]) + __uint_as_float(x1[j]) * RFE_SPLIT_INV) * inv_l, oh[16 + j], ol[16 + j]);
       }
       if (m0 + row < nq) {
         const size_t o = static_cast<size_t>(qrow + row) * 256 + head * 64 + hw * 32;

@@ -21,10 +21,6 @@ void launch_posenc(cudaStream_t s, const float* kpts_px, int n, int norm_h, int 
 void launch_kpts_to_float(cudaStream_t s, const int* k, int n, float* o);
 void launch_split_rows(cudaStream_t s, const float* src, int rows, int cols, int ld_src, float* dst, int ld_dst,
                        __half* hi, __half* lo, int ld_h);
-void launch_rope_split(cudaStream_t s, const float* qkv, int n, const float* cs, const float* sn, float scale,
-                       __half* q_hi, __half* q_lo, __half* k_hi, __half* k_lo, __half* vt_hi, __half* vt_lo, int ldv);
-void launch_softmax_split(cudaStream_t s, const float* S, int rows_total, int cols, int ld_s, __half* p_hi, __half* p_lo,
-                          int ld_p);
 void launch_ln_gelu_split(cudaStream_t s, const float* x, int rows, const float* g, const float* b, __half* hi,
                           __half* lo);
 void launch_matchability(cudaStream_t s, const float* x, int rows, const float* w, const float* b, float* out);

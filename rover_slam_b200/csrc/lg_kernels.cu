@@ -1,5 +1,5 @@
 // LightGlue kernels that are not tensor-core contractions: keypoint normalisation + Fourier positional
-// encoding, rotary embedding + head split, row softmax, LayerNorm+GELU, matchability, dual log-softmax
+// encoding, LayerNorm+GELU, matchability, dual log-softmax
 // statistics, row/column arg-max, mutual check + ordered compaction.
 // Reference: onnxmodel/lightglue_sim.onnx as run by src/Matchers/lightglue_onnx.cpp:210-214 (SURVEY.md
 // Appendix B), keypoint normalisation from src/Matchers/transform.cpp:19-32.
@@ -67,79 +67,6 @@ void launch_split_rows(cudaStream_t s, const float* src, int rows, int cols, int
   if (n == 0) return;
   split_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(src, rows, cols, ld_src, dst, ld_dst, hi, lo,
                                                                           ld_h);
-}
-
-// ---- rotary + scale + head split (nodes 20-51) ----------------------------------------------------------
-// qkv fp32 [N][768] with columns [q(256) | k(256) | v(256)], each head-major (h*64+d).
-// Q, K -> split-fp16 head-major [4][N][64]; V -> split-fp16 transposed [256][ldv].
-__global__ void rope_split_kernel(const float* __restrict__ qkv, int n, const float* __restrict__ cs,
-                                  const float* __restrict__ sn, float scale, __half* __restrict__ q_hi,
-                                  __half* __restrict__ q_lo, __half* __restrict__ k_hi, __half* __restrict__ k_lo,
-                                  __half* __restrict__ vt_hi, __half* __restrict__ vt_lo, int ldv) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over n * 128 pairs (h, f) f in 0..31
-  if (i >= n * 128) return;
-  const int row = i >> 7, pr = i & 127;
-  const int f = pr & 31;
-  const float c = cs[row * 32 + f], s = sn[row * 32 + f];
-  const float* base = qkv + static_cast<size_t>(row) * 768 + pr * 2;
-  const size_t o = static_cast<size_t>(pr >> 5) * n * 64 + static_cast<size_t>(row) * 64 + (pr & 31) * 2;
-  {
-    const float a = base[0], b = base[1];
-    const float r0 = (a * c + (-b) * s) * scale, r1 = (b * c + a * s) * scale;
-    __half h, l;
-    split_f32(r0, h, l); q_hi[o] = h; q_lo[o] = l;
-    split_f32(r1, h, l); q_hi[o + 1] = h; q_lo[o + 1] = l;
-  }
-  {
-    const float a = base[256], b = base[257];
-    const float r0 = (a * c + (-b) * s) * scale, r1 = (b * c + a * s) * scale;
-    __half h, l;
-    split_f32(r0, h, l); k_hi[o] = h; k_lo[o] = l;
-    split_f32(r1, h, l); k_hi[o + 1] = h; k_lo[o + 1] = l;
-  }
-  {
-    __half h, l;
-    split_f32(base[512], h, l);
-    vt_hi[static_cast<size_t>(pr * 2) * ldv + row] = h; vt_lo[static_cast<size_t>(pr * 2) * ldv + row] = l;
-    split_f32(base[513], h, l);
-    vt_hi[static_cast<size_t>(pr * 2 + 1) * ldv + row] = h; vt_lo[static_cast<size_t>(pr * 2 + 1) * ldv + row] = l;
-  }
-}
-void launch_rope_split(cudaStream_t s, const float* qkv, int n, const float* cs, const float* sn, float scale,
-                       __half* q_hi, __half* q_lo, __half* k_hi, __half* k_lo, __half* vt_hi, __half* vt_lo, int ldv) {
-  if (n == 0) return;
-  rope_split_kernel<<<(n * 128 + 255) / 256, 256, 0, s>>>(qkv, n, cs, sn, scale, q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo,
-                                                           ldv);
-}
-
-// ---- row softmax -> split-fp16 (one warp per row) ------------------------------------------------------------
-__global__ void __launch_bounds__(256) softmax_split_kernel(const float* __restrict__ S, int rows_total, int cols,
-                                                            int ld_s, __half* __restrict__ p_hi,
-                                                            __half* __restrict__ p_lo, int ld_p) {
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (wid >= rows_total) return;
-  const float* r = S + static_cast<size_t>(wid) * ld_s;
-  float mx = -INFINITY;
-  for (int j = lane; j < cols; j += 32) mx = fmaxf(mx, r[j]);
-  mx = warp_max(mx);
-  float sum = 0.0f;
-  for (int j = lane; j < cols; j += 32) sum += expf(r[j] - mx);
-  sum = warp_sum(sum);
-  __half* oh = p_hi + static_cast<size_t>(wid) * ld_p;
-  __half* ol = p_lo + static_cast<size_t>(wid) * ld_p;
-  for (int j = lane; j < cols; j += 32) {
-    const float p = expf(r[j] - mx) / sum;
-    __half h, l;
-    split_f32(p, h, l);
-    oh[j] = h;
-    ol[j] = l;
-  }
-}
-void launch_softmax_split(cudaStream_t s, const float* S, int rows_total, int cols, int ld_s, __half* p_hi, __half* p_lo,
-                          int ld_p) {
-  if (rows_total == 0) return;
-  softmax_split_kernel<<<(rows_total * 32 + 255) / 256, 256, 0, s>>>(S, rows_total, cols, ld_s, p_hi, p_lo, ld_p);
 }
 
 // ---- LayerNorm(512, eps 1e-5) + exact GELU -> split-fp16 (one warp per row; nodes 62-67) --------------------

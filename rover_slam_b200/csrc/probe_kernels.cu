@@ -1,0 +1,98 @@
+// Hardware probes (debug only, reached through rfe_debug_probe): measure tcgen05 behaviours the design depends on.
+//  probe 0: "row-shifted" K-major SWIZZLE_128B operand.  An A buffer of 136 rows x 128 B is written with the absolute-
+//           address swizzle (16-byte chunk index XOR address bits [7,10)); the MMA descriptor then starts at row s
+//           (base + s*128 B, NOT 1024-aligned) with base_offset = 0 / (s & 7) / ((8 - s) & 7).  Reports, per (s, mode),
+//           the max-abs error against the exact product A[s : s+128] B^T.  This decides whether a 3x3 conv can read
+//           its 9 taps from ONE halo tile in shared memory.
+#include "common.cuh"
+
+namespace rfe {
+
+__device__ __forceinline__ uint64_t make_desc_sw128_bo(uint32_t smem_addr, uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(base_offset & 7) << 49;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// a: [136][64] fp16, b: [64][64] fp16, out: [9 shifts][3 modes][128][64] fp32
+__global__ void __launch_bounds__(128, 1) probe_shift_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
+                                                             float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                 // 136 rows * 128 B = 17408 -> pad to 18432
+  uint8_t* sB = smem + 18432;         // 64 rows * 128 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 8192);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 136 * 8; i += 128) {     // 16-byte chunks
+    const int r = i >> 3, ch = i & 7;
+    const uint32_t addr = smem_u32(sA) + r * 128;
+    const int sw = ch ^ ((addr >> 7) & 7);
+    *reinterpret_cast<uint4*>(sA + r * 128 + sw * 16) = *reinterpret_cast<const uint4*>(a + r * 64 + ch * 8);
+  }
+  for (int i = threadIdx.x; i < 64 * 8; i += 128) {
+    const int r = i >> 3, ch = i & 7;
+    const uint32_t addr = smem_u32(sB) + r * 128;
+    const int sw = ch ^ ((addr >> 7) & 7);
+    *reinterpret_cast<uint4*>(sB + r * 128 + sw * 16) = *reinterpret_cast<const uint4*>(b + r * 64 + ch * 8);
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tptr, 64);
+    tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tptr;
+  constexpr uint32_t idesc = make_idesc_f16(128, 64);
+  int phase = 0;
+  for (int s = 0; s <= 8; ++s) {
+    for (int mode = 0; mode < 3; ++mode) {
+      const uint32_t bo = mode == 0 ? 0u : mode == 1 ? static_cast<uint32_t>(s & 7) : static_cast<uint32_t>((8 - s) & 7);
+      if (threadIdx.x == 0) {
+        tc_fence_after();
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = make_desc_sw128_bo(smem_u32(sA) + s * 128 + k * 32, bo);
+          const uint64_t db = make_desc_sw128_bo(smem_u32(sB) + k * 32, 0);
+          umma_f16(tmem, da, db, idesc, k > 0);
+        }
+        umma_commit(bar);
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      float* o = out + ((static_cast<size_t>(s) * 3 + mode) * 128 + warp * 32 + lane) * 64;
+      for (int c = 0; c < 64; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c, r);
+        tmem_ld_wait();
+        for (int j = 0; j < 16; ++j) o[c + j] = __uint_as_float(r[j]);
+      }
+      tc_fence_before();
+      __syncthreads();
+    }
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 64);
+  }
+}
+
+int launch_probe_shift(cudaStream_t s, const __half* a, const __half* b, float* out) {
+  const int smem = 18432 + 8192 + 64 + 1024;
+  if (cudaFuncSetAttribute(probe_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+  probe_shift_kernel<<<1, 128, smem, s>>>(a, b, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace rfe

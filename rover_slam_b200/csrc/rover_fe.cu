@@ -78,7 +78,6 @@ struct rfe_ctx {
   float *cs = nullptr, *sn = nullptr;             // [rows][32]
   float* x = nullptr;                             // [rows][256]
   SplitBuf cat;                                   // [rows][512]
-  float* qkv = nullptr;                           // [rows][768]
   SplitBuf q, k, vt;                              // q,k: [4][rows][64]; vt: [256][lg_ldv]
   int lg_ldv = 0;
   SplitBuf attn;                                  // [rows][256]
@@ -526,18 +525,30 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
   for (int i = 0; i < kLayers; ++i) {
     const LgLayer& L = c->layers[i];
     // ---------------- self attention ----------------
-    {
+    {   // qkv = x Wqkv^T + b ; rotary on q,k ; head split ; V transposed -- all in the GEMM epilogue
       Operand A{c->cat.hi, c->cat.lo, rows, 256, 512, 0, 1};
       Operand B{L.wqkv.w.hi, L.wqkv.w.lo, 768, 256, 256, 0, 1};
+      CUtensorMap ah, al, bh, bl;
+      if ((r = make_operand_maps(A, kBlockM, &ah, &al))) return r;
+      if ((r = make_operand_maps(B, 128, &bh, &bl))) return r;
       UmmaParams p = default_params();
+      p.num_k_steps = 4;
+      p.M = rows;
+      p.N = 768;
       p.bias = L.wqkv.bias;
-      p.out_f32 = c->qkv;
-      p.ld_f32 = 768;
-      if ((r = gemm_linear(c, "lg.wqkv", A, B, p, 128))) return r;
+      p.scale = kAttnScale;
+      p.cs = c->cs;
+      p.sn = c->sn;
+      p.out_hi = c->q.hi;
+      p.out_lo = c->q.lo;
+      p.k_hi = c->k.hi;
+      p.k_lo = c->k.lo;
+      p.vt_hi = c->vt.hi;
+      p.vt_lo = c->vt.lo;
+      p.ldv = c->lg_ldv;
+      p.head_stride = hs;
+      if ((r = launch_umma<128, A_GEMM, EPI_QKV>(c, "lg.wqkv_rope", ah, al, bh, bl, p, dim3((rows + 127) / 128, 6, 1)))) return r;
     }
-    launch_rope_split(s, c->qkv, rows, c->cs, c->sn, kAttnScale, c->q.hi, c->q.lo, c->k.hi, c->k.lo, c->vt.hi,
-                      c->vt.lo, c->lg_ldv);
-    c->launches++;
     if ((r = attention_fused(c, "lg.attn_self", c->q, c->k, rows, self_p, 2 * np, max_n))) return r;
     {
       Operand A{c->attn.hi, c->attn.lo, rows, 256, 256, 0, 1};
@@ -627,6 +638,10 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
   RFE_CUDA_CHECK(cudaGetLastError());
   return RFE_OK;
 }
+
+}  // namespace
+namespace rfe { int launch_probe_shift(cudaStream_t s, const __half* a, const __half* b, float* out); }
+namespace {
 
 int check_ctx(rfe_ctx* c) {
   if (!c) {
@@ -730,7 +745,7 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   A_(dev_alloc(c, &c->kpts, B * cap * 2));
   A_(dev_alloc(c, &c->kp_scores, B * cap));
   A_(dev_alloc(c, &c->desc, B * cap * 256));
-  RFE_CUDA_CHECK(cudaMallocHost(&c->h_counts, sizeof(int) * (B + 1)));
+  RFE_CUDA_CHECK(cudaMallocHost(&c->h_counts, sizeof(int) * (2 * B + 2)));
   // ---- LightGlue buffers ----
   c->lg_pairs = c->max_batch < kMaxPairs ? c->max_batch : kMaxPairs;   // pairs per rfe_lg_match_slots_batch
   c->lg_rows = 2 * c->lg_pairs * (c->cap + 8);
@@ -743,7 +758,6 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   A_(dev_alloc(c, &c->sn, R * 32));
   A_(dev_alloc(c, &c->x, R * 256));
   A_(split_alloc(c, &c->cat, R * 512));
-  A_(dev_alloc(c, &c->qkv, R * 768));
   A_(split_alloc(c, &c->q, R * 256));
   A_(split_alloc(c, &c->k, R * 256));
   A_(split_alloc(c, &c->vt, 256 * static_cast<size_t>(c->lg_ldv)));
@@ -926,6 +940,64 @@ int rfe_lg_match_slots(rfe_ctx* c, int slot0, int slot1, int norm_h, int norm_w,
   PairDesc pd{c->in_kpts, c->in_kpts + static_cast<size_t>(n0p) * 2, c->desc + static_cast<size_t>(slot0) * c->cap * 256,
               c->desc + static_cast<size_t>(slot1) * c->cap * 256, n0, n1, rslot};
   return lg_run(c, &pd, 1, norm_h, norm_w, thresh);
+}
+
+int rfe_match_pairs_u8(rfe_ctx* c, const uint8_t* gray, int h, int w, int stride, int n_pairs, float thresh,
+                       int32_t* kpts_xy, int32_t* kp_counts, int32_t* matches, float* mscores, int32_t* match_counts,
+                       int cap) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (!gray || !matches || !match_counts || !kp_counts || cap <= 0 || n_pairs <= 0 || n_pairs > c->lg_pairs) {
+    set_error("rfe_match_pairs_u8: null/invalid argument (at most %d pairs per call)", c->lg_pairs);
+    return RFE_ERR_INVALID;
+  }
+  const int B = 2 * n_pairs;
+  if ((r = check_image_args(c, h, w, stride, B))) return r;
+  cudaStream_t s = c->stream;
+  RFE_CUDA_CHECK(cudaEventRecord(c->ev0, s));
+  RFE_CUDA_CHECK(cudaMemcpyAsync(c->img, gray, static_cast<size_t>(B) * h * stride, cudaMemcpyHostToDevice, s));
+  if ((r = sp_run(c, c->img, h, w, stride, B))) return r;
+  int s0[kMaxPairs], s1[kMaxPairs];
+  for (int i = 0; i < n_pairs; ++i) {
+    s0[i] = 2 * i;
+    s1[i] = 2 * i + 1;
+  }
+  if ((r = rfe_lg_match_slots_batch(c, n_pairs, s0, s1, h, w, thresh))) return r;   // leaves the keypoint counts in h_counts
+  int rc = RFE_OK;
+  for (int b = 0; b < B; ++b) {
+    const int n = c->h_counts[b];
+    kp_counts[b] = n;
+    int m = n < c->cap ? n : c->cap;
+    if (cap < m) m = cap;
+    if (n > c->cap || n > cap) {
+      set_error("image %d has %d keypoints, capacity %d", b, n, cap < c->cap ? cap : c->cap);
+      rc = RFE_ERR_CAPACITY;
+    }
+    if (kpts_xy && m > 0)
+      RFE_CUDA_CHECK(cudaMemcpyAsync(kpts_xy + static_cast<size_t>(b) * cap * 2, c->kpts + static_cast<size_t>(b) * c->cap * 2,
+                                     sizeof(int) * 2 * m, cudaMemcpyDeviceToHost, s));
+  }
+  int* h_mc = c->h_counts + c->max_batch + 1;
+  RFE_CUDA_CHECK(cudaMemcpyAsync(h_mc, c->res_count, sizeof(int) * n_pairs, cudaMemcpyDeviceToHost, s));
+  RFE_CUDA_CHECK(cudaStreamSynchronize(s));
+  for (int i = 0; i < n_pairs; ++i) {
+    const int k = h_mc[i];
+    match_counts[i] = k;
+    const int m = k < cap ? k : cap;
+    if (m > 0) {
+      RFE_CUDA_CHECK(cudaMemcpyAsync(matches + static_cast<size_t>(i) * cap * 2, c->res_matches + static_cast<size_t>(i) * c->cap * 2,
+                                     sizeof(int) * 2 * m, cudaMemcpyDeviceToHost, s));
+      if (mscores)
+        RFE_CUDA_CHECK(cudaMemcpyAsync(mscores + static_cast<size_t>(i) * cap, c->res_scores + static_cast<size_t>(i) * c->cap,
+                                       sizeof(float) * m, cudaMemcpyDeviceToHost, s));
+    }
+  }
+  RFE_CUDA_CHECK(cudaEventRecord(c->ev1, s));
+  RFE_CUDA_CHECK(cudaStreamSynchronize(s));
+  float ms = 0.0f;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  c->timer_extract_ms += ms;
+  return rc;
 }
 
 int rfe_lg_read_result(rfe_ctx* c, int rslot, int32_t* matches, float* mscores, int* k, int cap) {
@@ -1124,6 +1196,40 @@ int rfe_debug_gemm(rfe_ctx* c, const float* a, const float* b, const float* bias
   cudaFree(dah); cudaFree(dal); cudaFree(dbh); cudaFree(dbl); cudaFree(dd);
   if (dbias) cudaFree(dbias);
   return r;
+}
+
+
+// Hardware probe 0 (see probe_kernels.cu): a [136][64], b [64][64] fp32 in (rounded to fp16), out [9][3][128][64] fp32.
+int rfe_debug_probe(rfe_ctx* c, int which, const float* a, const float* b, float* out) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (which != 0 || !a || !b || !out) {
+    set_error("rfe_debug_probe: invalid argument");
+    return RFE_ERR_INVALID;
+  }
+  std::vector<__half> ha(136 * 64), hb(64 * 64);
+  for (size_t i = 0; i < ha.size(); ++i) ha[i] = __float2half_rn(a[i]);
+  for (size_t i = 0; i < hb.size(); ++i) hb[i] = __float2half_rn(b[i]);
+  __half *da, *db;
+  float* dout;
+  const size_t no = 9 * 3 * 128 * 64;
+  RFE_CUDA_CHECK(cudaMalloc(&da, ha.size() * 2));
+  RFE_CUDA_CHECK(cudaMalloc(&db, hb.size() * 2));
+  RFE_CUDA_CHECK(cudaMalloc(&dout, no * 4));
+  RFE_CUDA_CHECK(cudaMemcpy(da, ha.data(), ha.size() * 2, cudaMemcpyHostToDevice));
+  RFE_CUDA_CHECK(cudaMemcpy(db, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
+  if (rfe::launch_probe_shift(c->stream, da, db, dout)) {
+    set_error("probe launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return RFE_ERR_CUDA;
+  }
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) {
+    set_error("probe failed: %s", cudaGetErrorString(e));
+    return RFE_ERR_CUDA;
+  }
+  RFE_CUDA_CHECK(cudaMemcpy(out, dout, no * 4, cudaMemcpyDeviceToHost));
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  return RFE_OK;
 }
 
 }  // extern "C"

@@ -27,15 +27,16 @@ __global__ void __launch_bounds__(256) conv1a_kernel(const uint8_t* __restrict__
 #pragma unroll
     for (int t = 0; t < 9; ++t) wr[j][t] = __ldg(w + (cg * 8 + j) * 9 + t);
   }
-  const size_t npix = static_cast<size_t>(B) * H * W;
-  const size_t base = static_cast<size_t>(blockIdx.x) * (32 * kConv1aIters) + (threadIdx.x >> 3);
+  const unsigned npix = static_cast<unsigned>(B) * H * W;       // < 2^31 for any supported batch
+  const unsigned base = blockIdx.x * (32u * kConv1aIters) + (threadIdx.x >> 3);
 #pragma unroll 1
   for (int it = 0; it < kConv1aIters; ++it) {
-    const size_t pix = base + static_cast<size_t>(it) * 32;
+    const unsigned pix = base + static_cast<unsigned>(it) * 32u;
     if (pix >= npix) return;
-    const int x = pix % W;
-    const int y = (pix / W) % H;
-    const int b = pix / (static_cast<size_t>(W) * H);
+    const unsigned rowi = pix / static_cast<unsigned>(W);
+    const int x = static_cast<int>(pix - rowi * W);
+    const int b = static_cast<int>(rowi / static_cast<unsigned>(H));
+    const int y = static_cast<int>(rowi - static_cast<unsigned>(b) * H);
     const uint8_t* im = img + static_cast<size_t>(b) * H * stride;
     float in[9];
 #pragma unroll
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(256) conv1a_kernel(const uint8_t* __restrict__
       acc = fmaxf(acc + br[j], 0.0f);
       split_f32(acc, hi[j], lo[j]);
     }
-    const size_t o = pix * 64 + cg * 8;
+    const size_t o = static_cast<size_t>(pix) * 64 + cg * 8;
     *reinterpret_cast<uint4*>(out_hi + o) = *reinterpret_cast<const uint4*>(hi);
     *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<const uint4*>(lo);
   }

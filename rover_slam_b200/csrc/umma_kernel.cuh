@@ -23,6 +23,7 @@ enum Epi {
   EPI_CONV = 1,      // bias + ReLU (+ 2x2 max-pool) -> split-fp16 NHWC
   EPI_DET = 2,       // bias + softmax over 65 + drop dustbin + 8x8 depth-to-space -> fp32 heat-map
   EPI_DESC = 3,      // bias + L2 normalise over N=256 -> fp32 NHWC
+  EPI_QKV = 4,       // LightGlue Wqkv: bias + rotary(q,k) * 64^-1/4 -> head-major split q,k ; v -> transposed split
 };
 
 struct UmmaParams {
@@ -48,6 +49,14 @@ struct UmmaParams {
   int relu;
   int pool;
   float scale;
+  // EPI_QKV only
+  const float* cs;         // [M][32] cos of the positional encoding
+  const float* sn;         // [M][32] sin
+  __half* k_hi;            // q goes to out_hi/out_lo, k here (both head-major [4][M][64], head_stride apart)
+  __half* k_lo;
+  __half* vt_hi;           // V^T [256][ldv]
+  __half* vt_lo;
+  int ldv;
 };
 
 constexpr int kBlockM = 128;
@@ -339,6 +348,54 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
                                     (v[j + 1] + __ldg(p.bias + n0 + c + j + 1)) / nrm,
                                     (v[j + 2] + __ldg(p.bias + n0 + c + j + 2)) / nrm,
                                     (v[j + 3] + __ldg(p.bias + n0 + c + j + 3)) / nrm);
+          }
+        }
+      }
+    } else if constexpr (EPI == EPI_QKV) {
+      // columns: [q (256) | k (256) | v (256)], each head-major h*64+d (weights were permuted at load time)
+      const int m = m0 + row;
+      const bool valid = m < p.M;
+      const int part = n0 >> 8;                         // 0 q, 1 k, 2 v   (BLOCK_N = 128 divides 256)
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 16) {
+        float v[16];
+        load16(c, v);
+        if (!valid) continue;
+        const int nb = n0 + c;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+        const int col = nb & 255;                       // h*64 + d
+        __align__(16) __half hh[16];
+        __align__(16) __half ll[16];
+        if (part < 2) {
+          const int f0 = (col & 63) >> 1;               // first of the 8 frequencies this chunk covers
+          const float4* c4 = reinterpret_cast<const float4*>(p.cs + static_cast<size_t>(m) * 32 + f0);
+          const float4* s4 = reinterpret_cast<const float4*>(p.sn + static_cast<size_t>(m) * 32 + f0);
+          const float4 ca = __ldg(c4), cb = __ldg(c4 + 1), sa = __ldg(s4), sb = __ldg(s4 + 1);
+          const float cc[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+          const float ss[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float a = v[2 * i], b = v[2 * i + 1];
+            split_f32((a * cc[i] + (-b) * ss[i]) * p.scale, hh[2 * i], ll[2 * i]);
+            split_f32((b * cc[i] + a * ss[i]) * p.scale, hh[2 * i + 1], ll[2 * i + 1]);
+          }
+          __half* dh = part == 0 ? p.out_hi : p.k_hi;
+          __half* dl = part == 0 ? p.out_lo : p.k_lo;
+          const size_t o = static_cast<size_t>(col >> 6) * p.head_stride + static_cast<size_t>(m) * 64 + (col & 63);
+          reinterpret_cast<uint4*>(dh + o)[0] = reinterpret_cast<const uint4*>(hh)[0];
+          reinterpret_cast<uint4*>(dh + o)[1] = reinterpret_cast<const uint4*>(hh)[1];
+          reinterpret_cast<uint4*>(dl + o)[0] = reinterpret_cast<const uint4*>(ll)[0];
+          reinterpret_cast<uint4*>(dl + o)[1] = reinterpret_cast<const uint4*>(ll)[1];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            split_f32(v[j], hh[j], ll[j]);
+            p.vt_hi[static_cast<size_t>(col + j) * p.ldv + m] = hh[j];
+            p.vt_lo[static_cast<size_t>(col + j) * p.ldv + m] = ll[j];
           }
         }
       }

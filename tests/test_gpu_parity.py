@@ -203,6 +203,19 @@ def test_batched_matching_equals_single(fe):
         assert len(m) > 50
 
 
+def test_match_pairs_one_call_pipeline(fe):
+    """rfe_match_pairs_u8 (host frames in, keypoints + matches out) == extract + match through the per-call API."""
+    imgs = np.stack([f for s in (50, 51) for f in synth.frame_pair(s, 240, 320, shift=(4, 6))])
+    kpts, res = fe.match_pairs(imgs)
+    kpts = [k.copy() for k in kpts]
+    res = [(m.copy(), s.copy()) for m, s in res]
+    feats = fe.extract(imgs)
+    for p in range(2):
+        assert np.array_equal(kpts[2 * p], feats[2 * p][0]) and np.array_equal(kpts[2 * p + 1], feats[2 * p + 1][0])
+        m, ms = fe.match(feats[2 * p][0], feats[2 * p + 1][0], feats[2 * p][2], feats[2 * p + 1][2], 240, 320)
+        assert np.array_equal(res[p][0], m) and np.array_equal(res[p][1], ms)
+
+
 def test_gpu_path_launches_kernels(fe):
     before = fe.kernel_launches()
     fe.extract(synth.frame(1, 64, 64))
