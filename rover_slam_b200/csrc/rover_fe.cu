@@ -44,6 +44,7 @@ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 struct rfe_ctx {
   int device = 0;
+  int num_sms = 148;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int max_batch = 8, max_h = 480, max_w = 768, cap = 4096;
@@ -252,8 +253,14 @@ int launch_umma(rfe_ctx* c, const char* tag, const CUtensorMap& a_hi, const CUte
     RFE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, umma_smem_bytes(BLOCK_N)));
     configured[c->device & 63] = true;
   }
+  // persistent launch: `grid` holds the tile counts (m, n, z); one CTA per SM walks the tiles round-robin
+  UmmaParams pp = p;
+  pp.tiles_m = static_cast<int>(grid.x);
+  pp.tiles_n = static_cast<int>(grid.y);
+  pp.num_tiles = static_cast<int>(grid.x * grid.y * grid.z);
+  const int ctas = pp.num_tiles < c->num_sms ? pp.num_tiles : c->num_sms;
   ProfScope ps(c, tag);
-  kern<<<grid, kUmmaThreads, umma_smem_bytes(BLOCK_N), c->stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+  kern<<<ctas, kUmmaThreads, umma_smem_bytes(BLOCK_N), c->stream>>>(a_hi, a_lo, b_hi, b_lo, pp);
   c->launches++;
   RFE_CUDA_CHECK(cudaGetLastError());
   return RFE_OK;
@@ -691,6 +698,7 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   RFE_CUDA_CHECK(cudaSetDevice(cfg->device));
   rfe_ctx* c = new rfe_ctx();
   c->device = cfg->device;
+  c->num_sms = prop.multiProcessorCount;
   c->max_batch = cfg->max_batch > 0 ? cfg->max_batch : 8;
   c->max_h = cfg->max_height > 0 ? cfg->max_height : 480;
   c->max_w = cfg->max_width > 0 ? cfg->max_width : 768;

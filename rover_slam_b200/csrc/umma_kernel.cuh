@@ -34,6 +34,7 @@ struct UmmaParams {
   int N;               // valid output columns
   int H, W;            // conv: spatial size of the conv output (before pooling); DET/DESC: coarse h, w
   int tiles_x, tiles_y;  // conv: 16x8 pixel tiles per image
+  int tiles_m, tiles_n, num_tiles;   // persistent tile scheduler: tile = (z * tiles_n + n) * tiles_m + m
   int a_batched, b_batched;  // GEMM: use blockIdx.z as the A / B tensor-map batch coordinate
   // epilogue
   const float* bias;       // [N] or null
@@ -94,10 +95,12 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
   constexpr int STAGE_BYTES = umma_stage_bytes(BLOCK_N);
   constexpr int STAGE_B = BLOCK_N * 128;
   constexpr int NACC0 = umma_num_acc0(AMODE);
-  constexpr int TMEM_COLS = umma_tmem_cols(BLOCK_N, AMODE);
-  constexpr int ACC_STRIDE = TMEM_COLS / (NACC0 + 1);        // column pitch between accumulators
+  constexpr int TILE_COLS = umma_tmem_cols(BLOCK_N, AMODE);  // TMEM columns of one output tile's accumulators
+  constexpr int NBUF = TILE_COLS <= 256 ? 2 : 1;             // accumulator sets: the epilogue of tile i overlaps the MMAs of tile i+1
+  constexpr int TMEM_COLS = NBUF * TILE_COLS;
+  constexpr int ACC_STRIDE = TILE_COLS / (NACC0 + 1);        // column pitch between accumulators
   constexpr int ACC1_COL = NACC0 * ACC_STRIDE;
-  static_assert(ACC_STRIDE >= BLOCK_N && (NACC0 + 1) * ACC_STRIDE <= 512, "TMEM budget");
+  static_assert(ACC_STRIDE >= BLOCK_N && TMEM_COLS <= 512, "TMEM budget");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
   static_assert(STAGES >= 2, "need at least two stages");
 
@@ -105,26 +108,33 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;       // [NBUF]
+  uint64_t* tmem_empty_bar = tmem_full_bar + NBUF;    // [NBUF]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + NBUF);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // ---- tile coordinates --------------------------------------------------------------------------
-  const int n0 = blockIdx.y * BLOCK_N;
-  int m0 = 0, img = 0, x0 = 0, y0 = 0;
-  if constexpr (AMODE == A_CONV3) {
-    int t = blockIdx.x;
-    const int tx = t % p.tiles_x;
-    t /= p.tiles_x;
-    const int ty = t % p.tiles_y;
-    img = t / p.tiles_y;
-    x0 = tx * 16;
-    y0 = ty * 8;
-  } else {
-    m0 = blockIdx.x * kBlockM;
-  }
+  // ---- persistent tile scheduler: static round-robin over (m, n, z) tiles; consecutive tiles share the B tile ------
+  struct Tile { int m0, n0, img, x0, y0, z; };
+  auto decode = [&](int tile) {
+    Tile t;
+    const int bx = tile % p.tiles_m;
+    const int rest = tile / p.tiles_m;
+    t.n0 = (rest % p.tiles_n) * BLOCK_N;
+    t.z = rest / p.tiles_n;
+    t.m0 = 0; t.img = 0; t.x0 = 0; t.y0 = 0;
+    if constexpr (AMODE == A_CONV3) {
+      const int tx = bx % p.tiles_x;
+      const int r2 = bx / p.tiles_x;
+      t.x0 = tx * 16;
+      t.y0 = (r2 % p.tiles_y) * 8;
+      t.img = r2 / p.tiles_y;
+    } else {
+      t.m0 = bx * kBlockM;
+    }
+    return t;
+  };
 
   // ---- one-time setup ------------------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
@@ -136,7 +146,10 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 4);      // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -153,6 +166,10 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const Tile tc = decode(tile);
+      const int m0 = tc.m0, n0 = tc.n0, img = tc.img, x0 = tc.x0, y0 = tc.y0;
+      (void)m0; (void)img; (void)x0; (void)y0;
       for (int ks = 0; ks < p.num_k_steps; ++ks) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = smem + stage * STAGE_BYTES;
@@ -164,11 +181,11 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
           tma_load_4d(st, &tmA_hi, &full_bar[stage], cc * 64, x0 + dx - 1, y0 + dy - 1, img);
           tma_load_4d(st + kStageABytes, &tmA_lo, &full_bar[stage], cc * 64, x0 + dx - 1, y0 + dy - 1, img);
         } else {
-          const int zb = p.a_batched ? blockIdx.z : 0;
+          const int zb = p.a_batched ? tc.z : 0;
           tma_load_3d(st, &tmA_hi, &full_bar[stage], ks * 64, m0, zb);
           tma_load_3d(st + kStageABytes, &tmA_lo, &full_bar[stage], ks * 64, m0, zb);
         }
-        const int zb = p.b_batched ? blockIdx.z : 0;
+        const int zb = p.b_batched ? tc.z : 0;
         tma_load_3d(st + 2 * kStageABytes, &tmB_hi, &full_bar[stage], ks * 64, n0, zb);
         tma_load_3d(st + 2 * kStageABytes + STAGE_B, &tmB_lo, &full_bar[stage], ks * 64, n0, zb);
         if (++stage == STAGES) {
@@ -176,14 +193,21 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
           phase ^= 1;
         }
       }
+      }
     }
   } else if (warp == 1) {
     // ===== MMA issuer ===========================================================================
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
-      const uint32_t acc1 = tmem_base + ACC1_COL;
       int stage = 0;
       uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it % NBUF;
+      const uint32_t tile_base = tmem_base + buf * TILE_COLS;
+      const uint32_t acc1 = tile_base + ACC1_COL;
+      mbar_wait(&tmem_empty_bar[buf], (((it / NBUF) & 1) ^ 1));     // the epilogue has drained this accumulator set
+      tc_fence_after();
       for (int ks = 0; ks < p.num_k_steps; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -191,12 +215,12 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
         const uint32_t a_lo = a_hi + kStageABytes;
         const uint32_t b_hi = a_hi + 2 * kStageABytes;
         const uint32_t b_lo = b_hi + STAGE_B;
-        uint32_t acc0 = tmem_base;
+        uint32_t acc0 = tile_base;
         bool first0 = (ks == 0);
         if constexpr (AMODE == A_CONV3) {       // one hi*hi accumulator per kernel row dy
           const int tap = ks / p.cin_chunks;
           const int dy = tap / 3;
-          acc0 = tmem_base + dy * ACC_STRIDE;
+          acc0 = tile_base + dy * ACC_STRIDE;
           first0 = (ks == dy * 3 * p.cin_chunks);
         }
 #pragma unroll
@@ -216,15 +240,22 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
           phase ^= 1;
         }
       }
-      umma_commit(tmem_full_bar);
+      umma_commit(&tmem_full_bar[buf]);
+      }
     }
   } else {
     // ===== epilogue warps ===========================================================================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;                // row of the 128-row tile
-    mbar_wait(tmem_full_bar, 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    const Tile tc = decode(tile);
+    const int m0 = tc.m0, n0 = tc.n0, img = tc.img, x0 = tc.x0, y0 = tc.y0;
+    (void)m0; (void)img; (void)x0; (void)y0;
+    const int buf = it % NBUF;
+    mbar_wait(&tmem_full_bar[buf], (it / NBUF) & 1);
     tc_fence_after();
-    const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t t0 = tmem_base + buf * TILE_COLS + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t t1 = t0 + ACC1_COL;
 
     auto load16 = [&](int col, float (&v)[16]) {
@@ -402,7 +433,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     } else {  // EPI_LINEAR
       const int m = m0 + row;
       const bool valid = m < p.M;
-      const size_t z = blockIdx.z;
+      const size_t z = tc.z;
       float* of = p.out_f32 ? p.out_f32 + z * p.bstride_f32 : nullptr;
       __half* oh = p.out_hi ? p.out_hi + z * p.bstride_h : nullptr;
       __half* ol = p.out_lo ? p.out_lo + z * p.bstride_h : nullptr;
@@ -490,6 +521,9 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       }
     }
     tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);     // hand the accumulator set back to the MMA warp
+    }
   }
 
   __syncthreads();
