@@ -2,14 +2,22 @@
 //     O[q] = softmax_k( Q[q] . K[k] ) V[k]          4 heads x 64 dims, Q and K pre-scaled by 64^-1/4
 // (lightglue_sim.onnx /inner_attn: Mul, Mul_1, MatMul, Softmax, MatMul_1 -- e.g. layer 0 self nodes 50-54,
 //  cross nodes 141-151; run by the reference at src/Matchers/lightglue_onnx.cpp:210-214).
-// The N x N score matrix never leaves the SM: one CTA owns a 128-query tile of one (image, head) and walks the
-// key tiles twice -- pass 1 finds the exact row maximum (the reference's softmax subtracts exactly that), pass 2
-// recomputes the scores, exponentiates, accumulates the row sum and feeds P = exp(S - max) straight back to the
-// tensor core from shared memory for O += P V.  The epilogue divides by the row sum.
+// The N x N score matrix never leaves the SM: one CTA owns a 128-query tile of one (problem, head) and walks the
+// 64-key tiles twice.
+//   pass 1: row maximum from the hi*hi product alone (one MMA instead of three; softmax is invariant to the constant
+//           that is subtracted, it only has to be within ~1e-3 of the true maximum to keep exp() in range);
+//   pass 2: fp32-equivalent scores, P = exp(S - max) through the SFU, row sums, P handed back to the tensor core
+//           through shared memory (K-major, 128-byte swizzle, double buffered) for O += P V.
+// The epilogue divides by the row sum.
+//
+// Tensor-core work per 64-key tile, using a [hi ; lo] concatenated B operand (the hi and lo planes of K and of V^T sit
+// next to each other in the stage, so one N=128 MMA computes a_hi*b_hi and a_hi*b_lo at once):
+//     S:  [S_hh | S_hl] = Q_hi [K_hi;K_lo]^T (N=128) ;  S_hl += Q_lo K_hi^T (N=64)        -> S = S_hh + 2^-11 S_hl
+//     O:  [O_hh | O_hl] += P_hi [V_hi;V_lo]^T (N=128);  O_hl += P_lo V_hi^T (N=64)
 //
 // CTA = 320 threads: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2..9 softmax/epilogue
-// (warp w and w+4 share TMEM lane quarter w%4 and split each 64-key tile's columns 32/32).
-// TMEM: 2 x (S_hh, S_x) score buffers of 64 columns + (O_hh, O_x) 2 x 64 = 384 columns.
+// (warp w and w+4 share TMEM lane quarter w%4 and split each tile's 64 columns 32/32).
+// TMEM: 2 score buffers x 128 columns + O 128 columns = 384 (512 allocated).
 #pragma once
 
 #include "common.cuh"
@@ -30,8 +38,8 @@ constexpr int kAttnStages = 3;
 constexpr int kAttnKeyTile = 64;
 constexpr int kAttnStageBytes = 4 * 8192;                       // K_hi, K_lo, Vt_hi, Vt_lo  (64 rows x 128 B each)
 constexpr int kAttnQBytes = 2 * 16384;                          // Q_hi, Q_lo (128 rows x 128 B)
-constexpr int kAttnPBytes = 2 * 16384;                          // P_hi, P_lo (128 rows x 128 B)
-constexpr int kAttnSmemBytes = kAttnQBytes + kAttnPBytes + kAttnStages * kAttnStageBytes + 1024 + 4096;
+constexpr int kAttnPBytes = 2 * 16384;                          // one P buffer: P_hi, P_lo (128 rows x 128 B)
+constexpr int kAttnSmemBytes = kAttnQBytes + 2 * kAttnPBytes + kAttnStages * kAttnStageBytes + 1024 + 4096;
 
 #ifdef __CUDACC__
 
@@ -53,17 +61,17 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // Q_hi | Q_lo
-  uint8_t* sP = smem + kAttnQBytes;                     // P_hi | P_lo
-  uint8_t* sKV = sP + kAttnPBytes;                      // stages
+  uint8_t* sP = smem + kAttnQBytes;                     // 2 x (P_hi | P_lo)
+  uint8_t* sKV = sP + 2 * kAttnPBytes;                  // stages: K_hi | K_lo | Vt_hi | Vt_lo
   uint8_t* tail = sKV + kAttnStages * kAttnStageBytes;
   uint64_t* q_full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* kv_full = q_full + 1;
   uint64_t* kv_empty = kv_full + kAttnStages;
   uint64_t* s_full = kv_empty + kAttnStages;            // [2]
   uint64_t* s_empty = s_full + 2;                       // [2]
-  uint64_t* p_full = s_empty + 2;
-  uint64_t* p_empty = p_full + 1;
-  uint64_t* o_full = p_empty + 1;
+  uint64_t* p_full = s_empty + 2;                       // [2]
+  uint64_t* p_empty = p_full + 2;                       // [2]
+  uint64_t* o_full = p_empty + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 1);
   float* stat = reinterpret_cast<float*>(tail + 256);   // [2][128] partial row max, then partial row sum
 
@@ -81,9 +89,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
     tma_prefetch_desc(&tmK_lo); tma_prefetch_desc(&tmV_hi); tma_prefetch_desc(&tmV_lo);
     mbar_init(q_full, 1);
     for (int s = 0; s < kAttnStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 8); }
-    mbar_init(p_full, 8);
-    mbar_init(p_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 8);
+      mbar_init(&p_full[s], 8); mbar_init(&p_empty[s], 1);
+    }
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -95,77 +104,80 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  // TMEM columns: S buffer b: hh at b*128, x at b*128+64 ; O: hh at 256, x at 320
+  // TMEM columns: score buffer b: [hh | hl] at b*128 ; O: [hh | hl] at 256
 
   if (warp == 0) {
+    // ===== TMA producer: Q once; pass 1 needs K_hi only, pass 2 the whole stage ================================
     if (elect_one()) {
       mbar_expect_tx(q_full, kAttnQBytes);
       tma_load_3d(sQ, &tmQ_hi, q_full, 0, qrow, head);
       tma_load_3d(sQ + 16384, &tmQ_lo, q_full, 0, qrow, head);
       for (int g = 0; g < 2 * T; ++g) {
         const int t = g < T ? g : g - T;
-        const bool with_v = g >= T;
+        const bool pass2 = g >= T;
         const int st = g % kAttnStages;
         mbar_wait(&kv_empty[st], ((g / kAttnStages) & 1) ^ 1);
         uint8_t* sb = sKV + st * kAttnStageBytes;
-        mbar_expect_tx(&kv_full[st], with_v ? kAttnStageBytes : kAttnStageBytes / 2);
+        mbar_expect_tx(&kv_full[st], pass2 ? kAttnStageBytes : 8192);
         tma_load_3d(sb, &tmK_hi, &kv_full[st], 0, krow + t * kAttnKeyTile, head);
-        tma_load_3d(sb + 8192, &tmK_lo, &kv_full[st], 0, krow + t * kAttnKeyTile, head);
-        if (with_v) {
+        if (pass2) {
+          tma_load_3d(sb + 8192, &tmK_lo, &kv_full[st], 0, krow + t * kAttnKeyTile, head);
           tma_load_3d(sb + 16384, &tmV_hi, &kv_full[st], krow + t * kAttnKeyTile, 0, head);
           tma_load_3d(sb + 24576, &tmV_lo, &kv_full[st], krow + t * kAttnKeyTile, 0, head);
         }
       }
     }
   } else if (warp == 1) {
+    // ===== MMA issuer ===========================================================================================
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_f16(128, 64);
+      constexpr uint32_t idesc64 = make_idesc_f16(128, 64);
+      constexpr uint32_t idesc128 = make_idesc_f16(128, 128);
       const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + 16384;
-      const uint32_t p_hi = smem_u32(sP), p_lo = p_hi + 16384;
-      const uint32_t o_hh = tmem_base + 256, o_x = tmem_base + 320;
+      const uint32_t o_base = tmem_base + 256;
       mbar_wait(q_full, 0);
-      auto issue_s = [&](int g) {
+      auto issue_s = [&](int g, bool full) {
         const int st = g % kAttnStages, b = g & 1;
         mbar_wait(&kv_full[st], (g / kAttnStages) & 1);
         mbar_wait(&s_empty[b], ((g >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t k_hi = smem_u32(sKV + st * kAttnStageBytes), k_lo = k_hi + 8192;
-        const uint32_t s_hh = tmem_base + b * 128, s_x = s_hh + 64;
+        const uint32_t k_hi = smem_u32(sKV + st * kAttnStageBytes);   // K_lo follows at +8192: [K_hi;K_lo] is one N=128 operand
+        const uint32_t s_base = tmem_base + b * 128;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint64_t dq_hi = make_sw128_kmajor_desc(q_hi + k * 32), dq_lo = make_sw128_kmajor_desc(q_lo + k * 32);
-          const uint64_t dk_hi = make_sw128_kmajor_desc(k_hi + k * 32), dk_lo = make_sw128_kmajor_desc(k_lo + k * 32);
-          umma_f16(s_hh, dq_hi, dk_hi, idesc, k > 0);
-          umma_f16(s_x, dq_hi, dk_lo, idesc, k > 0);
-          umma_f16(s_x, dq_lo, dk_hi, idesc, 1u);
+          const uint64_t dq_hi = make_sw128_kmajor_desc(q_hi + k * 32);
+          const uint64_t dk = make_sw128_kmajor_desc(k_hi + k * 32);
+          if (full) {
+            umma_f16(s_base, dq_hi, dk, idesc128, k > 0);                                      // [S_hh | S_hl]
+            umma_f16(s_base + 64, make_sw128_kmajor_desc(q_lo + k * 32), dk, idesc64, 1u);     // S_hl += Q_lo K_hi^T
+          } else {
+            umma_f16(s_base, dq_hi, dk, idesc64, k > 0);                                       // S_hh only
+          }
         }
         umma_commit(&s_full[b]);
       };
-      auto issue_pv = [&](int g, int t) {   // consumes P of tile t and the V^T half of stage g%ST
-        const int st = g % kAttnStages;
-        mbar_wait(p_full, t & 1);
+      auto issue_pv = [&](int g, int t) {   // consumes P buffer t&1 and the V^T half of stage g%ST
+        const int st = g % kAttnStages, pb = t & 1;
+        mbar_wait(&p_full[pb], (t >> 1) & 1);
         tc_fence_after();
-        const uint32_t v_hi = smem_u32(sKV + st * kAttnStageBytes) + 16384, v_lo = v_hi + 8192;
+        const uint32_t p_hi = smem_u32(sP + pb * kAttnPBytes), p_lo = p_hi + 16384;
+        const uint32_t v_hi = smem_u32(sKV + st * kAttnStageBytes) + 16384;   // V_lo follows at +8192
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint64_t dp_hi = make_sw128_kmajor_desc(p_hi + k * 32), dp_lo = make_sw128_kmajor_desc(p_lo + k * 32);
-          const uint64_t dv_hi = make_sw128_kmajor_desc(v_hi + k * 32), dv_lo = make_sw128_kmajor_desc(v_lo + k * 32);
-          const uint32_t acc = (t > 0 || k > 0) ? 1u : 0u;
-          umma_f16(o_hh, dp_hi, dv_hi, idesc, acc);
-          umma_f16(o_x, dp_hi, dv_lo, idesc, acc);
-          umma_f16(o_x, dp_lo, dv_hi, idesc, 1u);
+          const uint64_t dv = make_sw128_kmajor_desc(v_hi + k * 32);
+          umma_f16(o_base, make_sw128_kmajor_desc(p_hi + k * 32), dv, idesc128, (t > 0 || k > 0) ? 1u : 0u);
+          umma_f16(o_base + 64, make_sw128_kmajor_desc(p_lo + k * 32), dv, idesc64, 1u);
         }
         umma_commit(&kv_empty[st]);
-        umma_commit(p_empty);
+        umma_commit(&p_empty[pb]);
       };
-      // pass 1: scores only; the K stage is free as soon as its MMAs retire
+      // pass 1: hi*hi scores only; the K stage is free as soon as its MMAs retire
       for (int g = 0; g < T; ++g) {
-        issue_s(g);
+        issue_s(g, false);
         umma_commit(&kv_empty[g % kAttnStages]);
       }
       // pass 2: S(t) is issued before PV(t-1) so the softmax of tile t-1 overlaps the score MMAs of tile t
       for (int t = 0; t < T; ++t) {
-        issue_s(T + t);
+        issue_s(T + t, true);
         if (t > 0) issue_pv(T + t - 1, t - 1);
       }
       issue_pv(2 * T - 1, T - 1);
@@ -179,9 +191,44 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
     const int row = q * 32 + lane;
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float NEG = -INFINITY;
+    constexpr float kLog2e = 1.4426950408889634f;
 
-    auto load_scores = [&](int g, float (&s)[32]) {
+    // ---- pass 1: row maximum of the hi*hi scores ----
+    float mx = NEG;
+    for (int g = 0; g < T; ++g) {
       const int b = g & 1;
+      mbar_wait(&s_full[b], (g >> 1) & 1);
+      tc_fence_after();
+      uint32_t a0[16], a1[16];
+      const uint32_t base = tlane + b * 128 + hw * 32;
+      tmem_ld16(base, a0);
+      tmem_ld16(base + 16, a1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[b]);
+      const int c0 = g * kAttnKeyTile + hw * 32;
+      if (c0 + 32 <= nk) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(a0[j]), __uint_as_float(a1[j])));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (c0 + j < nk) mx = fmaxf(mx, __uint_as_float(a0[j]));
+          if (c0 + 16 + j < nk) mx = fmaxf(mx, __uint_as_float(a1[j]));
+        }
+      }
+    }
+    stat[hw * 128 + row] = mx;
+    named_bar_sync(1, 256);
+    mx = fmaxf(stat[row], stat[128 + row]);
+    named_bar_sync(1, 256);
+    const float mx_l2 = mx * kLog2e;
+
+    // ---- pass 2: P = exp(S - max) -> smem (K-major, 128-byte swizzle), row sum ----
+    float l = 0.0f;
+    for (int t = 0; t < T; ++t) {
+      const int g = T + t, b = g & 1, pb = t & 1;
       mbar_wait(&s_full[b], (g >> 1) & 1);
       tc_fence_after();
       uint32_t a0[16], a1[16], x0[16], x1[16];
@@ -194,50 +241,22 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[b]);
+      float s[32];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         s[j] = __uint_as_float(a0[j]) + __uint_as_float(x0[j]) * RFE_SPLIT_INV;
         s[16 + j] = __uint_as_float(a1[j]) + __uint_as_float(x1[j]) * RFE_SPLIT_INV;
       }
-    };
-
-    // ---- pass 1: exact row maximum ----
-    float mx = NEG;
-    for (int g = 0; g < T; ++g) {
-      float s[32];
-      load_scores(g, s);
-      const int c0 = g * kAttnKeyTile + hw * 32;
-      if (c0 + 32 <= nk) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, s[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < nk) mx = fmaxf(mx, s[j]);
-      }
-    }
-    stat[hw * 128 + row] = mx;
-    named_bar_sync(1, 256);
-    mx = fmaxf(stat[row], stat[128 + row]);
-    named_bar_sync(1, 256);
-
-    // ---- pass 2: P = exp(S - max) -> smem (K-major, 128-byte swizzle), row sum ----
-    float l = 0.0f;
-    uint8_t* prow_hi = sP + row * 128;
-    uint8_t* prow_lo = prow_hi + 16384;
-    for (int t = 0; t < T; ++t) {
-      float s[32];
-      load_scores(T + t, s);
       const int c0 = t * kAttnKeyTile + hw * 32;
+      const bool full = (c0 + 32 <= nk);
       __align__(16) __half2 ph[16];
       __align__(16) __half2 pl[16];
-      const bool full = (c0 + 32 <= nk);
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
-        // exp(s - max) through the SFU: ex2.approx((s - max) * log2 e); relative error <= 2^-22 + |s-max| * 2^-23,
-        // the same order as the 22-bit split-fp16 operand that carries P into the tensor core
-        float e0 = fast_exp2((s[j] - mx) * 1.4426950408889634f);
-        float e1 = fast_exp2((s[j + 1] - mx) * 1.4426950408889634f);
+        // exp(s - max) through the SFU: ex2.approx(s*log2e - max*log2e); relative error ~2^-22 + |s-max|*2^-23, the
+        // same order as the 22-bit split-fp16 operand that carries P into the tensor core
+        float e0 = fast_exp2(fmaf(s[j], kLog2e, -mx_l2));
+        float e1 = fast_exp2(fmaf(s[j + 1], kLog2e, -mx_l2));
         if (!full) {
           if (c0 + j >= nk) e0 = 0.0f;
           if (c0 + j + 1 >= nk) e1 = 0.0f;
@@ -248,7 +267,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
         ph[j >> 1] = h2;
         pl[j >> 1] = __floats2half2_rn((e0 - hf.x) * RFE_SPLIT_SCALE, (e1 - hf.y) * RFE_SPLIT_SCALE);
       }
-      mbar_wait(p_empty, (t & 1) ^ 1);       // PV(t-1) has consumed the previous P tile
+      mbar_wait(&p_empty[pb], ((t >> 1) & 1) ^ 1);       // PV(t-2) has consumed this P buffer
+      uint8_t* prow_hi = sP + pb * kAttnPBytes + row * 128;
+      uint8_t* prow_lo = prow_hi + 16384;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         const int sc = ((hw * 4 + ch) ^ (row & 7)) << 4;
@@ -257,7 +278,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       }
       fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[pb]);
     }
     stat[hw * 128 + row] = l;
     named_bar_sync(1, 256);
