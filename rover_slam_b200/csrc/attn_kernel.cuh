@@ -15,8 +15,9 @@
 //     S:  [S_hh | S_hl] = Q_hi [K_hi;K_lo]^T (N=128) ;  S_hl += Q_lo K_hi^T (N=64)        -> S = S_hh + 2^-11 S_hl
 //     O:  [O_hh | O_hl] += P_hi [V_hi;V_lo]^T (N=128);  O_hl += P_lo V_hi^T (N=64)
 //
-// CTA = 320 threads: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2..9 softmax/epilogue
-// (warp w and w+4 share TMEM lane quarter w%4 and split each tile's 64 columns 32/32).
+// CTA = 576 threads: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2..17 softmax/epilogue
+// (the four warps with the same w%4 share a TMEM lane quarter and split each tile's 64 columns 16/16/16/16: four
+// warps per scheduler hide the SFU / convert latencies of the exponentials).
 // TMEM: 2 score buffers x 128 columns + O 128 columns = 384 (512 allocated).
 #pragma once
 
@@ -33,7 +34,8 @@ struct AttnParams {
   __half* out_lo;
 };
 
-constexpr int kAttnThreads = 320;
+constexpr int kAttnSoftmaxWarps = 16;                             // 4 per TMEM lane quarter: 16 of a tile's 64 columns each
+constexpr int kAttnThreads = 64 + 32 * kAttnSoftmaxWarps;
 constexpr int kAttnStages = 3;
 constexpr int kAttnKeyTile = 64;
 constexpr int kAttnStageBytes = 4 * 8192;                       // K_hi, K_lo, Vt_hi, Vt_lo  (64 rows x 128 B each)
@@ -73,7 +75,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
   uint64_t* p_empty = p_full + 2;                       // [2]
   uint64_t* o_full = p_empty + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 1);
-  float* stat = reinterpret_cast<float*>(tail + 256);   // [2][128] partial row max, then partial row sum
+  float* stat = reinterpret_cast<float*>(tail + 256);   // [4][128] partial row max, then partial row sum
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int z = blockIdx.z;
@@ -90,8 +92,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
     mbar_init(q_full, 1);
     for (int s = 0; s < kAttnStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 8);
-      mbar_init(&p_full[s], 8); mbar_init(&p_empty[s], 1);
+      mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kAttnSoftmaxWarps);
+      mbar_init(&p_full[s], kAttnSoftmaxWarps); mbar_init(&p_empty[s], 1);
     }
     mbar_init(o_full, 1);
     fence_barrier_init();
@@ -185,13 +187,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
     }
   } else {
     // ===== softmax / epilogue warps =========================================================================
-    const int sw = warp - 2;                 // 0..7
+    const int sw = warp - 2;                 // 0..15
     const int q = warp & 3;                  // TMEM lane quarter
-    const int hw = sw >> 2;                  // which 32-column half of every 64-key tile (warps 2..5 -> 0, 6..9 -> 1)
+    const int cq = sw >> 2;                  // which 16-column quarter of every 64-key tile
     const int row = q * 32 + lane;
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float NEG = -INFINITY;
     constexpr float kLog2e = 1.4426950408889634f;
+    constexpr int kSmThreads = 32 * kAttnSoftmaxWarps;
 
     // ---- pass 1: row maximum of the hi*hi scores ----
     float mx = NEG;
@@ -199,30 +202,26 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       const int b = g & 1;
       mbar_wait(&s_full[b], (g >> 1) & 1);
       tc_fence_after();
-      uint32_t a0[16], a1[16];
-      const uint32_t base = tlane + b * 128 + hw * 32;
-      tmem_ld16(base, a0);
-      tmem_ld16(base + 16, a1);
+      uint32_t a0[16];
+      tmem_ld16(tlane + b * 128 + cq * 16, a0);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[b]);
-      const int c0 = g * kAttnKeyTile + hw * 32;
-      if (c0 + 32 <= nk) {
+      const int c0 = g * kAttnKeyTile + cq * 16;
+      if (c0 + 16 <= nk) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(a0[j]), __uint_as_float(a1[j])));
+        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(a0[j]));
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 16; ++j)
           if (c0 + j < nk) mx = fmaxf(mx, __uint_as_float(a0[j]));
-          if (c0 + 16 + j < nk) mx = fmaxf(mx, __uint_as_float(a1[j]));
-        }
       }
     }
-    stat[hw * 128 + row] = mx;
-    named_bar_sync(1, 256);
-    mx = fmaxf(stat[row], stat[128 + row]);
-    named_bar_sync(1, 256);
+    stat[cq * 128 + row] = mx;
+    named_bar_sync(1, kSmThreads);
+    mx = fmaxf(fmaxf(stat[row], stat[128 + row]), fmaxf(stat[256 + row], stat[384 + row]));
+    named_bar_sync(1, kSmThreads);
     const float mx_l2 = mx * kLog2e;
 
     // ---- pass 2: P = exp(S - max) -> smem (K-major, 128-byte swizzle), row sum ----
@@ -231,32 +230,26 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       const int g = T + t, b = g & 1, pb = t & 1;
       mbar_wait(&s_full[b], (g >> 1) & 1);
       tc_fence_after();
-      uint32_t a0[16], a1[16], x0[16], x1[16];
-      const uint32_t base = tlane + b * 128 + hw * 32;
+      uint32_t a0[16], x0[16];
+      const uint32_t base = tlane + b * 128 + cq * 16;
       tmem_ld16(base, a0);
-      tmem_ld16(base + 16, a1);
       tmem_ld16(base + 64, x0);
-      tmem_ld16(base + 80, x1);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[b]);
-      float s[32];
+      const int c0 = t * kAttnKeyTile + cq * 16;
+      const bool full = (c0 + 16 <= nk);
+      __align__(16) __half2 ph[8];
+      __align__(16) __half2 pl[8];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        s[j] = __uint_as_float(a0[j]) + __uint_as_float(x0[j]) * RFE_SPLIT_INV;
-        s[16 + j] = __uint_as_float(a1[j]) + __uint_as_float(x1[j]) * RFE_SPLIT_INV;
-      }
-      const int c0 = t * kAttnKeyTile + hw * 32;
-      const bool full = (c0 + 32 <= nk);
-      __align__(16) __half2 ph[16];
-      __align__(16) __half2 pl[16];
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
+      for (int j = 0; j < 16; j += 2) {
+        const float s0 = __uint_as_float(a0[j]) + __uint_as_float(x0[j]) * RFE_SPLIT_INV;
+        const float s1 = __uint_as_float(a0[j + 1]) + __uint_as_float(x0[j + 1]) * RFE_SPLIT_INV;
         // exp(s - max) through the SFU: ex2.approx(s*log2e - max*log2e); relative error ~2^-22 + |s-max|*2^-23, the
         // same order as the 22-bit split-fp16 operand that carries P into the tensor core
-        float e0 = fast_exp2(fmaf(s[j], kLog2e, -mx_l2));
-        float e1 = fast_exp2(fmaf(s[j + 1], kLog2e, -mx_l2));
+        float e0 = fast_exp2(fmaf(s0, kLog2e, -mx_l2));
+        float e1 = fast_exp2(fmaf(s1, kLog2e, -mx_l2));
         if (!full) {
           if (c0 + j >= nk) e0 = 0.0f;
           if (c0 + j + 1 >= nk) e1 = 0.0f;
@@ -271,8 +264,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       uint8_t* prow_hi = sP + pb * kAttnPBytes + row * 128;
       uint8_t* prow_lo = prow_hi + 16384;
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        const int sc = ((hw * 4 + ch) ^ (row & 7)) << 4;
+      for (int ch = 0; ch < 2; ++ch) {
+        const int sc = ((cq * 2 + ch) ^ (row & 7)) << 4;
         *reinterpret_cast<uint4*>(prow_hi + sc) = reinterpret_cast<const uint4*>(ph)[ch];
         *reinterpret_cast<uint4*>(prow_lo + sc) = reinterpret_cast<const uint4*>(pl)[ch];
       }
@@ -280,33 +273,29 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[pb]);
     }
-    stat[hw * 128 + row] = l;
-    named_bar_sync(1, 256);
-    l = stat[row] + stat[128 + row];
+    stat[cq * 128 + row] = l;
+    named_bar_sync(1, kSmThreads);
+    l = (stat[row] + stat[128 + row]) + (stat[256 + row] + stat[384 + row]);
 
     // ---- epilogue: O / l -> split-fp16 [rows][256] ----
     mbar_wait(o_full, 0);
     tc_fence_after();
     {
-      uint32_t a0[16], a1[16], x0[16], x1[16];
-      const uint32_t base = tlane + 256 + hw * 32;
+      uint32_t a0[16], x0[16];
+      const uint32_t base = tlane + 256 + cq * 16;
       tmem_ld16(base, a0);
-      tmem_ld16(base + 16, a1);
       tmem_ld16(base + 64, x0);
-      tmem_ld16(base + 80, x1);
       tmem_ld_wait();
-      __align__(16) __half oh[32];
-      __align__(16) __half ol[32];
+      __align__(16) __half oh[16];
+      __align__(16) __half ol[16];
       const float inv_l = 1.0f / l;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < 16; ++j)
         split_f32((__uint_as_float(a0[j]) + __uint_as_float(x0[j]) * RFE_SPLIT_INV) * inv_l, oh[j], ol[j]);
-        split_f32((__uint_as_float(a1[j]) + __uint_as_float(x1[j]) * RFE_SPLIT_INV) * inv_l, oh[16 + j], ol[16 + j]);
-      }
       if (m0 + row < nq) {
-        const size_t o = static_cast<size_t>(qrow + row) * 256 + head * 64 + hw * 32;
+        const size_t o = static_cast<size_t>(qrow + row) * 256 + head * 64 + cq * 16;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < 2; ++ch) {
           reinterpret_cast<uint4*>(p.out_hi + o)[ch] = reinterpret_cast<const uint4*>(oh)[ch];
           reinterpret_cast<uint4*>(p.out_lo + o)[ch] = reinterpret_cast<const uint4*>(ol)[ch];
         }

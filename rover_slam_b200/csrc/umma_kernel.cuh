@@ -199,6 +199,8 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     // ===== MMA issuer ===========================================================================
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
+      constexpr bool kConcatB = (NACC0 == 1) && (ACC_STRIDE == BLOCK_N) && (2 * BLOCK_N <= 256);
+      constexpr uint32_t idesc2 = make_idesc_f16(kBlockM, kConcatB ? 2 * BLOCK_N : BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -230,9 +232,17 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
           const uint64_t db_hi = make_sw128_kmajor_desc(b_hi + k * 32);
           const uint64_t db_lo = make_sw128_kmajor_desc(b_lo + k * 32);
           const uint32_t acc = (ks > 0 || k > 0) ? 1u : 0u;
-          umma_f16(acc0, da_hi, db_hi, idesc, (first0 && k == 0) ? 0u : 1u);
-          umma_f16(acc1, da_hi, db_lo, idesc, acc);
-          umma_f16(acc1, da_lo, db_hi, idesc, 1u);
+          if constexpr (kConcatB) {
+            // [acc0 | acc1] (+)= A_hi [B_hi;B_lo]^T in ONE N = 2*BLOCK_N MMA (B_lo follows B_hi in the stage and acc1
+            // follows acc0 in TMEM), then acc1 += A_lo B_hi^T: A_hi is read from shared memory once instead of twice
+            umma_f16(acc0, da_hi, db_hi, idesc2, acc);
+            umma_f16(acc1, da_lo, db_hi, idesc, 1u);
+            (void)db_lo;
+          } else {
+            umma_f16(acc0, da_hi, db_hi, idesc, (first0 && k == 0) ? 0u : 1u);
+            umma_f16(acc1, da_hi, db_lo, idesc, acc);
+            umma_f16(acc1, da_lo, db_hi, idesc, 1u);
+          }
         }
         umma_commit(&empty_bar[stage]);
         if (++stage == STAGES) {
