@@ -15,10 +15,11 @@
 //     S:  [S_hh | S_hl] = Q_hi [K_hi;K_lo]^T (N=128) ;  S_hl += Q_lo K_hi^T (N=64)        -> S = S_hh + 2^-11 S_hl
 //     O:  [O_hh | O_hl] += P_hi [V_hi;V_lo]^T (N=128);  O_hl += P_lo V_hi^T (N=64)
 //
-// CTA = 576 threads: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2..17 softmax/epilogue
+// CTA = 640 threads: warp 0 K producer, warp 1 MMA issuer (+ TMEM alloc), warp 2 V producer, warps 4..19 softmax/epilogue
 // (the four warps with the same w%4 share a TMEM lane quarter and split each tile's 64 columns 16/16/16/16: four
 // warps per scheduler hide the SFU / convert latencies of the exponentials).
-// TMEM: 2 score buffers x 128 columns + O 128 columns = 384 (512 allocated).
+// TMEM: 3 score buffers x 128 columns + O 128 columns = 512.  The score MMAs run two key tiles ahead of the P V MMAs so
+// that the TMEM -> registers -> exp -> shared memory -> fence -> mbarrier latency of the softmax stage is hidden.
 #pragma once
 
 #include "common.cuh"
@@ -35,13 +36,16 @@ struct AttnParams {
 };
 
 constexpr int kAttnSoftmaxWarps = 16;                             // 4 per TMEM lane quarter: 16 of a tile's 64 columns each
-constexpr int kAttnThreads = 64 + 32 * kAttnSoftmaxWarps;
-constexpr int kAttnStages = 3;
+constexpr int kAttnThreads = 128 + 32 * kAttnSoftmaxWarps;      // warps 0..3: K producer, MMA, V producer, idle
+constexpr int kAttnKStages = 4;
+constexpr int kAttnVStages = 3;
+constexpr int kAttnSBufs = 3;                                   // score buffers in TMEM: S runs two tiles ahead of P V
 constexpr int kAttnKeyTile = 64;
-constexpr int kAttnStageBytes = 4 * 8192;                       // K_hi, K_lo, Vt_hi, Vt_lo  (64 rows x 128 B each)
+constexpr int kAttnKVBytes = 2 * 8192;                          // one K stage (K_hi | K_lo) or one V stage (Vt_hi | Vt_lo)
 constexpr int kAttnQBytes = 2 * 16384;                          // Q_hi, Q_lo (128 rows x 128 B)
 constexpr int kAttnPBytes = 2 * 16384;                          // one P buffer: P_hi, P_lo (128 rows x 128 B)
-constexpr int kAttnSmemBytes = kAttnQBytes + 2 * kAttnPBytes + kAttnStages * kAttnStageBytes + 1024 + 4096;
+constexpr int kAttnSmemBytes =
+    kAttnQBytes + 2 * kAttnPBytes + (kAttnKStages + kAttnVStages) * kAttnKVBytes + 1024 + 4096;
 
 #ifdef __CUDACC__
 
@@ -64,14 +68,17 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // Q_hi | Q_lo
   uint8_t* sP = smem + kAttnQBytes;                     // 2 x (P_hi | P_lo)
-  uint8_t* sKV = sP + 2 * kAttnPBytes;                  // stages: K_hi | K_lo | Vt_hi | Vt_lo
-  uint8_t* tail = sKV + kAttnStages * kAttnStageBytes;
+  uint8_t* sK = sP + 2 * kAttnPBytes;                   // K stages: K_hi | K_lo
+  uint8_t* sV = sK + kAttnKStages * kAttnKVBytes;       // V stages: Vt_hi | Vt_lo
+  uint8_t* tail = sV + kAttnVStages * kAttnKVBytes;
   uint64_t* q_full = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* kv_full = q_full + 1;
-  uint64_t* kv_empty = kv_full + kAttnStages;
-  uint64_t* s_full = kv_empty + kAttnStages;            // [2]
-  uint64_t* s_empty = s_full + 2;                       // [2]
-  uint64_t* p_full = s_empty + 2;                       // [2]
+  uint64_t* k_full = q_full + 1;                        // [4]
+  uint64_t* k_empty = k_full + kAttnKStages;
+  uint64_t* v_full = k_empty + kAttnKStages;            // [3]
+  uint64_t* v_empty = v_full + kAttnVStages;
+  uint64_t* s_full = v_empty + kAttnVStages;            // [3]
+  uint64_t* s_empty = s_full + kAttnSBufs;              // [3]
+  uint64_t* p_full = s_empty + kAttnSBufs;              // [2]
   uint64_t* p_empty = p_full + 2;                       // [2]
   uint64_t* o_full = p_empty + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 1);
@@ -90,11 +97,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
     tma_prefetch_desc(&tmQ_hi); tma_prefetch_desc(&tmQ_lo); tma_prefetch_desc(&tmK_hi);
     tma_prefetch_desc(&tmK_lo); tma_prefetch_desc(&tmV_hi); tma_prefetch_desc(&tmV_lo);
     mbar_init(q_full, 1);
-    for (int s = 0; s < kAttnStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kAttnSoftmaxWarps);
-      mbar_init(&p_full[s], kAttnSoftmaxWarps); mbar_init(&p_empty[s], 1);
-    }
+    for (int s = 0; s < kAttnKStages; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+    for (int s = 0; s < kAttnVStages; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+    for (int s = 0; s < kAttnSBufs; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kAttnSoftmaxWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&p_full[s], kAttnSoftmaxWarps); mbar_init(&p_empty[s], 1); }
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -106,10 +112,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  // TMEM columns: score buffer b: [hh | hl] at b*128 ; O: [hh | hl] at 256
+  // TMEM columns: score buffer b: [hh | hl] at b*128 ; O: [hh | hl] at 384
 
   if (warp == 0) {
-    // ===== TMA producer: Q once; pass 1 needs K_hi only, pass 2 the whole stage ================================
+    // ===== K producer: Q once; pass 1 needs K_hi only, pass 2 both planes =====================================
     if (elect_one()) {
       mbar_expect_tx(q_full, kAttnQBytes);
       tma_load_3d(sQ, &tmQ_hi, q_full, 0, qrow, head);
@@ -117,16 +123,24 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       for (int g = 0; g < 2 * T; ++g) {
         const int t = g < T ? g : g - T;
         const bool pass2 = g >= T;
-        const int st = g % kAttnStages;
-        mbar_wait(&kv_empty[st], ((g / kAttnStages) & 1) ^ 1);
-        uint8_t* sb = sKV + st * kAttnStageBytes;
-        mbar_expect_tx(&kv_full[st], pass2 ? kAttnStageBytes : 8192);
-        tma_load_3d(sb, &tmK_hi, &kv_full[st], 0, krow + t * kAttnKeyTile, head);
-        if (pass2) {
-          tma_load_3d(sb + 8192, &tmK_lo, &kv_full[st], 0, krow + t * kAttnKeyTile, head);
-          tma_load_3d(sb + 16384, &tmV_hi, &kv_full[st], krow + t * kAttnKeyTile, 0, head);
-          tma_load_3d(sb + 24576, &tmV_lo, &kv_full[st], krow + t * kAttnKeyTile, 0, head);
-        }
+        const int st = g % kAttnKStages;
+        mbar_wait(&k_empty[st], ((g / kAttnKStages) & 1) ^ 1);
+        uint8_t* sb = sK + st * kAttnKVBytes;
+        mbar_expect_tx(&k_full[st], pass2 ? kAttnKVBytes : 8192);
+        tma_load_3d(sb, &tmK_hi, &k_full[st], 0, krow + t * kAttnKeyTile, head);
+        if (pass2) tma_load_3d(sb + 8192, &tmK_lo, &k_full[st], 0, krow + t * kAttnKeyTile, head);
+      }
+    }
+  } else if (warp == 2) {
+    // ===== V producer =================================================================================================
+    if (elect_one()) {
+      for (int t = 0; t < T; ++t) {
+        const int st = t % kAttnVStages;
+        mbar_wait(&v_empty[st], ((t / kAttnVStages) & 1) ^ 1);
+        uint8_t* sb = sV + st * kAttnKVBytes;
+        mbar_expect_tx(&v_full[st], kAttnKVBytes);
+        tma_load_3d(sb, &tmV_hi, &v_full[st], krow + t * kAttnKeyTile, 0, head);
+        tma_load_3d(sb + 8192, &tmV_lo, &v_full[st], krow + t * kAttnKeyTile, 0, head);
       }
     }
   } else if (warp == 1) {
@@ -135,14 +149,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       constexpr uint32_t idesc64 = make_idesc_f16(128, 64);
       constexpr uint32_t idesc128 = make_idesc_f16(128, 128);
       const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + 16384;
-      const uint32_t o_base = tmem_base + 256;
+      const uint32_t o_base = tmem_base + 384;
       mbar_wait(q_full, 0);
       auto issue_s = [&](int g, bool full) {
-        const int st = g % kAttnStages, b = g & 1;
-        mbar_wait(&kv_full[st], (g / kAttnStages) & 1);
-        mbar_wait(&s_empty[b], ((g >> 1) & 1) ^ 1);
+        const int st = g % kAttnKStages, b = g % kAttnSBufs;
+        mbar_wait(&k_full[st], (g / kAttnKStages) & 1);
+        mbar_wait(&s_empty[b], ((g / kAttnSBufs) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t k_hi = smem_u32(sKV + st * kAttnStageBytes);   // K_lo follows at +8192: [K_hi;K_lo] is one N=128 operand
+        const uint32_t k_hi = smem_u32(sK + st * kAttnKVBytes);   // K_lo follows at +8192: [K_hi;K_lo] is one N=128 operand
         const uint32_t s_base = tmem_base + b * 128;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -156,38 +170,38 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
           }
         }
         umma_commit(&s_full[b]);
+        umma_commit(&k_empty[st]);          // the K stage is free as soon as these MMAs retire
       };
-      auto issue_pv = [&](int g, int t) {   // consumes P buffer t&1 and the V^T half of stage g%ST
-        const int st = g % kAttnStages, pb = t & 1;
+      auto issue_pv = [&](int t) {          // consumes P buffer t&1 and V stage t%3
+        const int st = t % kAttnVStages, pb = t & 1;
+        mbar_wait(&v_full[st], (t / kAttnVStages) & 1);
         mbar_wait(&p_full[pb], (t >> 1) & 1);
         tc_fence_after();
         const uint32_t p_hi = smem_u32(sP + pb * kAttnPBytes), p_lo = p_hi + 16384;
-        const uint32_t v_hi = smem_u32(sKV + st * kAttnStageBytes) + 16384;   // V_lo follows at +8192
+        const uint32_t v_hi = smem_u32(sV + st * kAttnKVBytes);       // V_lo follows at +8192
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t dv = make_sw128_kmajor_desc(v_hi + k * 32);
           umma_f16(o_base, make_sw128_kmajor_desc(p_hi + k * 32), dv, idesc128, (t > 0 || k > 0) ? 1u : 0u);
           umma_f16(o_base + 64, make_sw128_kmajor_desc(p_lo + k * 32), dv, idesc64, 1u);
         }
-        umma_commit(&kv_empty[st]);
+        umma_commit(&v_empty[st]);
         umma_commit(&p_empty[pb]);
       };
-      // pass 1: hi*hi scores only; the K stage is free as soon as its MMAs retire
-      for (int g = 0; g < T; ++g) {
-        issue_s(g, false);
-        umma_commit(&kv_empty[g % kAttnStages]);
-      }
-      // pass 2: S(t) is issued before PV(t-1) so the softmax of tile t-1 overlaps the score MMAs of tile t
+      // pass 1: hi*hi scores only
+      for (int g = 0; g < T; ++g) issue_s(g, false);
+      // pass 2: the score MMAs run two tiles ahead of the P V MMAs
+      issue_s(T, true);
+      if (T > 1) issue_s(T + 1, true);
       for (int t = 0; t < T; ++t) {
-        issue_s(T + t, true);
-        if (t > 0) issue_pv(T + t - 1, t - 1);
+        if (t + 2 < T) issue_s(T + t + 2, true);
+        issue_pv(t);
       }
-      issue_pv(2 * T - 1, T - 1);
       umma_commit(o_full);
     }
-  } else {
+  } else if (warp >= 4) {
     // ===== softmax / epilogue warps =========================================================================
-    const int sw = warp - 2;                 // 0..15
+    const int sw = warp - 4;                 // 0..15
     const int q = warp & 3;                  // TMEM lane quarter
     const int cq = sw >> 2;                  // which 16-column quarter of every 64-key tile
     const int row = q * 32 + lane;
@@ -199,8 +213,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
     // ---- pass 1: row maximum of the hi*hi scores ----
     float mx = NEG;
     for (int g = 0; g < T; ++g) {
-      const int b = g & 1;
-      mbar_wait(&s_full[b], (g >> 1) & 1);
+      const int b = g % kAttnSBufs;
+      mbar_wait(&s_full[b], (g / kAttnSBufs) & 1);
       tc_fence_after();
       uint32_t a0[16];
       tmem_ld16(tlane + b * 128 + cq * 16, a0);
@@ -227,8 +241,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
     // ---- pass 2: P = exp(S - max) -> smem (K-major, 128-byte swizzle), row sum ----
     float l = 0.0f;
     for (int t = 0; t < T; ++t) {
-      const int g = T + t, b = g & 1, pb = t & 1;
-      mbar_wait(&s_full[b], (g >> 1) & 1);
+      const int g = T + t, b = g % kAttnSBufs, pb = t & 1;
+      mbar_wait(&s_full[b], (g / kAttnSBufs) & 1);
       tc_fence_after();
       uint32_t a0[16], x0[16];
       const uint32_t base = tlane + b * 128 + cq * 16;
@@ -282,7 +296,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
     tc_fence_after();
     {
       uint32_t a0[16], x0[16];
-      const uint32_t base = tlane + 256 + cq * 16;
+      const uint32_t base = tlane + 384 + cq * 16;
       tmem_ld16(base, a0);
       tmem_ld16(base + 64, x0);
       tmem_ld_wait();

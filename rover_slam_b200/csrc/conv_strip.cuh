@@ -1,0 +1,272 @@
+// 3x3 convolution 64 -> 64 channels (SuperPoint conv1b / conv2a / conv2b = 65 % of the extractor's FLOPs) as a
+// "strip" implicit GEMM that reads every activation from L2 ONCE instead of once per tap.
+//
+// Why a second conv kernel: umma_kernel's A_CONV3 mode fetches nine shifted 16x8-pixel TMA boxes per tile, i.e. each
+// input element crosses L2 -> shared memory 9 times and the kernel is bound by shared-memory bandwidth (ncu:
+// tensor pipe 44 % active, l1tex 65 %).  Here an M-tile is 128 consecutive pixels of ONE image row.  The probe in
+// probe_kernels.cu established that a K-major SWIZZLE_128B operand may start at any 128-byte row of a swizzled buffer
+// (the swizzle is a function of the absolute shared-memory address, base_offset = 0), so all three dx taps of an
+// input row are the SAME shared-memory row buffer (130 px x 128 B) read at start offsets 0 / 128 / 256 bytes, and the
+// three dy taps are three different row buffers.  A CTA walks down a 128-pixel-wide column strip two output rows
+// at a time with a 4-slot ring of input rows: each iteration loads only the two new rows.
+//
+//   per iteration (2 output rows x 128 px): A traffic 2 rows x 130 px x 256 B = 66.5 KB, weights 9 x 16 KB = 147 KB
+//   (umma_kernel: 2 tiles x 9 x 48 KB = 864 KB).
+//
+// CTA = 384 threads: warp 0 = TMA producer for input rows, warp 1 = MMA issuer (+TMEM alloc), warp 2 = TMA producer
+// for the per-tap weight tiles, warps 4..11 = epilogue (two warps per TMEM lane quarter, 32 channels each).
+// TMEM (512 columns): output row r in {0,1}: hi*hi accumulators per kernel row dy at r*256 + dy*64, the lo
+// accumulator at r*256 + 192 (per-kernel-row accumulators: see umma_kernel.cuh on accumulation truncation).
+// Epilogue: bias + ReLU (+ 2x2 max-pool: vertical partner = the same thread's other row, horizontal = lane ^ 1)
+// -> split-fp16 NHWC.
+#pragma once
+
+#include "common.cuh"
+
+namespace rfe {
+
+struct StripParams {
+  int B, H, W;              // input = output spatial size (before pooling)
+  int n_strips, n_segs;     // 128-px column strips per row, row segments per image
+  int seg_rows;             // rows per segment (even)
+  int num_items;            // B * n_strips * n_segs
+  int pool;
+  const float* bias;        // [64]
+  __half* out_hi;           // NHWC [B][Ho][Wo][64]
+  __half* out_lo;
+};
+
+constexpr int kStripThreads = 384;
+constexpr int kStripRowBytes = 130 * 128;        // one plane of one input row of the strip (with 1-px halo each side)
+constexpr int kStripSlotBytes = 17 * 1024;       // slot pitch (1024-aligned for the swizzle)
+constexpr int kStripRowSlots = 4;
+constexpr int kStripWStages = 4;
+constexpr int kStripWStageBytes = 2 * 8192;      // W_hi | W_lo of one tap: 64 couts x 128 B each
+constexpr int kStripSmemBytes =
+    2 * kStripRowSlots * kStripSlotBytes + kStripWStages * kStripWStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+#ifdef __CUDACC__
+
+// tmA_*: 4-D (C=64, W, H, B) box (64, 130, 1, 1);  tmW_*: 3-D (K=576, 64, 1) box (64, 64, 1)
+__global__ void __launch_bounds__(kStripThreads, 1)
+conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                    const StripParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sRowHi = smem;                                              // [4] slots
+  uint8_t* sRowLo = smem + kStripRowSlots * kStripSlotBytes;
+  uint8_t* sW = smem + 2 * kStripRowSlots * kStripSlotBytes;           // [4] stages
+  uint64_t* row_full = reinterpret_cast<uint64_t*>(sW + kStripWStages * kStripWStageBytes);
+  uint64_t* row_empty = row_full + kStripRowSlots;
+  uint64_t* w_full = row_empty + kStripRowSlots;
+  uint64_t* w_empty = w_full + kStripWStages;
+  uint64_t* acc_full = w_empty + kStripWStages;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmW_hi); tma_prefetch_desc(&tmW_lo);
+    for (int s = 0; s < kStripRowSlots; ++s) { mbar_init(&row_full[s], 1); mbar_init(&row_empty[s], 1); }
+    for (int s = 0; s < kStripWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // item -> (image, strip, segment); every role walks the same item sequence
+  auto item_coords = [&](int item, int& b, int& x0, int& y_begin, int& iters) {
+    const int sx = item % p.n_strips;
+    const int r = item / p.n_strips;
+    const int sg = r % p.n_segs;
+    b = r / p.n_segs;
+    x0 = sx * 128;
+    y_begin = sg * p.seg_rows;
+    const int rows = (p.H - y_begin) < p.seg_rows ? (p.H - y_begin) : p.seg_rows;
+    iters = rows >> 1;
+  };
+
+  if (warp == 0) {
+    // ===== input-row producer: row sequence number n -> slot n & 3 =====================================================
+    if (elect_one()) {
+      uint32_t n = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        int b, x0, y_begin, iters;
+        item_coords(item, b, x0, y_begin, iters);
+        const int nrows = 2 * iters + 2;                       // input rows y_begin-1 .. y_begin+2*iters
+        for (int k = 0; k < nrows; ++k, ++n) {
+          const int slot = n & 3;
+          mbar_wait(&row_empty[slot], ((n >> 2) & 1) ^ 1);
+          mbar_expect_tx(&row_full[slot], 2 * kStripRowBytes);
+          tma_load_4d(sRowHi + slot * kStripSlotBytes, &tmA_hi, &row_full[slot], 0, x0 - 1, y_begin - 1 + k, b);
+          tma_load_4d(sRowLo + slot * kStripSlotBytes, &tmA_lo, &row_full[slot], 0, x0 - 1, y_begin - 1 + k, b);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== weight producer: tap sequence number m -> stage m & 3 ======================================================
+    if (elect_one()) {
+      uint32_t m = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        int b, x0, y_begin, iters;
+        item_coords(item, b, x0, y_begin, iters);
+        for (int it = 0; it < iters; ++it)
+          for (int tap = 0; tap < 9; ++tap, ++m) {
+            const int st = m & 3;
+            mbar_wait(&w_empty[st], ((m >> 2) & 1) ^ 1);
+            mbar_expect_tx(&w_full[st], kStripWStageBytes);
+            tma_load_3d(sW + st * kStripWStageBytes, &tmW_hi, &w_full[st], tap * 64, 0, 0);
+            tma_load_3d(sW + st * kStripWStageBytes + 8192, &tmW_lo, &w_full[st], tap * 64, 0, 0);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer ==================================================================================================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_f16(128, 64);
+      uint32_t n_base = 0;     // row sequence number of the current item's first input row
+      uint32_t m = 0;          // tap sequence number
+      uint32_t gi = 0;         // iteration counter (accumulator hand-over phase)
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        int b, x0, y_begin, iters;
+        item_coords(item, b, x0, y_begin, iters);
+        for (int it = 0; it < iters; ++it, ++gi) {
+          mbar_wait(acc_empty, (gi & 1) ^ 1);                 // the epilogue has drained the accumulators
+          tc_fence_after();
+          for (int dy = 0; dy < 3; ++dy) {
+            for (int dx = 0; dx < 3; ++dx, ++m) {
+              const int st = m & 3;
+              mbar_wait(&w_full[st], (m >> 2) & 1);
+              const uint32_t w_hi = smem_u32(sW + st * kStripWStageBytes), w_lo = w_hi + 8192;
+#pragma unroll
+              for (int r = 0; r < 2; ++r) {
+                const uint32_t seq = n_base + 2 * it + r + dy;           // input row feeding output row r through kernel row dy
+                const int slot = seq & 3;
+                mbar_wait(&row_full[slot], (seq >> 2) & 1);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(sRowHi + slot * kStripSlotBytes) + dx * 128;
+                const uint32_t a_lo = smem_u32(sRowLo + slot * kStripSlotBytes) + dx * 128;
+                const uint32_t acc0 = tmem_base + r * 256 + dy * 64;
+                const uint32_t acc1 = tmem_base + r * 256 + 192;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t da_hi = make_sw128_kmajor_desc(a_hi + k * 32);
+                  const uint64_t da_lo = make_sw128_kmajor_desc(a_lo + k * 32);
+                  const uint64_t db_hi = make_sw128_kmajor_desc(w_hi + k * 32);
+                  const uint64_t db_lo = make_sw128_kmajor_desc(w_lo + k * 32);
+                  umma_f16(acc0, da_hi, db_hi, idesc, (dx > 0 || k > 0) ? 1u : 0u);
+                  umma_f16(acc1, da_hi, db_lo, idesc, (dy > 0 || dx > 0 || k > 0) ? 1u : 0u);
+                  umma_f16(acc1, da_lo, db_hi, idesc, 1u);
+                }
+              }
+              umma_commit(&w_empty[st]);
+            }
+            // input row (2*it + dy) is not read again by this item: rows 2it, 2it+1 are dead after dy = 0, 1;
+            // on the item's last iteration the two look-ahead rows die after dy = 2.
+            if (dy < 2) {
+              umma_commit(&row_empty[(n_base + 2 * it + dy) & 3]);
+            } else if (it == iters - 1) {
+              umma_commit(&row_empty[(n_base + 2 * it + 2) & 3]);
+              umma_commit(&row_empty[(n_base + 2 * it + 3) & 3]);
+            }
+          }
+          umma_commit(acc_full);
+        }
+        n_base += 2 * iters + 2;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue warps ==============================================================================================
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;               // channels [32*half, 32*half + 32)
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t gi = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int b, x0, y_begin, iters;
+      item_coords(item, b, x0, y_begin, iters);
+      const int x = x0 + q * 32 + lane;
+      const int Ho = p.pool ? p.H >> 1 : p.H, Wo = p.pool ? p.W >> 1 : p.W;
+      for (int it = 0; it < iters; ++it, ++gi) {
+        const int y = y_begin + 2 * it;
+        mbar_wait(acc_full, gi & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 32; c += 16) {
+          const int ch = half * 32 + c;
+          float v[2][16];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            uint32_t a0[16], a1[16], a2[16], xl[16];
+            const uint32_t base = tlane + r * 256 + ch;
+            tmem_ld16(base, a0);
+            tmem_ld16(base + 64, a1);
+            tmem_ld16(base + 128, a2);
+            tmem_ld16(base + 192, xl);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float t = ((__uint_as_float(a0[j]) + __uint_as_float(a1[j])) + __uint_as_float(a2[j])) +
+                              __uint_as_float(xl[j]) * RFE_SPLIT_INV + __ldg(p.bias + ch + j);
+              v[r][j] = fmaxf(t, 0.0f);
+            }
+          }
+          if (p.pool) {
+            __align__(16) __half hi[16];
+            __align__(16) __half lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float t = fmaxf(v[0][j], v[1][j]);
+              t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
+              split_f32(t, hi[j], lo[j]);
+            }
+            if ((lane & 1) == 0 && x < p.W) {
+              const size_t o = ((static_cast<size_t>(b) * Ho + (y >> 1)) * Wo + (x >> 1)) * 64 + ch;
+              reinterpret_cast<uint4*>(p.out_hi + o)[0] = reinterpret_cast<const uint4*>(hi)[0];
+              reinterpret_cast<uint4*>(p.out_hi + o)[1] = reinterpret_cast<const uint4*>(hi)[1];
+              reinterpret_cast<uint4*>(p.out_lo + o)[0] = reinterpret_cast<const uint4*>(lo)[0];
+              reinterpret_cast<uint4*>(p.out_lo + o)[1] = reinterpret_cast<const uint4*>(lo)[1];
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              __align__(16) __half hi[16];
+              __align__(16) __half lo[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) split_f32(v[r][j], hi[j], lo[j]);
+              if (x < p.W) {
+                const size_t o = ((static_cast<size_t>(b) * Ho + (y + r)) * Wo + x) * 64 + ch;
+                reinterpret_cast<uint4*>(p.out_hi + o)[0] = reinterpret_cast<const uint4*>(hi)[0];
+                reinterpret_cast<uint4*>(p.out_hi + o)[1] = reinterpret_cast<const uint4*>(hi)[1];
+                reinterpret_cast<uint4*>(p.out_lo + o)[0] = reinterpret_cast<const uint4*>(lo)[0];
+                reinterpret_cast<uint4*>(p.out_lo + o)[1] = reinterpret_cast<const uint4*>(lo)[1];
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+      }
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace rfe

@@ -11,6 +11,7 @@
 #include "kernels.h"
 #include "tensormap.h"
 #include "attn_kernel.cuh"
+#include "conv_strip.cuh"
 #include "umma_kernel.cuh"
 #include "weights.h"
 
@@ -97,6 +98,7 @@ struct rfe_ctx {
 
   // optional per-kernel CUDA-event profiling (rfe_profile)
   struct ProfRec { std::string tag; cudaEvent_t a, b; };
+  bool use_strip_conv = true;   // RFE_CONV_STRIP=0 falls back to the 9-box implicit GEMM for the 64->64 layers
   bool profiling = false;
   std::vector<ProfRec> prof;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pool;
@@ -342,6 +344,43 @@ int conv3x3(rfe_ctx* c, const char* tag, const SplitBuf& in, int B, int H, int W
   return launch_umma<128, A_CONV3, EPI_CONV>(c, tag, ah, al, bh, bl, p, grid);
 }
 
+// 3x3 conv 64 -> 64 (+ReLU, + optional 2x2 max-pool) with the strip kernel (conv_strip.cuh).
+int conv64_strip(rfe_ctx* c, const char* tag, const SplitBuf& in, int B, int H, int W, const SplitW& w, const SplitBuf& out,
+                 bool pool) {
+  static bool configured[64] = {};
+  if (!configured[c->device & 63]) {
+    RFE_CUDA_CHECK(cudaFuncSetAttribute(conv64_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStripSmemBytes));
+    configured[c->device & 63] = true;
+  }
+  const uint64_t dims[4] = {64, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+  const uint64_t strides[3] = {128, static_cast<uint64_t>(W) * 128, static_cast<uint64_t>(H) * W * 128};
+  const uint32_t box[4] = {64, 130, 1, 1};
+  CUtensorMap ah, al, wh, wl;
+  if (make_tmap_f16_sw128(&ah, in.hi, 4, dims, strides, box)) return RFE_ERR_CUDA;
+  if (make_tmap_f16_sw128(&al, in.lo, 4, dims, strides, box)) return RFE_ERR_CUDA;
+  Operand Wop{w.w.hi, w.w.lo, 64, 576, 576, 0, 1};
+  int r;
+  if ((r = make_operand_maps(Wop, 64, &wh, &wl))) return r;
+  StripParams p;
+  p.B = B;
+  p.H = H;
+  p.W = W;
+  p.n_strips = (W + 127) / 128;
+  p.seg_rows = 16;
+  p.n_segs = (H + p.seg_rows - 1) / p.seg_rows;
+  p.num_items = B * p.n_strips * p.n_segs;
+  p.pool = pool ? 1 : 0;
+  p.bias = w.bias;
+  p.out_hi = out.hi;
+  p.out_lo = out.lo;
+  const int ctas = p.num_items < c->num_sms ? p.num_items : c->num_sms;
+  ProfScope ps(c, tag);
+  conv64_strip_kernel<<<ctas, kStripThreads, kStripSmemBytes, c->stream>>>(ah, al, wh, wl, p);
+  c->launches++;
+  RFE_CUDA_CHECK(cudaGetLastError());
+  return RFE_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // SuperPoint: device in -> device-resident features
 // ------------------------------------------------------------------------------------------------
@@ -350,9 +389,15 @@ int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B) {
   int r;
   launch_conv1a(s, d_gray, stride, h, w, B, c->conv1a_w, c->conv1a_b, c->a1a.hi, c->a1a.lo);
   c->launches++;
-  if ((r = conv3x3(c, "sp.conv1b", c->a1a, B, h, w, 64, c->c1b, c->a1, true))) return r;
-  if ((r = conv3x3(c, "sp.conv2a", c->a1, B, h / 2, w / 2, 64, c->c2a, c->a2a, false))) return r;
-  if ((r = conv3x3(c, "sp.conv2b", c->a2a, B, h / 2, w / 2, 64, c->c2b, c->a2, true))) return r;
+  if (c->use_strip_conv) {
+    if ((r = conv64_strip(c, "sp.conv1b", c->a1a, B, h, w, c->c1b, c->a1, true))) return r;
+    if ((r = conv64_strip(c, "sp.conv2a", c->a1, B, h / 2, w / 2, c->c2a, c->a2a, false))) return r;
+    if ((r = conv64_strip(c, "sp.conv2b", c->a2a, B, h / 2, w / 2, c->c2b, c->a2, true))) return r;
+  } else {
+    if ((r = conv3x3(c, "sp.conv1b", c->a1a, B, h, w, 64, c->c1b, c->a1, true))) return r;
+    if ((r = conv3x3(c, "sp.conv2a", c->a1, B, h / 2, w / 2, 64, c->c2a, c->a2a, false))) return r;
+    if ((r = conv3x3(c, "sp.conv2b", c->a2a, B, h / 2, w / 2, 64, c->c2b, c->a2, true))) return r;
+  }
   if ((r = conv3x3(c, "sp.conv3a", c->a2, B, h / 4, w / 4, 64, c->c3a, c->a3a, false))) return r;
   if ((r = conv3x3(c, "sp.conv3b", c->a3a, B, h / 4, w / 4, 128, c->c3b, c->a3, true))) return r;
   const int hc = h / 8, wc = w / 8;
@@ -716,6 +761,7 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   }
   RFE_CUDA_CHECK(cudaEventCreate(&c->ev0));
   RFE_CUDA_CHECK(cudaEventCreate(&c->ev1));
+  if (getenv("RFE_CONV_STRIP")) c->use_strip_conv = atoi(getenv("RFE_CONV_STRIP")) != 0;
   const char* path = cfg->weights_path;
   if (!path) path = getenv("ROVER_FE_WEIGHTS");
   if (!path) path = "weights/rover_fe.rfw";

@@ -67,10 +67,13 @@ constexpr int kUmmaThreads = 192;
 
 __host__ __device__ constexpr int umma_stage_bytes(int block_n) { return 2 * kStageABytes + 2 * block_n * 128; }
 __host__ __device__ constexpr int umma_num_stages(int block_n) {
-  return (200 * 1024 / umma_stage_bytes(block_n)) > 6 ? 6 : (200 * 1024 / umma_stage_bytes(block_n));
+  return (192 * 1024 / umma_stage_bytes(block_n)) > 6 ? 6 : (192 * 1024 / umma_stage_bytes(block_n));
 }
+constexpr int kEpiStageWarpBytes = 8192;     // per epilogue warp: 32 rows x 256 B (fp32 x 64) or 2 planes x 32 rows x 128 B
+__host__ __device__ constexpr int umma_num_stages(int block_n);
 __host__ __device__ constexpr int umma_smem_bytes(int block_n) {
-  return umma_num_stages(block_n) * umma_stage_bytes(block_n) + 1024 /*align slack*/ + 256 /*barriers*/;
+  return umma_num_stages(block_n) * umma_stage_bytes(block_n) + 4 * kEpiStageWarpBytes + 1024 /*align slack*/ +
+         256 /*barriers*/;
 }
 // Number of hi*hi accumulators.  The tensor core adds each K=16 partial sum into the fp32 accumulator with
 // truncation, so the error grows linearly with the number of accumulation steps (measured: 1.1e-4 abs at K=512 on
@@ -106,7 +109,8 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;      // 4 x kEpiStageWarpBytes
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + 4 * kEpiStageWarpBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;       // [NBUF]
   uint64_t* tmem_empty_bar = tmem_full_bar + NBUF;    // [NBUF]
@@ -288,39 +292,104 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       }
     };
 
-    if constexpr (EPI == EPI_CONV) {
-      const int ry = row >> 4, rx = row & 15;
-      const int y = y0 + ry, x = x0 + rx;
-      const bool valid = (y < p.H) && (x < p.W);
-      const int Ho = p.pool ? p.H >> 1 : p.H, Wo = p.pool ? p.W >> 1 : p.W;
-      const int yo = p.pool ? y >> 1 : y, xo = p.pool ? x >> 1 : x;
-      const bool writer = valid && (!p.pool || (((rx | ry) & 1) == 0));
-      const size_t pix = (static_cast<size_t>(img) * Ho + yo) * Wo + xo;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 16) {
-        float v[16];
-        load16(c, v);
-        __align__(16) __half hi[16];
-        __align__(16) __half lo[16];
+    // ---- coalescing helpers: a thread owns one row of the tile, but a warp-wide store of "my row" touches 32 rows.
+    // Values are therefore transposed through a per-warp staging buffer (XOR-swizzled 16-byte chunks, conflict
+    // free) and written back row-contiguously: 2 rows x 256 B (fp32) or 4 rows x 128 B (fp16 plane) per instruction.
+    uint8_t* wst = epi_stage + q * kEpiStageWarpBytes;
+    auto load64 = [&](int col, float (&v)[64]) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float t = v[j] + __ldg(p.bias + n0 + c + j);
-          t = fmaxf(t, 0.0f);
-          if (p.pool) {
-            t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
-            t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 16));
+      for (int i = 0; i < 4; ++i) {
+        float t[16];
+        load16(col + 16 * i, t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[16 * i + j] = t[j];
+      }
+    };
+    // stage 64 fp32 of my row (256-byte rows)
+    auto stage_f32 = [&](const float (&v)[64]) {
+#pragma unroll
+      for (int ch = 0; ch < 16; ++ch)
+        *reinterpret_cast<float4*>(wst + lane * 256 + ((ch ^ (lane & 7)) << 4)) =
+            make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+    };
+    // staged fp32 chunk (r = 2*i + lane/16, ch = lane%16)
+    auto staged_f32 = [&](int i, int& r, int& ch) {
+      r = 2 * i + (lane >> 4);
+      ch = lane & 15;
+      return *reinterpret_cast<const float4*>(wst + r * 256 + ((ch ^ (r & 7)) << 4));
+    };
+    // stage 64 split-fp16 values of my row: hi plane at wst, lo plane at wst + 4096 (128-byte rows)
+    auto stage_split = [&](const float (&v)[64]) {
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        __align__(16) __half hh[8];
+        __align__(16) __half ll[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split_f32(v[8 * ch + j], hh[j], ll[j]);
+        const int off = lane * 128 + ((ch ^ (lane & 7)) << 4);
+        *reinterpret_cast<uint4*>(wst + off) = *reinterpret_cast<const uint4*>(hh);
+        *reinterpret_cast<uint4*>(wst + 4096 + off) = *reinterpret_cast<const uint4*>(ll);
+      }
+    };
+    // staged fp16 chunks of row r = 4*i + lane/8, chunk ch = lane%8 (8 halves)
+    auto staged_split = [&](int i, int& r, int& ch, uint4& h, uint4& l) {
+      r = 4 * i + (lane >> 3);
+      ch = lane & 7;
+      const int off = r * 128 + ((ch ^ (r & 7)) << 4);
+      h = *reinterpret_cast<const uint4*>(wst + off);
+      l = *reinterpret_cast<const uint4*>(wst + 4096 + off);
+    };
+
+    if constexpr (EPI == EPI_CONV) {
+      // lane <-> pixel (ry = 2q + lane/16, rx = lane%16) of the 16x8 tile; channels in groups of 64
+      const int Ho = p.pool ? p.H >> 1 : p.H, Wo = p.pool ? p.W >> 1 : p.W;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 64) {
+        float v[64];
+        load64(c, v);
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + j));
+          v[j] = fmaxf(v[j] + b4.x, 0.0f);
+          v[j + 1] = fmaxf(v[j + 1] + b4.y, 0.0f);
+          v[j + 2] = fmaxf(v[j + 2] + b4.z, 0.0f);
+          v[j + 3] = fmaxf(v[j + 3] + b4.w, 0.0f);
+        }
+        if (p.pool) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            float t = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+            v[j] = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 16));
           }
-          split_f32(t, hi[j], lo[j]);
         }
-        if (writer) {
-          const size_t o = pix * p.N + n0 + c;
-          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
-          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
-          dh[0] = reinterpret_cast<const uint4*>(hi)[0];
-          dh[1] = reinterpret_cast<const uint4*>(hi)[1];
-          dl[0] = reinterpret_cast<const uint4*>(lo)[0];
-          dl[1] = reinterpret_cast<const uint4*>(lo)[1];
+        stage_split(v);
+        __syncwarp();
+        // staged row r is the tile pixel (ry = 2q + r/16, rx = r%16); with pooling only rows r = 0,2,..,14 hold outputs
+        const int nrows_i = p.pool ? 2 : 8;           // instructions: 4 staged rows each
+#pragma unroll 1
+        for (int i = 0; i < nrows_i; ++i) {
+          int r, ch;
+          uint4 h, l;
+          if (p.pool) {
+            const int w = 4 * i + (lane >> 3);         // pooled pixel index 0..7 inside the warp's tile rows
+            ch = lane & 7;
+            r = 2 * w;                                 // staged row of the 2x2 block's top-left pixel
+            const int off = r * 128 + ((ch ^ (r & 7)) << 4);
+            h = *reinterpret_cast<const uint4*>(wst + off);
+            l = *reinterpret_cast<const uint4*>(wst + 4096 + off);
+          } else {
+            staged_split(i, r, ch, h, l);
+          }
+          const int ry = 2 * q + (r >> 4), rx = r & 15;
+          const int y = y0 + ry, x = x0 + rx;
+          if (y < p.H && x < p.W) {
+            const int yo = p.pool ? y >> 1 : y, xo = p.pool ? x >> 1 : x;
+            const size_t o = ((static_cast<size_t>(img) * Ho + yo) * Wo + xo) * p.N + n0 + c + ch * 8;
+            *reinterpret_cast<uint4*>(p.out_hi + o) = h;
+            *reinterpret_cast<uint4*>(p.out_lo + o) = l;
+          }
         }
+        __syncwarp();
       }
     } else if constexpr (EPI == EPI_DET) {
       // row = coarse pixel; 65 logits -> softmax -> first 64 -> 8x8 block of the heat-map
@@ -363,8 +432,6 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
         }
       }
     } else if constexpr (EPI == EPI_DESC) {
-      const int m = m0 + row;
-      const bool valid = m < p.M;
       float ss = 0.0f;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 16) {
@@ -378,65 +445,81 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       }
       const float nrm = fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 16) {
-        float v[16];
-        load16(c, v);
-        if (valid) {
-          float4* d = reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(m) * p.ld_f32 + n0 + c);
+      for (int c = 0; c < BLOCK_N; c += 64) {
+        float v[64];
+        load64(c, v);
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            d[j >> 2] = make_float4((v[j] + __ldg(p.bias + n0 + c + j)) / nrm,
-                                    (v[j + 1] + __ldg(p.bias + n0 + c + j + 1)) / nrm,
-                                    (v[j + 2] + __ldg(p.bias + n0 + c + j + 2)) / nrm,
-                                    (v[j + 3] + __ldg(p.bias + n0 + c + j + 3)) / nrm);
-          }
+        for (int j = 0; j < 64; ++j) v[j] = (v[j] + __ldg(p.bias + n0 + c + j)) / nrm;
+        stage_f32(v);
+        __syncwarp();
+#pragma unroll 1
+        for (int i = 0; i < 16; ++i) {
+          int r, ch;
+          const float4 t = staged_f32(i, r, ch);
+          const int mr = m0 + q * 32 + r;
+          if (mr < p.M) *reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(mr) * p.ld_f32 + n0 + c + ch * 4) = t;
         }
+        __syncwarp();
       }
     } else if constexpr (EPI == EPI_QKV) {
-      // columns: [q (256) | k (256) | v (256)], each head-major h*64+d (weights were permuted at load time)
+      // columns: [q (256) | k (256) | v (256)], each head-major h*64+d (weights were permuted at load time);
+      // a 64-column group is exactly one head of one of q / k / v
       const int m = m0 + row;
       const bool valid = m < p.M;
       const int part = n0 >> 8;                         // 0 q, 1 k, 2 v   (BLOCK_N = 128 divides 256)
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 16) {
-        float v[16];
-        load16(c, v);
-        if (!valid) continue;
+      for (int c = 0; c < BLOCK_N; c += 64) {
+        float v[64];
+        load64(c, v);
         const int nb = n0 + c;
+        const int head = (nb & 255) >> 6;
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
+        for (int j = 0; j < 64; j += 4) {
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
           v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
         }
-        const int col = nb & 255;                       // h*64 + d
-        __align__(16) __half hh[16];
-        __align__(16) __half ll[16];
         if (part < 2) {
-          const int f0 = (col & 63) >> 1;               // first of the 8 frequencies this chunk covers
-          const float4* c4 = reinterpret_cast<const float4*>(p.cs + static_cast<size_t>(m) * 32 + f0);
-          const float4* s4 = reinterpret_cast<const float4*>(p.sn + static_cast<size_t>(m) * 32 + f0);
-          const float4 ca = __ldg(c4), cb = __ldg(c4 + 1), sa = __ldg(s4), sb = __ldg(s4 + 1);
-          const float cc[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-          const float ss[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+          if (valid) {
+            const float4* c4 = reinterpret_cast<const float4*>(p.cs + static_cast<size_t>(m) * 32);
+            const float4* s4 = reinterpret_cast<const float4*>(p.sn + static_cast<size_t>(m) * 32);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float a = v[2 * i], b = v[2 * i + 1];
-            split_f32((a * cc[i] + (-b) * ss[i]) * p.scale, hh[2 * i], ll[2 * i]);
-            split_f32((b * cc[i] + a * ss[i]) * p.scale, hh[2 * i + 1], ll[2 * i + 1]);
+            for (int g = 0; g < 8; ++g) {
+              const float4 cc = __ldg(c4 + g), sn = __ldg(s4 + g);
+              const float cv[4] = {cc.x, cc.y, cc.z, cc.w}, sv[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int f = 4 * g + i;
+                const float a = v[2 * f], b = v[2 * f + 1];
+                v[2 * f] = (a * cv[i] + (-b) * sv[i]) * p.scale;
+                v[2 * f + 1] = (b * cv[i] + a * sv[i]) * p.scale;
+              }
+            }
           }
+          stage_split(v);
+          __syncwarp();
           __half* dh = part == 0 ? p.out_hi : p.k_hi;
           __half* dl = part == 0 ? p.out_lo : p.k_lo;
-          const size_t o = static_cast<size_t>(col >> 6) * p.head_stride + static_cast<size_t>(m) * 64 + (col & 63);
-          reinterpret_cast<uint4*>(dh + o)[0] = reinterpret_cast<const uint4*>(hh)[0];
-          reinterpret_cast<uint4*>(dh + o)[1] = reinterpret_cast<const uint4*>(hh)[1];
-          reinterpret_cast<uint4*>(dl + o)[0] = reinterpret_cast<const uint4*>(ll)[0];
-          reinterpret_cast<uint4*>(dl + o)[1] = reinterpret_cast<const uint4*>(ll)[1];
-        } else {
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i) {
+            int r, ch;
+            uint4 h, l;
+            staged_split(i, r, ch, h, l);
+            const int mr = m0 + q * 32 + r;
+            if (mr < p.M) {
+              const size_t o = static_cast<size_t>(head) * p.head_stride + static_cast<size_t>(mr) * 64 + ch * 8;
+              *reinterpret_cast<uint4*>(dh + o) = h;
+              *reinterpret_cast<uint4*>(dl + o) = l;
+            }
+          }
+          __syncwarp();
+        } else if (valid) {
+          // V^T [256][ldv]: lanes are consecutive rows m -> each store instruction writes 64 contiguous bytes
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            split_f32(v[j], hh[j], ll[j]);
-            p.vt_hi[static_cast<size_t>(col + j) * p.ldv + m] = hh[j];
-            p.vt_lo[static_cast<size_t>(col + j) * p.ldv + m] = ll[j];
+          for (int j = 0; j < 64; ++j) {
+            __half h, l;
+            split_f32(v[j], h, l);
+            p.vt_hi[static_cast<size_t>((nb & 255) + j) * p.ldv + m] = h;
+            p.vt_lo[static_cast<size_t>((nb & 255) + j) * p.ldv + m] = l;
           }
         }
       }
@@ -449,67 +532,94 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       __half* ol = p.out_lo ? p.out_lo + z * p.bstride_h : nullptr;
       const float* res = p.residual ? p.residual + z * p.bstride_res : nullptr;
       const bool vec_ok = ((p.ld_f32 & 3) == 0) && ((p.ld_h & 7) == 0) && ((p.ld_res & 3) == 0);
+      constexpr int GROUP = BLOCK_N >= 64 ? 64 : BLOCK_N;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 16) {
-        float v[16];
-        load16(c, v);
-        if (!valid) continue;
+      for (int c = 0; c < BLOCK_N; c += GROUP) {
         const int nb = n0 + c;
-        if (nb >= p.N) continue;
-        if (nb + 16 <= p.N && vec_ok) {
-          // ---- full 16-column chunk: vectorised path ----
+        if (nb >= p.N) break;                                   // warp-uniform
+        float v[64];
+        load64(c, v);
+        if (nb + 64 <= p.N && vec_ok) {
+          // ---- full 64-column group: coalesced path through the staging buffer ----
           if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
+            for (int j = 0; j < 64; j += 4) {
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
               v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
             }
           }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] *= p.scale;
-          if (res) {
-            const float4* r4 = reinterpret_cast<const float4*>(res + static_cast<size_t>(m) * p.ld_res + nb);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 t4 = r4[j];
-              v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+          for (int j = 0; j < 64; ++j) v[j] *= p.scale;
+          if (res) {   // residual tile: coalesced global loads -> staging -> my row
+#pragma unroll 1
+            for (int i = 0; i < 16; ++i) {
+              const int r = 2 * i + (lane >> 4), ch = lane & 15;
+              const int mr = m0 + q * 32 + r;
+              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (mr < p.M) t = *reinterpret_cast<const float4*>(res + static_cast<size_t>(mr) * p.ld_res + nb + ch * 4);
+              *reinterpret_cast<float4*>(wst + r * 256 + ((ch ^ (r & 7)) << 4)) = t;
             }
+            __syncwarp();
+#pragma unroll
+            for (int ch = 0; ch < 16; ++ch) {
+              const float4 t = *reinterpret_cast<const float4*>(wst + lane * 256 + ((ch ^ (lane & 7)) << 4));
+              v[4 * ch] += t.x; v[4 * ch + 1] += t.y; v[4 * ch + 2] += t.z; v[4 * ch + 3] += t.w;
+            }
+            __syncwarp();
           }
           if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+            for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.0f);
           }
           if (of) {
-            float4* o4 = reinterpret_cast<float4*>(of + static_cast<size_t>(m) * p.ld_f32 + nb);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            stage_f32(v);
+            __syncwarp();
+#pragma unroll 1
+            for (int i = 0; i < 16; ++i) {
+              int r, ch;
+              const float4 t = staged_f32(i, r, ch);
+              const int mr = m0 + q * 32 + r;
+              if (mr < p.M) *reinterpret_cast<float4*>(of + static_cast<size_t>(mr) * p.ld_f32 + nb + ch * 4) = t;
+            }
+            __syncwarp();
           }
           if (oh) {
-            __align__(16) __half hh[16];
-            __align__(16) __half ll[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) split_f32(v[j], hh[j], ll[j]);
             if (p.transpose_h) {
+              if (valid) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                oh[static_cast<size_t>(nb + j) * p.ld_h + m] = hh[j];
-                ol[static_cast<size_t>(nb + j) * p.ld_h + m] = ll[j];
+                for (int j = 0; j < 64; ++j) {
+                  __half h, l;
+                  split_f32(v[j], h, l);
+                  oh[static_cast<size_t>(nb + j) * p.ld_h + m] = h;
+                  ol[static_cast<size_t>(nb + j) * p.ld_h + m] = l;
+                }
               }
             } else {
-              const size_t o = p.head_major ? static_cast<size_t>(nb >> 6) * p.head_stride + static_cast<size_t>(m) * 64 + (nb & 63)
-                                            : static_cast<size_t>(m) * p.ld_h + nb;
-              reinterpret_cast<uint4*>(oh + o)[0] = reinterpret_cast<const uint4*>(hh)[0];
-              reinterpret_cast<uint4*>(oh + o)[1] = reinterpret_cast<const uint4*>(hh)[1];
-              reinterpret_cast<uint4*>(ol + o)[0] = reinterpret_cast<const uint4*>(ll)[0];
-              reinterpret_cast<uint4*>(ol + o)[1] = reinterpret_cast<const uint4*>(ll)[1];
+              stage_split(v);
+              __syncwarp();
+#pragma unroll 1
+              for (int i = 0; i < 8; ++i) {
+                int r, ch;
+                uint4 h, l;
+                staged_split(i, r, ch, h, l);
+                const int mr = m0 + q * 32 + r;
+                if (mr < p.M) {
+                  const size_t o = p.head_major ? static_cast<size_t>(nb >> 6) * p.head_stride + static_cast<size_t>(mr) * 64 + ch * 8
+                                                : static_cast<size_t>(mr) * p.ld_h + nb + ch * 8;
+                  *reinterpret_cast<uint4*>(oh + o) = h;
+                  *reinterpret_cast<uint4*>(ol + o) = l;
+                }
+              }
+              __syncwarp();
             }
           }
           continue;
         }
-        // ---- ragged tail: scalar path ----
+        // ---- ragged tail / unaligned pitches: scalar path ----
+        if (!valid) continue;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = n0 + c + j;
+        for (int j = 0; j < 64; ++j) {
+          const int n = nb + j;
           if (n < p.N) {
             float t = v[j];
             if (p.bias) t += __ldg(p.bias + n);
