@@ -33,6 +33,7 @@ struct AttnParams {
   int q_row0[kAttnMaxProblems], k_row0[kAttnMaxProblems];  // row offsets inside the head-major Q / K tensors and the V^T columns
   __half* out_hi;            // split-fp16 [rows][256]
   __half* out_lo;
+  unsigned long long* prof;  // optional [16] cycle counters written by CTA (0,0,0): where the MMA / softmax roles wait
 };
 
 constexpr int kAttnSoftmaxWarps = 16;                             // 4 per TMEM lane quarter: 16 of a tile's 64 columns each
@@ -150,11 +151,19 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       constexpr uint32_t idesc128 = make_idesc_f16(128, 128);
       const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + 16384;
       const uint32_t o_base = tmem_base + 384;
+      const bool prof = p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      long long w_k = 0, w_se = 0, w_v = 0, w_p = 0;
+      const long long t_begin = clock64();
       mbar_wait(q_full, 0);
+      const long long t_q = clock64();
       auto issue_s = [&](int g, bool full) {
         const int st = g % kAttnKStages, b = g % kAttnSBufs;
+        long long c0 = clock64();
         mbar_wait(&k_full[st], (g / kAttnKStages) & 1);
+        long long c1 = clock64();
         mbar_wait(&s_empty[b], ((g / kAttnSBufs) & 1) ^ 1);
+        w_k += c1 - c0;
+        w_se += clock64() - c1;
         tc_fence_after();
         const uint32_t k_hi = smem_u32(sK + st * kAttnKVBytes);   // K_lo follows at +8192: [K_hi;K_lo] is one N=128 operand
         const uint32_t s_base = tmem_base + b * 128;
@@ -174,8 +183,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       };
       auto issue_pv = [&](int t) {          // consumes P buffer t&1 and V stage t%3
         const int st = t % kAttnVStages, pb = t & 1;
+        long long c0 = clock64();
         mbar_wait(&v_full[st], (t / kAttnVStages) & 1);
+        long long c1 = clock64();
         mbar_wait(&p_full[pb], (t >> 1) & 1);
+        w_v += c1 - c0;
+        w_p += clock64() - c1;
         tc_fence_after();
         const uint32_t p_hi = smem_u32(sP + pb * kAttnPBytes), p_lo = p_hi + 16384;
         const uint32_t v_hi = smem_u32(sV + st * kAttnKVBytes);       // V_lo follows at +8192
@@ -190,6 +203,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       };
       // pass 1: hi*hi scores only
       for (int g = 0; g < T; ++g) issue_s(g, false);
+      const long long t_p1 = clock64();
       // pass 2: the score MMAs run two tiles ahead of the P V MMAs
       issue_s(T, true);
       if (T > 1) issue_s(T + 1, true);
@@ -198,6 +212,17 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
         issue_pv(t);
       }
       umma_commit(o_full);
+      if (prof) {
+        const long long t_end = clock64();
+        p.prof[0] = t_q - t_begin;      // wait for Q
+        p.prof[1] = t_p1 - t_q;         // pass 1 issue time
+        p.prof[2] = t_end - t_p1;       // pass 2 issue time
+        p.prof[3] = w_k;                // waiting for K tiles
+        p.prof[4] = w_se;               // waiting for a free score buffer
+        p.prof[5] = w_v;                // waiting for V tiles
+        p.prof[6] = w_p;                // waiting for P (softmax)
+        p.prof[7] = T;
+      }
     }
   } else if (warp >= 4) {
     // ===== softmax / epilogue warps =========================================================================

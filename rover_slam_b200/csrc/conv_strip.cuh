@@ -15,8 +15,13 @@
 //
 // CTA = 384 threads: warp 0 = TMA producer for input rows, warp 1 = MMA issuer (+TMEM alloc), warp 2 = TMA producer
 // for the per-tap weight tiles, warps 4..11 = epilogue (two warps per TMEM lane quarter, 32 channels each).
-// TMEM (512 columns): output row r in {0,1}: hi*hi accumulators per kernel row dy at r*256 + dy*64, the lo
-// accumulator at r*256 + 192 (per-kernel-row accumulators: see umma_kernel.cuh on accumulation truncation).
+// Tensor-core cost model (probe 1 in probe_kernels.cu): an SS-mode MMA costs max(~60, N/2) cycles, so N = 64 wastes
+// half the pipe.  Each k16 step therefore issues  A_hi x [W_hi;W_lo]^T  as ONE N=128 MMA (hi*hi and hi*lo products
+// land in adjacent accumulators) plus  A_lo x W_hi^T  (N=64): 2 instructions instead of 3.
+// TMEM (384 of 512 columns): output row r in {0,1} at r*192: [hh_a | hl | hh_b].  Kernel rows dy = 0,2 accumulate
+// hi*hi into hh_a with the weights staged as [hi;lo] (MMA at column 0), dy = 1 into hh_b with the weights staged as
+// [lo;hi] (MMA at column 64), so both share the one lo accumulator hl; two hi*hi accumulators halve the number of
+// truncating accumulation steps per accumulator (see umma_kernel.cuh on accumulation truncation).
 // Epilogue: bias + ReLU (+ 2x2 max-pool: vertical partner = the same thread's other row, horizontal = lane ^ 1)
 // -> split-fp16 NHWC.
 #pragma once
@@ -40,7 +45,7 @@ constexpr int kStripThreads = 384;
 constexpr int kStripRowBytes = 130 * 128;        // one plane of one input row of the strip (with 1-px halo each side)
 constexpr int kStripSlotBytes = 17 * 1024;       // slot pitch (1024-aligned for the swizzle)
 constexpr int kStripRowSlots = 4;
-constexpr int kStripWStages = 4;
+constexpr int kStripWStages = 4;                 // per tap: [W_hi | W_lo] (dy = 0,2) or [W_lo | W_hi] (dy = 1)
 constexpr int kStripWStageBytes = 2 * 8192;      // W_hi | W_lo of one tap: 64 couts x 128 B each
 constexpr int kStripSmemBytes =
     2 * kStripRowSlots * kStripSlotBytes + kStripWStages * kStripWStageBytes + 1024 /*align*/ + 256 /*barriers*/;
@@ -125,15 +130,17 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             const int st = m & 3;
             mbar_wait(&w_empty[st], ((m >> 2) & 1) ^ 1);
             mbar_expect_tx(&w_full[st], kStripWStageBytes);
-            tma_load_3d(sW + st * kStripWStageBytes, &tmW_hi, &w_full[st], tap * 64, 0, 0);
-            tma_load_3d(sW + st * kStripWStageBytes + 8192, &tmW_lo, &w_full[st], tap * 64, 0, 0);
+            const bool swapped = (tap / 3) == 1;        // kernel row 1: [lo;hi]
+            tma_load_3d(sW + st * kStripWStageBytes + (swapped ? 8192 : 0), &tmW_hi, &w_full[st], tap * 64, 0, 0);
+            tma_load_3d(sW + st * kStripWStageBytes + (swapped ? 0 : 8192), &tmW_lo, &w_full[st], tap * 64, 0, 0);
           }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer ==================================================================================================
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_f16(128, 64);
+      constexpr uint32_t idesc64 = make_idesc_f16(128, 64);
+      constexpr uint32_t idesc128 = make_idesc_f16(128, 128);
       uint32_t n_base = 0;     // row sequence number of the current item's first input row
       uint32_t m = 0;          // tap sequence number
       uint32_t gi = 0;         // iteration counter (accumulator hand-over phase)
@@ -147,7 +154,8 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             for (int dx = 0; dx < 3; ++dx, ++m) {
               const int st = m & 3;
               mbar_wait(&w_full[st], (m >> 2) & 1);
-              const uint32_t w_hi = smem_u32(sW + st * kStripWStageBytes), w_lo = w_hi + 8192;
+              const uint32_t w_cat = smem_u32(sW + st * kStripWStageBytes);          // [hi;lo] (dy 0,2) or [lo;hi] (dy 1)
+              const uint32_t w_hi = w_cat + (dy == 1 ? 8192 : 0);
 #pragma unroll
               for (int r = 0; r < 2; ++r) {
                 const uint32_t seq = n_base + 2 * it + r + dy;           // input row feeding output row r through kernel row dy
@@ -156,17 +164,23 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 tc_fence_after();
                 const uint32_t a_hi = smem_u32(sRowHi + slot * kStripSlotBytes) + dx * 128;
                 const uint32_t a_lo = smem_u32(sRowLo + slot * kStripSlotBytes) + dx * 128;
-                const uint32_t acc0 = tmem_base + r * 256 + dy * 64;
-                const uint32_t acc1 = tmem_base + r * 256 + 192;
+                const uint32_t row_base = tmem_base + r * 192;
+                const uint32_t d_cat = row_base + (dy == 1 ? 64 : 0);    // [hh_a | hl] or [hl | hh_b]
+                const uint32_t d_hl = row_base + 64;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   const uint64_t da_hi = make_sw128_kmajor_desc(a_hi + k * 32);
                   const uint64_t da_lo = make_sw128_kmajor_desc(a_lo + k * 32);
+                  const uint64_t db_cat = make_sw128_kmajor_desc(w_cat + k * 32);
                   const uint64_t db_hi = make_sw128_kmajor_desc(w_hi + k * 32);
-                  const uint64_t db_lo = make_sw128_kmajor_desc(w_lo + k * 32);
-                  umma_f16(acc0, da_hi, db_hi, idesc, (dx > 0 || k > 0) ? 1u : 0u);
-                  umma_f16(acc1, da_hi, db_lo, idesc, (dy > 0 || dx > 0 || k > 0) ? 1u : 0u);
-                  umma_f16(acc1, da_lo, db_hi, idesc, 1u);
+                  if (dy == 1 && dx == 0 && k == 0) {
+                    // first touch of hh_b while hl already holds dy = 0: two N=64 MMAs with different accumulate flags
+                    umma_f16(row_base + 128, da_hi, db_hi, idesc64, 0u);                                  // hh_b  = A_hi W_hi
+                    umma_f16(d_hl, da_hi, make_sw128_kmajor_desc(w_cat + k * 32), idesc64, 1u);          // hl   += A_hi W_lo
+                  } else {
+                    umma_f16(d_cat, da_hi, db_cat, idesc128, (dy == 0 && dx == 0 && k == 0) ? 0u : 1u);
+                  }
+                  umma_f16(d_hl, da_lo, db_hi, idesc64, 1u);                                               // hl   += A_lo W_hi
                 }
               }
               umma_commit(&w_empty[st]);
@@ -206,17 +220,16 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           float v[2][16];
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
-            uint32_t a0[16], a1[16], a2[16], xl[16];
-            const uint32_t base = tlane + r * 256 + ch;
-            tmem_ld16(base, a0);
-            tmem_ld16(base + 64, a1);
-            tmem_ld16(base + 128, a2);
-            tmem_ld16(base + 192, xl);
+            uint32_t a0[16], a1[16], xl[16];
+            const uint32_t base = tlane + r * 192 + ch;
+            tmem_ld16(base, a0);            // hh_a
+            tmem_ld16(base + 128, a1);      // hh_b
+            tmem_ld16(base + 64, xl);       // hl
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float t = ((__uint_as_float(a0[j]) + __uint_as_float(a1[j])) + __uint_as_float(a2[j])) +
-                              __uint_as_float(xl[j]) * RFE_SPLIT_INV + __ldg(p.bias + ch + j);
+              const float t = (__uint_as_float(a0[j]) + __uint_as_float(a1[j])) + __uint_as_float(xl[j]) * RFE_SPLIT_INV +
+                              __ldg(p.bias + ch + j);
               v[r][j] = fmaxf(t, 0.0f);
             }
           }

@@ -95,4 +95,80 @@ int launch_probe_shift(cudaStream_t s, const __half* a, const __half* b, float* 
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+
+//  probe 1: tensor-pipe issue cost.  `reps` back-to-back tcgen05.mma (M=128, K=16, kind::f16, both operands in shared
+//           memory, 128-byte swizzle) per N in {64, 128, 256}, timed with clock64 from issue of the first to the
+//           mbarrier completion of the last.  out[i] = cycles per MMA.  Variant b uses a different A tile for every
+//           other MMA.  One CTA, so no bandwidth contention: this is the per-SM floor for SS-mode MMAs.
+__global__ void __launch_bounds__(128, 1) probe_mma_rate_kernel(float* __restrict__ out, int reps) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                 // 2 x 16 KB
+  uint8_t* sB = smem + 32768;         // 32 KB (256 rows)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 65536);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  for (int i = threadIdx.x; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;   // fp16 1.0
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) {
+    tmem_alloc(tptr, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tptr;
+  int phase = 0;
+  int slot = 0;
+  for (int variant = 0; variant < 2; ++variant) {
+    for (int ni = 0; ni < 3; ++ni) {
+      const int n = 64 << ni;
+      const uint32_t idesc = make_idesc_f16(128, n);
+      long long t0 = 0, t1 = 0;
+      if (threadIdx.x == 0) {
+        t0 = clock64();
+        for (int i = 0; i < reps; ++i) {
+          const uint32_t a = smem_u32(sA) + ((variant && (i & 1)) ? 16384 : 0) + (i & 3) * 32;
+          umma_f16(tmem, make_sw128_kmajor_desc(a), make_sw128_kmajor_desc(smem_u32(sB) + (i & 3) * 32), idesc, 1u);
+        }
+        umma_commit(bar);
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      if (threadIdx.x == 0) {
+        t1 = clock64();
+        out[slot] = static_cast<float>(t1 - t0) / reps;
+      }
+      ++slot;
+      __syncthreads();
+    }
+  }
+  // issue-only cost (no completion wait between): N=64, measure issue loop time
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_f16(128, 64);
+    const long long t0 = clock64();
+    for (int i = 0; i < reps; ++i)
+      umma_f16(tmem, make_sw128_kmajor_desc(smem_u32(sA)), make_sw128_kmajor_desc(smem_u32(sB)), idesc, 1u);
+    const long long t1 = clock64();
+    umma_commit(bar);
+    out[slot] = static_cast<float>(t1 - t0) / reps;
+  }
+  mbar_wait(bar, phase);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+int launch_probe_mma_rate(cudaStream_t s, float* out, int reps) {
+  const int smem = 65536 + 64 + 1024;
+  if (cudaFuncSetAttribute(probe_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+  probe_mma_rate_kernel<<<1, 128, smem, s>>>(out, reps);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 }  // namespace rfe

@@ -90,6 +90,7 @@ struct rfe_ctx {
   float *rmax = nullptr, *rlog = nullptr, *cmax = nullptr, *clog = nullptr, *ls = nullptr, *max0 = nullptr;
   int *m0 = nullptr, *m1 = nullptr;
   float* S_dbg = nullptr;
+  unsigned long long* attn_prof = nullptr;   // armed by rfe_debug_read("lg.attn_prof")
   int dbg_n0 = 0, dbg_n1 = 0, dbg_off0 = 0, dbg_off1 = 0;
   // match results: [max_batch] slots
   int* res_matches = nullptr;   // [slots][cap][2]
@@ -338,7 +339,6 @@ int conv3x3(rfe_ctx* c, const char* tag, const SplitBuf& in, int B, int H, int W
   p.out_hi = out.hi;
   p.out_lo = out.lo;
   p.pool = pool ? 1 : 0;
-  p.relu = 1;
   dim3 grid(p.tiles_x * p.tiles_y * B, w.n / block_n, 1);
   if (block_n == 64) return launch_umma<64, A_CONV3, EPI_CONV>(c, tag, ah, al, bh, bl, p, grid);
   return launch_umma<128, A_CONV3, EPI_CONV>(c, tag, ah, al, bh, bl, p, grid);
@@ -505,6 +505,7 @@ int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitB
   AttnParams p = problems;
   p.out_hi = c->attn.hi;
   p.out_lo = c->attn.lo;
+  p.prof = c->attn_prof;
   dim3 grid((max_nq + 127) / 128, 4, nprob);
   ProfScope ps(c, tag);
   attn_kernel<<<grid, kAttnThreads, kAttnSmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
@@ -692,7 +693,10 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
 }
 
 }  // namespace
-namespace rfe { int launch_probe_shift(cudaStream_t s, const __half* a, const __half* b, float* out); }
+namespace rfe {
+int launch_probe_shift(cudaStream_t s, const __half* a, const __half* b, float* out);
+int launch_probe_mma_rate(cudaStream_t s, float* out, int reps);
+}
 namespace {
 
 int check_ctx(rfe_ctx* c) {
@@ -1186,6 +1190,18 @@ int rfe_debug_read(rfe_ctx* c, const char* name, void* dst, size_t capacity, siz
     }
     fb = c->S_dbg;
     n = static_cast<size_t>(c->dbg_n0) * c->dbg_n1;
+  } else if (s == "lg.attn_prof") {   // 16 x u64 cycle counters of the last attention launch (first request arms it)
+    if (!c->attn_prof) {
+      if ((r = dev_alloc(c, &c->attn_prof, 16))) return r;
+      *bytes = 0;
+      return RFE_OK;
+    }
+    *bytes = 16 * sizeof(unsigned long long);
+    if (dst) {
+      RFE_CUDA_CHECK(cudaMemcpyAsync(dst, c->attn_prof, *bytes < capacity ? *bytes : capacity, cudaMemcpyDeviceToHost, c->stream));
+      RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    return RFE_OK;
   } else {
     set_error("rfe_debug_read: unknown tensor '%s'", name);
     return RFE_ERR_INVALID;
@@ -1257,6 +1273,23 @@ int rfe_debug_gemm(rfe_ctx* c, const float* a, const float* b, const float* bias
 int rfe_debug_probe(rfe_ctx* c, int which, const float* a, const float* b, float* out) {
   int r = check_ctx(c);
   if (r) return r;
+  if (which == 1 && out) {      // MMA issue-rate probe: out[0..6] = cycles per MMA (see probe_kernels.cu)
+    float* dout1;
+    RFE_CUDA_CHECK(cudaMalloc(&dout1, 16 * 4));
+    RFE_CUDA_CHECK(cudaMemset(dout1, 0, 16 * 4));
+    if (rfe::launch_probe_mma_rate(c->stream, dout1, 512)) {
+      set_error("probe launch failed");
+      return RFE_ERR_CUDA;
+    }
+    cudaError_t e1 = cudaStreamSynchronize(c->stream);
+    if (e1 != cudaSuccess) {
+      set_error("probe 1 failed: %s", cudaGetErrorString(e1));
+      return RFE_ERR_CUDA;
+    }
+    RFE_CUDA_CHECK(cudaMemcpy(out, dout1, 16 * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dout1);
+    return RFE_OK;
+  }
   if (which != 0 || !a || !b || !out) {
     set_error("rfe_debug_probe: invalid argument");
     return RFE_ERR_INVALID;

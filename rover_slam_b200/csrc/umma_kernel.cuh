@@ -19,7 +19,7 @@ namespace rfe {
 
 enum AMode { A_GEMM = 0, A_CONV3 = 1 };
 enum Epi {
-  EPI_LINEAR = 0,    // (acc + bias) * scale (+ residual) -> fp32 and/or split-fp16, optional transposed split store
+  EPI_LINEAR = 0,    // (acc + bias) * scale (+ residual) -> fp32 and/or split-fp16 (row-major, head-major or transposed)
   EPI_CONV = 1,      // bias + ReLU (+ 2x2 max-pool) -> split-fp16 NHWC
   EPI_DET = 2,       // bias + softmax over 65 + drop dustbin + 8x8 depth-to-space -> fp32 heat-map
   EPI_DESC = 3,      // bias + L2 normalise over N=256 -> fp32 NHWC
@@ -47,7 +47,6 @@ struct UmmaParams {
   int transpose_h;
   int head_major;          // split store as [n/64][M][64] (attention heads), head_stride elements apart
   long long head_stride;
-  int relu;
   int pool;
   float scale;
   // EPI_QKV only
@@ -550,38 +549,41 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
           }
 #pragma unroll
           for (int j = 0; j < 64; ++j) v[j] *= p.scale;
-          if (res) {   // residual tile: coalesced global loads -> staging -> my row
-#pragma unroll 1
-            for (int i = 0; i < 16; ++i) {
-              const int r = 2 * i + (lane >> 4), ch = lane & 15;
-              const int mr = m0 + q * 32 + r;
-              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (mr < p.M) t = *reinterpret_cast<const float4*>(res + static_cast<size_t>(mr) * p.ld_res + nb + ch * 4);
-              *reinterpret_cast<float4*>(wst + r * 256 + ((ch ^ (r & 7)) << 4)) = t;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int ch = 0; ch < 16; ++ch) {
-              const float4 t = *reinterpret_cast<const float4*>(wst + lane * 256 + ((ch ^ (lane & 7)) << 4));
-              v[4 * ch] += t.x; v[4 * ch + 1] += t.y; v[4 * ch + 2] += t.z; v[4 * ch + 3] += t.w;
-            }
-            __syncwarp();
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.0f);
-          }
-          if (of) {
+          if (of || res) {
+            // fp32 tile through the staging buffer; the residual is added during the row-contiguous write-out, where
+            // its global loads are coalesced exactly like the stores (all 16 loads of a thread are in flight together)
             stage_f32(v);
             __syncwarp();
-#pragma unroll 1
+            float4 rr[16];
+            if (res) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int r = 2 * i + (lane >> 4), ch = lane & 15;
+                const int mr = m0 + q * 32 + r;
+                rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (mr < p.M) rr[i] = *reinterpret_cast<const float4*>(res + static_cast<size_t>(mr) * p.ld_res + nb + ch * 4);
+              }
+            }
+#pragma unroll
             for (int i = 0; i < 16; ++i) {
               int r, ch;
-              const float4 t = staged_f32(i, r, ch);
+              float4 t = staged_f32(i, r, ch);
               const int mr = m0 + q * 32 + r;
-              if (mr < p.M) *reinterpret_cast<float4*>(of + static_cast<size_t>(mr) * p.ld_f32 + nb + ch * 4) = t;
+              if (res) {
+                t.x += rr[i].x; t.y += rr[i].y; t.z += rr[i].z; t.w += rr[i].w;
+                *reinterpret_cast<float4*>(wst + r * 256 + ((ch ^ (r & 7)) << 4)) = t;   // keep the sum for the split store
+              }
+              if (of && mr < p.M) *reinterpret_cast<float4*>(of + static_cast<size_t>(mr) * p.ld_f32 + nb + ch * 4) = t;
             }
             __syncwarp();
+            if (res && oh) {   // re-read my row (now including the residual)
+#pragma unroll
+              for (int ch = 0; ch < 16; ++ch) {
+                const float4 t = *reinterpret_cast<const float4*>(wst + lane * 256 + ((ch ^ (lane & 7)) << 4));
+                v[4 * ch] = t.x; v[4 * ch + 1] = t.y; v[4 * ch + 2] = t.z; v[4 * ch + 3] = t.w;
+              }
+              __syncwarp();
+            }
           }
           if (oh) {
             if (p.transpose_h) {
@@ -625,7 +627,6 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
             if (p.bias) t += __ldg(p.bias + n);
             t *= p.scale;
             if (res) t += res[static_cast<size_t>(m) * p.ld_res + n];
-            if (p.relu) t = fmaxf(t, 0.0f);
             if (of) of[static_cast<size_t>(m) * p.ld_f32 + n] = t;
             if (oh) {
               __half h, l;

@@ -16,3 +16,23 @@ for s in range(9):
     ref = a[s:s + 128].astype(np.float64) @ b.astype(np.float64).T
     errs = [np.abs(out[s, m] - ref).max() for m in range(3)]
     print(f"  {s}   " + "   ".join(f"{e:12.3e}" for e in errs))
+
+import ctypes as C
+o = np.zeros(16, np.float32)
+fe._check(fe.lib.rfe_debug_probe(fe.ctx, 1, None, None, o.ctypes.data_as(C.c_void_p)))
+print("probe 1: cycles per tcgen05.mma (M=128, K=16, SS operands), 512 back-to-back, one CTA")
+print("  same A tile      : N=64 %.1f  N=128 %.1f  N=256 %.1f" % tuple(o[0:3]))
+print("  alternating A    : N=64 %.1f  N=128 %.1f  N=256 %.1f" % tuple(o[3:6]))
+print("  issue-loop only  : N=64 %.1f cycles per instruction issued" % o[6])
+
+# attention role timing (cycles) on a 2000-keypoint pair
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+from oracle import synth
+fe2 = FrontEnd(max_batch=2, max_height=64, max_width=64, max_keypoints=2048)
+k0, k1, d0, d1, _ = synth.lightglue_inputs(2000, 5)
+fe2.debug_read("lg.attn_prof")          # arm
+fe2.match(k0, k1, d0, d1, 480, 640)
+pr = fe2.debug_read("lg.attn_prof").view(np.uint64)
+names = ["wait Q", "pass1 issue loop", "pass2 issue loop", "wait K", "wait free S buffer", "wait V", "wait P (softmax)", "key tiles"]
+print("attention MMA-thread cycle breakdown (CTA 0 of the last launch):")
+for n, v in zip(names, pr[:8]): print(f"  {n:22s} {int(v)}")
