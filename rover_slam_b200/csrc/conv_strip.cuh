@@ -39,6 +39,7 @@ struct StripParams {
   const float* bias;        // [64]
   __half* out_hi;           // NHWC [B][Ho][Wo][64]
   __half* out_lo;
+  unsigned long long* prof;   // optional [8] cycle counters of CTA 0's MMA thread
 };
 
 constexpr int kStripThreads = 384;
@@ -58,7 +59,8 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                     const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                     const StripParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by offsetting the __shared__ array itself (keeps the shared address space: STS/LDS, not generic)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sRowHi = smem;                                              // [4] slots
   uint8_t* sRowLo = smem + kStripRowSlots * kStripSlotBytes;
   uint8_t* sW = smem + 2 * kStripRowSlots * kStripSlotBytes;           // [4] stages
@@ -144,23 +146,31 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       uint32_t n_base = 0;     // row sequence number of the current item's first input row
       uint32_t m = 0;          // tap sequence number
       uint32_t gi = 0;         // iteration counter (accumulator hand-over phase)
+      long long w_acc = 0, w_w = 0, w_row = 0;
+      const long long t_begin = clock64();
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         int b, x0, y_begin, iters;
         item_coords(item, b, x0, y_begin, iters);
         for (int it = 0; it < iters; ++it, ++gi) {
+          long long c0 = clock64();
           mbar_wait(acc_empty, (gi & 1) ^ 1);                 // the epilogue has drained the accumulators
+          w_acc += clock64() - c0;
           tc_fence_after();
           for (int dy = 0; dy < 3; ++dy) {
             for (int dx = 0; dx < 3; ++dx, ++m) {
               const int st = m & 3;
+              long long c1 = clock64();
               mbar_wait(&w_full[st], (m >> 2) & 1);
+              w_w += clock64() - c1;
               const uint32_t w_cat = smem_u32(sW + st * kStripWStageBytes);          // [hi;lo] (dy 0,2) or [lo;hi] (dy 1)
               const uint32_t w_hi = w_cat + (dy == 1 ? 8192 : 0);
 #pragma unroll
               for (int r = 0; r < 2; ++r) {
                 const uint32_t seq = n_base + 2 * it + r + dy;           // input row feeding output row r through kernel row dy
                 const int slot = seq & 3;
+                long long c2 = clock64();
                 mbar_wait(&row_full[slot], (seq >> 2) & 1);
+                w_row += clock64() - c2;
                 tc_fence_after();
                 const uint32_t a_hi = smem_u32(sRowHi + slot * kStripSlotBytes) + dx * 128;
                 const uint32_t a_lo = smem_u32(sRowLo + slot * kStripSlotBytes) + dx * 128;
@@ -197,6 +207,13 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           umma_commit(acc_full);
         }
         n_base += 2 * iters + 2;
+      }
+      if (p.prof && blockIdx.x == 0) {
+        p.prof[0] = clock64() - t_begin;   // whole MMA-thread loop
+        p.prof[1] = w_acc;                 // waiting for the epilogue to drain TMEM
+        p.prof[2] = w_w;                   // waiting for weight tiles
+        p.prof[3] = w_row;                 // waiting for input rows
+        p.prof[4] = gi;                    // iterations
       }
     }
   } else if (warp >= 4) {

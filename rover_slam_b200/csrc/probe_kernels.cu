@@ -23,7 +23,8 @@ __device__ __forceinline__ uint64_t make_desc_sw128_bo(uint32_t smem_addr, uint3
 __global__ void __launch_bounds__(128, 1) probe_shift_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
                                                              float* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by offsetting the __shared__ array itself (keeps the shared address space: STS/LDS, not generic)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;                 // 136 rows * 128 B = 17408 -> pad to 18432
   uint8_t* sB = smem + 18432;         // 64 rows * 128 B
   uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 8192);
@@ -102,7 +103,8 @@ int launch_probe_shift(cudaStream_t s, const __half* a, const __half* b, float* 
 //           other MMA.  One CTA, so no bandwidth contention: this is the per-SM floor for SS-mode MMAs.
 __global__ void __launch_bounds__(128, 1) probe_mma_rate_kernel(float* __restrict__ out, int reps) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by offsetting the __shared__ array itself (keeps the shared address space: STS/LDS, not generic)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;                 // 2 x 16 KB
   uint8_t* sB = smem + 32768;         // 32 KB (256 rows)
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 65536);
@@ -146,6 +148,22 @@ __global__ void __launch_bounds__(128, 1) probe_mma_rate_kernel(float* __restric
       __syncthreads();
     }
   }
+  // row-shifted A start (+128 B, +256 B: the dx taps of the strip convolution), N = 128
+  for (int sh = 1; sh <= 2; ++sh) {
+    const uint32_t idesc = make_idesc_f16(128, 128);
+    long long t0 = 0;
+    if (threadIdx.x == 0) {
+      t0 = clock64();
+      for (int i = 0; i < reps; ++i)
+        umma_f16(tmem, make_sw128_kmajor_desc(smem_u32(sA) + sh * 128 + (i & 3) * 32),
+                 make_sw128_kmajor_desc(smem_u32(sB) + (i & 3) * 32), idesc, 1u);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    if (threadIdx.x == 0) out[7 + sh] = static_cast<float>(clock64() - t0) / reps;
+    __syncthreads();
+  }
   // issue-only cost (no completion wait between): N=64, measure issue loop time
   if (threadIdx.x == 0) {
     const uint32_t idesc = make_idesc_f16(128, 64);
@@ -154,7 +172,7 @@ __global__ void __launch_bounds__(128, 1) probe_mma_rate_kernel(float* __restric
       umma_f16(tmem, make_sw128_kmajor_desc(smem_u32(sA)), make_sw128_kmajor_desc(smem_u32(sB)), idesc, 1u);
     const long long t1 = clock64();
     umma_commit(bar);
-    out[slot] = static_cast<float>(t1 - t0) / reps;
+    out[6] = static_cast<float>(t1 - t0) / reps;
   }
   mbar_wait(bar, phase);
   __syncthreads();

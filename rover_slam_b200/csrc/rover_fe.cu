@@ -90,6 +90,7 @@ struct rfe_ctx {
   float *rmax = nullptr, *rlog = nullptr, *cmax = nullptr, *clog = nullptr, *ls = nullptr, *max0 = nullptr;
   int *m0 = nullptr, *m1 = nullptr;
   float* S_dbg = nullptr;
+  const char* prof_tag = nullptr;            // $RFE_PROF_TAG: the launch tag whose UMMA role counters are recorded
   unsigned long long* attn_prof = nullptr;   // armed by rfe_debug_read("lg.attn_prof")
   int dbg_n0 = 0, dbg_n1 = 0, dbg_off0 = 0, dbg_off1 = 0;
   // match results: [max_batch] slots
@@ -261,9 +262,10 @@ int launch_umma(rfe_ctx* c, const char* tag, const CUtensorMap& a_hi, const CUte
   pp.tiles_m = static_cast<int>(grid.x);
   pp.tiles_n = static_cast<int>(grid.y);
   pp.num_tiles = static_cast<int>(grid.x * grid.y * grid.z);
+  pp.prof = (c->attn_prof && c->prof_tag && !strcmp(tag, c->prof_tag)) ? c->attn_prof + 16 : nullptr;
   const int ctas = pp.num_tiles < c->num_sms ? pp.num_tiles : c->num_sms;
   ProfScope ps(c, tag);
-  kern<<<ctas, kUmmaThreads, umma_smem_bytes(BLOCK_N), c->stream>>>(a_hi, a_lo, b_hi, b_lo, pp);
+  kern<<<ctas, umma_threads(BLOCK_N, EPI), umma_smem_bytes(BLOCK_N), c->stream>>>(a_hi, a_lo, b_hi, b_lo, pp);
   c->launches++;
   RFE_CUDA_CHECK(cudaGetLastError());
   return RFE_OK;
@@ -373,6 +375,7 @@ int conv64_strip(rfe_ctx* c, const char* tag, const SplitBuf& in, int B, int H, 
   p.bias = w.bias;
   p.out_hi = out.hi;
   p.out_lo = out.lo;
+  p.prof = (c->attn_prof && !strcmp(tag, "sp.conv1b")) ? c->attn_prof + 8 : nullptr;
   const int ctas = p.num_items < c->num_sms ? p.num_items : c->num_sms;
   ProfScope ps(c, tag);
   conv64_strip_kernel<<<ctas, kStripThreads, kStripSmemBytes, c->stream>>>(ah, al, wh, wl, p);
@@ -611,7 +614,7 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
       p.out_hi = c->cat.hi + 256;
       p.out_lo = c->cat.lo + 256;
       p.ld_h = 512;
-      if ((r = gemm_linear(c, "lg.out_proj", A, B, p, 64))) return r;
+      if ((r = gemm_linear(c, "lg.out_proj", A, B, p, 128))) return r;
     }
     if ((r = ffn_block(c, rows, L.s_ffn0, L.s_ln_w, L.s_ln_b, L.s_ffn3))) return r;
     // ---------------- cross attention ----------------
@@ -625,7 +628,7 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
       p.out_lo = c->q.lo;
       p.head_major = 1;
       p.head_stride = hs;
-      if ((r = gemm_linear(c, "lg.to_qk", A, B, p, 64))) return r;
+      if ((r = gemm_linear(c, "lg.to_qk", A, B, p, 128))) return r;
     }
     {
       Operand A{c->cat.hi, c->cat.lo, rows, 256, 512, 0, 1};
@@ -636,7 +639,7 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
       p.out_lo = c->vt.lo;
       p.transpose_h = 1;
       p.ld_h = c->lg_ldv;
-      if ((r = gemm_linear(c, "lg.to_v", A, B, p, 64))) return r;
+      if ((r = gemm_linear(c, "lg.to_v", A, B, p, 128))) return r;
     }
     if ((r = attention_fused(c, "lg.attn_cross", c->q, c->q, rows, cross_p, 2 * np, max_n))) return r;
     {
@@ -647,7 +650,7 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
       p.out_hi = c->cat.hi + 256;
       p.out_lo = c->cat.lo + 256;
       p.ld_h = 512;
-      if ((r = gemm_linear(c, "lg.to_out", A, B, p, 64))) return r;
+      if ((r = gemm_linear(c, "lg.to_out", A, B, p, 128))) return r;
     }
     if ((r = ffn_block(c, rows, L.c_ffn0, L.c_ln_w, L.c_ln_b, L.c_ffn3))) return r;
   }
@@ -661,7 +664,7 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
     p.out_hi = c->md.hi;
     p.out_lo = c->md.lo;
     p.ld_h = 256;
-    if ((r = gemm_linear(c, "lg.final_proj", A, B, p, 64))) return r;
+    if ((r = gemm_linear(c, "lg.final_proj", A, B, p, 128))) return r;
   }
   launch_matchability(s, c->x, rows, c->match_w, c->match_b, c->ls);
   c->launches++;
@@ -765,6 +768,7 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   }
   RFE_CUDA_CHECK(cudaEventCreate(&c->ev0));
   RFE_CUDA_CHECK(cudaEventCreate(&c->ev1));
+  c->prof_tag = getenv("RFE_PROF_TAG");
   if (getenv("RFE_CONV_STRIP")) c->use_strip_conv = atoi(getenv("RFE_CONV_STRIP")) != 0;
   const char* path = cfg->weights_path;
   if (!path) path = getenv("ROVER_FE_WEIGHTS");
@@ -1192,11 +1196,11 @@ int rfe_debug_read(rfe_ctx* c, const char* name, void* dst, size_t capacity, siz
     n = static_cast<size_t>(c->dbg_n0) * c->dbg_n1;
   } else if (s == "lg.attn_prof") {   // 16 x u64 cycle counters of the last attention launch (first request arms it)
     if (!c->attn_prof) {
-      if ((r = dev_alloc(c, &c->attn_prof, 16))) return r;
+      if ((r = dev_alloc(c, &c->attn_prof, 32))) return r;
       *bytes = 0;
       return RFE_OK;
     }
-    *bytes = 16 * sizeof(unsigned long long);
+    *bytes = 32 * sizeof(unsigned long long);
     if (dst) {
       RFE_CUDA_CHECK(cudaMemcpyAsync(dst, c->attn_prof, *bytes < capacity ? *bytes : capacity, cudaMemcpyDeviceToHost, c->stream));
       RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));

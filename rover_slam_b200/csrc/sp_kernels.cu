@@ -82,28 +82,56 @@ constexpr int RW = NT_W + 2 * NHALO;  // 104
 constexpr int RH = NT_H + 2 * NHALO;  // 72
 constexpr int NMS_THREADS = 512;
 
+// out[i] = max(v[i .. i+8]) for i = 0..7 with 44 max operations (log-step doubling) instead of 64
+__device__ __forceinline__ void max9_run8(const float (&v)[16], float (&out)[8]) {
+  float a1[15], a2[13], a4[8];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) a1[i] = fmaxf(v[i], v[i + 1]);
+#pragma unroll
+  for (int i = 0; i < 13; ++i) a2[i] = fmaxf(a1[i], a1[i + 2]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a4[i] = fmaxf(a2[i], a2[i + 4]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[i] = fmaxf(a4[i], v[i + 8]);
+}
+
 // dst(y,x) = max over the 9x9 window of src, for (y,x) in the region shrunk by `e_out` from the full
-// halo region; src must be valid on the region shrunk by e_out - 4.  tmp is scratch.
+// halo region; src must be valid on the region shrunk by e_out - 4.  tmp is scratch.  Separable; every thread
+// produces a run of 8 outputs from 16 loads (2 shared-memory loads per output instead of 9).
 __device__ __forceinline__ void pool9(const float* src, float* tmp, float* dst, int e_out) {
+  const float NEG = -INFINITY;
   const int ex = e_out, ey = e_out - NR;  // horizontal pass rows: [ey, RH-ey), cols [ex, RW-ex)
   const int w = RW - 2 * ex, h = RH - 2 * ey;
-  for (int i = threadIdx.x; i < w * h; i += NMS_THREADS) {
-    const int y = ey + i / w, x = ex + i % w;
-    const float* r = src + y * RW + x;
-    float m = r[-4];
+  const int runs = (w + 7) >> 3;
+  for (int i = threadIdx.x; i < runs * h; i += NMS_THREADS) {
+    const int y = ey + i / runs, x0 = ex + (i % runs) * 8;
+    const float* r = src + y * RW;
+    float v[16], o[8];
 #pragma unroll
-    for (int d = -3; d <= 4; ++d) m = fmaxf(m, r[d]);
-    tmp[y * RW + x] = m;
+    for (int j = 0; j < 16; ++j) {
+      const int x = x0 - 4 + j;
+      v[j] = x < RW ? r[x] : NEG;
+    }
+    max9_run8(v, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (x0 + j < RW - ex) tmp[y * RW + x0 + j] = o[j];
   }
   __syncthreads();
   const int h2 = RH - 2 * e_out;
-  for (int i = threadIdx.x; i < w * h2; i += NMS_THREADS) {
-    const int y = e_out + i / w, x = ex + i % w;
-    const float* r = tmp + y * RW + x;
-    float m = r[-4 * RW];
+  const int vruns = (h2 + 7) >> 3;
+  for (int i = threadIdx.x; i < w * vruns; i += NMS_THREADS) {
+    const int x = ex + i % w, y0 = e_out + (i / w) * 8;
+    float v[16], o[8];
 #pragma unroll
-    for (int d = -3; d <= 4; ++d) m = fmaxf(m, r[d * RW]);
-    dst[y * RW + x] = m;
+    for (int j = 0; j < 16; ++j) {
+      const int y = y0 - 4 + j;
+      v[j] = y < RH ? tmp[y * RW + x] : NEG;
+    }
+    max9_run8(v, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (y0 + j < RH - e_out) dst[(y0 + j) * RW + x] = o[j];
   }
   __syncthreads();
 }

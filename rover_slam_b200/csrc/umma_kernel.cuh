@@ -57,21 +57,26 @@ struct UmmaParams {
   __half* vt_hi;           // V^T [256][ldv]
   __half* vt_lo;
   int ldv;
+  unsigned long long* prof;   // optional [8] cycle counters written by CTA 0 (MMA thread: 0-3, epilogue warp 2: 4-7)
 };
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                  // fp16 elements = one 128-byte swizzle row
 constexpr int kStageABytes = kBlockM * 128;  // one of A_hi / A_lo
-constexpr int kUmmaThreads = 192;
+// epilogue warps: two per TMEM lane quarter (each takes every other 64-column group) for the wide row-wise epilogues
+__host__ __device__ constexpr int umma_epi_warps(int block_n, int epi) {
+  return (block_n >= 128 && (epi == 0 || epi == 1 || epi == 4)) ? 8 : 4;
+}
+__host__ __device__ constexpr int umma_threads(int block_n, int epi) { return 64 + 32 * umma_epi_warps(block_n, epi); }
 
 __host__ __device__ constexpr int umma_stage_bytes(int block_n) { return 2 * kStageABytes + 2 * block_n * 128; }
 __host__ __device__ constexpr int umma_num_stages(int block_n) {
   return (192 * 1024 / umma_stage_bytes(block_n)) > 6 ? 6 : (192 * 1024 / umma_stage_bytes(block_n));
 }
-constexpr int kEpiStageWarpBytes = 8192;     // per epilogue warp: 32 rows x 256 B (fp32 x 64) or 2 planes x 32 rows x 128 B
+constexpr int kEpiStageWarpBytes = 4096;     // per epilogue warp: 32 rows x 128 B (32 fp32 or 64 fp16 per row)
 __host__ __device__ constexpr int umma_num_stages(int block_n);
 __host__ __device__ constexpr int umma_smem_bytes(int block_n) {
-  return umma_num_stages(block_n) * umma_stage_bytes(block_n) + 4 * kEpiStageWarpBytes + 1024 /*align slack*/ +
+  return umma_num_stages(block_n) * umma_stage_bytes(block_n) + 8 * kEpiStageWarpBytes + 1024 /*align slack*/ +
          256 /*barriers*/;
 }
 // Number of hi*hi accumulators.  The tensor core adds each K=16 partial sum into the fp32 accumulator with
@@ -89,7 +94,7 @@ __host__ __device__ constexpr int umma_tmem_cols(int block_n, int amode) {
 #ifdef __CUDACC__
 
 template <int BLOCK_N, int AMODE, int EPI>
-__global__ void __launch_bounds__(kUmmaThreads, 1)
+__global__ void __launch_bounds__(umma_threads(BLOCK_N, EPI), 1)
 umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
             const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
             const UmmaParams p) {
@@ -107,9 +112,12 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
   static_assert(STAGES >= 2, "need at least two stages");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;      // 4 x kEpiStageWarpBytes
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + 4 * kEpiStageWarpBytes);
+  // 1024-byte alignment by offsetting the __shared__ array itself (keeps the shared address space: STS/LDS, not generic)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int EPI_WARPS = umma_epi_warps(BLOCK_N, EPI);
+  constexpr int NHALF = EPI_WARPS / 4;                   // warps sharing a TMEM lane quarter
+  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;      // 8 x kEpiStageWarpBytes
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + 8 * kEpiStageWarpBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;       // [NBUF]
   uint64_t* tmem_empty_bar = tmem_full_bar + NBUF;    // [NBUF]
@@ -151,7 +159,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     }
     for (int b = 0; b < NBUF; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 4);      // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[b], EPI_WARPS);      // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -207,14 +215,20 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      long long w_te = 0, w_full = 0;
+      const long long t_begin = clock64();
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int buf = it % NBUF;
       const uint32_t tile_base = tmem_base + buf * TILE_COLS;
       const uint32_t acc1 = tile_base + ACC1_COL;
+      long long c0 = clock64();
       mbar_wait(&tmem_empty_bar[buf], (((it / NBUF) & 1) ^ 1));     // the epilogue has drained this accumulator set
+      w_te += clock64() - c0;
       tc_fence_after();
       for (int ks = 0; ks < p.num_k_steps; ++ks) {
+        c0 = clock64();
         mbar_wait(&full_bar[stage], phase);
+        w_full += clock64() - c0;
         tc_fence_after();
         const uint32_t a_hi = smem_u32(smem + stage * STAGE_BYTES);
         const uint32_t a_lo = a_hi + kStageABytes;
@@ -255,18 +269,28 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       }
       umma_commit(&tmem_full_bar[buf]);
       }
+      if (p.prof && blockIdx.x == 0) {
+        p.prof[0] = clock64() - t_begin;   // MMA-thread loop
+        p.prof[1] = w_te;                  // waiting for the epilogue (TMEM drain)
+        p.prof[2] = w_full;                // waiting for TMA (operands)
+        p.prof[3] = it;                    // tiles
+      }
     }
   } else {
     // ===== epilogue warps ===========================================================================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;                // row of the 128-row tile
     int it = 0;
+    long long w_tf = 0;
+    const long long e_begin = clock64();
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
     const Tile tc = decode(tile);
     const int m0 = tc.m0, n0 = tc.n0, img = tc.img, x0 = tc.x0, y0 = tc.y0;
     (void)m0; (void)img; (void)x0; (void)y0;
     const int buf = it % NBUF;
+    const long long e0 = clock64();
     mbar_wait(&tmem_full_bar[buf], (it / NBUF) & 1);
+    w_tf += clock64() - e0;
     tc_fence_after();
     const uint32_t t0 = tmem_base + buf * TILE_COLS + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t t1 = t0 + ACC1_COL;
@@ -292,9 +316,11 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     };
 
     // ---- coalescing helpers: a thread owns one row of the tile, but a warp-wide store of "my row" touches 32 rows.
-    // Values are therefore transposed through a per-warp staging buffer (XOR-swizzled 16-byte chunks, conflict
-    // free) and written back row-contiguously: 2 rows x 256 B (fp32) or 4 rows x 128 B (fp16 plane) per instruction.
-    uint8_t* wst = epi_stage + q * kEpiStageWarpBytes;
+    // Values are therefore transposed through a per-warp staging buffer of 32 rows x 128 B (XOR-swizzled 16-byte
+    // chunks, conflict free) and written back row-contiguously, 4 rows x 128 B per instruction.
+    const int ew = warp - 2;                     // epilogue warp index
+    const int half = ew >> 2;                    // which of the NHALF column-group phases this warp takes
+    uint8_t* wst = epi_stage + ew * kEpiStageWarpBytes;
     auto load64 = [&](int col, float (&v)[64]) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -304,46 +330,62 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
         for (int j = 0; j < 16; ++j) v[16 * i + j] = t[j];
       }
     };
-    // stage 64 fp32 of my row (256-byte rows)
-    auto stage_f32 = [&](const float (&v)[64]) {
-#pragma unroll
-      for (int ch = 0; ch < 16; ++ch)
-        *reinterpret_cast<float4*>(wst + lane * 256 + ((ch ^ (lane & 7)) << 4)) =
-            make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+    auto st_row = [&](int ch, const uint4& x) {          // chunk ch (0..7) of MY row
+      *reinterpret_cast<uint4*>(wst + lane * 128 + ((ch ^ (lane & 7)) << 4)) = x;
     };
-    // staged fp32 chunk (r = 2*i + lane/16, ch = lane%16)
-    auto staged_f32 = [&](int i, int& r, int& ch) {
-      r = 2 * i + (lane >> 4);
-      ch = lane & 15;
-      return *reinterpret_cast<const float4*>(wst + r * 256 + ((ch ^ (r & 7)) << 4));
+    auto ld_row = [&](int ch) {                            // chunk ch of MY row
+      return *reinterpret_cast<const uint4*>(wst + lane * 128 + ((ch ^ (lane & 7)) << 4));
     };
-    // stage 64 split-fp16 values of my row: hi plane at wst, lo plane at wst + 4096 (128-byte rows)
-    auto stage_split = [&](const float (&v)[64]) {
-#pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        __align__(16) __half hh[8];
-        __align__(16) __half ll[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) split_f32(v[8 * ch + j], hh[j], ll[j]);
-        const int off = lane * 128 + ((ch ^ (lane & 7)) << 4);
-        *reinterpret_cast<uint4*>(wst + off) = *reinterpret_cast<const uint4*>(hh);
-        *reinterpret_cast<uint4*>(wst + 4096 + off) = *reinterpret_cast<const uint4*>(ll);
-      }
-    };
-    // staged fp16 chunks of row r = 4*i + lane/8, chunk ch = lane%8 (8 halves)
-    auto staged_split = [&](int i, int& r, int& ch, uint4& h, uint4& l) {
+    auto ld_staged = [&](int i, int& r, int& ch) {         // instruction i (0..7): row r = 4i + lane/8, chunk ch = lane%8
       r = 4 * i + (lane >> 3);
       ch = lane & 7;
-      const int off = r * 128 + ((ch ^ (r & 7)) << 4);
-      h = *reinterpret_cast<const uint4*>(wst + off);
-      l = *reinterpret_cast<const uint4*>(wst + 4096 + off);
+      return *reinterpret_cast<const uint4*>(wst + r * 128 + ((ch ^ (r & 7)) << 4));
+    };
+    auto st_staged = [&](int r, int ch, const uint4& x) {
+      *reinterpret_cast<uint4*>(wst + r * 128 + ((ch ^ (r & 7)) << 4)) = x;
+    };
+    // stage 32 fp32 (v[off .. off+32)) of my row
+    auto stage_f32x32 = [&](const float (&v)[64], int off) {
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const float4 t = make_float4(v[off + 4 * ch], v[off + 4 * ch + 1], v[off + 4 * ch + 2], v[off + 4 * ch + 3]);
+        st_row(ch, *reinterpret_cast<const uint4*>(&t));
+      }
+    };
+    // coalesced store of a split 64-column group: off(r, ch) returns the element offset of chunk ch (8 halves) of staged
+    // row r, or -1 when that row is not to be written.  One plane at a time through the 4 KB staging buffer.
+    auto store_split = [&](const float (&v)[64], auto&& off, __half* dh, __half* dl) {
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          __align__(16) __half x[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __half h, l;
+            split_f32(v[8 * ch + j], h, l);
+            x[j] = pl ? l : h;
+          }
+          st_row(ch, *reinterpret_cast<const uint4*>(x));
+        }
+        __syncwarp();
+        __half* d = pl ? dl : dh;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int r, ch;
+          const uint4 x = ld_staged(i, r, ch);
+          const long long o = off(r, ch);
+          if (o >= 0) *reinterpret_cast<uint4*>(d + o) = x;
+        }
+        __syncwarp();
+      }
     };
 
     if constexpr (EPI == EPI_CONV) {
       // lane <-> pixel (ry = 2q + lane/16, rx = lane%16) of the 16x8 tile; channels in groups of 64
       const int Ho = p.pool ? p.H >> 1 : p.H, Wo = p.pool ? p.W >> 1 : p.W;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 64) {
+      for (int c = half * 64; c < BLOCK_N; c += 64 * NHALF) {
         float v[64];
         load64(c, v);
 #pragma unroll
@@ -361,34 +403,16 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
             v[j] = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 16));
           }
         }
-        stage_split(v);
-        __syncwarp();
-        // staged row r is the tile pixel (ry = 2q + r/16, rx = r%16); with pooling only rows r = 0,2,..,14 hold outputs
-        const int nrows_i = p.pool ? 2 : 8;           // instructions: 4 staged rows each
-#pragma unroll 1
-        for (int i = 0; i < nrows_i; ++i) {
-          int r, ch;
-          uint4 h, l;
-          if (p.pool) {
-            const int w = 4 * i + (lane >> 3);         // pooled pixel index 0..7 inside the warp's tile rows
-            ch = lane & 7;
-            r = 2 * w;                                 // staged row of the 2x2 block's top-left pixel
-            const int off = r * 128 + ((ch ^ (r & 7)) << 4);
-            h = *reinterpret_cast<const uint4*>(wst + off);
-            l = *reinterpret_cast<const uint4*>(wst + 4096 + off);
-          } else {
-            staged_split(i, r, ch, h, l);
-          }
+        // staged row r is the tile pixel (ry = 2q + r/16, rx = r%16); with pooling only the 2x2 blocks' top-left
+        // pixels (r = 0, 2, .., 14) are written
+        store_split(v, [&](int r, int ch) -> long long {
           const int ry = 2 * q + (r >> 4), rx = r & 15;
           const int y = y0 + ry, x = x0 + rx;
-          if (y < p.H && x < p.W) {
-            const int yo = p.pool ? y >> 1 : y, xo = p.pool ? x >> 1 : x;
-            const size_t o = ((static_cast<size_t>(img) * Ho + yo) * Wo + xo) * p.N + n0 + c + ch * 8;
-            *reinterpret_cast<uint4*>(p.out_hi + o) = h;
-            *reinterpret_cast<uint4*>(p.out_lo + o) = l;
-          }
-        }
-        __syncwarp();
+          if (y >= p.H || x >= p.W) return -1;
+          if (p.pool && (((r >> 4) | rx) & 1)) return -1;
+          const int yo = p.pool ? y >> 1 : y, xo = p.pool ? x >> 1 : x;
+          return static_cast<long long>(((static_cast<size_t>(img) * Ho + yo) * Wo + xo) * p.N + n0 + c + ch * 8);
+        }, p.out_hi, p.out_lo);
       }
     } else if constexpr (EPI == EPI_DET) {
       // row = coarse pixel; 65 logits -> softmax -> first 64 -> 8x8 block of the heat-map
@@ -449,16 +473,20 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
         load64(c, v);
 #pragma unroll
         for (int j = 0; j < 64; ++j) v[j] = (v[j] + __ldg(p.bias + n0 + c + j)) / nrm;
-        stage_f32(v);
-        __syncwarp();
-#pragma unroll 1
-        for (int i = 0; i < 16; ++i) {
-          int r, ch;
-          const float4 t = staged_f32(i, r, ch);
-          const int mr = m0 + q * 32 + r;
-          if (mr < p.M) *reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(mr) * p.ld_f32 + n0 + c + ch * 4) = t;
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          stage_f32x32(v, 32 * hb);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            int r, ch;
+            const uint4 x = ld_staged(i, r, ch);
+            const int mr = m0 + q * 32 + r;
+            if (mr < p.M)
+              *reinterpret_cast<uint4*>(p.out_f32 + static_cast<size_t>(mr) * p.ld_f32 + n0 + c + 32 * hb + ch * 4) = x;
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     } else if constexpr (EPI == EPI_QKV) {
       // columns: [q (256) | k (256) | v (256)], each head-major h*64+d (weights were permuted at load time);
@@ -467,7 +495,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       const bool valid = m < p.M;
       const int part = n0 >> 8;                         // 0 q, 1 k, 2 v   (BLOCK_N = 128 divides 256)
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 64) {
+      for (int c = half * 64; c < BLOCK_N; c += 64 * NHALF) {
         float v[64];
         load64(c, v);
         const int nb = n0 + c;
@@ -494,23 +522,11 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
               }
             }
           }
-          stage_split(v);
-          __syncwarp();
-          __half* dh = part == 0 ? p.out_hi : p.k_hi;
-          __half* dl = part == 0 ? p.out_lo : p.k_lo;
-#pragma unroll 1
-          for (int i = 0; i < 8; ++i) {
-            int r, ch;
-            uint4 h, l;
-            staged_split(i, r, ch, h, l);
+          store_split(v, [&](int r, int ch) -> long long {
             const int mr = m0 + q * 32 + r;
-            if (mr < p.M) {
-              const size_t o = static_cast<size_t>(head) * p.head_stride + static_cast<size_t>(mr) * 64 + ch * 8;
-              *reinterpret_cast<uint4*>(dh + o) = h;
-              *reinterpret_cast<uint4*>(dl + o) = l;
-            }
-          }
-          __syncwarp();
+            if (mr >= p.M) return -1;
+            return static_cast<long long>(static_cast<size_t>(head) * p.head_stride + static_cast<size_t>(mr) * 64 + ch * 8);
+          }, part == 0 ? p.out_hi : p.k_hi, part == 0 ? p.out_lo : p.k_lo);
         } else if (valid) {
           // V^T [256][ldv]: lanes are consecutive rows m -> each store instruction writes 64 contiguous bytes
 #pragma unroll
@@ -531,9 +547,8 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       __half* ol = p.out_lo ? p.out_lo + z * p.bstride_h : nullptr;
       const float* res = p.residual ? p.residual + z * p.bstride_res : nullptr;
       const bool vec_ok = ((p.ld_f32 & 3) == 0) && ((p.ld_h & 7) == 0) && ((p.ld_res & 3) == 0);
-      constexpr int GROUP = BLOCK_N >= 64 ? 64 : BLOCK_N;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += GROUP) {
+      for (int c = half * 64; c < BLOCK_N; c += 64 * NHALF) {
         const int nb = n0 + c;
         if (nb >= p.N) break;                                   // warp-uniform
         float v[64];
@@ -550,39 +565,47 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 64; ++j) v[j] *= p.scale;
           if (of || res) {
-            // fp32 tile through the staging buffer; the residual is added during the row-contiguous write-out, where
-            // its global loads are coalesced exactly like the stores (all 16 loads of a thread are in flight together)
-            stage_f32(v);
-            __syncwarp();
-            float4 rr[16];
-            if (res) {
+            // fp32 tile in two 32-column halves; the residual is added during the row-contiguous write-out, where its
+            // global loads are coalesced exactly like the stores (all 8 loads of a thread are in flight together)
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int r = 2 * i + (lane >> 4), ch = lane & 15;
-                const int mr = m0 + q * 32 + r;
-                rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (mr < p.M) rr[i] = *reinterpret_cast<const float4*>(res + static_cast<size_t>(mr) * p.ld_res + nb + ch * 4);
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              int r, ch;
-              float4 t = staged_f32(i, r, ch);
-              const int mr = m0 + q * 32 + r;
+            for (int hb = 0; hb < 2; ++hb) {
+              float4 rr[8];
               if (res) {
-                t.x += rr[i].x; t.y += rr[i].y; t.z += rr[i].z; t.w += rr[i].w;
-                *reinterpret_cast<float4*>(wst + r * 256 + ((ch ^ (r & 7)) << 4)) = t;   // keep the sum for the split store
-              }
-              if (of && mr < p.M) *reinterpret_cast<float4*>(of + static_cast<size_t>(mr) * p.ld_f32 + nb + ch * 4) = t;
-            }
-            __syncwarp();
-            if (res && oh) {   // re-read my row (now including the residual)
 #pragma unroll
-              for (int ch = 0; ch < 16; ++ch) {
-                const float4 t = *reinterpret_cast<const float4*>(wst + lane * 256 + ((ch ^ (lane & 7)) << 4));
-                v[4 * ch] = t.x; v[4 * ch + 1] = t.y; v[4 * ch + 2] = t.z; v[4 * ch + 3] = t.w;
+                for (int i = 0; i < 8; ++i) {
+                  const int r = 4 * i + (lane >> 3), ch = lane & 7;
+                  const int mr = m0 + q * 32 + r;
+                  rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (mr < p.M)
+                    rr[i] = *reinterpret_cast<const float4*>(res + static_cast<size_t>(mr) * p.ld_res + nb + 32 * hb + ch * 4);
+                }
+              }
+              stage_f32x32(v, 32 * hb);
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                int r, ch;
+                uint4 x = ld_staged(i, r, ch);
+                float4 t = *reinterpret_cast<float4*>(&x);
+                const int mr = m0 + q * 32 + r;
+                if (res) {
+                  t.x += rr[i].x; t.y += rr[i].y; t.z += rr[i].z; t.w += rr[i].w;
+                  st_staged(r, ch, *reinterpret_cast<const uint4*>(&t));     // keep the sum for the split store
+                }
+                if (of && mr < p.M)
+                  *reinterpret_cast<float4*>(of + static_cast<size_t>(mr) * p.ld_f32 + nb + 32 * hb + ch * 4) = t;
               }
               __syncwarp();
+              if (res && oh) {   // re-read my row (now including the residual)
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                  const uint4 x = ld_row(ch);
+                  const float4 t = *reinterpret_cast<const float4*>(&x);
+                  v[32 * hb + 4 * ch] = t.x; v[32 * hb + 4 * ch + 1] = t.y;
+                  v[32 * hb + 4 * ch + 2] = t.z; v[32 * hb + 4 * ch + 3] = t.w;
+                }
+                __syncwarp();
+              }
             }
           }
           if (oh) {
@@ -597,22 +620,12 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
                 }
               }
             } else {
-              stage_split(v);
-              __syncwarp();
-#pragma unroll 1
-              for (int i = 0; i < 8; ++i) {
-                int r, ch;
-                uint4 h, l;
-                staged_split(i, r, ch, h, l);
+              store_split(v, [&](int r, int ch) -> long long {
                 const int mr = m0 + q * 32 + r;
-                if (mr < p.M) {
-                  const size_t o = p.head_major ? static_cast<size_t>(nb >> 6) * p.head_stride + static_cast<size_t>(mr) * 64 + ch * 8
-                                                : static_cast<size_t>(mr) * p.ld_h + nb + ch * 8;
-                  *reinterpret_cast<uint4*>(oh + o) = h;
-                  *reinterpret_cast<uint4*>(ol + o) = l;
-                }
-              }
-              __syncwarp();
+                if (mr >= p.M) return -1;
+                return p.head_major ? static_cast<long long>(static_cast<size_t>(nb >> 6) * p.head_stride + static_cast<size_t>(mr) * 64 + ch * 8)
+                                    : static_cast<long long>(static_cast<size_t>(mr) * p.ld_h + nb + ch * 8);
+              }, oh, ol);
             }
           }
           continue;
@@ -644,6 +657,10 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);     // hand the accumulator set back to the MMA warp
+    }
+    if (p.prof && blockIdx.x == 0 && warp == 2 && lane == 0) {
+      p.prof[4] = clock64() - e_begin;     // epilogue-warp loop
+      p.prof[5] = w_tf;                    // waiting for accumulators
     }
   }
 

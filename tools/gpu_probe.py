@@ -24,6 +24,7 @@ print("probe 1: cycles per tcgen05.mma (M=128, K=16, SS operands), 512 back-to-b
 print("  same A tile      : N=64 %.1f  N=128 %.1f  N=256 %.1f" % tuple(o[0:3]))
 print("  alternating A    : N=64 %.1f  N=128 %.1f  N=256 %.1f" % tuple(o[3:6]))
 print("  issue-loop only  : N=64 %.1f cycles per instruction issued" % o[6])
+print("  A start +128 B   : N=128 %.1f   A start +256 B: N=128 %.1f" % (o[8], o[9]))
 
 # attention role timing (cycles) on a 2000-keypoint pair
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
@@ -36,3 +37,11 @@ pr = fe2.debug_read("lg.attn_prof").view(np.uint64)
 names = ["wait Q", "pass1 issue loop", "pass2 issue loop", "wait K", "wait free S buffer", "wait V", "wait P (softmax)", "key tiles"]
 print("attention MMA-thread cycle breakdown (CTA 0 of the last launch):")
 for n, v in zip(names, pr[:8]): print(f"  {n:22s} {int(v)}")
+
+# strip conv (conv1b) MMA-thread breakdown on one 480x640 frame batch of 8
+fe3 = FrontEnd(max_batch=8, max_height=480, max_width=640, max_keypoints=4096)
+fe3.debug_read("lg.attn_prof")          # arm (shared counter buffer; conv1b uses slots 8..)
+imgs = np.stack([synth.frame(s, 480, 640) for s in range(8)])
+fe3.extract(imgs, want_desc=False)
+pr = fe3.debug_read("lg.attn_prof").view(np.uint64)
+print("strip conv1b MMA-thread cycles (CTA 0): total %d, wait TMEM drain %d, wait weights %d, wait rows %d, iterations %d" % tuple(int(v) for v in pr[8:13]))
