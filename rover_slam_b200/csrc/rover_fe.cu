@@ -614,7 +614,7 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
       p.out_hi = c->cat.hi + 256;
       p.out_lo = c->cat.lo + 256;
       p.ld_h = 512;
-      if ((r = gemm_linear(c, "lg.out_proj", A, B, p, 128))) return r;
+      if ((r = gemm_linear(c, "lg.out_proj", A, B, p, 64))) return r;
     }
     if ((r = ffn_block(c, rows, L.s_ffn0, L.s_ln_w, L.s_ln_b, L.s_ffn3))) return r;
     // ---------------- cross attention ----------------
@@ -628,7 +628,7 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
       p.out_lo = c->q.lo;
       p.head_major = 1;
       p.head_stride = hs;
-      if ((r = gemm_linear(c, "lg.to_qk", A, B, p, 128))) return r;
+      if ((r = gemm_linear(c, "lg.to_qk", A, B, p, 64))) return r;
     }
     {
       Operand A{c->cat.hi, c->cat.lo, rows, 256, 512, 0, 1};
@@ -639,7 +639,7 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
       p.out_lo = c->vt.lo;
       p.transpose_h = 1;
       p.ld_h = c->lg_ldv;
-      if ((r = gemm_linear(c, "lg.to_v", A, B, p, 128))) return r;
+      if ((r = gemm_linear(c, "lg.to_v", A, B, p, 64))) return r;
     }
     if ((r = attention_fused(c, "lg.attn_cross", c->q, c->q, rows, cross_p, 2 * np, max_n))) return r;
     {
@@ -650,7 +650,7 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
       p.out_hi = c->cat.hi + 256;
       p.out_lo = c->cat.lo + 256;
       p.ld_h = 512;
-      if ((r = gemm_linear(c, "lg.to_out", A, B, p, 128))) return r;
+      if ((r = gemm_linear(c, "lg.to_out", A, B, p, 64))) return r;
     }
     if ((r = ffn_block(c, rows, L.c_ffn0, L.c_ln_w, L.c_ln_b, L.c_ffn3))) return r;
   }
@@ -664,7 +664,7 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
     p.out_hi = c->md.hi;
     p.out_lo = c->md.lo;
     p.ld_h = 256;
-    if ((r = gemm_linear(c, "lg.final_proj", A, B, p, 128))) return r;
+    if ((r = gemm_linear(c, "lg.final_proj", A, B, p, 64))) return r;
   }
   launch_matchability(s, c->x, rows, c->match_w, c->match_b, c->ls);
   c->launches++;

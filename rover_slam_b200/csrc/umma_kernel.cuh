@@ -65,7 +65,9 @@ constexpr int kBlockK = 64;                  // fp16 elements = one 128-byte swi
 constexpr int kStageABytes = kBlockM * 128;  // one of A_hi / A_lo
 // epilogue warps: two per TMEM lane quarter (each takes every other 64-column group) for the wide row-wise epilogues
 __host__ __device__ constexpr int umma_epi_warps(int block_n, int epi) {
-  return (block_n >= 128 && (epi == 0 || epi == 1 || epi == 4)) ? 8 : 4;
+  // measured: 8 warps (two per quarter) were SLOWER than 4 (ffn0 42 vs 33 us): the epilogue is bound by TMEM reads and
+  // memory latency, not by issue slots, and 10 warps cap the kernel at 168 registers.  Kept parameterised.
+  return (block_n >= 512 && epi == 0) ? 8 : 4;
 }
 __host__ __device__ constexpr int umma_threads(int block_n, int epi) { return 64 + 32 * umma_epi_warps(block_n, epi); }
 
