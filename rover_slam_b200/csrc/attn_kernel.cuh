@@ -5,7 +5,9 @@
 // The N x N score matrix never leaves the SM: one CTA owns a 128-query tile of one (problem, head) and walks the
 // 64-key tiles twice.
 //   pass 1: row maximum from the hi*hi product alone (one MMA instead of three; softmax is invariant to the constant
-//           that is subtracted, it only has to be within ~1e-3 of the true maximum to keep exp() in range);
+//           that is subtracted, it only has to be within ~1e-3 of the true maximum to keep exp() in range).  Pass 1
+//           walks 128-key tiles (N = 128 MMAs, the size at which an SS-mode MMA is math- rather than shared-memory-
+//           bound) through a 7-deep ring of K_hi stages that borrows the P and V buffers pass 2 uses later;
 //   pass 2: fp32-equivalent scores, P = exp(S - max) through the SFU, row sums, P handed back to the tensor core
 //           through shared memory (K-major, 128-byte swizzle, double buffered) for O += P V.
 // The epilogue divides by the row sum.
@@ -15,9 +17,11 @@
 //     S:  [S_hh | S_hl] = Q_hi [K_hi;K_lo]^T (N=128) ;  S_hl += Q_lo K_hi^T (N=64)        -> S = S_hh + 2^-11 S_hl
 //     O:  [O_hh | O_hl] += P_hi [V_hi;V_lo]^T (N=128);  O_hl += P_lo V_hi^T (N=64)
 //
-// CTA = 640 threads: warp 0 K producer, warp 1 MMA issuer (+ TMEM alloc), warp 2 V producer, warps 4..19 softmax/epilogue
-// (the four warps with the same w%4 share a TMEM lane quarter and split each tile's 64 columns 16/16/16/16: four
-// warps per scheduler hide the SFU / convert latencies of the exponentials).
+// CTA = 640 threads: warps 0..15 softmax/epilogue (the four warps with the same w%4 share a TMEM lane quarter and split
+// each tile's 64 columns 16/16/16/16: four warps per scheduler hide the SFU / convert latencies of the exponentials),
+// warp 16 K producer, warp 17 V producer, warp 19 MMA issuer (+ TMEM alloc).  The single-thread roles sit in the
+// HIGHEST warp ids on purpose: the warp scheduler arbitrates highest-warp-id-first, so the thread that feeds the
+// tensor pipe is never starved by the sixteen softmax warps sharing its schedulers.
 // TMEM: 3 score buffers x 128 columns + O 128 columns = 512.  The score MMAs run two key tiles ahead of the P V MMAs so
 // that the TMEM -> registers -> exp -> shared memory -> fence -> mbarrier latency of the softmax stage is hidden.
 #pragma once
@@ -37,7 +41,8 @@ struct AttnParams {
 };
 
 constexpr int kAttnSoftmaxWarps = 16;                             // 4 per TMEM lane quarter: 16 of a tile's 64 columns each
-constexpr int kAttnThreads = 128 + 32 * kAttnSoftmaxWarps;      // warps 0..3: K producer, MMA, V producer, idle
+constexpr int kAttnThreads = 128 + 32 * kAttnSoftmaxWarps;      // + warps 16..19: K producer, V producer, idle, MMA
+constexpr int kAttnWarpK = kAttnSoftmaxWarps, kAttnWarpV = kAttnSoftmaxWarps + 1, kAttnWarpMma = kAttnSoftmaxWarps + 3;
 constexpr int kAttnKStages = 4;
 constexpr int kAttnVStages = 3;
 constexpr int kAttnSBufs = 3;                                   // score buffers in TMEM: S runs two tiles ahead of P V
@@ -45,6 +50,7 @@ constexpr int kAttnKeyTile = 64;
 constexpr int kAttnKVBytes = 2 * 8192;                          // one K stage (K_hi | K_lo) or one V stage (Vt_hi | Vt_lo)
 constexpr int kAttnQBytes = 2 * 16384;                          // Q_hi, Q_lo (128 rows x 128 B)
 constexpr int kAttnPBytes = 2 * 16384;                          // one P buffer: P_hi, P_lo (128 rows x 128 B)
+constexpr int kAttnP1Stages = 7;                                // pass-1 K_hi ring: 128 keys x 128 B per stage, in sP | sV
 constexpr int kAttnSmemBytes =
     kAttnQBytes + 2 * kAttnPBytes + (kAttnKStages + kAttnVStages) * kAttnKVBytes + 1024 + 4096;
 
@@ -69,10 +75,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
   // 1024-byte alignment by offsetting the __shared__ array itself (keeps the shared address space: STS/LDS, not generic)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                                   // Q_hi | Q_lo
-  uint8_t* sP = smem + kAttnQBytes;                     // 2 x (P_hi | P_lo)
-  uint8_t* sK = sP + 2 * kAttnPBytes;                   // K stages: K_hi | K_lo
-  uint8_t* sV = sK + kAttnKStages * kAttnKVBytes;       // V stages: Vt_hi | Vt_lo
+  uint8_t* sK = smem + kAttnQBytes;                     // K stages: K_hi | K_lo
+  uint8_t* sP = sK + kAttnKStages * kAttnKVBytes;       // 2 x (P_hi | P_lo)
+  uint8_t* sV = sP + 2 * kAttnPBytes;                   // V stages: Vt_hi | Vt_lo
   uint8_t* tail = sV + kAttnVStages * kAttnKVBytes;
+  uint8_t* s1 = sP;                                     // pass 1: 7 stages of 16 KB (128 keys of K_hi) over sP | sV
+  static_assert(2 * kAttnPBytes + kAttnVStages * kAttnKVBytes == kAttnP1Stages * 16384, "pass-1 ring covers sP | sV");
   uint64_t* q_full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* k_full = q_full + 1;                        // [4]
   uint64_t* k_empty = k_full + kAttnKStages;
@@ -83,8 +91,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
   uint64_t* p_full = s_empty + kAttnSBufs;              // [2]
   uint64_t* p_empty = p_full + 2;                       // [2]
   uint64_t* o_full = p_empty + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 1);
-  float* stat = reinterpret_cast<float*>(tail + 256);   // [4][128] partial row max, then partial row sum
+  uint64_t* k1_full = o_full + 1;                       // [7]
+  uint64_t* k1_empty = k1_full + kAttnP1Stages;         // [7]
+  uint64_t* p1_done = k1_empty + kAttnP1Stages;         // all pass-1 MMAs have retired: sP | sV may be rewritten
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(p1_done + 1);
+  float* stat = reinterpret_cast<float*>(tail + 512);   // [4][128] partial row max, then partial row sum
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int z = blockIdx.z;
@@ -93,9 +104,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
   const int m0 = blockIdx.x * 128;
   if (m0 >= nq) return;                                 // uniform per CTA
   const int T = (nk + kAttnKeyTile - 1) / kAttnKeyTile;
+  const int T1 = (nk + 127) / 128;                      // pass-1 tiles (128 keys)
   const int qrow = p.q_row0[z] + m0, krow = p.k_row0[z];
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kAttnWarpK && lane == 0) {
     tma_prefetch_desc(&tmQ_hi); tma_prefetch_desc(&tmQ_lo); tma_prefetch_desc(&tmK_hi);
     tma_prefetch_desc(&tmK_lo); tma_prefetch_desc(&tmV_hi); tma_prefetch_desc(&tmV_lo);
     mbar_init(q_full, 1);
@@ -104,9 +116,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
     for (int s = 0; s < kAttnSBufs; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kAttnSoftmaxWarps); }
     for (int s = 0; s < 2; ++s) { mbar_init(&p_full[s], kAttnSoftmaxWarps); mbar_init(&p_empty[s], 1); }
     mbar_init(o_full, 1);
+    for (int s = 0; s < kAttnP1Stages; ++s) { mbar_init(&k1_full[s], 1); mbar_init(&k1_empty[s], 1); }
+    mbar_init(p1_done, 1);
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kAttnWarpMma) {
     tmem_alloc(tmem_ptr_smem, 512);
     tmem_relinquish();
   }
@@ -116,26 +130,33 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_ptr_smem;
   // TMEM columns: score buffer b: [hh | hl] at b*128 ; O: [hh | hl] at 384
 
-  if (warp == 0) {
+  if (warp == kAttnWarpK) {
     // ===== K producer: Q once; pass 1 needs K_hi only, pass 2 both planes =====================================
     if (elect_one()) {
       mbar_expect_tx(q_full, kAttnQBytes);
       tma_load_3d(sQ, &tmQ_hi, q_full, 0, qrow, head);
       tma_load_3d(sQ + 16384, &tmQ_lo, q_full, 0, qrow, head);
-      for (int g = 0; g < 2 * T; ++g) {
-        const int t = g < T ? g : g - T;
-        const bool pass2 = g >= T;
-        const int st = g % kAttnKStages;
-        mbar_wait(&k_empty[st], ((g / kAttnKStages) & 1) ^ 1);
+      for (int g = 0; g < T1; ++g) {           // pass 1: 128 keys of K_hi per stage
+        const int st = g % kAttnP1Stages;
+        mbar_wait(&k1_empty[st], ((g / kAttnP1Stages) & 1) ^ 1);
+        uint8_t* sb = s1 + st * 16384;
+        mbar_expect_tx(&k1_full[st], 16384);
+        tma_load_3d(sb, &tmK_hi, &k1_full[st], 0, krow + g * 128, head);
+        tma_load_3d(sb + 8192, &tmK_hi, &k1_full[st], 0, krow + g * 128 + 64, head);
+      }
+      for (int t = 0; t < T; ++t) {            // pass 2: the sK ring is untouched by pass 1, so these loads run ahead
+        const int st = t % kAttnKStages;
+        mbar_wait(&k_empty[st], ((t / kAttnKStages) & 1) ^ 1);
         uint8_t* sb = sK + st * kAttnKVBytes;
-        mbar_expect_tx(&k_full[st], pass2 ? kAttnKVBytes : 8192);
+        mbar_expect_tx(&k_full[st], kAttnKVBytes);
         tma_load_3d(sb, &tmK_hi, &k_full[st], 0, krow + t * kAttnKeyTile, head);
-        if (pass2) tma_load_3d(sb + 8192, &tmK_lo, &k_full[st], 0, krow + t * kAttnKeyTile, head);
+        tma_load_3d(sb + 8192, &tmK_lo, &k_full[st], 0, krow + t * kAttnKeyTile, head);
       }
     }
-  } else if (warp == 2) {
+  } else if (warp == kAttnWarpV) {
     // ===== V producer =================================================================================================
     if (elect_one()) {
+      mbar_wait(p1_done, 0);                   // the V stages double as pass-1 K_hi stages
       for (int t = 0; t < T; ++t) {
         const int st = t % kAttnVStages;
         mbar_wait(&v_empty[st], ((t / kAttnVStages) & 1) ^ 1);
@@ -145,7 +166,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
         tma_load_3d(sb + 8192, &tmV_lo, &v_full[st], krow + t * kAttnKeyTile, 0, head);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kAttnWarpMma) {
     // ===== MMA issuer ===========================================================================================
     if (elect_one()) {
       constexpr uint32_t idesc64 = make_idesc_f16(128, 64);
@@ -157,10 +178,28 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       const long long t_begin = clock64();
       mbar_wait(q_full, 0);
       const long long t_q = clock64();
-      auto issue_s = [&](int g, bool full) {
-        const int st = g % kAttnKStages, b = g % kAttnSBufs;
+      auto issue_s1 = [&](int g) {          // pass 1: S_hh of 128 keys, one N=128 MMA per k-step
+        const int st = g % kAttnP1Stages, b = g % kAttnSBufs;
         long long c0 = clock64();
-        mbar_wait(&k_full[st], (g / kAttnKStages) & 1);
+        mbar_wait(&k1_full[st], (g / kAttnP1Stages) & 1);
+        long long c1 = clock64();
+        mbar_wait(&s_empty[b], ((g / kAttnSBufs) & 1) ^ 1);
+        w_k += c1 - c0;
+        w_se += clock64() - c1;
+        tc_fence_after();
+        const uint32_t k_hi = smem_u32(s1 + st * 16384);
+        const uint32_t s_base = tmem_base + b * 128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(s_base, make_sw128_kmajor_desc(q_hi + k * 32), make_sw128_kmajor_desc(k_hi + k * 32), idesc128, k > 0);
+        umma_commit(&s_full[b]);
+        umma_commit(&k1_empty[st]);
+      };
+      auto issue_s = [&](int t) {           // pass 2: fp32-equivalent scores of key tile t (S buffer index continues at T1)
+        const int g = T1 + t;
+        const int st = t % kAttnKStages, b = g % kAttnSBufs;
+        long long c0 = clock64();
+        mbar_wait(&k_full[st], (t / kAttnKStages) & 1);
         long long c1 = clock64();
         mbar_wait(&s_empty[b], ((g / kAttnSBufs) & 1) ^ 1);
         w_k += c1 - c0;
@@ -170,14 +209,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
         const uint32_t s_base = tmem_base + b * 128;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint64_t dq_hi = make_sw128_kmajor_desc(q_hi + k * 32);
           const uint64_t dk = make_sw128_kmajor_desc(k_hi + k * 32);
-          if (full) {
-            umma_f16(s_base, dq_hi, dk, idesc128, k > 0);                                      // [S_hh | S_hl]
-            umma_f16(s_base + 64, make_sw128_kmajor_desc(q_lo + k * 32), dk, idesc64, 1u);     // S_hl += Q_lo K_hi^T
-          } else {
-            umma_f16(s_base, dq_hi, dk, idesc64, k > 0);                                       // S_hh only
-          }
+          umma_f16(s_base, make_sw128_kmajor_desc(q_hi + k * 32), dk, idesc128, k > 0);        // [S_hh | S_hl]
+          umma_f16(s_base + 64, make_sw128_kmajor_desc(q_lo + k * 32), dk, idesc64, 1u);       // S_hl += Q_lo K_hi^T
         }
         umma_commit(&s_full[b]);
         umma_commit(&k_empty[st]);          // the K stage is free as soon as these MMAs retire
@@ -203,13 +237,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
         umma_commit(&p_empty[pb]);
       };
       // pass 1: hi*hi scores only
-      for (int g = 0; g < T; ++g) issue_s(g, false);
+      for (int g = 0; g < T1; ++g) issue_s1(g);
+      umma_commit(p1_done);
       const long long t_p1 = clock64();
       // pass 2: the score MMAs run two tiles ahead of the P V MMAs
-      issue_s(T, true);
-      if (T > 1) issue_s(T + 1, true);
+      issue_s(0);
+      if (T > 1) issue_s(1);
       for (int t = 0; t < T; ++t) {
-        if (t + 2 < T) issue_s(T + t + 2, true);
+        if (t + 2 < T) issue_s(t + 2);
         issue_pv(t);
       }
       umma_commit(o_full);
@@ -225,9 +260,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
         p.prof[7] = T;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < kAttnSoftmaxWarps) {
     // ===== softmax / epilogue warps =========================================================================
-    const int sw = warp - 4;                 // 0..15
+    const int sw = warp;                     // 0..15
     const int q = warp & 3;                  // TMEM lane quarter
     const int cq = sw >> 2;                  // which 16-column quarter of every 64-key tile
     const int row = q * 32 + lane;
@@ -238,23 +273,23 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
 
     // ---- pass 1: row maximum of the hi*hi scores ----
     float mx = NEG;
-    for (int g = 0; g < T; ++g) {
+    for (int g = 0; g < T1; ++g) {
       const int b = g % kAttnSBufs;
       mbar_wait(&s_full[b], (g / kAttnSBufs) & 1);
       tc_fence_after();
-      uint32_t a0[16];
-      tmem_ld16(tlane + b * 128 + cq * 16, a0);
+      uint32_t a0[32];
+      tmem_ld32(tlane + b * 128 + cq * 32, a0);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[b]);
-      const int c0 = g * kAttnKeyTile + cq * 16;
-      if (c0 + 16 <= nk) {
+      const int c0 = g * 128 + cq * 32;
+      if (c0 + 32 <= nk) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(a0[j]));
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(a0[j]));
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
+        for (int j = 0; j < 32; ++j)
           if (c0 + j < nk) mx = fmaxf(mx, __uint_as_float(a0[j]));
       }
     }
@@ -267,7 +302,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
     // ---- pass 2: P = exp(S - max) -> smem (K-major, 128-byte swizzle), row sum ----
     float l = 0.0f;
     for (int t = 0; t < T; ++t) {
-      const int g = T + t, b = g % kAttnSBufs, pb = t & 1;
+      const int g = T1 + t, b = g % kAttnSBufs, pb = t & 1;
       mbar_wait(&s_full[b], (g / kAttnSBufs) & 1);
       tc_fence_after();
       uint32_t a0[16], x0[16];
@@ -345,7 +380,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
   }
 
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kAttnWarpMma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

@@ -13,8 +13,9 @@
 //   per iteration (2 output rows x 128 px): A traffic 2 rows x 130 px x 256 B = 66.5 KB, weights 9 x 16 KB = 147 KB
 //   (umma_kernel: 2 tiles x 9 x 48 KB = 864 KB).
 //
-// CTA = 384 threads: warp 0 = TMA producer for input rows, warp 1 = MMA issuer (+TMEM alloc), warp 2 = TMA producer
-// for the per-tap weight tiles, warps 4..11 = epilogue (two warps per TMEM lane quarter, 32 channels each).
+// CTA = 384 threads: warps 0..7 = epilogue (two warps per TMEM lane quarter, 32 channels each), warp 8 = TMA producer
+// for input rows, warp 9 = TMA producer for the per-tap weight tiles, warp 11 = MMA issuer (+TMEM alloc).  The
+// single-thread roles have the highest warp ids: the scheduler arbitrates highest-id-first.
 // Tensor-core cost model (probe 1 in probe_kernels.cu): an SS-mode MMA costs max(~60, N/2) cycles, so N = 64 wastes
 // half the pipe.  Each k16 step therefore issues  A_hi x [W_hi;W_lo]^T  as ONE N=128 MMA (hi*hi and hi*lo products
 // land in adjacent accumulators) plus  A_lo x W_hi^T  (N=64): 2 instructions instead of 3.
@@ -43,6 +44,7 @@ struct StripParams {
 };
 
 constexpr int kStripThreads = 384;
+constexpr int kStripWarpRows = 8, kStripWarpW = 9, kStripWarpMma = 11;
 constexpr int kStripRowBytes = 130 * 128;        // one plane of one input row of the strip (with 1-px halo each side)
 constexpr int kStripSlotBytes = 17 * 1024;       // slot pitch (1024-aligned for the swizzle)
 constexpr int kStripRowSlots = 4;
@@ -74,7 +76,7 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kStripWarpRows && lane == 0) {
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmW_hi); tma_prefetch_desc(&tmW_lo);
     for (int s = 0; s < kStripRowSlots; ++s) { mbar_init(&row_full[s], 1); mbar_init(&row_empty[s], 1); }
     for (int s = 0; s < kStripWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
@@ -82,7 +84,7 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     mbar_init(acc_empty, 8);
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kStripWarpMma) {
     tmem_alloc(tmem_ptr_smem, 512);
     tmem_relinquish();
   }
@@ -103,7 +105,7 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     iters = rows >> 1;
   };
 
-  if (warp == 0) {
+  if (warp == kStripWarpRows) {
     // ===== input-row producer: row sequence number n -> slot n & 3 =====================================================
     if (elect_one()) {
       uint32_t n = 0;
@@ -120,7 +122,7 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         }
       }
     }
-  } else if (warp == 2) {
+  } else if (warp == kStripWarpW) {
     // ===== weight producer: tap sequence number m -> stage m & 3 ======================================================
     if (elect_one()) {
       uint32_t m = 0;
@@ -138,7 +140,7 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kStripWarpMma) {
     // ===== MMA issuer ==================================================================================================
     if (elect_one()) {
       constexpr uint32_t idesc64 = make_idesc_f16(128, 64);
@@ -216,10 +218,10 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         p.prof[4] = gi;                    // iterations
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // ===== epilogue warps ==============================================================================================
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;               // channels [32*half, 32*half + 32)
+    const int half = warp >> 2;                     // channels [32*half, 32*half + 32)
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t gi = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
@@ -231,31 +233,40 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const int y = y_begin + 2 * it;
         mbar_wait(acc_full, gi & 1);
         tc_fence_after();
-#pragma unroll 1
+        // all of this warp's accumulator values first (2 rows x 32 channels), so the accumulators go back to the MMA
+        // warp before the bias / pool / split / store work starts (the single accumulator set is not double-buffered)
+        float v[2][32];
+#pragma unroll
         for (int c = 0; c < 32; c += 16) {
-          const int ch = half * 32 + c;
-          float v[2][16];
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
             uint32_t a0[16], a1[16], xl[16];
-            const uint32_t base = tlane + r * 192 + ch;
+            const uint32_t base = tlane + r * 192 + half * 32 + c;
             tmem_ld16(base, a0);            // hh_a
             tmem_ld16(base + 128, a1);      // hh_b
             tmem_ld16(base + 64, xl);       // hl
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float t = (__uint_as_float(a0[j]) + __uint_as_float(a1[j])) + __uint_as_float(xl[j]) * RFE_SPLIT_INV +
-                              __ldg(p.bias + ch + j);
-              v[r][j] = fmaxf(t, 0.0f);
-            }
+            for (int j = 0; j < 16; ++j)
+              v[r][c + j] = (__uint_as_float(a0[j]) + __uint_as_float(a1[j])) + __uint_as_float(xl[j]) * RFE_SPLIT_INV;
           }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+#pragma unroll
+        for (int c = 0; c < 32; c += 16) {
+          const int ch = half * 32 + c;
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[r][c + j] = fmaxf(v[r][c + j] + __ldg(p.bias + ch + j), 0.0f);
           if (p.pool) {
             __align__(16) __half hi[16];
             __align__(16) __half lo[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              float t = fmaxf(v[0][j], v[1][j]);
+              float t = fmaxf(v[0][c + j], v[1][c + j]);
               t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
               split_f32(t, hi[j], lo[j]);
             }
@@ -272,7 +283,7 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
               __align__(16) __half hi[16];
               __align__(16) __half lo[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) split_f32(v[r][j], hi[j], lo[j]);
+              for (int j = 0; j < 16; ++j) split_f32(v[r][c + j], hi[j], lo[j]);
               if (x < p.W) {
                 const size_t o = ((static_cast<size_t>(b) * Ho + (y + r)) * Wo + x) * 64 + ch;
                 reinterpret_cast<uint4*>(p.out_hi + o)[0] = reinterpret_cast<const uint4*>(hi)[0];
@@ -283,15 +294,12 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty);
       }
     }
   }
 
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kStripWarpMma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

@@ -189,4 +189,121 @@ int launch_probe_mma_rate(cudaStream_t s, float* out, int reps) {
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+//  probe 2: A operand from TMEM ("TS" mode).  Each thread packs its fp16 A row (64 values -> 32 columns of half2, low
+//           half = even k) and writes it with tcgen05.st.32x32b; the MMA for k-step k reads A at column base + 8*k.
+//           Checks D = A B^T and times back-to-back TS MMAs for N = 64 / 128 (out[8192 + i]).
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(128, 1) probe_ts_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
+                                                          float* __restrict__ out, int reps) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sB = smem;                 // 128 rows * 128 B (rows 64.. repeat b)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 16384);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 128 * 8; i += 128) {
+    const int r = i >> 3, ch = i & 7;
+    const uint32_t addr = smem_u32(sB) + r * 128;
+    const int sw = ch ^ ((addr >> 7) & 7);
+    *reinterpret_cast<uint4*>(sB + r * 128 + sw * 16) = *reinterpret_cast<const uint4*>(b + (r & 63) * 64 + ch * 8);
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tptr, 256);
+    tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tptr;
+  const uint32_t a_col = 128;                     // A lives in columns [128, 160)
+  {
+    const uint32_t* arow = reinterpret_cast<const uint32_t*>(a + static_cast<size_t>(threadIdx.x) * 64);
+    const uint32_t tl = tmem + (static_cast<uint32_t>(warp * 32) << 16) + a_col;
+#pragma unroll
+    for (int c = 0; c < 32; c += 8) {
+      uint32_t r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = arow[c + j];
+      tmem_st8(tl + c, r);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  int phase = 0;
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_f16(128, 64);
+    for (int k = 0; k < 4; ++k)
+      umma_f16_ts(tmem, tmem + a_col + k * 8, make_sw128_kmajor_desc(smem_u32(sB) + k * 32), idesc, k > 0);
+    umma_commit(bar);
+  }
+  mbar_wait(bar, phase);
+  phase ^= 1;
+  tc_fence_after();
+  {
+    float* o = out + static_cast<size_t>(warp * 32 + lane) * 64;
+    for (int c = 0; c < 64; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c, r);
+      tmem_ld_wait();
+      for (int j = 0; j < 16; ++j) o[c + j] = __uint_as_float(r[j]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  // timing: TS MMAs, N = 64 and N = 128, then a 2:1 mix SS N=128 + TS N=64 (the attention inner loop)
+  for (int v = 0; v < 3; ++v) {
+    long long t0 = 0;
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      constexpr uint32_t id64 = make_idesc_f16(128, 64), id128 = make_idesc_f16(128, 128);
+      t0 = clock64();
+      for (int i = 0; i < reps; ++i) {
+        const uint64_t db = make_sw128_kmajor_desc(smem_u32(sB) + (i & 3) * 32);
+        if (v == 0) umma_f16_ts(tmem, tmem + a_col + (i & 3) * 8, db, id64, 1u);
+        else if (v == 1) umma_f16_ts(tmem, tmem + a_col + (i & 3) * 8, db, id128, 1u);
+        else {
+          umma_f16(tmem, make_sw128_kmajor_desc(smem_u32(sB) + (i & 3) * 32), db, id128, 1u);
+          umma_f16_ts(tmem + 64, tmem + a_col + (i & 3) * 8, db, id64, 1u);
+        }
+      }
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    if (threadIdx.x == 0) out[8192 + v] = static_cast<float>(clock64() - t0) / reps;
+    __syncthreads();
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+int launch_probe_ts(cudaStream_t s, const __half* a, const __half* b, float* out, int reps) {
+  const int smem = 16384 + 64 + 1024;
+  probe_ts_kernel<<<1, 128, smem, s>>>(a, b, out, reps);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 }  // namespace rfe

@@ -250,7 +250,7 @@ struct ProfScope {   // records a CUDA event pair around one launch when profili
 
 template <int BLOCK_N, int AMODE, int EPI>
 int launch_umma(rfe_ctx* c, const char* tag, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
-                const CUtensorMap& b_lo, const UmmaParams& p, dim3 grid) {
+                const CUtensorMap& b_lo, const UmmaParams& p, dim3 grid, const EpiMaps* em = nullptr) {
   static bool configured[64] = {};
   auto kern = umma_kernel<BLOCK_N, AMODE, EPI>;
   if (!configured[c->device & 63]) {
@@ -265,7 +265,8 @@ int launch_umma(rfe_ctx* c, const char* tag, const CUtensorMap& a_hi, const CUte
   pp.prof = (c->attn_prof && c->prof_tag && !strcmp(tag, c->prof_tag)) ? c->attn_prof + 16 : nullptr;
   const int ctas = pp.num_tiles < c->num_sms ? pp.num_tiles : c->num_sms;
   ProfScope ps(c, tag);
-  kern<<<ctas, umma_threads(BLOCK_N, EPI), umma_smem_bytes(BLOCK_N), c->stream>>>(a_hi, a_lo, b_hi, b_lo, pp);
+  static const EpiMaps kNoMaps = {};
+  kern<<<ctas, umma_threads(BLOCK_N, EPI), umma_smem_bytes(BLOCK_N), c->stream>>>(a_hi, a_lo, b_hi, b_lo, em ? *em : kNoMaps, pp);
   c->launches++;
   RFE_CUDA_CHECK(cudaGetLastError());
   return RFE_OK;
@@ -289,6 +290,24 @@ int make_operand_maps(const Operand& o, int box_rows, CUtensorMap* mh, CUtensorM
   return RFE_OK;
 }
 
+// 3-D output map for the TMA-store epilogue: (cols, rows, batch) with a 32 x 32 box; fp32 tiles are staged with the
+// 128-byte swizzle (32 x 4 B per row), fp16 planes with the 64-byte swizzle (32 x 2 B per row).
+int make_out_map(CUtensorMap* m, const void* base, bool f32, int cols, int rows, long long ld, int batch, long long bstride) {
+  const size_t es = f32 ? 4 : 2;
+  const uint64_t dims[3] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(rows), static_cast<uint64_t>(batch > 1 ? batch : 1)};
+  const uint64_t strides[2] = {static_cast<uint64_t>(ld) * es,
+                               static_cast<uint64_t>(batch > 1 ? bstride : static_cast<long long>(rows) * ld) * es};
+  const uint32_t box[3] = {32, 32, 1};
+  return make_tmap(m, f32 ? 1 : 0, f32 ? 3 : 2, base, 3, dims, strides, box) ? RFE_ERR_CUDA : RFE_OK;
+}
+// head-major planes [heads][rows][64]
+int make_head_map(CUtensorMap* m, const void* base, int rows, long long head_stride, int heads) {
+  const uint64_t dims[3] = {64, static_cast<uint64_t>(rows), static_cast<uint64_t>(heads)};
+  const uint64_t strides[2] = {128, static_cast<uint64_t>(head_stride) * 2};
+  const uint32_t box[3] = {32, 32, 1};
+  return make_tmap(m, 0, 2, base, 3, dims, strides, box) ? RFE_ERR_CUDA : RFE_OK;
+}
+
 UmmaParams default_params() {
   UmmaParams p;
   memset(&p, 0, sizeof(p));
@@ -310,8 +329,21 @@ int gemm_linear(rfe_ctx* c, const char* tag, const Operand& A, const Operand& B,
   p.b_batched = B.batch > 1;
   const int z = A.batch > B.batch ? A.batch : B.batch;
   dim3 grid((A.rows + kBlockM - 1) / kBlockM, (B.rows + block_n - 1) / block_n, z);
-  if (block_n == 64) return launch_umma<64, A_GEMM, EPI_LINEAR>(c, tag, ah, al, bh, bl, p, grid);
-  return launch_umma<128, A_GEMM, EPI_LINEAR>(c, tag, ah, al, bh, bl, p, grid);
+  EpiMaps em;
+  memset(&em, 0, sizeof(em));
+  if (p.out_f32 && (r = make_out_map(&em.f32, p.out_f32, true, p.N, p.M, p.ld_f32, z, p.bstride_f32))) return r;
+  if (p.residual && (r = make_out_map(&em.res, p.residual, true, p.N, p.M, p.ld_res, z, p.bstride_res))) return r;
+  if (p.out_hi && !p.transpose_h) {
+    if (p.head_major) {
+      if ((r = make_head_map(&em.h_hi, p.out_hi, p.M, p.head_stride, p.N / 64))) return r;
+      if ((r = make_head_map(&em.h_lo, p.out_lo, p.M, p.head_stride, p.N / 64))) return r;
+    } else {
+      if ((r = make_out_map(&em.h_hi, p.out_hi, false, p.N, p.M, p.ld_h, z, p.bstride_h))) return r;
+      if ((r = make_out_map(&em.h_lo, p.out_lo, false, p.N, p.M, p.ld_h, z, p.bstride_h))) return r;
+    }
+  }
+  if (block_n == 64) return launch_umma<64, A_GEMM, EPI_LINEAR>(c, tag, ah, al, bh, bl, p, grid, &em);
+  return launch_umma<128, A_GEMM, EPI_LINEAR>(c, tag, ah, al, bh, bl, p, grid, &em);
 }
 
 // 3x3 conv (pad 1) + bias + ReLU (+ 2x2 max-pool), NHWC split-fp16 in/out.
@@ -390,7 +422,7 @@ int conv64_strip(rfe_ctx* c, const char* tag, const SplitBuf& in, int B, int H, 
 int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B) {
   cudaStream_t s = c->stream;
   int r;
-  launch_conv1a(s, d_gray, stride, h, w, B, c->conv1a_w, c->conv1a_b, c->a1a.hi, c->a1a.lo);
+  { ProfScope ps_(c, "sp.conv1a"); launch_conv1a(s, d_gray, stride, h, w, B, c->conv1a_w, c->conv1a_b, c->a1a.hi, c->a1a.lo); }
   c->launches++;
   if (c->use_strip_conv) {
     if ((r = conv64_strip(c, "sp.conv1b", c->a1a, B, h, w, c->c1b, c->a1, true))) return r;
@@ -440,10 +472,10 @@ int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B) {
     p.ld_f32 = 256;
     if ((r = launch_umma<256, A_GEMM, EPI_DESC>(c, "sp.convDb_l2norm", ah, al, bh, bl, p, dim3((npix + 127) / 128, 1, 1)))) return r;
   }
-  launch_nms(s, c->heat, c->nmsmap, B, h, w);
-  launch_select(s, c->nmsmap, B, h, w, kDetThreshold, c->cap, c->row_cnt, c->row_off, c->kp_counts, c->kpts,
-                c->kp_scores);
-  launch_desc_sample(s, c->dense, hc, wc, B, c->kpts, c->kp_counts, c->cap, c->desc);
+  { ProfScope ps_(c, "sp.nms"); launch_nms(s, c->heat, c->nmsmap, B, h, w); }
+  { ProfScope ps_(c, "sp.select"); launch_select(s, c->nmsmap, B, h, w, kDetThreshold, c->cap, c->row_cnt, c->row_off, c->kp_counts, c->kpts,
+                c->kp_scores); }
+  { ProfScope ps_(c, "sp.desc_sample"); launch_desc_sample(s, c->dense, hc, wc, B, c->kpts, c->kp_counts, c->cap, c->desc); }
   c->launches += 5;
   RFE_CUDA_CHECK(cudaGetLastError());
   c->last_batch = B;
@@ -467,7 +499,7 @@ int ffn_block(rfe_ctx* c, int rows, const SplitW& ffn0, const float* ln_w, const
     p.ld_f32 = 512;
     if ((r = gemm_linear(c, "lg.ffn0", A, B, p, 128))) return r;
   }
-  launch_ln_gelu_split(c->stream, c->hid, rows, ln_w, ln_b, c->hs.hi, c->hs.lo);
+  { ProfScope ps_(c, "lg.ln_gelu"); launch_ln_gelu_split(c->stream, c->hid, rows, ln_w, ln_b, c->hs.hi, c->hs.lo); }
   c->launches++;
   {   // x = x + hs @ ffn3^T + b ; refresh split(x) in cat[:, 0:256]
     Operand A{c->hs.hi, c->hs.lo, rows, 512, 512, 0, 1};
@@ -554,14 +586,14 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
   }
   for (int i = 0; i < np; ++i) {
     const PairDesc& pd = pairs[i];
-    launch_posenc(s, pd.kpts0, pd.n0, norm_h, norm_w, c->posenc_w, c->cs + static_cast<size_t>(off0[i]) * 32,
-                  c->sn + static_cast<size_t>(off0[i]) * 32);
-    launch_posenc(s, pd.kpts1, pd.n1, norm_h, norm_w, c->posenc_w, c->cs + static_cast<size_t>(off1[i]) * 32,
-                  c->sn + static_cast<size_t>(off1[i]) * 32);
-    launch_split_rows(s, pd.desc0, pd.n0, 256, 256, c->x + static_cast<size_t>(off0[i]) * 256, 256,
-                      c->cat.hi + static_cast<size_t>(off0[i]) * 512, c->cat.lo + static_cast<size_t>(off0[i]) * 512, 512);
-    launch_split_rows(s, pd.desc1, pd.n1, 256, 256, c->x + static_cast<size_t>(off1[i]) * 256, 256,
-                      c->cat.hi + static_cast<size_t>(off1[i]) * 512, c->cat.lo + static_cast<size_t>(off1[i]) * 512, 512);
+    { ProfScope ps_(c, "lg.posenc"); launch_posenc(s, pd.kpts0, pd.n0, norm_h, norm_w, c->posenc_w, c->cs + static_cast<size_t>(off0[i]) * 32,
+                  c->sn + static_cast<size_t>(off0[i]) * 32); }
+    { ProfScope ps_(c, "lg.posenc"); launch_posenc(s, pd.kpts1, pd.n1, norm_h, norm_w, c->posenc_w, c->cs + static_cast<size_t>(off1[i]) * 32,
+                  c->sn + static_cast<size_t>(off1[i]) * 32); }
+    { ProfScope ps_(c, "lg.split_rows"); launch_split_rows(s, pd.desc0, pd.n0, 256, 256, c->x + static_cast<size_t>(off0[i]) * 256, 256,
+                      c->cat.hi + static_cast<size_t>(off0[i]) * 512, c->cat.lo + static_cast<size_t>(off0[i]) * 512, 512); }
+    { ProfScope ps_(c, "lg.split_rows"); launch_split_rows(s, pd.desc1, pd.n1, 256, 256, c->x + static_cast<size_t>(off1[i]) * 256, 256,
+                      c->cat.hi + static_cast<size_t>(off1[i]) * 512, c->cat.lo + static_cast<size_t>(off1[i]) * 512, 512); }
     c->launches += 4;
   }
   AttnParams self_p, cross_p;
@@ -603,7 +635,12 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
       p.vt_lo = c->vt.lo;
       p.ldv = c->lg_ldv;
       p.head_stride = hs;
-      if ((r = launch_umma<128, A_GEMM, EPI_QKV>(c, "lg.wqkv_rope", ah, al, bh, bl, p, dim3((rows + 127) / 128, 6, 1)))) return r;
+      EpiMaps em;
+      memset(&em, 0, sizeof(em));
+      if ((r = make_head_map(&em.h_hi, c->q.hi, rows, hs, 4)) || (r = make_head_map(&em.h_lo, c->q.lo, rows, hs, 4)) ||
+          (r = make_head_map(&em.k_hi, c->k.hi, rows, hs, 4)) || (r = make_head_map(&em.k_lo, c->k.lo, rows, hs, 4)))
+        return r;
+      if ((r = launch_umma<128, A_GEMM, EPI_QKV>(c, "lg.wqkv_rope", ah, al, bh, bl, p, dim3((rows + 127) / 128, 6, 1), &em))) return r;
     }
     if ((r = attention_fused(c, "lg.attn_self", c->q, c->k, rows, self_p, 2 * np, max_n))) return r;
     {
@@ -666,7 +703,7 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
     p.ld_h = 256;
     if ((r = gemm_linear(c, "lg.final_proj", A, B, p, 64))) return r;
   }
-  launch_matchability(s, c->x, rows, c->match_w, c->match_b, c->ls);
+  { ProfScope ps_(c, "lg.matchability"); launch_matchability(s, c->x, rows, c->match_w, c->match_b, c->ls); }
   c->launches++;
   for (int i = 0; i < np; ++i) {
     const int n0 = pairs[i].n0, n1 = pairs[i].n1, rslot = pairs[i].rslot;
@@ -679,12 +716,12 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
       p.ld_f32 = ld;
       if ((r = gemm_linear(c, "lg.sim", A, B, p, 128))) return r;
     }
-    launch_lse(s, c->sim, n0, n1, ld, c->rmax, c->rlog, c->cmax, c->clog);
-    launch_argmax(s, c->sim, n0, n1, ld, c->rmax, c->rlog, c->cmax, c->clog, c->ls + off0[i], c->ls + off1[i], c->max0,
-                  c->m0, c->m1, c->S_dbg);
-    launch_match_compact(s, c->max0, c->m0, c->m1, n0, kFilterThreshold, thresh,
+    { ProfScope ps_(c, "lg.lse"); launch_lse(s, c->sim, n0, n1, ld, c->rmax, c->rlog, c->cmax, c->clog); }
+    { ProfScope ps_(c, "lg.argmax"); launch_argmax(s, c->sim, n0, n1, ld, c->rmax, c->rlog, c->cmax, c->clog, c->ls + off0[i], c->ls + off1[i], c->max0,
+                  c->m0, c->m1, c->S_dbg); }
+    { ProfScope ps_(c, "lg.compact"); launch_match_compact(s, c->max0, c->m0, c->m1, n0, kFilterThreshold, thresh,
                          c->res_matches + static_cast<size_t>(rslot) * c->cap * 2,
-                         c->res_scores + static_cast<size_t>(rslot) * c->cap, c->res_count + rslot);
+                         c->res_scores + static_cast<size_t>(rslot) * c->cap, c->res_count + rslot); }
     c->launches += 5;
     c->dbg_n0 = n0;
     c->dbg_n1 = n1;
@@ -699,6 +736,7 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
 namespace rfe {
 int launch_probe_shift(cudaStream_t s, const __half* a, const __half* b, float* out);
 int launch_probe_mma_rate(cudaStream_t s, float* out, int reps);
+int launch_probe_ts(cudaStream_t s, const __half* a, const __half* b, float* out, int reps);
 }
 namespace {
 
@@ -975,8 +1013,8 @@ int rfe_lg_match_slots_batch(rfe_ctx* c, int n_pairs, const int* slot0, const in
     koff += round_up(n0, 8);
     float* k1 = c->in_kpts + koff * 2;
     koff += round_up(n1, 8);
-    launch_kpts_to_float(c->stream, c->kpts + static_cast<size_t>(s0) * c->cap * 2, n0, k0);
-    launch_kpts_to_float(c->stream, c->kpts + static_cast<size_t>(s1) * c->cap * 2, n1, k1);
+    { ProfScope ps_(c, "lg.kpts_to_float"); launch_kpts_to_float(c->stream, c->kpts + static_cast<size_t>(s0) * c->cap * 2, n0, k0); }
+    { ProfScope ps_(c, "lg.kpts_to_float"); launch_kpts_to_float(c->stream, c->kpts + static_cast<size_t>(s1) * c->cap * 2, n1, k1); }
     c->launches += 2;
     pd[i] = PairDesc{k0, k1, c->desc + static_cast<size_t>(s0) * c->cap * 256, c->desc + static_cast<size_t>(s1) * c->cap * 256,
                      n0, n1, i};
@@ -996,8 +1034,8 @@ int rfe_lg_match_slots(rfe_ctx* c, int slot0, int slot1, int norm_h, int norm_w,
   const int n0 = c->h_counts[slot0] < c->cap ? c->h_counts[slot0] : c->cap;
   const int n1 = c->h_counts[slot1] < c->cap ? c->h_counts[slot1] : c->cap;
   const int n0p = round_up(n0, 8);
-  launch_kpts_to_float(c->stream, c->kpts + static_cast<size_t>(slot0) * c->cap * 2, n0, c->in_kpts);
-  launch_kpts_to_float(c->stream, c->kpts + static_cast<size_t>(slot1) * c->cap * 2, n1, c->in_kpts + static_cast<size_t>(n0p) * 2);
+  { ProfScope ps_(c, "lg.kpts_to_float"); launch_kpts_to_float(c->stream, c->kpts + static_cast<size_t>(slot0) * c->cap * 2, n0, c->in_kpts); }
+  { ProfScope ps_(c, "lg.kpts_to_float"); launch_kpts_to_float(c->stream, c->kpts + static_cast<size_t>(slot1) * c->cap * 2, n1, c->in_kpts + static_cast<size_t>(n0p) * 2); }
   c->launches += 2;
   PairDesc pd{c->in_kpts, c->in_kpts + static_cast<size_t>(n0p) * 2, c->desc + static_cast<size_t>(slot0) * c->cap * 256,
               c->desc + static_cast<size_t>(slot1) * c->cap * 256, n0, n1, rslot};
@@ -1242,7 +1280,8 @@ int rfe_debug_gemm(rfe_ctx* c, const float* a, const float* b, const float* bias
   RFE_CUDA_CHECK(cudaMalloc(&dal, ah.size() * 2));
   RFE_CUDA_CHECK(cudaMalloc(&dbh, bh.size() * 2));
   RFE_CUDA_CHECK(cudaMalloc(&dbl, bh.size() * 2));
-  RFE_CUDA_CHECK(cudaMalloc(&dd, static_cast<size_t>(m) * n * 4));
+  const int ldd = round_up(n, 4);      // the TMA-store epilogue needs a 16-byte row pitch
+  RFE_CUDA_CHECK(cudaMalloc(&dd, static_cast<size_t>(m) * ldd * 4));
   RFE_CUDA_CHECK(cudaMemcpy(dah, ah.data(), ah.size() * 2, cudaMemcpyHostToDevice));
   RFE_CUDA_CHECK(cudaMemcpy(dal, al.data(), al.size() * 2, cudaMemcpyHostToDevice));
   RFE_CUDA_CHECK(cudaMemcpy(dbh, bh.data(), bh.size() * 2, cudaMemcpyHostToDevice));
@@ -1256,7 +1295,7 @@ int rfe_debug_gemm(rfe_ctx* c, const float* a, const float* b, const float* bias
   UmmaParams p = default_params();
   p.bias = dbias;
   p.out_f32 = dd;
-  p.ld_f32 = n;
+  p.ld_f32 = ldd;
   r = gemm_linear(c, "debug.gemm", A, Bo, p, n <= 64 ? 64 : 128);
   if (!r) {
     cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -1264,7 +1303,7 @@ int rfe_debug_gemm(rfe_ctx* c, const float* a, const float* b, const float* bias
       set_error("debug gemm failed: %s", cudaGetErrorString(e));
       r = RFE_ERR_CUDA;
     } else {
-      cudaMemcpy(d, dd, static_cast<size_t>(m) * n * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy2D(d, static_cast<size_t>(n) * 4, dd, static_cast<size_t>(ldd) * 4, static_cast<size_t>(n) * 4, m, cudaMemcpyDeviceToHost);
     }
   }
   cudaFree(dah); cudaFree(dal); cudaFree(dbh); cudaFree(dbl); cudaFree(dd);
@@ -1292,6 +1331,31 @@ int rfe_debug_probe(rfe_ctx* c, int which, const float* a, const float* b, float
     }
     RFE_CUDA_CHECK(cudaMemcpy(out, dout1, 16 * 4, cudaMemcpyDeviceToHost));
     cudaFree(dout1);
+    return RFE_OK;
+  }
+  if (which == 2 && a && b && out) {   // TS-mode probe: a [128][64], b [64][64] fp32 in, out [8192 + 8] fp32
+    std::vector<__half> ha2(128 * 64), hb2(64 * 64);
+    for (size_t i = 0; i < ha2.size(); ++i) ha2[i] = __float2half_rn(a[i]);
+    for (size_t i = 0; i < hb2.size(); ++i) hb2[i] = __float2half_rn(b[i]);
+    __half *da2, *db2;
+    float* do2;
+    RFE_CUDA_CHECK(cudaMalloc(&da2, ha2.size() * 2));
+    RFE_CUDA_CHECK(cudaMalloc(&db2, hb2.size() * 2));
+    RFE_CUDA_CHECK(cudaMalloc(&do2, (8192 + 8) * 4));
+    RFE_CUDA_CHECK(cudaMemset(do2, 0, (8192 + 8) * 4));
+    RFE_CUDA_CHECK(cudaMemcpy(da2, ha2.data(), ha2.size() * 2, cudaMemcpyHostToDevice));
+    RFE_CUDA_CHECK(cudaMemcpy(db2, hb2.data(), hb2.size() * 2, cudaMemcpyHostToDevice));
+    if (rfe::launch_probe_ts(c->stream, da2, db2, do2, 512)) {
+      set_error("probe launch failed");
+      return RFE_ERR_CUDA;
+    }
+    cudaError_t e2 = cudaStreamSynchronize(c->stream);
+    if (e2 != cudaSuccess) {
+      set_error("probe 2 failed: %s", cudaGetErrorString(e2));
+      return RFE_ERR_CUDA;
+    }
+    RFE_CUDA_CHECK(cudaMemcpy(out, do2, (8192 + 8) * 4, cudaMemcpyDeviceToHost));
+    cudaFree(da2); cudaFree(db2); cudaFree(do2);
     return RFE_OK;
   }
   if (which != 0 || !a || !b || !out) {

@@ -13,6 +13,11 @@ namespace rfe {
 int make_tmap_f16_sw128(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                         const uint64_t* strides_bytes, const uint32_t* box);
 
+// Generic form: dtype 0 = fp16, 1 = fp32; swizzle 0 = none, 1 = 32 B, 2 = 64 B, 3 = 128 B.  Encoded maps are cached per
+// thread by (base, geometry): the launch sequences re-use the same few dozen maps every layer / every step.
+int make_tmap(CUtensorMap* out, int dtype, int swizzle, const void* base, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box);
+
 void set_error(const char* fmt, ...);
 const char* get_error();
 

@@ -6,8 +6,9 @@
 // the SuperPoint conv stack; softmax-65 + 8x8 depth-to-space for the detector head; channel L2-norm for
 // the descriptor head; bias/scale/residual/transpose variants for LightGlue's linears and attention).
 //
-// CTA = 192 threads: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer
-// (one elected lane), warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31).
+// CTA: warps 0..E-1 = epilogue (E = 4 or 8; warp w owns TMEM lanes 32*(w%4)..+31), warp E = TMA producer (one elected
+// lane), warp E+1 = TMEM allocator + MMA issuer (one elected lane).  The single-thread roles have the highest warp
+// ids because the warp scheduler arbitrates highest-id-first: the MMA issuer must never wait behind epilogue warps.
 // Pipeline: NUM_STAGES smem stages {A_hi, A_lo, B_hi, B_lo}, full/empty mbarriers, one tmem_full barrier.
 // Replaces (reference): every Conv/MatMul node that ONNXRuntime executes for superpoint.onnx /
 // lightglue_sim.onnx (src/Extractors/superpoint_onnx.cc:133-136, src/Matchers/lightglue_onnx.cpp:210-214).
@@ -60,6 +61,13 @@ struct UmmaParams {
   unsigned long long* prof;   // optional [8] cycle counters written by CTA 0 (MMA thread: 0-3, epilogue warp 2: 4-7)
 };
 
+// TMA maps used by the LINEAR / QKV epilogues (unused members are never dereferenced).  All are 3-D:
+//   f32, res : fp32 (N, M, Z), box {32, 32, 1}, SWIZZLE_128B (32 rows x 128 B staged per warp)
+//   h_*, k_* : fp16 planes, box {32, 32, 1}, SWIZZLE_64B; row-major (N, M, Z) or head-major (64, M, heads)
+struct EpiMaps {
+  CUtensorMap f32, res, h_hi, h_lo, k_hi, k_lo;
+};
+
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                  // fp16 elements = one 128-byte swizzle row
 constexpr int kStageABytes = kBlockM * 128;  // one of A_hi / A_lo
@@ -67,7 +75,11 @@ constexpr int kStageABytes = kBlockM * 128;  // one of A_hi / A_lo
 __host__ __device__ constexpr int umma_epi_warps(int block_n, int epi) {
   // measured: 8 warps (two per quarter) were SLOWER than 4 (ffn0 42 vs 33 us): the epilogue is bound by TMEM reads and
   // memory latency, not by issue slots, and 10 warps cap the kernel at 168 registers.  Kept parameterised.
-  return (block_n >= 512 && epi == 0) ? 8 : 4;
+  // LINEAR / QKV: two warps per TMEM lane quarter, each taking every other 32-column chunk (32 accumulator values per
+  // thread keep the kernel far below the 204-register cap of a 320-thread CTA, so the two warps of a scheduler overlap
+  // each other's TMEM / shared-memory / TMA latencies).  The row-wise CONV / DET / DESC epilogues keep one warp per quarter.
+  (void)block_n;
+  return (epi == 0 || epi == 4) ? 8 : 4;
 }
 __host__ __device__ constexpr int umma_threads(int block_n, int epi) { return 64 + 32 * umma_epi_warps(block_n, epi); }
 
@@ -99,7 +111,7 @@ template <int BLOCK_N, int AMODE, int EPI>
 __global__ void __launch_bounds__(umma_threads(BLOCK_N, EPI), 1)
 umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
             const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-            const UmmaParams p) {
+            const __grid_constant__ EpiMaps em, const UmmaParams p) {
   constexpr int STAGES = umma_num_stages(BLOCK_N);
   constexpr int STAGE_BYTES = umma_stage_bytes(BLOCK_N);
   constexpr int STAGE_B = BLOCK_N * 128;
@@ -123,10 +135,12 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;       // [NBUF]
   uint64_t* tmem_empty_bar = tmem_full_bar + NBUF;    // [NBUF]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + NBUF);
+  uint64_t* res_bar = tmem_empty_bar + NBUF;          // [8] one per epilogue warp: residual tile landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int WARP_TMA = EPI_WARPS, WARP_MMA = EPI_WARPS + 1;
 
   // ---- persistent tile scheduler: static round-robin over (m, n, z) tiles; consecutive tiles share the B tile ------
   struct Tile { int m0, n0, img, x0, y0, z; };
@@ -150,7 +164,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
   };
 
   // ---- one-time setup ------------------------------------------------------------------------------
-  if (warp == 0 && lane == 0) {
+  if (warp == WARP_TMA && lane == 0) {
     tma_prefetch_desc(&tmA_hi);
     tma_prefetch_desc(&tmA_lo);
     tma_prefetch_desc(&tmB_hi);
@@ -163,9 +177,10 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       mbar_init(&tmem_full_bar[b], 1);
       mbar_init(&tmem_empty_bar[b], EPI_WARPS);      // one arrival per epilogue warp
     }
+    for (int w = 0; w < 8; ++w) mbar_init(&res_bar[w], 1);
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == WARP_MMA) {
     tmem_alloc(tmem_ptr_smem, TMEM_COLS);
     tmem_relinquish();
   }
@@ -174,7 +189,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 0) {
+  if (warp == WARP_TMA) {
     // ===== TMA producer =====================================================================
     if (elect_one()) {
       int stage = 0;
@@ -208,7 +223,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == WARP_MMA) {
     // ===== MMA issuer ===========================================================================
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
@@ -283,6 +298,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;                // row of the 128-row tile
     int it = 0;
+    uint32_t res_phase = 0;
     long long w_tf = 0;
     const long long e_begin = clock64();
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -320,7 +336,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     // ---- coalescing helpers: a thread owns one row of the tile, but a warp-wide store of "my row" touches 32 rows.
     // Values are therefore transposed through a per-warp staging buffer of 32 rows x 128 B (XOR-swizzled 16-byte
     // chunks, conflict free) and written back row-contiguously, 4 rows x 128 B per instruction.
-    const int ew = warp - 2;                     // epilogue warp index
+    const int ew = warp;                         // epilogue warp index
     const int half = ew >> 2;                    // which of the NHALF column-group phases this warp takes
     uint8_t* wst = epi_stage + ew * kEpiStageWarpBytes;
     auto load64 = [&](int col, float (&v)[64]) {
@@ -490,29 +506,69 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
           __syncwarp();
         }
       }
-    } else if constexpr (EPI == EPI_QKV) {
-      // columns: [q (256) | k (256) | v (256)], each head-major h*64+d (weights were permuted at load time);
-      // a 64-column group is exactly one head of one of q / k / v
-      const int m = m0 + row;
+    } else {
+      // ===== EPI_LINEAR / EPI_QKV: 32-column chunks, TMA-stored through this warp's 4 KB staging buffer ===========
+      // A thread owns one row of the tile (its TMEM lane).  Per chunk: accumulators -> registers -> bias / scale /
+      // rotary / residual -> staged row-wise in the swizzle of the output tensor map -> ONE bulk tensor store per
+      // plane issued by lane 0 (no per-thread global addressing, rows beyond M and columns beyond N are clipped by the
+      // TMA unit).  The residual tile arrives the same way (bulk tensor load into the staging buffer, prefetched
+      // before the TMEM reads).  The accumulator set is handed back to the MMA warp right after the last TMEM read.
+      const int row0 = m0 + q * 32;
+      const int m = row0 + lane;
       const bool valid = m < p.M;
-      const int part = n0 >> 8;                         // 0 q, 1 k, 2 v   (BLOCK_N = 128 divides 256)
+      const int z = tc.z;
+      const bool has_res = (EPI == EPI_LINEAR) && p.residual != nullptr;
+      uint64_t* rbar = &res_bar[ew];
+      int c_last = -1;
+      for (int c = half * 32; c < BLOCK_N && n0 + c < p.N; c += 64) c_last = c;
+      if (c_last < 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      }
 #pragma unroll 1
-      for (int c = half * 64; c < BLOCK_N; c += 64 * NHALF) {
-        float v[64];
-        load64(c, v);
+      for (int c = half * 32; c <= c_last; c += 64) {
         const int nb = n0 + c;
-        const int head = (nb & 255) >> 6;
-#pragma unroll
-        for (int j = 0; j < 64; j += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        if (has_res && lane == 0) {
+          bulk_wait_read<0>();                         // earlier stores have finished reading the staging buffer
+          mbar_expect_tx(rbar, 4096);
+          tma_load_3d(wst, &em.res, rbar, nb, row0, z);
         }
-        if (part < 2) {
-          if (valid) {
-            const float4* c4 = reinterpret_cast<const float4*>(p.cs + static_cast<size_t>(m) * 32);
-            const float4* s4 = reinterpret_cast<const float4*>(p.sn + static_cast<size_t>(m) * 32);
+        float v[32];
+        {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(t0 + c, r0);
+          tmem_ld32(t1 + c, r1);
+          tmem_ld_wait();
+          if (c == c_last) {                           // last TMEM read of this tile by this warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+          }
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]) * RFE_SPLIT_INV;
+        }
+        if (p.bias) {
+          if (nb + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
+          }
+        }
+        if constexpr (EPI == EPI_QKV) {
+          // columns: [q (256) | k (256) | v (256)], each head-major h*64+d (weights were permuted at load time);
+          // a 32-column chunk is half a head of one of q / k / v: frequencies (nb & 63)/2 .. +16
+          if ((n0 >> 8) < 2 && valid) {
+            const float4* c4 = reinterpret_cast<const float4*>(p.cs + static_cast<size_t>(m) * 32 + ((nb & 63) >> 1));
+            const float4* s4 = reinterpret_cast<const float4*>(p.sn + static_cast<size_t>(m) * 32 + ((nb & 63) >> 1));
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
               const float4 cc = __ldg(c4 + g), sn = __ldg(s4 + g);
               const float cv[4] = {cc.x, cc.y, cc.z, cc.w}, sv[4] = {sn.x, sn.y, sn.z, sn.w};
 #pragma unroll
@@ -524,150 +580,106 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
               }
             }
           }
-          store_split(v, [&](int r, int ch) -> long long {
-            const int mr = m0 + q * 32 + r;
-            if (mr >= p.M) return -1;
-            return static_cast<long long>(static_cast<size_t>(head) * p.head_stride + static_cast<size_t>(mr) * 64 + ch * 8);
-          }, part == 0 ? p.out_hi : p.k_hi, part == 0 ? p.out_lo : p.k_lo);
-        } else if (valid) {
-          // V^T [256][ldv]: lanes are consecutive rows m -> each store instruction writes 64 contiguous bytes
+        } else {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            __half h, l;
-            split_f32(v[j], h, l);
-            p.vt_hi[static_cast<size_t>((nb & 255) + j) * p.ldv + m] = h;
-            p.vt_lo[static_cast<size_t>((nb & 255) + j) * p.ldv + m] = l;
+          for (int j = 0; j < 32; ++j) v[j] *= p.scale;
+        }
+        if (has_res) {
+          mbar_wait(rbar, res_phase);
+          res_phase ^= 1;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const float4 t = *reinterpret_cast<const float4*>(wst + lane * 128 + ((ch ^ (lane & 7)) << 4));
+            v[4 * ch] += t.x; v[4 * ch + 1] += t.y; v[4 * ch + 2] += t.z; v[4 * ch + 3] += t.w;
           }
         }
-      }
-    } else {  // EPI_LINEAR
-      const int m = m0 + row;
-      const bool valid = m < p.M;
-      const size_t z = tc.z;
-      float* of = p.out_f32 ? p.out_f32 + z * p.bstride_f32 : nullptr;
-      __half* oh = p.out_hi ? p.out_hi + z * p.bstride_h : nullptr;
-      __half* ol = p.out_lo ? p.out_lo + z * p.bstride_h : nullptr;
-      const float* res = p.residual ? p.residual + z * p.bstride_res : nullptr;
-      const bool vec_ok = ((p.ld_f32 & 3) == 0) && ((p.ld_h & 7) == 0) && ((p.ld_res & 3) == 0);
-#pragma unroll 1
-      for (int c = half * 64; c < BLOCK_N; c += 64 * NHALF) {
-        const int nb = n0 + c;
-        if (nb >= p.N) break;                                   // warp-uniform
-        float v[64];
-        load64(c, v);
-        if (nb + 64 <= p.N && vec_ok) {
-          // ---- full 64-column group: coalesced path through the staging buffer ----
-          if (p.bias) {
+        if (EPI == EPI_LINEAR && p.out_f32) {
+          if (!has_res && lane == 0) bulk_wait_read<0>();
+          __syncwarp();                                // everyone has read the residual / the old tile has been fetched
 #pragma unroll
-            for (int j = 0; j < 64; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
+          for (int ch = 0; ch < 8; ++ch)
+            *reinterpret_cast<float4*>(wst + lane * 128 + ((ch ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&em.f32, wst, nb, row0, z);
+            bulk_commit();
           }
-#pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] *= p.scale;
-          if (of || res) {
-            // fp32 tile in two 32-column halves; the residual is added during the row-contiguous write-out, where its
-            // global loads are coalesced exactly like the stores (all 8 loads of a thread are in flight together)
-#pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {
-              float4 rr[8];
-              if (res) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const int r = 4 * i + (lane >> 3), ch = lane & 7;
-                  const int mr = m0 + q * 32 + r;
-                  rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (mr < p.M)
-                    rr[i] = *reinterpret_cast<const float4*>(res + static_cast<size_t>(mr) * p.ld_res + nb + 32 * hb + ch * 4);
-                }
-              }
-              stage_f32x32(v, 32 * hb);
-              __syncwarp();
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                int r, ch;
-                uint4 x = ld_staged(i, r, ch);
-                float4 t = *reinterpret_cast<float4*>(&x);
-                const int mr = m0 + q * 32 + r;
-                if (res) {
-                  t.x += rr[i].x; t.y += rr[i].y; t.z += rr[i].z; t.w += rr[i].w;
-                  st_staged(r, ch, *reinterpret_cast<const uint4*>(&t));     // keep the sum for the split store
-                }
-                if (of && mr < p.M)
-                  *reinterpret_cast<float4*>(of + static_cast<size_t>(mr) * p.ld_f32 + nb + 32 * hb + ch * 4) = t;
-              }
-              __syncwarp();
-              if (res && oh) {   // re-read my row (now including the residual)
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                  const uint4 x = ld_row(ch);
-                  const float4 t = *reinterpret_cast<const float4*>(&x);
-                  v[32 * hb + 4 * ch] = t.x; v[32 * hb + 4 * ch + 1] = t.y;
-                  v[32 * hb + 4 * ch + 2] = t.z; v[32 * hb + 4 * ch + 3] = t.w;
-                }
-                __syncwarp();
-              }
-            }
-          }
-          if (oh) {
-            if (p.transpose_h) {
-              if (valid) {
-#pragma unroll
-                for (int j = 0; j < 64; ++j) {
-                  __half h, l;
-                  split_f32(v[j], h, l);
-                  oh[static_cast<size_t>(nb + j) * p.ld_h + m] = h;
-                  ol[static_cast<size_t>(nb + j) * p.ld_h + m] = l;
-                }
-              }
-            } else {
-              store_split(v, [&](int r, int ch) -> long long {
-                const int mr = m0 + q * 32 + r;
-                if (mr >= p.M) return -1;
-                return p.head_major ? static_cast<long long>(static_cast<size_t>(nb >> 6) * p.head_stride + static_cast<size_t>(mr) * 64 + ch * 8)
-                                    : static_cast<long long>(static_cast<size_t>(mr) * p.ld_h + nb + ch * 8);
-              }, oh, ol);
-            }
-          }
-          continue;
         }
-        // ---- ragged tail / unaligned pitches: scalar path ----
-        if (!valid) continue;
+        const bool is_v = (EPI == EPI_QKV) && (n0 >> 8) == 2;
+        if (EPI == EPI_QKV || p.out_hi) {
+          uint32_t ph[16], pl[16];
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          const int n = nb + j;
-          if (n < p.N) {
-            float t = v[j];
-            if (p.bias) t += __ldg(p.bias + n);
-            t *= p.scale;
-            if (res) t += res[static_cast<size_t>(m) * p.ld_res + n];
-            if (of) of[static_cast<size_t>(m) * p.ld_f32 + n] = t;
-            if (oh) {
-              __half h, l;
-              split_f32(t, h, l);
-              const size_t o = p.transpose_h ? static_cast<size_t>(n) * p.ld_h + m
-                             : p.head_major ? static_cast<size_t>(n >> 6) * p.head_stride + static_cast<size_t>(m) * 64 + (n & 63)
-                                            : static_cast<size_t>(m) * p.ld_h + n;
-              oh[o] = h;
-              ol[o] = l;
+          for (int j = 0; j < 16; ++j) {
+            const __half2 h2 = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            const float2 hf = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn((v[2 * j] - hf.x) * RFE_SPLIT_SCALE, (v[2 * j + 1] - hf.y) * RFE_SPLIT_SCALE);
+            ph[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            pl[j] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
+          if (is_v || (EPI == EPI_LINEAR && p.transpose_h)) {
+            // transposed planes [col][ld]: lanes are consecutive rows -> every store instruction writes 64 contiguous bytes
+            if (valid) {
+              __half* th = is_v ? p.vt_hi : p.out_hi + static_cast<size_t>(z) * p.bstride_h;
+              __half* tl = is_v ? p.vt_lo : p.out_lo + static_cast<size_t>(z) * p.bstride_h;
+              const int ldt = is_v ? p.ldv : p.ld_h;
+              const int col0 = is_v ? (nb & 255) : nb;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const __half2 h2 = *reinterpret_cast<const __half2*>(&ph[j]);
+                const __half2 l2 = *reinterpret_cast<const __half2*>(&pl[j]);
+                if (col0 + 2 * j < (is_v ? 256 : p.N)) {
+                  th[static_cast<size_t>(col0 + 2 * j) * ldt + m] = __low2half(h2);
+                  tl[static_cast<size_t>(col0 + 2 * j) * ldt + m] = __low2half(l2);
+                }
+                if (col0 + 2 * j + 1 < (is_v ? 256 : p.N)) {
+                  th[static_cast<size_t>(col0 + 2 * j + 1) * ldt + m] = __high2half(h2);
+                  tl[static_cast<size_t>(col0 + 2 * j + 1) * ldt + m] = __high2half(l2);
+                }
+              }
+            }
+          } else {
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              const int so = lane * 64 + ((ch ^ ((lane >> 1) & 3)) << 4);
+              *reinterpret_cast<uint4*>(wst + so) = make_uint4(ph[4 * ch], ph[4 * ch + 1], ph[4 * ch + 2], ph[4 * ch + 3]);
+              *reinterpret_cast<uint4*>(wst + 2048 + so) = make_uint4(pl[4 * ch], pl[4 * ch + 1], pl[4 * ch + 2], pl[4 * ch + 3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              const bool to_k = (EPI == EPI_QKV) && (n0 >> 8) == 1;
+              const bool hm = (EPI == EPI_QKV) || p.head_major;
+              const int c0 = hm ? (nb & 63) : nb;
+              const int c2 = hm ? ((nb & 255) >> 6) : z;
+              tma_store_3d(to_k ? &em.k_hi : &em.h_hi, wst, c0, row0, c2);
+              tma_store_3d(to_k ? &em.k_lo : &em.h_lo, wst + 2048, c0, row0, c2);
+              bulk_commit();
             }
           }
         }
       }
     }
+    if constexpr (EPI != EPI_LINEAR && EPI != EPI_QKV) {
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);     // hand the accumulator set back to the MMA warp
     }
-    if (p.prof && blockIdx.x == 0 && warp == 2 && lane == 0) {
+    }
+    if constexpr (EPI == EPI_LINEAR || EPI == EPI_QKV) {
+      if (lane == 0) bulk_wait<0>();       // the staging buffers must outlive the last bulk stores
+    }
+    if (p.prof && blockIdx.x == 0 && warp == 0 && lane == 0) {
       p.prof[4] = clock64() - e_begin;     // epilogue-warp loop
       p.prof[5] = w_tf;                    // waiting for accumulators
     }
   }
 
   __syncthreads();
-  if (warp == 1) {
+  if (warp == WARP_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
