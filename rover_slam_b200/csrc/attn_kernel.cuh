@@ -26,6 +26,8 @@
 // that the TMEM -> registers -> exp -> shared memory -> fence -> mbarrier latency of the softmax stage is hidden.
 #pragma once
 
+#include <cuda/std/type_traits>
+
 #include "common.cuh"
 
 namespace rfe {
@@ -50,7 +52,7 @@ constexpr int kAttnKeyTile = 64;
 constexpr int kAttnKVBytes = 2 * 8192;                          // one K stage (K_hi | K_lo) or one V stage (Vt_hi | Vt_lo)
 constexpr int kAttnQBytes = 2 * 16384;                          // Q_hi, Q_lo (128 rows x 128 B)
 constexpr int kAttnPBytes = 2 * 16384;                          // one P buffer: P_hi, P_lo (128 rows x 128 B)
-constexpr int kAttnP1Stages = 7;                                // pass-1 K_hi ring: 128 keys x 128 B per stage, in sP | sV
+constexpr int kAttnP1Stages = 5;                                // pass-1 K_hi ring: 128 keys x 128 B per stage: sP (4) + last V stage
 constexpr int kAttnSmemBytes =
     kAttnQBytes + 2 * kAttnPBytes + (kAttnKStages + kAttnVStages) * kAttnKVBytes + 1024 + 4096;
 
@@ -67,6 +69,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // tensor maps: Q and K: 3-D (64, rows_total, 4 heads), box (64, 128) resp. (64, 64); V^T: 3-D (cols_total, 64, 4), box (64, 64)
+// PROF = true compiles the clock64 role counters in (tools/gpu_probe.py); the production instantiation has none: the
+// MMA thread's issue loop is on the critical path and every clock read costs it tens of cycles.
+template <bool PROF>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ CUtensorMap tmQ_lo,
             const __grid_constant__ CUtensorMap tmK_hi, const __grid_constant__ CUtensorMap tmK_lo,
@@ -79,8 +84,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
   uint8_t* sP = sK + kAttnKStages * kAttnKVBytes;       // 2 x (P_hi | P_lo)
   uint8_t* sV = sP + 2 * kAttnPBytes;                   // V stages: Vt_hi | Vt_lo
   uint8_t* tail = sV + kAttnVStages * kAttnKVBytes;
-  uint8_t* s1 = sP;                                     // pass 1: 7 stages of 16 KB (128 keys of K_hi) over sP | sV
-  static_assert(2 * kAttnPBytes + kAttnVStages * kAttnKVBytes == kAttnP1Stages * 16384, "pass-1 ring covers sP | sV");
+  // pass 1: 5 stages of 16 KB (128 keys of K_hi): the two P buffers and the LAST V stage, so that the first two V
+  // tiles (and all K stages) of pass 2 are prefetched while pass 1 is still running
+  auto s1_stage = [&](int st) { return st < 4 ? sP + st * 16384 : sV + (kAttnVStages - 1) * kAttnKVBytes; };
+  static_assert(2 * kAttnPBytes == 4 * 16384 && kAttnKVBytes == 16384 && kAttnP1Stages == 5, "pass-1 ring layout");
   uint64_t* q_full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* k_full = q_full + 1;                        // [4]
   uint64_t* k_empty = k_full + kAttnKStages;
@@ -97,6 +104,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(p1_done + 1);
   float* stat = reinterpret_cast<float*>(tail + 512);   // [4][128] partial row max, then partial row sum
 
+  auto tick = [&]() -> long long { return PROF ? clock64() : 0; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int z = blockIdx.z;
   const int head = blockIdx.y;
@@ -139,7 +147,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       for (int g = 0; g < T1; ++g) {           // pass 1: 128 keys of K_hi per stage
         const int st = g % kAttnP1Stages;
         mbar_wait(&k1_empty[st], ((g / kAttnP1Stages) & 1) ^ 1);
-        uint8_t* sb = s1 + st * 16384;
+        uint8_t* sb = s1_stage(st);
         mbar_expect_tx(&k1_full[st], 16384);
         tma_load_3d(sb, &tmK_hi, &k1_full[st], 0, krow + g * 128, head);
         tma_load_3d(sb + 8192, &tmK_hi, &k1_full[st], 0, krow + g * 128 + 64, head);
@@ -156,9 +164,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
   } else if (warp == kAttnWarpV) {
     // ===== V producer =================================================================================================
     if (elect_one()) {
-      mbar_wait(p1_done, 0);                   // the V stages double as pass-1 K_hi stages
       for (int t = 0; t < T; ++t) {
         const int st = t % kAttnVStages;
+        if (t == kAttnVStages - 1) mbar_wait(p1_done, 0);   // the last V stage doubles as a pass-1 K_hi stage
         mbar_wait(&v_empty[st], ((t / kAttnVStages) & 1) ^ 1);
         uint8_t* sb = sV + st * kAttnKVBytes;
         mbar_expect_tx(&v_full[st], kAttnKVBytes);
@@ -173,21 +181,21 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       constexpr uint32_t idesc128 = make_idesc_f16(128, 128);
       const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + 16384;
       const uint32_t o_base = tmem_base + 384;
-      const bool prof = p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-      long long w_k = 0, w_se = 0, w_v = 0, w_p = 0;
-      const long long t_begin = clock64();
+      const bool prof = PROF && p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      long long w_k = 0, w_se = 0, w_v = 0, w_p = 0, w_k1 = 0, w_se1 = 0;
+      const long long t_begin = tick();
       mbar_wait(q_full, 0);
-      const long long t_q = clock64();
+      const long long t_q = tick();
       auto issue_s1 = [&](int g) {          // pass 1: S_hh of 128 keys, one N=128 MMA per k-step
         const int st = g % kAttnP1Stages, b = g % kAttnSBufs;
-        long long c0 = clock64();
+        long long c0 = tick();
         mbar_wait(&k1_full[st], (g / kAttnP1Stages) & 1);
-        long long c1 = clock64();
+        long long c1 = tick();
         mbar_wait(&s_empty[b], ((g / kAttnSBufs) & 1) ^ 1);
-        w_k += c1 - c0;
-        w_se += clock64() - c1;
+        w_k1 += c1 - c0;
+        w_se1 += tick() - c1;
         tc_fence_after();
-        const uint32_t k_hi = smem_u32(s1 + st * 16384);
+        const uint32_t k_hi = smem_u32(s1_stage(st));
         const uint32_t s_base = tmem_base + b * 128;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -198,12 +206,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       auto issue_s = [&](int t) {           // pass 2: fp32-equivalent scores of key tile t (S buffer index continues at T1)
         const int g = T1 + t;
         const int st = t % kAttnKStages, b = g % kAttnSBufs;
-        long long c0 = clock64();
+        long long c0 = tick();
         mbar_wait(&k_full[st], (t / kAttnKStages) & 1);
-        long long c1 = clock64();
+        long long c1 = tick();
         mbar_wait(&s_empty[b], ((g / kAttnSBufs) & 1) ^ 1);
         w_k += c1 - c0;
-        w_se += clock64() - c1;
+        w_se += tick() - c1;
         tc_fence_after();
         const uint32_t k_hi = smem_u32(sK + st * kAttnKVBytes);   // K_lo follows at +8192: [K_hi;K_lo] is one N=128 operand
         const uint32_t s_base = tmem_base + b * 128;
@@ -218,12 +226,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       };
       auto issue_pv = [&](int t) {          // consumes P buffer t&1 and V stage t%3
         const int st = t % kAttnVStages, pb = t & 1;
-        long long c0 = clock64();
+        long long c0 = tick();
         mbar_wait(&v_full[st], (t / kAttnVStages) & 1);
-        long long c1 = clock64();
+        long long c1 = tick();
         mbar_wait(&p_full[pb], (t >> 1) & 1);
         w_v += c1 - c0;
-        w_p += clock64() - c1;
+        w_p += tick() - c1;
         tc_fence_after();
         const uint32_t p_hi = smem_u32(sP + pb * kAttnPBytes), p_lo = p_hi + 16384;
         const uint32_t v_hi = smem_u32(sV + st * kAttnKVBytes);       // V_lo follows at +8192
@@ -239,7 +247,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       // pass 1: hi*hi scores only
       for (int g = 0; g < T1; ++g) issue_s1(g);
       umma_commit(p1_done);
-      const long long t_p1 = clock64();
+      const long long t_p1 = tick();
       // pass 2: the score MMAs run two tiles ahead of the P V MMAs
       issue_s(0);
       if (T > 1) issue_s(1);
@@ -249,7 +257,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       }
       umma_commit(o_full);
       if (prof) {
-        const long long t_end = clock64();
+        const long long t_end = tick();
         p.prof[0] = t_q - t_begin;      // wait for Q
         p.prof[1] = t_p1 - t_q;         // pass 1 issue time
         p.prof[2] = t_end - t_p1;       // pass 2 issue time
@@ -258,6 +266,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
         p.prof[5] = w_v;                // waiting for V tiles
         p.prof[6] = w_p;                // waiting for P (softmax)
         p.prof[7] = T;
+        p.prof[8] = w_k1;               // pass 1: waiting for K tiles
+        p.prof[9] = w_se1;              // pass 1: waiting for a free score buffer
       }
     }
   } else if (warp < kAttnSoftmaxWarps) {
@@ -300,8 +310,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
     const float mx_l2 = mx * kLog2e;
 
     // ---- pass 2: P = exp(S - max) -> smem (K-major, 128-byte swizzle), row sum ----
-    float l = 0.0f;
-    for (int t = 0; t < T; ++t) {
+    // Packed fp32x2 arithmetic throughout (FFMA2 / FADD2 / FMUL2): the sixteen softmax warps share the SM's issue slots
+    // with the MMA thread, and this loop, not the tensor pipe, was the limiter of pass 2.  Only the last key tile can be
+    // ragged, so the column mask lives in a separate instantiation of the tile body.
+    f32x2 lsum = pk2(0.0f, 0.0f);
+    const f32x2 kL2 = pk2(kLog2e, kLog2e), kL2s = pk2(kLog2e * RFE_SPLIT_INV, kLog2e * RFE_SPLIT_INV);
+    const f32x2 nmx = pk2(-mx_l2, -mx_l2);
+    auto tile_body = [&](int t, auto masked_tag) {
+      constexpr bool kMasked = decltype(masked_tag)::value;
       const int g = T1 + t, b = g % kAttnSBufs, pb = t & 1;
       mbar_wait(&s_full[b], (g / kAttnSBufs) & 1);
       tc_fence_after();
@@ -314,26 +330,23 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[b]);
       const int c0 = t * kAttnKeyTile + cq * 16;
-      const bool full = (c0 + 16 <= nk);
-      __align__(16) __half2 ph[8];
-      __align__(16) __half2 pl[8];
+      uint32_t ph[8], pl[8];
 #pragma unroll
-      for (int j = 0; j < 16; j += 2) {
-        const float s0 = __uint_as_float(a0[j]) + __uint_as_float(x0[j]) * RFE_SPLIT_INV;
-        const float s1 = __uint_as_float(a0[j + 1]) + __uint_as_float(x0[j + 1]) * RFE_SPLIT_INV;
+      for (int j = 0; j < 8; ++j) {
         // exp(s - max) through the SFU: ex2.approx(s*log2e - max*log2e); relative error ~2^-22 + |s-max|*2^-23, the
         // same order as the 22-bit split-fp16 operand that carries P into the tensor core
-        float e0 = fast_exp2(fmaf(s0, kLog2e, -mx_l2));
-        float e1 = fast_exp2(fmaf(s1, kLog2e, -mx_l2));
-        if (!full) {
-          if (c0 + j >= nk) e0 = 0.0f;
-          if (c0 + j + 1 >= nk) e1 = 0.0f;
+        f32x2 x = fma2(pk2u(a0[2 * j], a0[2 * j + 1]), kL2, nmx);
+        x = fma2(pk2u(x0[2 * j], x0[2 * j + 1]), kL2s, x);
+        float x_0, x_1;
+        upk2(x, x_0, x_1);
+        float e0 = fast_exp2(x_0), e1 = fast_exp2(x_1);
+        if (kMasked) {
+          if (c0 + 2 * j >= nk) e0 = 0.0f;
+          if (c0 + 2 * j + 1 >= nk) e1 = 0.0f;
         }
-        l += e0 + e1;
-        const __half2 h2 = __floats2half2_rn(e0, e1);
-        const float2 hf = __half22float2(h2);
-        ph[j >> 1] = h2;
-        pl[j >> 1] = __floats2half2_rn((e0 - hf.x) * RFE_SPLIT_SCALE, (e1 - hf.y) * RFE_SPLIT_SCALE);
+        const f32x2 e = pk2(e0, e1);
+        lsum = add2(lsum, e);
+        split2(e, ph[j], pl[j]);
       }
       mbar_wait(&p_empty[pb], ((t >> 1) & 1) ^ 1);       // PV(t-2) has consumed this P buffer
       uint8_t* prow_hi = sP + pb * kAttnPBytes + row * 128;
@@ -341,12 +354,22 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         const int sc = ((cq * 2 + ch) ^ (row & 7)) << 4;
-        *reinterpret_cast<uint4*>(prow_hi + sc) = reinterpret_cast<const uint4*>(ph)[ch];
-        *reinterpret_cast<uint4*>(prow_lo + sc) = reinterpret_cast<const uint4*>(pl)[ch];
+        *reinterpret_cast<uint4*>(prow_hi + sc) = make_uint4(ph[4 * ch], ph[4 * ch + 1], ph[4 * ch + 2], ph[4 * ch + 3]);
+        *reinterpret_cast<uint4*>(prow_lo + sc) = make_uint4(pl[4 * ch], pl[4 * ch + 1], pl[4 * ch + 2], pl[4 * ch + 3]);
       }
       fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[pb]);
+    };
+    const int t_full = (nk % kAttnKeyTile) ? T - 1 : T;
+#pragma unroll 1
+    for (int t = 0; t < t_full; ++t) tile_body(t, cuda::std::false_type{});
+    if (t_full < T) tile_body(T - 1, cuda::std::true_type{});
+    float l;
+    {
+      float l0, l1;
+      upk2(lsum, l0, l1);
+      l = l0 + l1;
     }
     stat[cq * 128 + row] = l;
     named_bar_sync(1, kSmThreads);

@@ -75,6 +75,10 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // The cycle-counter reads around the MMA issuer's waits stay in the production build ON PURPOSE: an A/B on the same
+  // B200 (profiles/r01_strip_clock_ab.txt) measured conv1b at 485 us with them and 560 us without (conv2a 169 vs 196):
+  // the reads pace the issuing thread; bounding its run-ahead with an mbarrier instead did not reproduce the gain.
+  auto tick = [&]() -> long long { return clock64(); };
 
   if (warp == kStripWarpRows && lane == 0) {
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmW_hi); tma_prefetch_desc(&tmW_lo);
@@ -149,30 +153,30 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       uint32_t m = 0;          // tap sequence number
       uint32_t gi = 0;         // iteration counter (accumulator hand-over phase)
       long long w_acc = 0, w_w = 0, w_row = 0;
-      const long long t_begin = clock64();
+      const long long t_begin = tick();
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         int b, x0, y_begin, iters;
         item_coords(item, b, x0, y_begin, iters);
         for (int it = 0; it < iters; ++it, ++gi) {
-          long long c0 = clock64();
+          long long c0 = tick();
           mbar_wait(acc_empty, (gi & 1) ^ 1);                 // the epilogue has drained the accumulators
-          w_acc += clock64() - c0;
+          w_acc += tick() - c0;
           tc_fence_after();
           for (int dy = 0; dy < 3; ++dy) {
             for (int dx = 0; dx < 3; ++dx, ++m) {
               const int st = m & 3;
-              long long c1 = clock64();
+              long long c1 = tick();
               mbar_wait(&w_full[st], (m >> 2) & 1);
-              w_w += clock64() - c1;
+              w_w += tick() - c1;
               const uint32_t w_cat = smem_u32(sW + st * kStripWStageBytes);          // [hi;lo] (dy 0,2) or [lo;hi] (dy 1)
               const uint32_t w_hi = w_cat + (dy == 1 ? 8192 : 0);
 #pragma unroll
               for (int r = 0; r < 2; ++r) {
                 const uint32_t seq = n_base + 2 * it + r + dy;           // input row feeding output row r through kernel row dy
                 const int slot = seq & 3;
-                long long c2 = clock64();
+                long long c2 = tick();
                 mbar_wait(&row_full[slot], (seq >> 2) & 1);
-                w_row += clock64() - c2;
+                w_row += tick() - c2;
                 tc_fence_after();
                 const uint32_t a_hi = smem_u32(sRowHi + slot * kStripSlotBytes) + dx * 128;
                 const uint32_t a_lo = smem_u32(sRowLo + slot * kStripSlotBytes) + dx * 128;
@@ -211,7 +215,7 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         n_base += 2 * iters + 2;
       }
       if (p.prof && blockIdx.x == 0) {
-        p.prof[0] = clock64() - t_begin;   // whole MMA-thread loop
+        p.prof[0] = tick() - t_begin;   // whole MMA-thread loop
         p.prof[1] = w_acc;                 // waiting for the epilogue to drain TMEM
         p.prof[2] = w_w;                   // waiting for weight tiles
         p.prof[3] = w_row;                 // waiting for input rows

@@ -523,7 +523,8 @@ int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitB
                     const AttnParams& problems, int nprob, int max_nq) {
   static bool configured[64] = {};
   if (!configured[c->device & 63]) {
-    RFE_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    RFE_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    RFE_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
     configured[c->device & 63] = true;
   }
   CUtensorMap qh, ql, kh, kl, vh, vl;
@@ -543,7 +544,8 @@ int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitB
   p.prof = c->attn_prof;
   dim3 grid((max_nq + 127) / 128, 4, nprob);
   ProfScope ps(c, tag);
-  attn_kernel<<<grid, kAttnThreads, kAttnSmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
+  if (p.prof) attn_kernel<true><<<grid, kAttnThreads, kAttnSmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
+  else attn_kernel<false><<<grid, kAttnThreads, kAttnSmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
   c->launches++;
   RFE_CUDA_CHECK(cudaGetLastError());
   return RFE_OK;

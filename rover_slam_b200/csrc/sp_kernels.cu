@@ -10,67 +10,75 @@
 namespace rfe {
 
 // ------------------------------------------------------------------------------------------------
-// conv1a: one thread = one pixel x 8 output channels
+// conv1a: thread = (run of 8 pixels of one image row) x (8 output channels)
 // ------------------------------------------------------------------------------------------------
-// thread = (pixel slot, 8-channel group); the 72 weights of the group live in registers and the thread walks
-// kConv1aIters pixels, so a warp stores 4 pixels x 128 B = 512 contiguous bytes per plane per iteration.
-constexpr int kConv1aIters = 16;
+// The 72 weights of the channel group live in registers as 36 channel PAIRS and every tap is one packed FFMA2
+// (two IEEE fp32 FMAs per issue slot, same operation order as a scalar fmaf chain: bit-identical results).  The
+// 3 x 10 input window of the run is loaded and scaled once and slides along x, so a pixel costs 36 FFMA2 + the
+// bias / ReLU / split-fp16 epilogue instead of 72 FFMA + 9 guarded byte loads.  A warp covers 4 runs x 8 groups:
+// each store instruction writes 4 full 128-byte lines per plane.  Bound: HBM writes (256 B out per 1 B in).
+constexpr int kConv1aRun = 8;
 __global__ void __launch_bounds__(256) conv1a_kernel(const uint8_t* __restrict__ img, int stride, int H, int W, int B,
                                                      const float* __restrict__ w /*[64][9]*/,
                                                      const float* __restrict__ bias, __half* __restrict__ out_hi,
                                                      __half* __restrict__ out_lo) {
   const int cg = threadIdx.x & 7;
-  float wr[8][9], br[8];
+  f32x2 wr[4][9], br[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    br[j] = __ldg(bias + cg * 8 + j);
+  for (int jp = 0; jp < 4; ++jp) {
+    const int c = cg * 8 + 2 * jp;
+    br[jp] = pk2(__ldg(bias + c), __ldg(bias + c + 1));
 #pragma unroll
-    for (int t = 0; t < 9; ++t) wr[j][t] = __ldg(w + (cg * 8 + j) * 9 + t);
+    for (int t = 0; t < 9; ++t) wr[jp][t] = pk2(__ldg(w + c * 9 + t), __ldg(w + (c + 1) * 9 + t));
   }
-  const unsigned npix = static_cast<unsigned>(B) * H * W;       // < 2^31 for any supported batch
-  const unsigned base = blockIdx.x * (32u * kConv1aIters) + (threadIdx.x >> 3);
-#pragma unroll 1
-  for (int it = 0; it < kConv1aIters; ++it) {
-    const unsigned pix = base + static_cast<unsigned>(it) * 32u;
-    if (pix >= npix) return;
-    const unsigned rowi = pix / static_cast<unsigned>(W);
-    const int x = static_cast<int>(pix - rowi * W);
-    const int b = static_cast<int>(rowi / static_cast<unsigned>(H));
-    const int y = static_cast<int>(rowi - static_cast<unsigned>(b) * H);
-    const uint8_t* im = img + static_cast<size_t>(b) * H * stride;
-    float in[9];
+  const unsigned runs_per_row = static_cast<unsigned>(W) / kConv1aRun;        // W is a multiple of 8
+  const unsigned total = static_cast<unsigned>(B) * H * runs_per_row;
+  const unsigned run = blockIdx.x * 32u + (threadIdx.x >> 3);
+  if (run >= total) return;
+  const unsigned rowi = run / runs_per_row;
+  const int x0 = static_cast<int>(run - rowi * runs_per_row) * kConv1aRun;
+  const int b = static_cast<int>(rowi / static_cast<unsigned>(H));
+  const int y = static_cast<int>(rowi - static_cast<unsigned>(b) * H);
+  const uint8_t* im = img + static_cast<size_t>(b) * H * stride;
+  float in[3][kConv1aRun + 2];
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
+  for (int dy = 0; dy < 3; ++dy) {
+    const int yy = y + dy - 1;
+    const bool rv = yy >= 0 && yy < H;
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int yy = y + dy - 1, xx = x + dx - 1;
-        float v = 0.0f;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-          v = static_cast<float>(__ldg(im + static_cast<size_t>(yy) * stride + xx)) * 0.003921568859368563f;  // transform.cpp:8
-        in[dy * 3 + dx] = v;
-      }
-    __align__(16) __half hi[8];
-    __align__(16) __half lo[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float acc = 0.0f;
-#pragma unroll
-      for (int t = 0; t < 9; ++t) acc = fmaf(in[t], wr[j][t], acc);
-      acc = fmaxf(acc + br[j], 0.0f);
-      split_f32(acc, hi[j], lo[j]);
+    for (int i = 0; i < kConv1aRun + 2; ++i) {
+      const int xx = x0 - 1 + i;
+      float v = 0.0f;
+      if (rv && xx >= 0 && xx < W)
+        v = static_cast<float>(__ldg(im + static_cast<size_t>(yy) * stride + xx)) * 0.003921568859368563f;  // transform.cpp:8
+      in[dy][i] = v;
     }
-    const size_t o = static_cast<size_t>(pix) * 64 + cg * 8;
-    *reinterpret_cast<uint4*>(out_hi + o) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<const uint4*>(lo);
+  }
+  const size_t obase = (static_cast<size_t>(rowi) * W + x0) * 64 + cg * 8;
+#pragma unroll
+  for (int px = 0; px < kConv1aRun; ++px) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      f32x2 acc = pk2(0.0f, 0.0f);
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) acc = fma2(pk2(in[dy][px + dx], in[dy][px + dx]), wr[jp][dy * 3 + dx], acc);
+      acc = add2(acc, br[jp]);
+      float a0, a1;
+      upk2(acc, a0, a1);
+      split2(pk2(fmaxf(a0, 0.0f), fmaxf(a1, 0.0f)), hi[jp], lo[jp]);
+    }
+    *reinterpret_cast<uint4*>(out_hi + obase + static_cast<size_t>(px) * 64) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(out_lo + obase + static_cast<size_t>(px) * 64) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
 void launch_conv1a(cudaStream_t s, const uint8_t* img, int stride, int H, int W, int B, const float* w,
                    const float* bias, __half* out_hi, __half* out_lo) {
-  const size_t npix = static_cast<size_t>(B) * H * W;
-  const size_t per_block = 32 * kConv1aIters;
-  conv1a_kernel<<<static_cast<unsigned>((npix + per_block - 1) / per_block), 256, 0, s>>>(img, stride, H, W, B, w, bias,
-                                                                                        out_hi, out_lo);
+  const size_t runs = static_cast<size_t>(B) * H * (W / kConv1aRun);
+  conv1a_kernel<<<static_cast<unsigned>((runs + 31) / 32), 256, 0, s>>>(img, stride, H, W, B, w, bias, out_hi, out_lo);
 }
 
 // ------------------------------------------------------------------------------------------------

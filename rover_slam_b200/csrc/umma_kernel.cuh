@@ -140,6 +140,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  auto tick = [&]() -> long long { return p.prof ? clock64() : 0; };   // role counters only when armed
   constexpr int WARP_TMA = EPI_WARPS, WARP_MMA = EPI_WARPS + 1;
 
   // ---- persistent tile scheduler: static round-robin over (m, n, z) tiles; consecutive tiles share the B tile ------
@@ -233,19 +234,19 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       uint32_t phase = 0;
       int it = 0;
       long long w_te = 0, w_full = 0;
-      const long long t_begin = clock64();
+      const long long t_begin = tick();
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int buf = it % NBUF;
       const uint32_t tile_base = tmem_base + buf * TILE_COLS;
       const uint32_t acc1 = tile_base + ACC1_COL;
-      long long c0 = clock64();
+      long long c0 = tick();
       mbar_wait(&tmem_empty_bar[buf], (((it / NBUF) & 1) ^ 1));     // the epilogue has drained this accumulator set
-      w_te += clock64() - c0;
+      w_te += tick() - c0;
       tc_fence_after();
       for (int ks = 0; ks < p.num_k_steps; ++ks) {
-        c0 = clock64();
+        c0 = tick();
         mbar_wait(&full_bar[stage], phase);
-        w_full += clock64() - c0;
+        w_full += tick() - c0;
         tc_fence_after();
         const uint32_t a_hi = smem_u32(smem + stage * STAGE_BYTES);
         const uint32_t a_lo = a_hi + kStageABytes;
@@ -287,7 +288,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       umma_commit(&tmem_full_bar[buf]);
       }
       if (p.prof && blockIdx.x == 0) {
-        p.prof[0] = clock64() - t_begin;   // MMA-thread loop
+        p.prof[0] = tick() - t_begin;   // MMA-thread loop
         p.prof[1] = w_te;                  // waiting for the epilogue (TMEM drain)
         p.prof[2] = w_full;                // waiting for TMA (operands)
         p.prof[3] = it;                    // tiles
@@ -300,15 +301,15 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     int it = 0;
     uint32_t res_phase = 0;
     long long w_tf = 0;
-    const long long e_begin = clock64();
+    const long long e_begin = tick();
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
     const Tile tc = decode(tile);
     const int m0 = tc.m0, n0 = tc.n0, img = tc.img, x0 = tc.x0, y0 = tc.y0;
     (void)m0; (void)img; (void)x0; (void)y0;
     const int buf = it % NBUF;
-    const long long e0 = clock64();
+    const long long e0 = tick();
     mbar_wait(&tmem_full_bar[buf], (it / NBUF) & 1);
-    w_tf += clock64() - e0;
+    w_tf += tick() - e0;
     tc_fence_after();
     const uint32_t t0 = tmem_base + buf * TILE_COLS + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t t1 = t0 + ACC1_COL;
@@ -673,7 +674,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       if (lane == 0) bulk_wait<0>();       // the staging buffers must outlive the last bulk stores
     }
     if (p.prof && blockIdx.x == 0 && warp == 0 && lane == 0) {
-      p.prof[4] = clock64() - e_begin;     // epilogue-warp loop
+      p.prof[4] = tick() - e_begin;     // epilogue-warp loop
       p.prof[5] = w_tf;                    // waiting for accumulators
     }
   }

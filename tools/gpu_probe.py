@@ -37,6 +37,8 @@ pr = fe2.debug_read("lg.attn_prof").view(np.uint64)
 names = ["wait Q", "pass1 issue loop", "pass2 issue loop", "wait K", "wait free S buffer", "wait V", "wait P (softmax)", "key tiles"]
 print("attention MMA-thread cycle breakdown (CTA 0 of the last launch):")
 for n, v in zip(names, pr[:8]): print(f"  {n:22s} {int(v)}")
+print(f"  pass 1 only: wait K {int(pr[8])}, wait free S buffer {int(pr[9])}")
+print(f"  softmax warp 0, pass 2: loop {int(pr[10])}, wait scores {int(pr[11])}, wait free P buffer {int(pr[12])}")
 
 # strip conv (conv1b) MMA-thread breakdown on one 480x640 frame batch of 8
 fe3 = FrontEnd(max_batch=8, max_height=480, max_width=640, max_keypoints=4096)

@@ -9,9 +9,12 @@ import bench
 from rover_slam_b200 import FrontEnd
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+arm = len(sys.argv) > 2 and sys.argv[2] == "arm"      # arm the in-kernel role counters (attention runs its PROF build)
 P = 4
 B = 2 * P
 fe = FrontEnd(max_batch=B, max_height=bench.H, max_width=bench.W, max_keypoints=4096)
+if arm:
+    fe.debug_read("lg.attn_prof")
 frames = torch.from_numpy(bench.make_pairs(P, 1).reshape(B, bench.H, bench.W)).cuda()
 sa, sb = list(range(0, B, 2)), list(range(1, B, 2))
 def step():
