@@ -24,8 +24,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 H, W = 480, 640
-CONV1B_FLOPS_PER_FRAME = 2 * 9 * 64 * 64 * H * W          # 22.65 GFLOP
-SP_FLOPS_PER_FRAME = 52.10e9
+SP_FLOPS_PER_FRAME = 52.10e9                               # SURVEY.md Appendix A
+ATTN_DRAM_BYTES_PER_LAUNCH = None                          # filled from profiles/ once the ncu --set full capture exists
 
 
 def peaks():
@@ -36,33 +36,53 @@ def peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
-class ClockSampler(threading.Thread):
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+class ClockSampler:
+    """`nvidia-smi -lms 50` running beside the timed regions (one process, so the samples really fall under load)."""
 
-    def run(self):
+    def __init__(self, index):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(index),
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            cells = [c.strip() for c in line.split(",")]
+            if len(cells) >= 7:
+                self.rows.append(cells)
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                self.proc.wait(timeout=3)
             except Exception:
-                pass
-            time.sleep(0.2)
+                self.proc.kill()
+            self.thread.join(timeout=2)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
+        rows = []
+        for r in self.rows:
+            try:
+                rows.append((float(r[0]), float(r[1]), float(r[2]), r[3:7]))
+            except ValueError:
+                pass
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        busy = [r for r in rows if r[2] > 0.5 * max(x[2] for x in rows)] or rows      # samples taken under load (by power draw)
+        sm = sorted(r[0] for r in busy)
         reasons = []
         for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
-            if any(r[3 + i].lower().startswith("active") for r in self.rows):
+            if any(r[3][i].lower().startswith("active") for r in busy):
                 reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": rows[0][1], "reasons": reasons, "samples": len(rows),
+                "samples_under_load": len(busy), "power_w_max": max(r[2] for r in rows)}
 
 
 def make_pairs(n_pairs, seed0):
@@ -144,7 +164,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=4, help="frame pairs per step per GPU")
+    ap.add_argument("--pairs", type=int, default=8, help="frame pairs per step per GPU")
     ap.add_argument("--cpu-pairs", type=int, default=2, help="pairs timed for cpu_baseline (rank 0, N=1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -209,13 +229,23 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # keypoint counts of every input set (for the attention kernel's algorithmic FLOPs): one untimed pass
+    attn_flops_sets = []
+    for i in range(n_sets):
+        step_device(i)
+        fe.sync()
+        n = [len(fe.read_slot(b, want_desc=False)[0]) for b in range(B)]
+        # per attention launch: problems (n0,n0), (n1,n1) [self] or (n0,n1), (n1,n0) [cross]; 4 heads x (QK^T + PV) x 2*nq*nk*64
+        self_f = sum(1024.0 * n[2 * p] ** 2 + 1024.0 * n[2 * p + 1] ** 2 for p in range(P))
+        cross_f = sum(2 * 1024.0 * n[2 * p] * n[2 * p + 1] for p in range(P))
+        attn_flops_sets.append((self_f + cross_f) / 2.0)          # mean over the self and the cross launch of a layer
+
     # ---- device-resident throughput ("value") ----
     for i in range(args.warmup):
         step_device(i)
     barrier()
     sampler = ClockSampler(local)
-    sampler.start()
-    fe.profile(True)
+    fe.profile(True, select="lg.attn")          # events only around the dominant kernel (18 launches per step)
     launches0 = fe.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -225,14 +255,12 @@ def main():
     barrier()
     launches = fe.kernel_launches() - launches0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    conv1b_ms, conv1b_n = fe.profile_read("sp.conv1b", reset=False)
-    all_ms, all_n = fe.profile_read(None, reset=True)
+    attn_ms, attn_n = fe.profile_read("lg.attn", reset=True)
     fe.profile(False)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
     nmatch = [len(fe.read_result(p)[0]) for p in range(P)]
     frames_total = 2 * P * args.steps * world
     value = frames_total / (ms_total / 1e3)
+    attn_flops = sum(attn_flops_sets[i % n_sets] for i in range(args.steps)) / args.steps     # mean per launch
 
     # ---- end to end through the host API ("e2e") ----
     for i in range(2):
@@ -246,14 +274,32 @@ def main():
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = 2 * P * e_steps * world / e2e_s
+    sampler.stop()
+
+    # ---- per-kernel breakdown (untimed extra pass, every launch bracketed by events) ----
+    fe.profile(True)
+    for i in range(3):
+        step_device(i)
+    fe.sync()
+    all_ms, all_n = fe.profile_read(None)
+    breakdown = {}
+    for tag in ["sp.conv1a", "sp.conv1b", "sp.conv2", "sp.conv3", "sp.conv4", "sp.convPa", "sp.convDa", "sp.convPb", "sp.convDb", "sp.nms",
+                "sp.select", "sp.desc_sample", "lg.prepare", "lg.wqkv", "lg.attn", "lg.out_proj", "lg.ffn0", "lg.ln_gelu", "lg.ffn3",
+                "lg.to_qk", "lg.to_v", "lg.to_out", "lg.final_proj", "lg.matchability", "lg.sim", "lg.assign"]:
+        ms, n = fe.profile_read(tag)
+        if n:
+            breakdown[tag] = round(1e3 * ms / 3, 1)
+    attn_share = breakdown.get("lg.attn", 0.0) / (1e3 * all_ms / 3) if all_ms else None
+    fe.profile_read(None, reset=True)
+    fe.profile(False)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     tf_peak, hbm_peak, peak_src = peaks()
-    per_launch_ms = conv1b_ms / max(conv1b_n, 1)
-    achieved = CONV1B_FLOPS_PER_FRAME * B / (per_launch_ms / 1e3) / 1e12 if conv1b_n else 0.0
+    per_launch_ms = attn_ms / max(attn_n, 1)
+    achieved = attn_flops / (per_launch_ms / 1e3) / 1e12 if attn_n else 0.0
     line = {
         "metric": "frames/sec (extract+match) on 640x480", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -261,19 +307,21 @@ def main():
         "config": {"workload": "BASELINE config 5 shape: 640x480 synthetic frame pairs, SuperPoint on both frames + one LightGlue match per pair",
                    "pairs_per_step_per_gpu": P, "frames_per_step_per_gpu": B, "keypoints_per_frame": "about 2000 (no top-K, threshold 0.0005)",
                    "parallelism": f"dp{world} (independent pairs per GPU; NCCL only scatters the input shards)",
-                   "l2": "per-step activation working set about 2.5 GB >> 126 MB L2; 4 distinct input sets cycled",
+                   "l2": f"per-step activation working set about {0.31 * B:.1f} GB >> 126 MB L2; 4 distinct input sets cycled",
                    "matches_last_step": nmatch},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d // e_steps, "d2h_bytes_per_step": d2h // e_steps,
                 "steps": e_steps},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "umma_kernel<64,A_CONV3,EPI_CONV> (sp.conv1b: 3x3 conv 64->64 + ReLU + 2x2 pool)",
+        "roofline": {"bound": "tensor", "kernel": "attn_kernel (lg.attn_self / lg.attn_cross: fused 4-head attention of all pairs, 18 launches per step)",
                      "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak if tf_peak else None,
-                     "traffic": None, "peak_source": peak_src, "launch_ms": per_launch_ms, "launches_timed": conv1b_n,
-                     "algorithmic_flops_per_launch": CONV1B_FLOPS_PER_FRAME * B,
-                     "executed_mma_flops_per_launch": 3 * CONV1B_FLOPS_PER_FRAME * B,
-                     "share_of_step": conv1b_ms / all_ms if all_ms else None,
-                     "note": "split-fp16 runs 3 MMAs per algorithmic MAC: frac <= 1/3 by construction"},
+                     "traffic": ATTN_DRAM_BYTES_PER_LAUNCH, "peak_source": peak_src, "launch_ms": per_launch_ms, "launches_timed": attn_n,
+                     "algorithmic_flops_per_launch": attn_flops,
+                     "executed_mma_flops_per_launch": 3.5 * attn_flops,
+                     "share_of_step": attn_share,
+                     "note": "split-fp16: 3 MMAs per algorithmic MAC for QK^T and PV plus a hi-only max pass = 3.5x: frac <= 0.286 by construction; "
+                             "traffic = dram bytes of one launch from the ncu --set full capture under profiles/ (4 pairs)"},
+        "kernel_us_per_step": breakdown,
     }
     if world == 1 and args.cpu_pairs > 0:
         threads, avail = pick_cpu_threads()

@@ -111,6 +111,9 @@ long long rfe_kernel_launches(rfe_ctx* ctx);
  * "sp.convPb_softmax", "sp.convDb_l2norm", "lg.wqkv", "lg.attn_qk", "lg.attn_pv", "lg.ffn0", "lg.sim", ...
  * rfe_profile_read sums the launches whose tag starts with `prefix` (NULL = all); synchronises. */
 int rfe_profile(rfe_ctx* ctx, int enable);
+/* Restrict the recording to launches whose tag starts with `prefix` (NULL or "" = every launch): bench.py times only the
+ * dominant kernel inside its timed region so that the event records do not perturb the throughput number. */
+int rfe_profile_select(rfe_ctx* ctx, const char* prefix);
 int rfe_profile_read(rfe_ctx* ctx, const char* prefix, double* total_ms, long long* launches, int reset);
 /* Test hook: copy a named intermediate device tensor of the last call to the host (fp32 or raw bytes).
  * Returns the byte size of the tensor through *bytes; copies min(*bytes, capacity). */

@@ -69,6 +69,7 @@ def load_library():
     lib.rfe_kernel_launches.argtypes = [vp]
     lib.rfe_kernel_launches.restype = C.c_longlong
     lib.rfe_profile.argtypes = [vp, ci]
+    lib.rfe_profile_select.argtypes = [vp, C.c_char_p]
     lib.rfe_profile_read.argtypes = [vp, C.c_char_p, P(C.c_double), P(C.c_longlong), ci]
     lib.rfe_debug_read.argtypes = [vp, C.c_char_p, vp, C.c_size_t, P(C.c_size_t)]
     lib.rfe_debug_gemm.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci]
@@ -204,7 +205,9 @@ class FrontEnd:
     def kernel_launches(self) -> int:
         return int(self.lib.rfe_kernel_launches(self.ctx))
 
-    def profile(self, enable: bool = True):
+    def profile(self, enable: bool = True, select: str | None = None):
+        """Per-launch CUDA-event timing; `select` restricts it to tags with that prefix."""
+        self._check(self.lib.rfe_profile_select(self.ctx, None if select is None else select.encode()))
         self._check(self.lib.rfe_profile(self.ctx, 1 if enable else 0))
 
     def profile_read(self, prefix: str | None = None, reset: bool = False):

@@ -16,6 +16,30 @@ void launch_desc_sample(cudaStream_t s, const float* dense, int h, int w, int B,
                         int cap, float* desc);
 
 // ---- LightGlue -------------------------------------------------------------------------------------------
+constexpr int kLgMaxImages = 32;          // images (2 per pair) handled by one batched launch
+struct LgImages {                         // inputs of one batched LightGlue pass, one entry per image
+  const float* kpts_f[kLgMaxImages];      // pixel keypoints fp32 [n][2] (host API) or null
+  const int* kpts_i[kLgMaxImages];        // pixel keypoints int32 [n][2] (device hand-off from SuperPoint) or null
+  const float* desc[kLgMaxImages];        // descriptors fp32 [n][256]
+  int n[kLgMaxImages];                    // keypoints
+  int row0[kLgMaxImages];                 // first row of the image in the concatenated LightGlue state
+  int count;
+};
+struct LgAssign {                         // the assignment stage of all pairs of a batch (blockIdx.y = pair)
+  const float* sim[kLgMaxImages / 2];     // [n0][ld] similarity of pair p
+  int n0[kLgMaxImages / 2], n1[kLgMaxImages / 2], ld[kLgMaxImages / 2];
+  int off0[kLgMaxImages / 2], off1[kLgMaxImages / 2];   // row offsets of the two images (index the per-row vectors)
+  int* matches[kLgMaxImages / 2];         // [cap][2] result slot of pair p
+  float* mscores[kLgMaxImages / 2];
+  int* count[kLgMaxImages / 2];
+  int pairs, max_n0, max_n1;
+};
+// positional encoding + residual-stream initialisation (x = desc, cat[:, :256] = split(desc)) for every image
+void launch_lg_prepare(cudaStream_t s, const LgImages& im, int max_n, int norm_h, int norm_w, const float* wr, float* cs,
+                       float* sn, float* x, __half* cat_hi, __half* cat_lo);
+// dual log-softmax statistics, both arg-maxes and the mutual-match compaction for all pairs
+void launch_lg_assign(cudaStream_t s, const LgAssign& a, float* rmax, float* rlog, float* cmax, float* clog,
+                      const float* ls, float* max0, int* m0, int* m1, float filter, float thresh, float* S_dbg);
 void launch_posenc(cudaStream_t s, const float* kpts_px, int n, int norm_h, int norm_w, const float* wr, float* cs,
                    float* sn);
 void launch_kpts_to_float(cudaStream_t s, const int* k, int n, float* o);

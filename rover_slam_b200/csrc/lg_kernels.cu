@@ -331,4 +331,249 @@ void launch_match_compact(cudaStream_t s, const float* max0, const int* m0, cons
   match_compact_kernel<<<1, 1024, 0, s>>>(max0, m0, m1, n0, filter, thresh, matches, mscores, count);
 }
 
+// ================================================================================================
+// Batched forms: one launch covers every image / every pair of a LightGlue batch
+// ================================================================================================
+// lg_prepare: one warp per keypoint row.  Keypoint normalisation (transform.cpp:19-32) + Fourier positional encoding
+// (nodes 0-17) + x = desc, cat[:, 0:256] = split(desc).  grid = (ceil(max_n / 8), images).
+__global__ void __launch_bounds__(256) lg_prepare_kernel(const LgImages im, float shift_x, float shift_y, float scale,
+                                                         const float* __restrict__ wr, float* __restrict__ cs,
+                                                         float* __restrict__ sn, float* __restrict__ x,
+                                                         __half* __restrict__ cat_hi, __half* __restrict__ cat_lo) {
+  const int img = blockIdx.y;
+  const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (k >= im.n[img]) return;
+  float px, py;
+  if (im.kpts_i[img]) {
+    px = static_cast<float>(im.kpts_i[img][2 * k]);
+    py = static_cast<float>(im.kpts_i[img][2 * k + 1]);
+  } else {
+    px = im.kpts_f[img][2 * k];
+    py = im.kpts_f[img][2 * k + 1];
+  }
+  const size_t row = static_cast<size_t>(im.row0[img]) + k;
+  const float xn = (px - shift_x) / scale;
+  const float yn = (py - shift_y) / scale;
+  const float ph = xn * wr[2 * lane] + yn * wr[2 * lane + 1];
+  cs[row * 32 + lane] = cosf(ph);
+  sn[row * 32 + lane] = sinf(ph);
+  const float4* d4 = reinterpret_cast<const float4*>(im.desc[img] + static_cast<size_t>(k) * 256);
+  const float4 a = d4[lane], b = d4[32 + lane];          // columns 4*lane.., 128 + 4*lane..
+  float4* x4 = reinterpret_cast<float4*>(x + row * 256);
+  x4[lane] = a;
+  x4[32 + lane] = b;
+  uint32_t h0, l0, h1, l1;
+  split2(pk2(a.x, a.y), h0, l0);
+  split2(pk2(a.z, a.w), h1, l1);
+  *reinterpret_cast<uint2*>(cat_hi + row * 512 + 4 * lane) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(cat_lo + row * 512 + 4 * lane) = make_uint2(l0, l1);
+  split2(pk2(b.x, b.y), h0, l0);
+  split2(pk2(b.z, b.w), h1, l1);
+  *reinterpret_cast<uint2*>(cat_hi + row * 512 + 128 + 4 * lane) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(cat_lo + row * 512 + 128 + 4 * lane) = make_uint2(l0, l1);
+}
+void launch_lg_prepare(cudaStream_t s, const LgImages& im, int max_n, int norm_h, int norm_w, const float* wr, float* cs,
+                       float* sn, float* x, __half* cat_hi, __half* cat_lo) {
+  if (im.count == 0 || max_n == 0) return;
+  const float sx = static_cast<float>(norm_w) / 2.0f, sy = static_cast<float>(norm_h) / 2.0f;
+  const float sc = static_cast<float>(norm_w > norm_h ? norm_w : norm_h) / 2.0f;
+  lg_prepare_kernel<<<dim3((max_n + 7) / 8, im.count), 256, 0, s>>>(im, sx, sy, sc, wr, cs, sn, x, cat_hi, cat_lo);
+}
+
+// Row statistics / row arg-max: one warp per row, blockIdx.y = pair.  Column statistics / arg-max: block = 32 columns x
+// 32 row-lanes.  Per-row vectors are indexed by the row's position in the concatenated LightGlue state.
+__global__ void __launch_bounds__(256) row_lse_batch_kernel(const LgAssign a, float* __restrict__ rmax,
+                                                            float* __restrict__ rlog) {
+  const int pr = blockIdx.y;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int n0 = a.n0[pr], n1 = a.n1[pr];
+  if (i >= n0) return;
+  const float* r = a.sim[pr] + static_cast<size_t>(i) * a.ld[pr];
+  float mx = -INFINITY;
+  for (int j = lane; j < n1; j += 32) mx = fmaxf(mx, r[j]);
+  mx = warp_max(mx);
+  float sum = 0.0f;
+  for (int j = lane; j < n1; j += 32) sum += expf(r[j] - mx);
+  sum = warp_sum(sum);
+  if (lane == 0) {
+    rmax[a.off0[pr] + i] = mx;
+    rlog[a.off0[pr] + i] = logf(sum);
+  }
+}
+__global__ void __launch_bounds__(1024) col_lse_batch_kernel(const LgAssign a, float* __restrict__ cmax,
+                                                             float* __restrict__ clog) {
+  __shared__ float red[32][33];
+  const int pr = blockIdx.y;
+  const int n0 = a.n0[pr], n1 = a.n1[pr], ld = a.ld[pr];
+  if (blockIdx.x * 32 >= n1) return;
+  const float* sim = a.sim[pr];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  float mx = -INFINITY;
+  if (j < n1)
+    for (int i = ty; i < n0; i += 32) mx = fmaxf(mx, sim[static_cast<size_t>(i) * ld + j]);
+  red[ty][tx] = mx;
+  __syncthreads();
+  if (ty == 0) {
+    float m = red[0][tx];
+    for (int k = 1; k < 32; ++k) m = fmaxf(m, red[k][tx]);
+    red[0][tx] = m;
+  }
+  __syncthreads();
+  mx = red[0][tx];
+  __syncthreads();
+  float sum = 0.0f;
+  if (j < n1)
+    for (int i = ty; i < n0; i += 32) sum += expf(sim[static_cast<size_t>(i) * ld + j] - mx);
+  red[ty][tx] = sum;
+  __syncthreads();
+  if (ty == 0 && j < n1) {
+    float sacc = 0.0f;
+    for (int k = 0; k < 32; ++k) sacc += red[k][tx];
+    cmax[a.off1[pr] + j] = mx;
+    clog[a.off1[pr] + j] = logf(sacc);
+  }
+}
+__global__ void __launch_bounds__(256) row_argmax_batch_kernel(const LgAssign a, const float* __restrict__ rmax,
+                                                               const float* __restrict__ rlog,
+                                                               const float* __restrict__ cmax,
+                                                               const float* __restrict__ clog, const float* __restrict__ ls,
+                                                               float* __restrict__ max0, int* __restrict__ m0,
+                                                               float* __restrict__ S_dbg) {
+  const int pr = blockIdx.y;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int n0 = a.n0[pr], n1 = a.n1[pr];
+  if (i >= n0) return;
+  const float* r = a.sim[pr] + static_cast<size_t>(i) * a.ld[pr];
+  const int o0 = a.off0[pr], o1 = a.off1[pr];
+  const float rm = rmax[o0 + i], rl = rlog[o0 + i], a0 = ls[o0 + i];
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = lane; j < n1; j += 32) {
+    const float sc = assign_score(r[j], rm, rl, cmax[o1 + j], clog[o1 + j], a0, ls[o1 + j]);
+    if (S_dbg && pr == a.pairs - 1) S_dbg[static_cast<size_t>(i) * n1 + j] = sc;
+    if (sc > best) {
+      best = sc;
+      bi = j;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) {
+      best = ob;
+      bi = oi;
+    }
+  }
+  if (lane == 0) {
+    max0[o0 + i] = best;
+    m0[o0 + i] = bi;
+  }
+}
+__global__ void __launch_bounds__(1024) col_argmax_batch_kernel(const LgAssign a, const float* __restrict__ rmax,
+                                                                const float* __restrict__ rlog,
+                                                                const float* __restrict__ cmax,
+                                                                const float* __restrict__ clog, const float* __restrict__ ls,
+                                                                int* __restrict__ m1) {
+  __shared__ float rb[32][33];
+  __shared__ int ri[32][33];
+  const int pr = blockIdx.y;
+  const int n0 = a.n0[pr], n1 = a.n1[pr], ld = a.ld[pr];
+  if (blockIdx.x * 32 >= n1) return;
+  const float* sim = a.sim[pr];
+  const int o0 = a.off0[pr], o1 = a.off1[pr];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  if (j < n1) {
+    const float cm = cmax[o1 + j], cl = clog[o1 + j], a1 = ls[o1 + j];
+    for (int i = ty; i < n0; i += 32) {
+      const float sc = assign_score(sim[static_cast<size_t>(i) * ld + j], rmax[o0 + i], rlog[o0 + i], cm, cl, ls[o0 + i], a1);
+      if (sc > best) {
+        best = sc;
+        bi = i;
+      }
+    }
+  }
+  rb[ty][tx] = best;
+  ri[ty][tx] = bi;
+  __syncthreads();
+  if (ty == 0 && j < n1) {
+    for (int k = 1; k < 32; ++k) {
+      const float ob = rb[k][tx];
+      const int oi = ri[k][tx];
+      if (ob > best || (ob == best && oi < bi)) {
+        best = ob;
+        bi = oi;
+      }
+    }
+    m1[o1 + j] = bi;
+  }
+}
+__global__ void __launch_bounds__(1024) match_compact_batch_kernel(const LgAssign a, const float* __restrict__ max0,
+                                                                   const int* __restrict__ m0, const int* __restrict__ m1,
+                                                                   float filter, float thresh) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  const int pr = blockIdx.x;
+  const int n0 = a.n0[pr], o0 = a.off0[pr], o1 = a.off1[pr];
+  int* matches = a.matches[pr];
+  float* mscores = a.mscores[pr];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n0; base += 1024) {
+    const int i = base + threadIdx.x;
+    float ms = 0.0f;
+    int j = 0;
+    if (i < n0) {
+      j = m0[o0 + i];
+      const bool mutual = (m1[o1 + j] == i);
+      ms = mutual ? expf(max0[o0 + i]) : 0.0f;
+    }
+    const int keep = (i < n0 && ms > filter && ms > thresh) ? 1 : 0;
+    int incl = keep;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      int ws = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, ws, o);
+        if (lane >= o) ws += t;
+      }
+      warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    const int pos = carry + (w ? warp_sums[w - 1] : 0) + incl - keep;
+    if (keep) {
+      matches[2 * pos] = i;
+      matches[2 * pos + 1] = j;
+      mscores[pos] = ms;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = pos + keep;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *a.count[pr] = carry;
+}
+void launch_lg_assign(cudaStream_t s, const LgAssign& a, float* rmax, float* rlog, float* cmax, float* clog,
+                      const float* ls, float* max0, int* m0, int* m1, float filter, float thresh, float* S_dbg) {
+  if (a.pairs == 0) return;
+  const dim3 grow((a.max_n0 + 7) / 8, a.pairs), gcol((a.max_n1 + 31) / 32, a.pairs);
+  row_lse_batch_kernel<<<grow, 256, 0, s>>>(a, rmax, rlog);
+  col_lse_batch_kernel<<<gcol, 1024, 0, s>>>(a, cmax, clog);
+  row_argmax_batch_kernel<<<grow, 256, 0, s>>>(a, rmax, rlog, cmax, clog, ls, max0, m0, S_dbg);
+  col_argmax_batch_kernel<<<gcol, 1024, 0, s>>>(a, rmax, rlog, cmax, clog, ls, m1);
+  match_compact_batch_kernel<<<a.pairs, 1024, 0, s>>>(a, max0, m0, m1, filter, thresh);
+}
+
 }  // namespace rfe

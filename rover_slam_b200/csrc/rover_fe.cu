@@ -92,7 +92,7 @@ struct rfe_ctx {
   float* S_dbg = nullptr;
   const char* prof_tag = nullptr;            // $RFE_PROF_TAG: the launch tag whose UMMA role counters are recorded
   unsigned long long* attn_prof = nullptr;   // armed by rfe_debug_read("lg.attn_prof")
-  int dbg_n0 = 0, dbg_n1 = 0, dbg_off0 = 0, dbg_off1 = 0;
+  int dbg_n0 = 0, dbg_n1 = 0, dbg_off0 = 0, dbg_off1 = 0, dbg_pair = 0;
   // match results: [max_batch] slots
   int* res_matches = nullptr;   // [slots][cap][2]
   float* res_scores = nullptr;  // [slots][cap]
@@ -102,6 +102,7 @@ struct rfe_ctx {
   struct ProfRec { std::string tag; cudaEvent_t a, b; };
   bool use_strip_conv = true;   // RFE_CONV_STRIP=0 falls back to the 9-box implicit GEMM for the 64->64 layers
   bool profiling = false;
+  std::string prof_prefix;                   // rfe_profile_select
   std::vector<ProfRec> prof;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pool;
 
@@ -231,6 +232,7 @@ struct ProfScope {   // records a CUDA event pair around one launch when profili
   cudaEvent_t b = nullptr;
   ProfScope(rfe_ctx* ctx, const char* tag) : c(ctx) {
     if (!c->profiling || c->prof.size() >= 8192) return;
+    if (!c->prof_prefix.empty() && strncmp(tag, c->prof_prefix.c_str(), c->prof_prefix.size()) != 0) return;
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     if (!c->prof_pool.empty()) {
       ev = c->prof_pool.back();
@@ -552,8 +554,10 @@ int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitB
 }
 
 struct PairDesc {      // one LightGlue problem: device-resident pixel keypoints [n][2] and descriptors [n][256]
-  const float* kpts0;
+  const float* kpts0;  // fp32 keypoints (host API) ...
   const float* kpts1;
+  const int* ikpts0;   // ... or int32 keypoints left on the device by SuperPoint (exactly one of the two forms is set)
+  const int* ikpts1;
   const float* desc0;
   const float* desc1;
   int n0, n1;
@@ -586,17 +590,23 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
     set_error("LightGlue batch needs %d rows, ctx capacity %d", rows, c->lg_rows);
     return RFE_ERR_CAPACITY;
   }
-  for (int i = 0; i < np; ++i) {
-    const PairDesc& pd = pairs[i];
-    { ProfScope ps_(c, "lg.posenc"); launch_posenc(s, pd.kpts0, pd.n0, norm_h, norm_w, c->posenc_w, c->cs + static_cast<size_t>(off0[i]) * 32,
-                  c->sn + static_cast<size_t>(off0[i]) * 32); }
-    { ProfScope ps_(c, "lg.posenc"); launch_posenc(s, pd.kpts1, pd.n1, norm_h, norm_w, c->posenc_w, c->cs + static_cast<size_t>(off1[i]) * 32,
-                  c->sn + static_cast<size_t>(off1[i]) * 32); }
-    { ProfScope ps_(c, "lg.split_rows"); launch_split_rows(s, pd.desc0, pd.n0, 256, 256, c->x + static_cast<size_t>(off0[i]) * 256, 256,
-                      c->cat.hi + static_cast<size_t>(off0[i]) * 512, c->cat.lo + static_cast<size_t>(off0[i]) * 512, 512); }
-    { ProfScope ps_(c, "lg.split_rows"); launch_split_rows(s, pd.desc1, pd.n1, 256, 256, c->x + static_cast<size_t>(off1[i]) * 256, 256,
-                      c->cat.hi + static_cast<size_t>(off1[i]) * 512, c->cat.lo + static_cast<size_t>(off1[i]) * 512, 512); }
-    c->launches += 4;
+  {   // positional encodings + residual-stream initialisation of every image: ONE launch
+    LgImages im;
+    memset(&im, 0, sizeof(im));
+    int mx = 0;
+    for (int i = 0; i < np; ++i) {
+      const PairDesc& pd = pairs[i];
+      im.kpts_f[2 * i] = pd.kpts0;      im.kpts_i[2 * i] = pd.ikpts0;      im.desc[2 * i] = pd.desc0;
+      im.n[2 * i] = pd.n0;              im.row0[2 * i] = off0[i];
+      im.kpts_f[2 * i + 1] = pd.kpts1;  im.kpts_i[2 * i + 1] = pd.ikpts1;  im.desc[2 * i + 1] = pd.desc1;
+      im.n[2 * i + 1] = pd.n1;          im.row0[2 * i + 1] = off1[i];
+      mx = pd.n0 > mx ? pd.n0 : mx;
+      mx = pd.n1 > mx ? pd.n1 : mx;
+    }
+    im.count = 2 * np;
+    ProfScope ps_(c, "lg.prepare");
+    launch_lg_prepare(s, im, mx, norm_h, norm_w, c->posenc_w, c->cs, c->sn, c->x, c->cat.hi, c->cat.lo);
+    c->launches++;
   }
   AttnParams self_p, cross_p;
   memset(&self_p, 0, sizeof(self_p));
@@ -707,28 +717,43 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
   }
   { ProfScope ps_(c, "lg.matchability"); launch_matchability(s, c->x, rows, c->match_w, c->match_b, c->ls); }
   c->launches++;
+  LgAssign as;
+  memset(&as, 0, sizeof(as));
   for (int i = 0; i < np; ++i) {
     const int n0 = pairs[i].n0, n1 = pairs[i].n1, rslot = pairs[i].rslot;
     const int ld = round_up(n1, 8);
+    float* sim = c->sim + static_cast<size_t>(i) * c->cap * c->lg_ld;
     {
       Operand A{c->md.hi + static_cast<size_t>(off0[i]) * 256, c->md.lo + static_cast<size_t>(off0[i]) * 256, n0, 256, 256, 0, 1};
       Operand B{c->md.hi + static_cast<size_t>(off1[i]) * 256, c->md.lo + static_cast<size_t>(off1[i]) * 256, n1, 256, 256, 0, 1};
       UmmaParams p = default_params();
-      p.out_f32 = c->sim;
+      p.out_f32 = sim;
       p.ld_f32 = ld;
       if ((r = gemm_linear(c, "lg.sim", A, B, p, 128))) return r;
     }
-    { ProfScope ps_(c, "lg.lse"); launch_lse(s, c->sim, n0, n1, ld, c->rmax, c->rlog, c->cmax, c->clog); }
-    { ProfScope ps_(c, "lg.argmax"); launch_argmax(s, c->sim, n0, n1, ld, c->rmax, c->rlog, c->cmax, c->clog, c->ls + off0[i], c->ls + off1[i], c->max0,
-                  c->m0, c->m1, c->S_dbg); }
-    { ProfScope ps_(c, "lg.compact"); launch_match_compact(s, c->max0, c->m0, c->m1, n0, kFilterThreshold, thresh,
-                         c->res_matches + static_cast<size_t>(rslot) * c->cap * 2,
-                         c->res_scores + static_cast<size_t>(rslot) * c->cap, c->res_count + rslot); }
-    c->launches += 5;
+    as.sim[i] = sim;
+    as.n0[i] = n0;
+    as.n1[i] = n1;
+    as.ld[i] = ld;
+    as.off0[i] = off0[i];
+    as.off1[i] = off1[i];
+    as.matches[i] = c->res_matches + static_cast<size_t>(rslot) * c->cap * 2;
+    as.mscores[i] = c->res_scores + static_cast<size_t>(rslot) * c->cap;
+    as.count[i] = c->res_count + rslot;
+    as.max_n0 = n0 > as.max_n0 ? n0 : as.max_n0;
+    as.max_n1 = n1 > as.max_n1 ? n1 : as.max_n1;
     c->dbg_n0 = n0;
     c->dbg_n1 = n1;
     c->dbg_off0 = off0[i];
     c->dbg_off1 = off1[i];
+    c->dbg_pair = i;
+  }
+  as.pairs = np;
+  {   // dual log-softmax statistics, both arg-maxes, mutual check + compaction of ALL pairs: five launches
+    ProfScope ps_(c, "lg.assign");
+    launch_lg_assign(s, as, c->rmax, c->rlog, c->cmax, c->clog, c->ls, c->max0, c->m0, c->m1, kFilterThreshold, thresh,
+                     c->S_dbg);
+    c->launches += 5;
   }
   RFE_CUDA_CHECK(cudaGetLastError());
   return RFE_OK;
@@ -867,15 +892,15 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   A_(dev_alloc(c, &c->hid, R * 512));
   A_(split_alloc(c, &c->hs, R * 512));
   A_(split_alloc(c, &c->md, R * 256));
-  A_(dev_alloc(c, &c->sim, cap * LD));
-  A_(dev_alloc(c, &c->rmax, cap));
-  A_(dev_alloc(c, &c->rlog, cap));
-  A_(dev_alloc(c, &c->cmax, cap));
-  A_(dev_alloc(c, &c->clog, cap));
+  A_(dev_alloc(c, &c->sim, static_cast<size_t>(c->lg_pairs) * cap * LD));   // one similarity matrix per pair of a batch
+  A_(dev_alloc(c, &c->rmax, R));      // per-row vectors of the assignment stage, indexed like the LightGlue rows
+  A_(dev_alloc(c, &c->rlog, R));
+  A_(dev_alloc(c, &c->cmax, R));
+  A_(dev_alloc(c, &c->clog, R));
   A_(dev_alloc(c, &c->ls, R));
-  A_(dev_alloc(c, &c->max0, cap));
-  A_(dev_alloc(c, &c->m0, cap));
-  A_(dev_alloc(c, &c->m1, cap));
+  A_(dev_alloc(c, &c->max0, R));
+  A_(dev_alloc(c, &c->m0, R));
+  A_(dev_alloc(c, &c->m1, R));
   A_(dev_alloc(c, &c->res_matches, B * cap * 2));
   A_(dev_alloc(c, &c->res_scores, B * cap));
   A_(dev_alloc(c, &c->res_count, B));
@@ -1006,20 +1031,12 @@ int rfe_lg_match_slots_batch(rfe_ctx* c, int n_pairs, const int* slot0, const in
   RFE_CUDA_CHECK(cudaMemcpyAsync(c->h_counts, c->kp_counts, sizeof(int) * c->last_batch, cudaMemcpyDeviceToHost, c->stream));
   RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   PairDesc pd[kMaxPairs];
-  size_t koff = 0;
   for (int i = 0; i < n_pairs; ++i) {
     const int s0 = slot0[i], s1 = slot1[i];
     const int n0 = c->h_counts[s0] < c->cap ? c->h_counts[s0] : c->cap;
     const int n1 = c->h_counts[s1] < c->cap ? c->h_counts[s1] : c->cap;
-    float* k0 = c->in_kpts + koff * 2;
-    koff += round_up(n0, 8);
-    float* k1 = c->in_kpts + koff * 2;
-    koff += round_up(n1, 8);
-    { ProfScope ps_(c, "lg.kpts_to_float"); launch_kpts_to_float(c->stream, c->kpts + static_cast<size_t>(s0) * c->cap * 2, n0, k0); }
-    { ProfScope ps_(c, "lg.kpts_to_float"); launch_kpts_to_float(c->stream, c->kpts + static_cast<size_t>(s1) * c->cap * 2, n1, k1); }
-    c->launches += 2;
-    pd[i] = PairDesc{k0, k1, c->desc + static_cast<size_t>(s0) * c->cap * 256, c->desc + static_cast<size_t>(s1) * c->cap * 256,
-                     n0, n1, i};
+    pd[i] = PairDesc{nullptr, nullptr, c->kpts + static_cast<size_t>(s0) * c->cap * 2, c->kpts + static_cast<size_t>(s1) * c->cap * 2,
+                     c->desc + static_cast<size_t>(s0) * c->cap * 256, c->desc + static_cast<size_t>(s1) * c->cap * 256, n0, n1, i};
   }
   return lg_run(c, pd, n_pairs, norm_h, norm_w, thresh);
 }
@@ -1035,12 +1052,8 @@ int rfe_lg_match_slots(rfe_ctx* c, int slot0, int slot1, int norm_h, int norm_w,
   RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   const int n0 = c->h_counts[slot0] < c->cap ? c->h_counts[slot0] : c->cap;
   const int n1 = c->h_counts[slot1] < c->cap ? c->h_counts[slot1] : c->cap;
-  const int n0p = round_up(n0, 8);
-  { ProfScope ps_(c, "lg.kpts_to_float"); launch_kpts_to_float(c->stream, c->kpts + static_cast<size_t>(slot0) * c->cap * 2, n0, c->in_kpts); }
-  { ProfScope ps_(c, "lg.kpts_to_float"); launch_kpts_to_float(c->stream, c->kpts + static_cast<size_t>(slot1) * c->cap * 2, n1, c->in_kpts + static_cast<size_t>(n0p) * 2); }
-  c->launches += 2;
-  PairDesc pd{c->in_kpts, c->in_kpts + static_cast<size_t>(n0p) * 2, c->desc + static_cast<size_t>(slot0) * c->cap * 256,
-              c->desc + static_cast<size_t>(slot1) * c->cap * 256, n0, n1, rslot};
+  PairDesc pd{nullptr, nullptr, c->kpts + static_cast<size_t>(slot0) * c->cap * 2, c->kpts + static_cast<size_t>(slot1) * c->cap * 2,
+              c->desc + static_cast<size_t>(slot0) * c->cap * 256, c->desc + static_cast<size_t>(slot1) * c->cap * 256, n0, n1, rslot};
   return lg_run(c, &pd, 1, norm_h, norm_w, thresh);
 }
 
@@ -1147,8 +1160,8 @@ int rfe_lg_match(rfe_ctx* c, const float* kpts0, int n0, const float* kpts1, int
   RFE_CUDA_CHECK(cudaMemcpyAsync(c->in_kpts + static_cast<size_t>(n0p) * 2, kpts1, sizeof(float) * 2 * n1, cudaMemcpyHostToDevice, s));
   RFE_CUDA_CHECK(cudaMemcpyAsync(c->in_desc, desc0, sizeof(float) * 256 * n0, cudaMemcpyHostToDevice, s));
   RFE_CUDA_CHECK(cudaMemcpyAsync(c->in_desc + static_cast<size_t>(n0p) * 256, desc1, sizeof(float) * 256 * n1, cudaMemcpyHostToDevice, s));
-  PairDesc pd{c->in_kpts, c->in_kpts + static_cast<size_t>(n0p) * 2, c->in_desc, c->in_desc + static_cast<size_t>(n0p) * 256,
-              n0, n1, 0};
+  PairDesc pd{c->in_kpts, c->in_kpts + static_cast<size_t>(n0p) * 2, nullptr, nullptr, c->in_desc,
+              c->in_desc + static_cast<size_t>(n0p) * 256, n0, n1, 0};
   if ((r = lg_run(c, &pd, 1, norm_h, norm_w, thresh))) return r;
   r = rfe_lg_read_result(c, 0, matches, mscores, k, n0);
   cudaEventRecord(c->ev1, s);
@@ -1172,6 +1185,13 @@ int rfe_profile(rfe_ctx* c, int enable) {
   int r = check_ctx(c);
   if (r) return r;
   c->profiling = enable != 0;
+  return RFE_OK;
+}
+
+int rfe_profile_select(rfe_ctx* c, const char* prefix) {
+  int r = check_ctx(c);
+  if (r) return r;
+  c->prof_prefix = prefix ? prefix : "";
   return RFE_OK;
 }
 
@@ -1225,7 +1245,7 @@ int rfe_debug_read(rfe_ctx* c, const char* name, void* dst, size_t capacity, siz
   else if (s == "sp.nms") { fb = c->nmsmap; n = B * H * W; }
   else if (s == "sp.dense") { fb = c->dense; n = B * H * W / 64 * 256; }
   else if (s == "lg.x") { fb = c->x; n = static_cast<size_t>(c->dbg_off1 + c->dbg_n1) * 256; }
-  else if (s == "lg.sim") { fb = c->sim; n = static_cast<size_t>(c->dbg_n0) * round_up(c->dbg_n1, 8); }
+  else if (s == "lg.sim") { fb = c->sim + static_cast<size_t>(c->dbg_pair) * c->cap * c->lg_ld; n = static_cast<size_t>(c->dbg_n0) * round_up(c->dbg_n1, 8); }
   else if (s == "lg.S") {
     if (!c->S_dbg) {   // first request arms the capture; the NEXT match fills it
       if ((r = dev_alloc(c, &c->S_dbg, static_cast<size_t>(c->cap) * c->cap))) return r;

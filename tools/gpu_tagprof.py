@@ -10,7 +10,7 @@ from rover_slam_b200 import FrontEnd
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 arm = len(sys.argv) > 2 and sys.argv[2] == "arm"      # arm the in-kernel role counters (attention runs its PROF build)
-P = 4
+P = int(os.environ.get("RFE_PAIRS", "4"))
 B = 2 * P
 fe = FrontEnd(max_batch=B, max_height=bench.H, max_width=bench.W, max_keypoints=4096)
 if arm:
@@ -28,9 +28,9 @@ for _ in range(steps):
     step()
 fe.sync()
 tags = ["sp.conv1a", "sp.conv1b", "sp.conv2a", "sp.conv2b", "sp.conv3a", "sp.conv3b", "sp.conv4a", "sp.conv4b", "sp.convPa", "sp.convDa",
-        "sp.convPb_softmax", "sp.convDb_l2norm", "sp.nms", "sp.select", "sp.desc_sample", "lg.kpts_to_float", "lg.posenc", "lg.split_rows",
+        "sp.convPb_softmax", "sp.convDb_l2norm", "sp.nms", "sp.select", "sp.desc_sample", "lg.prepare",
         "lg.wqkv_rope", "lg.attn_self", "lg.out_proj", "lg.ffn0", "lg.ln_gelu", "lg.ffn3", "lg.to_qk", "lg.to_v", "lg.attn_cross", "lg.to_out",
-        "lg.final_proj", "lg.matchability", "lg.sim", "lg.lse", "lg.argmax", "lg.compact"]
+        "lg.final_proj", "lg.matchability", "lg.sim", "lg.assign"]
 tot, _ = fe.profile_read(None)
 print(f"{'tag':22s} {'launches/step':>13s} {'us/launch':>10s} {'us/step':>10s} {'share':>7s}")
 acc = 0.0
