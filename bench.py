@@ -5,8 +5,8 @@ A "step" = one batch of PAIRS 640x480 frame pairs: both frames of every pair are
 SuperPoint launch sequence over 2*PAIRS frames), then every pair is matched.  frames/s = 2*PAIRS*steps / time.
   value : inputs already resident in HBM, features handed from the extractor to the matcher on the device
           (rfe_sp_extract_device + rfe_lg_match_slots), device-timed with CUDA events, max over ranks.
-  e2e   : the same work through the reference-facing host API (rfe_sp_extract_u8 / rfe_lg_match: host images in,
-          host keypoints+descriptors out, host features in, host matches out), copies inside the timed region.
+  e2e   : the same work through the host API (rfe_pairs_submit / rfe_pairs_collect: pinned host images in, host keypoints
+          and matches out), every H2D / D2H copy inside the timed region, two batches in flight.
   --impl reference : the reference's CPU path for the same workload -- its two ONNX graphs restated on torch-CPU
           (oracle/, stand-in for ONNXRuntime-CPU which is not installable here), all host threads, one pair per step.
 """
@@ -208,13 +208,20 @@ def main():
 
     h2d = d2h = 0
 
-    def step_host(i):
-        # the public end-to-end call: pinned host frames in, host keypoints + matches out (rfe_match_pairs_u8)
-        nonlocal h2d, d2h
-        imgs = host_sets[i % n_sets].numpy()
-        kpts, res = fe.match_pairs(imgs)
-        h2d += imgs.nbytes
-        d2h += sum(k.nbytes for k in kpts) + 4 * len(kpts) + sum(m.nbytes + s.nbytes for m, s in res) + 4 * len(res)
+    host_np = [host_sets[i].numpy() for i in range(n_sets)]      # views of the pinned buffers
+
+    def run_host(n_steps):
+        # the public end-to-end calls: pinned host frames in (rfe_pairs_submit), host keypoints + matches out
+        # (rfe_pairs_collect), two batches in flight so that the host-side matcher set-up of batch i overlaps SuperPoint
+        # of batch i+1 on the GPU.  Every step copies its own inputs H2D and its own results D2H.
+        fe.pairs_submit(host_np[0])
+        if n_steps > 1:
+            fe.pairs_submit(host_np[1 % n_sets])
+        for i in range(n_steps):
+            fe.pairs_collect_begin()                    # enqueue LightGlue + result copies of batch i
+            if i + 2 < n_steps:
+                fe.pairs_submit(host_np[(i + 2) % n_sets])   # queue the next batch behind it BEFORE blocking
+            kpts, res = fe.pairs_collect_end()
 
     def barrier():
         torch.cuda.synchronize()
@@ -263,15 +270,15 @@ def main():
     attn_flops = sum(attn_flops_sets[i % n_sets] for i in range(args.steps)) / args.steps     # mean per launch
 
     # ---- end to end through the host API ("e2e") ----
-    for i in range(2):
-        step_host(i)
-    h2d = d2h = 0
+    run_host(2)
     barrier()
+    tb0 = fe.transfer_bytes()
     t0 = time.perf_counter()
     e_steps = max(3, args.steps // 2)
-    for i in range(e_steps):
-        step_host(i)
+    run_host(e_steps)
     barrier()
+    tb1 = fe.transfer_bytes()
+    h2d, d2h = tb1[0] - tb0[0], tb1[1] - tb0[1]          # bytes the library actually copied (counted at the cudaMemcpyAsync calls)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = 2 * P * e_steps * world / e2e_s
     sampler.stop()

@@ -99,12 +99,30 @@ int rfe_lg_match_slots_batch(rfe_ctx* ctx, int n_pairs, const int* slot0, const 
 int rfe_match_pairs_u8(rfe_ctx* ctx, const uint8_t* gray, int h, int w, int stride_bytes, int n_pairs, float match_thresh,
                        int32_t* kpts_xy, int32_t* kp_counts, int32_t* matches, float* mscores, int32_t* match_counts,
                        int cap);
+/* Pipelined form of rfe_match_pairs_u8 for a STREAM of batches (Tracking feeds frames continuously).  submit() copies
+ * the images to the device and enqueues SuperPoint; collect() returns the results of the OLDEST submitted batch: it waits
+ * for that batch's keypoint counts, enqueues LightGlue, copies keypoints and matches back.  Up to two batches may be in
+ * flight -- submit(A) submit(B) collect(A) submit(C) collect(B) ... -- so the GPU runs SuperPoint of the next batch while
+ * the host lays out the matcher of the previous one.  `gray` must stay valid until the matching collect() returns (use
+ * pinned memory for a truly asynchronous copy).  Output layout as rfe_match_pairs_u8; matches/mscores receive up to n0
+ * entries per pair (the first match_counts[p] are valid). */
+int rfe_pairs_submit(rfe_ctx* ctx, const uint8_t* gray, int h, int w, int stride_bytes, int n_pairs);
+int rfe_pairs_collect(rfe_ctx* ctx, float match_thresh, int32_t* kpts_xy, int32_t* kp_counts, int32_t* matches,
+                      float* mscores, int32_t* match_counts, int cap);
+/* rfe_pairs_collect in two halves, so that the NEXT batch can be submitted before the host blocks: begin() enqueues the
+ * matcher and the result copies (the output arrays must stay valid until end()), end() waits for exactly those copies.
+ * Steady state of a stream:  collect_begin(i); submit(i+2); collect_end(i);  -- the GPU queue never drains. */
+int rfe_pairs_collect_begin(rfe_ctx* ctx, float match_thresh, int32_t* kpts_xy, int32_t* matches, float* mscores, int cap);
+int rfe_pairs_collect_end(rfe_ctx* ctx, int32_t* kp_counts, int32_t* match_counts);
 /* Copy a match result to the host (synchronises). */
 int rfe_lg_read_result(rfe_ctx* ctx, int rslot, int32_t* matches, float* mscores, int* k, int cap);
 
 /* ---- timers / introspection --------------------------------------------------------------------- */
 /* Accumulated GPU milliseconds (CUDA events) of "extractor" / "matcher" calls, like the reference's GetTimer. */
 double rfe_get_timer_ms(rfe_ctx* ctx, const char* name);
+/* Bytes the pipelined path (rfe_pairs_submit / rfe_pairs_collect, rfe_match_pairs_u8) has copied host->device and
+ * device->host so far. */
+int rfe_transfer_bytes(rfe_ctx* ctx, unsigned long long* h2d, unsigned long long* d2h);
 /* Number of kernels the library has launched on this ctx so far. */
 long long rfe_kernel_launches(rfe_ctx* ctx);
 /* Per-kernel timing with CUDA events on the ctx stream (off by default).  Tags: "sp.conv1b", "sp.conv2a", ...,

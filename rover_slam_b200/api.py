@@ -63,9 +63,14 @@ def load_library():
     lib.rfe_lg_match_slots.argtypes = [vp, ci, ci, ci, ci, cf, ci]
     lib.rfe_lg_match_slots_batch.argtypes = [vp, ci, vp, vp, ci, ci, cf]
     lib.rfe_match_pairs_u8.argtypes = [vp, vp, ci, ci, ci, ci, cf, vp, vp, vp, vp, vp, ci]
+    lib.rfe_pairs_submit.argtypes = [vp, vp, ci, ci, ci, ci]
+    lib.rfe_pairs_collect.argtypes = [vp, cf, vp, vp, vp, vp, vp, ci]
+    lib.rfe_pairs_collect_begin.argtypes = [vp, cf, vp, vp, vp, ci]
+    lib.rfe_pairs_collect_end.argtypes = [vp, vp, vp]
     lib.rfe_lg_read_result.argtypes = [vp, ci, vp, vp, vp, ci]
     lib.rfe_get_timer_ms.argtypes = [vp, C.c_char_p]
     lib.rfe_get_timer_ms.restype = C.c_double
+    lib.rfe_transfer_bytes.argtypes = [vp, P(C.c_ulonglong), P(C.c_ulonglong)]
     lib.rfe_kernel_launches.argtypes = [vp]
     lib.rfe_kernel_launches.restype = C.c_longlong
     lib.rfe_profile.argtypes = [vp, ci]
@@ -191,6 +196,50 @@ class FrontEnd:
         kpts = [kp[i, :kc[i]] for i in range(b)] if want_kpts else None
         return kpts, [(m[i, :mc[i]], ms[i, :mc[i]]) for i in range(npairs)]
 
+    def pairs_submit(self, images: np.ndarray):
+        """Pipelined matching, step 1: images uint8 [2*P, H, W] (pinned host memory for an asynchronous copy).  The array
+        must stay alive until the matching pairs_collect()."""
+        b, h, w = images.shape
+        self._inflight = getattr(self, "_inflight", [])
+        self._inflight.append(images)
+        self._check(self.lib.rfe_pairs_submit(self.ctx, _ptr(images), h, w, w, b // 2))
+
+    def pairs_collect(self, thresh: float = 0.0, want_kpts: bool = True):
+        """Pipelined matching, step 2: results of the oldest submitted batch, same form as match_pairs()."""
+        imgs = self._inflight.pop(0)
+        b = imgs.shape[0]
+        npairs, cap = b // 2, self.cap
+        if not hasattr(self, "_mp_buf") or self._mp_buf[0].shape[0] != b:
+            self._mp_buf = (np.empty((b, cap, 2), np.int32), np.zeros(b, np.int32), np.empty((npairs, cap, 2), np.int32),
+                            np.empty((npairs, cap), np.float32), np.zeros(npairs, np.int32))
+        kp, kc, m, ms, mc = self._mp_buf
+        self._check(self.lib.rfe_pairs_collect(self.ctx, thresh, _ptr(kp) if want_kpts else None, _ptr(kc), _ptr(m), _ptr(ms),
+                                               _ptr(mc), cap))
+        kpts = [kp[i, :kc[i]] for i in range(b)] if want_kpts else None
+        return kpts, [(m[i, :mc[i]], ms[i, :mc[i]]) for i in range(npairs)]
+
+    def pairs_collect_begin(self, thresh: float = 0.0, want_kpts: bool = True):
+        """First half of pairs_collect(): enqueue the matcher and the result copies of the oldest submitted batch."""
+        imgs = self._inflight.pop(0)
+        b = imgs.shape[0]
+        npairs, cap = b // 2, self.cap
+        # two result buffer sets: the arrays handed out by the previous collect stay valid while this one is filled
+        self._mp_sets = getattr(self, "_mp_sets", {})
+        self._mp_flip = 1 - getattr(self, "_mp_flip", 0)
+        key = (b, self._mp_flip)
+        if key not in self._mp_sets:
+            self._mp_sets[key] = (np.empty((b, cap, 2), np.int32), np.zeros(b, np.int32), np.empty((npairs, cap, 2), np.int32),
+                                  np.empty((npairs, cap), np.float32), np.zeros(npairs, np.int32))
+        self._collecting = (self._mp_sets[key], b, npairs, want_kpts)
+        kp, kc, m, ms, mc = self._mp_sets[key]
+        self._check(self.lib.rfe_pairs_collect_begin(self.ctx, thresh, _ptr(kp) if want_kpts else None, _ptr(m), _ptr(ms), cap))
+
+    def pairs_collect_end(self):
+        (kp, kc, m, ms, mc), b, npairs, want_kpts = self._collecting
+        self._check(self.lib.rfe_pairs_collect_end(self.ctx, _ptr(kc), _ptr(mc)))
+        kpts = [kp[i, :kc[i]] for i in range(b)] if want_kpts else None
+        return kpts, [(m[i, :mc[i]], ms[i, :mc[i]]) for i in range(npairs)]
+
     def read_result(self, rslot: int = 0):
         m = np.empty((self.cap, 2), np.int32)
         s = np.empty(self.cap, np.float32)
@@ -201,6 +250,12 @@ class FrontEnd:
     # ---- introspection -----------------------------------------------------------------------------
     def timer_ms(self, name: str) -> float:
         return float(self.lib.rfe_get_timer_ms(self.ctx, name.encode()))
+
+    def transfer_bytes(self):
+        """(host->device, device->host) bytes copied by the pair-matching path so far."""
+        a, b = C.c_ulonglong(0), C.c_ulonglong(0)
+        self._check(self.lib.rfe_transfer_bytes(self.ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def kernel_launches(self) -> int:
         return int(self.lib.rfe_kernel_launches(self.ctx))

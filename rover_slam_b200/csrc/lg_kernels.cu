@@ -70,19 +70,21 @@ void launch_split_rows(cudaStream_t s, const float* src, int rows, int cols, int
 }
 
 // ---- LayerNorm(512, eps 1e-5) + exact GELU -> split-fp16 (one warp per row; nodes 62-67) --------------------
+// Lane l owns columns 128 j + 4 l .. + 3 (j = 0..3): float4 loads, 8-byte stores per plane, packed split.
 __global__ void __launch_bounds__(256) ln_gelu_split_kernel(const float* __restrict__ x, int rows,
                                                             const float* __restrict__ g, const float* __restrict__ b,
                                                             __half* __restrict__ hi, __half* __restrict__ lo) {
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= rows) return;
-  const float* r = x + static_cast<size_t>(wid) * 512;
+  const float4* r4 = reinterpret_cast<const float4*>(x + static_cast<size_t>(wid) * 512);
   float v[16];
   float s = 0.0f;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    v[j] = r[j * 32 + lane];
-    s += v[j];
+  for (int j = 0; j < 4; ++j) {
+    const float4 t = r4[j * 32 + lane];
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    s += (t.x + t.y) + (t.z + t.w);
   }
   const float mean = warp_sum(s) * (1.0f / 512.0f);
   float q = 0.0f;
@@ -94,14 +96,21 @@ __global__ void __launch_bounds__(256) ln_gelu_split_kernel(const float* __restr
   const float var = warp_sum(q) * (1.0f / 512.0f);
   const float rstd = 1.0f / sqrtf(var + 1e-5f);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int c = j * 32 + lane;
-    const float y = (v[j] - mean) * rstd * g[c] + b[c];
-    const float ge = (y * (erff(y / 1.4142135381698608f) + 1.0f)) * 0.5f;
-    __half h, l;
-    split_f32(ge, h, l);
-    hi[static_cast<size_t>(wid) * 512 + c] = h;
-    lo[static_cast<size_t>(wid) * 512 + c] = l;
+  for (int j = 0; j < 4; ++j) {
+    const int c = j * 128 + lane * 4;
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + c)), b4 = __ldg(reinterpret_cast<const float4*>(b + c));
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+    float ge[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float y = (v[4 * j + i] - mean) * rstd * gg[i] + bb[i];
+      ge[i] = (y * (erff(y / 1.4142135381698608f) + 1.0f)) * 0.5f;
+    }
+    uint32_t h0, l0, h1, l1;
+    split2(pk2(ge[0], ge[1]), h0, l0);
+    split2(pk2(ge[2], ge[3]), h1, l1);
+    *reinterpret_cast<uint2*>(hi + static_cast<size_t>(wid) * 512 + c) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(lo + static_cast<size_t>(wid) * 512 + c) = make_uint2(l0, l1);
   }
 }
 void launch_ln_gelu_split(cudaStream_t s, const float* x, int rows, const float* g, const float* b, __half* hi,

@@ -73,6 +73,19 @@ struct rfe_ctx {
   float* desc = nullptr;        // [max_batch][cap][256]
   int last_batch = 0, last_h = 0, last_w = 0;
   int* h_counts = nullptr;      // pinned [max_batch]
+  // pipelined pair matching (rfe_pairs_submit / rfe_pairs_collect): two feature-slot sets (set k = slots
+  // [k*max_batch, (k+1)*max_batch)), up to two batches in flight
+  struct Pending { int set, n_pairs, h, w; };
+  Pending pending[2];
+  int n_pending = 0, next_set = 0;
+  cudaEvent_t ev_counts[2] = {nullptr, nullptr};
+  cudaEvent_t ev_done = nullptr;     // results of the batch being collected have landed on the host
+  int collecting_pairs = 0;          // > 0 between rfe_pairs_collect_begin and rfe_pairs_collect_end
+  int collecting_rc = 0;
+  int collecting_counts[2 * 16];
+  int* h_counts2 = nullptr;     // pinned [2][max_batch] keypoint counts of the two sets
+  int* h_mcounts = nullptr;     // pinned [max_batch] match counts
+  unsigned long long bytes_h2d = 0, bytes_d2h = 0;   // host<->device traffic of the pipelined path (rfe_transfer_bytes)
 
   // ---- LightGlue buffers (sized for 2*cap rows) ----
   int lg_rows = 0, lg_ld = 0, lg_pairs = 1;   // row capacity, padded key count, pairs per batched match
@@ -421,7 +434,7 @@ int conv64_strip(rfe_ctx* c, const char* tag, const SplitBuf& in, int B, int H, 
 // ------------------------------------------------------------------------------------------------
 // SuperPoint: device in -> device-resident features
 // ------------------------------------------------------------------------------------------------
-int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B) {
+int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B, int slot_base = 0) {
   cudaStream_t s = c->stream;
   int r;
   { ProfScope ps_(c, "sp.conv1a"); launch_conv1a(s, d_gray, stride, h, w, B, c->conv1a_w, c->conv1a_b, c->a1a.hi, c->a1a.lo); }
@@ -475,9 +488,13 @@ int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B) {
     if ((r = launch_umma<256, A_GEMM, EPI_DESC>(c, "sp.convDb_l2norm", ah, al, bh, bl, p, dim3((npix + 127) / 128, 1, 1)))) return r;
   }
   { ProfScope ps_(c, "sp.nms"); launch_nms(s, c->heat, c->nmsmap, B, h, w); }
-  { ProfScope ps_(c, "sp.select"); launch_select(s, c->nmsmap, B, h, w, kDetThreshold, c->cap, c->row_cnt, c->row_off, c->kp_counts, c->kpts,
-                c->kp_scores); }
-  { ProfScope ps_(c, "sp.desc_sample"); launch_desc_sample(s, c->dense, hc, wc, B, c->kpts, c->kp_counts, c->cap, c->desc); }
+  int* kp_counts = c->kp_counts + slot_base;
+  int* kpts = c->kpts + static_cast<size_t>(slot_base) * c->cap * 2;
+  float* kp_scores = c->kp_scores + static_cast<size_t>(slot_base) * c->cap;
+  float* desc = c->desc + static_cast<size_t>(slot_base) * c->cap * 256;
+  { ProfScope ps_(c, "sp.select"); launch_select(s, c->nmsmap, B, h, w, kDetThreshold, c->cap, c->row_cnt, c->row_off, kp_counts, kpts,
+                kp_scores); }
+  { ProfScope ps_(c, "sp.desc_sample"); launch_desc_sample(s, c->dense, hc, wc, B, kpts, kp_counts, c->cap, desc); }
   c->launches += 5;
   RFE_CUDA_CHECK(cudaGetLastError());
   c->last_batch = B;
@@ -868,11 +885,16 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   A_(dev_alloc(c, &c->dense, coarse * 256));
   A_(dev_alloc(c, &c->row_cnt, B * H));
   A_(dev_alloc(c, &c->row_off, B * H));
-  A_(dev_alloc(c, &c->kp_counts, B));
-  A_(dev_alloc(c, &c->kpts, B * cap * 2));
-  A_(dev_alloc(c, &c->kp_scores, B * cap));
-  A_(dev_alloc(c, &c->desc, B * cap * 256));
+  A_(dev_alloc(c, &c->kp_counts, 2 * B));            // two feature-slot sets (see rfe_pairs_submit)
+  A_(dev_alloc(c, &c->kpts, 2 * B * cap * 2));
+  A_(dev_alloc(c, &c->kp_scores, 2 * B * cap));
+  A_(dev_alloc(c, &c->desc, 2 * B * cap * 256));
   RFE_CUDA_CHECK(cudaMallocHost(&c->h_counts, sizeof(int) * (2 * B + 2)));
+  RFE_CUDA_CHECK(cudaMallocHost(&c->h_counts2, sizeof(int) * 2 * B));
+  RFE_CUDA_CHECK(cudaMallocHost(&c->h_mcounts, sizeof(int) * B));
+  RFE_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_counts[0], cudaEventDisableTiming));
+  RFE_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_counts[1], cudaEventDisableTiming));
+  RFE_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
   // ---- LightGlue buffers ----
   c->lg_pairs = c->max_batch < kMaxPairs ? c->max_batch : kMaxPairs;   // pairs per rfe_lg_match_slots_batch
   c->lg_rows = 2 * c->lg_pairs * (c->cap + 8);
@@ -916,6 +938,11 @@ void rfe_destroy(rfe_ctx* c) {
   cudaDeviceSynchronize();
   for (void* p : c->allocs) cudaFree(p);
   if (c->h_counts) cudaFreeHost(c->h_counts);
+  if (c->h_counts2) cudaFreeHost(c->h_counts2);
+  if (c->h_mcounts) cudaFreeHost(c->h_mcounts);
+  for (int i = 0; i < 2; ++i)
+    if (c->ev_counts[i]) cudaEventDestroy(c->ev_counts[i]);
+  if (c->ev_done) cudaEventDestroy(c->ev_done);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -1057,6 +1084,146 @@ int rfe_lg_match_slots(rfe_ctx* c, int slot0, int slot1, int norm_h, int norm_w,
   return lg_run(c, &pd, 1, norm_h, norm_w, thresh);
 }
 
+int rfe_pairs_submit(rfe_ctx* c, const uint8_t* gray, int h, int w, int stride, int n_pairs) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (!gray || n_pairs <= 0 || n_pairs > c->lg_pairs) {
+    set_error("rfe_pairs_submit: null/invalid argument (at most %d pairs per batch)", c->lg_pairs);
+    return RFE_ERR_INVALID;
+  }
+  if (c->n_pending >= 2) {
+    set_error("rfe_pairs_submit: two batches are already waiting; call rfe_pairs_collect first");
+    return RFE_ERR_INVALID;
+  }
+  const int B = 2 * n_pairs;
+  if ((r = check_image_args(c, h, w, stride, B))) return r;
+  cudaStream_t s = c->stream;
+  const int set = c->next_set;
+  // one image staging buffer is enough: the copy of batch k+1 is ordered after SuperPoint of batch k on the stream
+  RFE_CUDA_CHECK(cudaMemcpyAsync(c->img, gray, static_cast<size_t>(B) * h * stride, cudaMemcpyHostToDevice, s));
+  c->bytes_h2d += static_cast<size_t>(B) * h * stride;
+  if ((r = sp_run(c, c->img, h, w, stride, B, set * c->max_batch))) return r;
+  RFE_CUDA_CHECK(cudaMemcpyAsync(c->h_counts2 + set * c->max_batch, c->kp_counts + set * c->max_batch, sizeof(int) * B,
+                                 cudaMemcpyDeviceToHost, s));
+  RFE_CUDA_CHECK(cudaEventRecord(c->ev_counts[set], s));
+  c->pending[c->n_pending++] = rfe_ctx::Pending{set, n_pairs, h, w};
+  c->next_set ^= 1;
+  return RFE_OK;
+}
+
+int rfe_pairs_collect_begin(rfe_ctx* c, float thresh, int32_t* kpts_xy, int32_t* matches, float* mscores, int cap) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (!matches || cap <= 0) {
+    set_error("rfe_pairs_collect_begin: null/invalid argument");
+    return RFE_ERR_INVALID;
+  }
+  if (c->n_pending == 0 || c->collecting_pairs) {
+    set_error("rfe_pairs_collect_begin: nothing was submitted, or the previous collect was not ended");
+    return RFE_ERR_INVALID;
+  }
+  const rfe_ctx::Pending pd0 = c->pending[0];
+  c->pending[0] = c->pending[1];
+  --c->n_pending;
+  cudaStream_t s = c->stream;
+  const int B = 2 * pd0.n_pairs, base = pd0.set * c->max_batch;
+  // the keypoint counts size the LightGlue launches: wait for THIS batch's SuperPoint only -- a batch submitted after it
+  // keeps the GPU busy while the host lays out and enqueues the matcher below
+  RFE_CUDA_CHECK(cudaEventSynchronize(c->ev_counts[pd0.set]));
+  const int* hc = c->h_counts2 + base;
+  PairDesc pd[kMaxPairs];
+  int rc = RFE_OK;
+  for (int i = 0; i < pd0.n_pairs; ++i) {
+    const int s0 = base + 2 * i, s1 = s0 + 1;
+    const int n0 = hc[2 * i] < c->cap ? hc[2 * i] : c->cap;
+    const int n1 = hc[2 * i + 1] < c->cap ? hc[2 * i + 1] : c->cap;
+    pd[i] = PairDesc{nullptr, nullptr, c->kpts + static_cast<size_t>(s0) * c->cap * 2, c->kpts + static_cast<size_t>(s1) * c->cap * 2,
+                     c->desc + static_cast<size_t>(s0) * c->cap * 256, c->desc + static_cast<size_t>(s1) * c->cap * 256, n0, n1, i};
+  }
+  if ((r = lg_run(c, pd, pd0.n_pairs, pd0.h, pd0.w, thresh))) return r;
+  // Results go back in as few copies as possible (a small device-to-host copy costs ~10 us of stream time, and a batch
+  // has 3 arrays per pair): when the caller's capacity equals the ctx capacity the slot arrays are copied whole.
+  const bool bulk = (cap == c->cap);
+  for (int b = 0; b < B; ++b) {
+    const int n = hc[b];
+    c->collecting_counts[b] = n;
+    int m = n < c->cap ? n : c->cap;
+    if (cap < m) m = cap;
+    if (n > c->cap || n > cap) {
+      set_error("image %d has %d keypoints, capacity %d", b, n, cap < c->cap ? cap : c->cap);
+      rc = RFE_ERR_CAPACITY;
+    }
+    if (kpts_xy && m > 0 && !bulk) {
+      RFE_CUDA_CHECK(cudaMemcpyAsync(kpts_xy + static_cast<size_t>(b) * cap * 2, c->kpts + static_cast<size_t>(base + b) * c->cap * 2,
+                                     sizeof(int) * 2 * m, cudaMemcpyDeviceToHost, s));
+      c->bytes_d2h += sizeof(int) * 2 * m;
+    }
+  }
+  if (kpts_xy && bulk) {
+    RFE_CUDA_CHECK(cudaMemcpyAsync(kpts_xy, c->kpts + static_cast<size_t>(base) * c->cap * 2, sizeof(int) * 2 * c->cap * B,
+                                   cudaMemcpyDeviceToHost, s));
+    c->bytes_d2h += sizeof(int) * 2 * c->cap * B;
+  }
+  RFE_CUDA_CHECK(cudaMemcpyAsync(c->h_mcounts, c->res_count, sizeof(int) * pd0.n_pairs, cudaMemcpyDeviceToHost, s));
+  c->bytes_d2h += sizeof(int) * (pd0.n_pairs + B);
+  if (bulk) {
+    RFE_CUDA_CHECK(cudaMemcpyAsync(matches, c->res_matches, sizeof(int) * 2 * c->cap * pd0.n_pairs, cudaMemcpyDeviceToHost, s));
+    c->bytes_d2h += sizeof(int) * 2 * c->cap * pd0.n_pairs;
+    if (mscores) {
+      RFE_CUDA_CHECK(cudaMemcpyAsync(mscores, c->res_scores, sizeof(float) * c->cap * pd0.n_pairs, cudaMemcpyDeviceToHost, s));
+      c->bytes_d2h += sizeof(float) * c->cap * pd0.n_pairs;
+    }
+  } else {
+    // a pair has at most n0 matches: copy that upper bound now instead of synchronising once more for the exact count
+    for (int i = 0; i < pd0.n_pairs; ++i) {
+      int m = pd[i].n0 < cap ? pd[i].n0 : cap;
+      if (pd[i].n0 == 0 || pd[i].n1 == 0) m = 0;
+      if (m > 0) {
+        RFE_CUDA_CHECK(cudaMemcpyAsync(matches + static_cast<size_t>(i) * cap * 2, c->res_matches + static_cast<size_t>(i) * c->cap * 2,
+                                       sizeof(int) * 2 * m, cudaMemcpyDeviceToHost, s));
+        c->bytes_d2h += sizeof(int) * 2 * m;
+        if (mscores) {
+          RFE_CUDA_CHECK(cudaMemcpyAsync(mscores + static_cast<size_t>(i) * cap, c->res_scores + static_cast<size_t>(i) * c->cap,
+                                         sizeof(float) * m, cudaMemcpyDeviceToHost, s));
+          c->bytes_d2h += sizeof(float) * m;
+        }
+      }
+    }
+  }
+  RFE_CUDA_CHECK(cudaEventRecord(c->ev_done, s));
+  c->collecting_pairs = pd0.n_pairs;
+  c->collecting_rc = rc;
+  c->last_batch = B;   // slot queries (rfe_sp_read_slot) refer to set 0 only; the pipelined path is self-contained
+  return RFE_OK;
+}
+
+int rfe_pairs_collect_end(rfe_ctx* c, int32_t* kp_counts, int32_t* match_counts) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (!kp_counts || !match_counts || !c->collecting_pairs) {
+    set_error("rfe_pairs_collect_end: null argument or no collect in progress");
+    return RFE_ERR_INVALID;
+  }
+  // wait for THIS batch's results only: work submitted after rfe_pairs_collect_begin keeps running behind the event
+  RFE_CUDA_CHECK(cudaEventSynchronize(c->ev_done));
+  for (int b = 0; b < 2 * c->collecting_pairs; ++b) kp_counts[b] = c->collecting_counts[b];
+  for (int i = 0; i < c->collecting_pairs; ++i) match_counts[i] = c->h_mcounts[i];
+  c->collecting_pairs = 0;
+  if (c->collecting_rc == RFE_ERR_CAPACITY) set_error("an image of the batch has more keypoints than the capacity");
+  return c->collecting_rc;
+}
+
+int rfe_pairs_collect(rfe_ctx* c, float thresh, int32_t* kpts_xy, int32_t* kp_counts, int32_t* matches, float* mscores,
+                      int32_t* match_counts, int cap) {
+  if (!kp_counts || !match_counts) {
+    set_error("rfe_pairs_collect: null argument");
+    return RFE_ERR_INVALID;
+  }
+  int r = rfe_pairs_collect_begin(c, thresh, kpts_xy, matches, mscores, cap);
+  if (r) return r;
+  return rfe_pairs_collect_end(c, kp_counts, match_counts);
+}
+
 int rfe_match_pairs_u8(rfe_ctx* c, const uint8_t* gray, int h, int w, int stride, int n_pairs, float thresh,
                        int32_t* kpts_xy, int32_t* kp_counts, int32_t* matches, float* mscores, int32_t* match_counts,
                        int cap) {
@@ -1066,53 +1233,19 @@ int rfe_match_pairs_u8(rfe_ctx* c, const uint8_t* gray, int h, int w, int stride
     set_error("rfe_match_pairs_u8: null/invalid argument (at most %d pairs per call)", c->lg_pairs);
     return RFE_ERR_INVALID;
   }
-  const int B = 2 * n_pairs;
-  if ((r = check_image_args(c, h, w, stride, B))) return r;
-  cudaStream_t s = c->stream;
-  RFE_CUDA_CHECK(cudaEventRecord(c->ev0, s));
-  RFE_CUDA_CHECK(cudaMemcpyAsync(c->img, gray, static_cast<size_t>(B) * h * stride, cudaMemcpyHostToDevice, s));
-  if ((r = sp_run(c, c->img, h, w, stride, B))) return r;
-  int s0[kMaxPairs], s1[kMaxPairs];
-  for (int i = 0; i < n_pairs; ++i) {
-    s0[i] = 2 * i;
-    s1[i] = 2 * i + 1;
+  if (c->n_pending) {
+    set_error("rfe_match_pairs_u8: batches submitted with rfe_pairs_submit are still in flight");
+    return RFE_ERR_INVALID;
   }
-  if ((r = rfe_lg_match_slots_batch(c, n_pairs, s0, s1, h, w, thresh))) return r;   // leaves the keypoint counts in h_counts
-  int rc = RFE_OK;
-  for (int b = 0; b < B; ++b) {
-    const int n = c->h_counts[b];
-    kp_counts[b] = n;
-    int m = n < c->cap ? n : c->cap;
-    if (cap < m) m = cap;
-    if (n > c->cap || n > cap) {
-      set_error("image %d has %d keypoints, capacity %d", b, n, cap < c->cap ? cap : c->cap);
-      rc = RFE_ERR_CAPACITY;
-    }
-    if (kpts_xy && m > 0)
-      RFE_CUDA_CHECK(cudaMemcpyAsync(kpts_xy + static_cast<size_t>(b) * cap * 2, c->kpts + static_cast<size_t>(b) * c->cap * 2,
-                                     sizeof(int) * 2 * m, cudaMemcpyDeviceToHost, s));
-  }
-  int* h_mc = c->h_counts + c->max_batch + 1;
-  RFE_CUDA_CHECK(cudaMemcpyAsync(h_mc, c->res_count, sizeof(int) * n_pairs, cudaMemcpyDeviceToHost, s));
-  RFE_CUDA_CHECK(cudaStreamSynchronize(s));
-  for (int i = 0; i < n_pairs; ++i) {
-    const int k = h_mc[i];
-    match_counts[i] = k;
-    const int m = k < cap ? k : cap;
-    if (m > 0) {
-      RFE_CUDA_CHECK(cudaMemcpyAsync(matches + static_cast<size_t>(i) * cap * 2, c->res_matches + static_cast<size_t>(i) * c->cap * 2,
-                                     sizeof(int) * 2 * m, cudaMemcpyDeviceToHost, s));
-      if (mscores)
-        RFE_CUDA_CHECK(cudaMemcpyAsync(mscores + static_cast<size_t>(i) * cap, c->res_scores + static_cast<size_t>(i) * c->cap,
-                                       sizeof(float) * m, cudaMemcpyDeviceToHost, s));
-    }
-  }
-  RFE_CUDA_CHECK(cudaEventRecord(c->ev1, s));
-  RFE_CUDA_CHECK(cudaStreamSynchronize(s));
+  RFE_CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
+  if ((r = rfe_pairs_submit(c, gray, h, w, stride, n_pairs))) return r;
+  r = rfe_pairs_collect(c, thresh, kpts_xy, kp_counts, matches, mscores, match_counts, cap);
+  cudaEventRecord(c->ev1, c->stream);
+  cudaStreamSynchronize(c->stream);
   float ms = 0.0f;
   cudaEventElapsedTime(&ms, c->ev0, c->ev1);
   c->timer_extract_ms += ms;
-  return rc;
+  return r;
 }
 
 int rfe_lg_read_result(rfe_ctx* c, int rslot, int32_t* matches, float* mscores, int* k, int cap) {
@@ -1180,6 +1313,13 @@ double rfe_get_timer_ms(rfe_ctx* c, const char* name) {
 }
 
 long long rfe_kernel_launches(rfe_ctx* c) { return c ? c->launches : 0; }
+
+int rfe_transfer_bytes(rfe_ctx* c, unsigned long long* h2d, unsigned long long* d2h) {
+  if (!c) return RFE_ERR_INVALID;
+  if (h2d) *h2d = c->bytes_h2d;
+  if (d2h) *d2h = c->bytes_d2h;
+  return RFE_OK;
+}
 
 int rfe_profile(rfe_ctx* c, int enable) {
   int r = check_ctx(c);

@@ -82,10 +82,10 @@ void launch_conv1a(cudaStream_t s, const uint8_t* img, int stride, int H, int W,
 }
 
 // ------------------------------------------------------------------------------------------------
-// NMS: fused tile kernel.  Tile 64x32 outputs, halo 20 = 5 chained 9x9 max-pools.
+// NMS: fused tile kernel.  Tile 80x48 outputs, halo 20 = 5 chained 9x9 max-pools (211 KB of shared memory).
 // ------------------------------------------------------------------------------------------------
 namespace {
-constexpr int NT_W = 64, NT_H = 32, NHALO = 20, NR = 4;
+constexpr int NT_W = 80, NT_H = 48, NHALO = 20, NR = 4;   // 640 = 8 x 80, 480 = 10 x 48: no ragged tiles; halo overhead 2.75x
 constexpr int RW = NT_W + 2 * NHALO;  // 104
 constexpr int RH = NT_H + 2 * NHALO;  // 72
 constexpr int NMS_THREADS = 512;

@@ -220,3 +220,35 @@ def test_gpu_path_launches_kernels(fe):
     before = fe.kernel_launches()
     fe.extract(synth.frame(1, 64, 64))
     assert fe.kernel_launches() - before >= 15
+
+
+def test_pipelined_pairs_equal_one_shot_calls(fe):
+    """rfe_pairs_submit / rfe_pairs_collect with two batches in flight return exactly what rfe_match_pairs_u8 returns."""
+    batches = [np.stack([f for s in range(2) for f in synth.frame_pair(40 + 10 * b + s, 240, 320, shift=(4, 2))]) for b in range(3)]
+    ref = []
+    for imgs in batches:
+        kp, res = fe.match_pairs(imgs)
+        ref.append(([k.copy() for k in kp], [(m.copy(), s.copy()) for m, s in res]))
+    out = []
+    fe.pairs_submit(batches[0])
+    for i in range(3):
+        if i + 1 < 3:
+            fe.pairs_submit(batches[i + 1])
+        kp, res = fe.pairs_collect()
+        out.append(([k.copy() for k in kp], [(m.copy(), s.copy()) for m, s in res]))
+    # ... and the begin / submit / end ordering that keeps the GPU queue full
+    out2 = []
+    fe.pairs_submit(batches[0])
+    fe.pairs_submit(batches[1])
+    for i in range(3):
+        fe.pairs_collect_begin()
+        if i + 2 < 3:
+            fe.pairs_submit(batches[i + 2])
+        kp, res = fe.pairs_collect_end()
+        out2.append(([k.copy() for k in kp], [(m.copy(), s.copy()) for m, s in res]))
+    for (rk, rr), (ok, orr) in zip(ref + ref, out + out2):
+        for a, b in zip(rk, ok):
+            assert np.array_equal(a, b)
+        for (rm, rs), (om, os_) in zip(rr, orr):
+            assert np.array_equal(rm, om) and np.array_equal(rs, os_)
+            assert len(rm) > 20
