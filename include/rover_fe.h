@@ -74,6 +74,26 @@ int rfe_sp_extract_device(rfe_ctx* ctx, const uint8_t* d_gray, int h, int w, int
 /* Copy slot b's features to the host (synchronises).  Any output pointer may be NULL. */
 int rfe_sp_read_slot(rfe_ctx* ctx, int slot, int32_t* kpts_xy, float* scores, float* desc, int32_t* count, int cap);
 
+/* Sign-binarised descriptors of slot b: what Frame::binarize_descriptors (src/Frame.cc:1034-1043) and
+ * KeyFrame::binarize_descriptors (src/KeyFrame.cc:113-123) compute on the host with cv::threshold(row, 0, 1, THRESH_BINARY)
+ * before every DBoW3 transform -- here written by the descriptor sampler while the values are in registers.
+ * bin: [n][256] uchar, 1 where the descriptor element is > 0 (the CV_8UC1 layout of mDescriptors_bin). */
+int rfe_sp_read_slot_bin(rfe_ctx* ctx, int slot, uint8_t* bin, int32_t* count, int cap);
+/* The same operation for host descriptors that did not come from a slot.  bin [n][256] 0/1 and/or bits [n][8] uint32
+ * (bit j%32 of word j/32 = element j); either may be NULL. */
+int rfe_binarize_descriptors(rfe_ctx* ctx, const float* desc, int n, uint8_t* bin, uint32_t* bits);
+
+/* ---- L2 projection matching -------------------------------------------------------- */
+/* Best and second-best L2 distance of every query descriptor over ITS OWN candidate list: the inner loop of
+ * SPmatcher::SearchByProjection / SearchByProjection1 / Fuse and Frame::ComputeStereoMatches (src/Matchers/SPmatcher.cc
+ * 1225-1250, distance = cv::norm(a, b, NORM_L2), SPmatcher.cc:2184-2189).  q [nq][256], db [nd][256]; query i examines
+ * db rows cand_idx[cand_off[i] .. cand_off[i+1]) in that order with the reference's update rule (strict <, so the first
+ * of equal distances wins; both distances start at init_dist, 256 in the reference).  best_idx / second_idx are -1 when
+ * no candidate beat init_dist.  second_dist / second_idx may be NULL. */
+int rfe_l2_best2(rfe_ctx* ctx, const float* q, int nq, const float* db, int nd, const int32_t* cand_off,
+                 const int32_t* cand_idx, float init_dist, float* best_dist, int32_t* best_idx, float* second_dist,
+                 int32_t* second_idx);
+
 /* ---- LightGlue -------------------------------------------------------------------------------- */
 /* Host in / host out.  kpts*_px: [n][2] pixel coordinates (x, y); desc*: [n][256].  Keypoints are
  * normalised as the reference does, (kpt - (norm_w/2, norm_h/2)) / (max(norm_w, norm_h)/2).

@@ -1,0 +1,47 @@
+"""CPU restatement of the host-side descriptor helpers next to the learned front end.
+TEST INFRASTRUCTURE ONLY: imported by tests/, never by the product.
+
+  binarize_descriptors  <- Frame::binarize_descriptors     src/Frame.cc:1034-1043, KeyFrame.cc:113-123
+  l2_best2              <- the candidate loop of SPmatcher::SearchByProjection*   src/Matchers/SPmatcher.cc:1225-1250
+                           with DescriptorDistance_sp = cv::norm(a, b, NORM_L2)   src/Matchers/SPmatcher.cc:2184-2189
+Parity: the reference has no test or fixture for these functions ("parity unpinned"); both are a few lines of host C++ and
+are restated literally.
+"""
+import numpy as np
+
+
+def binarize_descriptors(desc: np.ndarray) -> np.ndarray:
+    """cv::threshold(row, tmp, 0, 1, THRESH_BINARY) then uchar(tmp): 1 where the element is > 0, else 0."""
+    return (np.asarray(desc, np.float32) > 0).astype(np.uint8)
+
+
+def pack_bits(b: np.ndarray) -> np.ndarray:
+    """[N,256] 0/1 -> [N,8] uint32, bit j%32 of word j//32 = element j."""
+    w = b.reshape(len(b), 8, 32).astype(np.uint64) << np.arange(32, dtype=np.uint64)
+    return w.sum(axis=2).astype(np.uint32)
+
+
+def descriptor_distance_sp(a: np.ndarray, b: np.ndarray) -> np.float32:
+    """cv::norm(a, b, NORM_L2) on CV_32F rows: float difference, double accumulation, sqrt, cast to float."""
+    d = (np.asarray(a, np.float32) - np.asarray(b, np.float32)).astype(np.float64)
+    return np.float32(np.sqrt(np.sum(d * d)))
+
+
+def l2_best2(q, db, cand_off, cand_idx, init_dist=256.0):
+    """For every query: walk its candidate list in order; `if dist < best: second = best; best = dist elif dist < second:
+    second = dist` with both starting at init_dist (SPmatcher.cc:1211-1250).  Returns best/second distance and index."""
+    nq = len(q)
+    b1 = np.full(nq, init_dist, np.float32)
+    b2 = np.full(nq, init_dist, np.float32)
+    i1 = np.full(nq, -1, np.int32)
+    i2 = np.full(nq, -1, np.int32)
+    for i in range(nq):
+        for c in range(cand_off[i], cand_off[i + 1]):
+            idx = int(cand_idx[c])
+            dist = descriptor_distance_sp(q[i], db[idx])
+            if dist < b1[i]:
+                b2[i], i2[i] = b1[i], i1[i]
+                b1[i], i1[i] = dist, idx
+            elif dist < b2[i]:
+                b2[i], i2[i] = dist, idx
+    return b1, i1, b2, i2

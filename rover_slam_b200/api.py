@@ -59,6 +59,9 @@ def load_library():
     lib.rfe_sp_extract_u8.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp, vp, vp, ci]
     lib.rfe_sp_extract_device.argtypes = [vp, vp, ci, ci, ci, ci]
     lib.rfe_sp_read_slot.argtypes = [vp, ci, vp, vp, vp, vp, ci]
+    lib.rfe_sp_read_slot_bin.argtypes = [vp, ci, vp, vp, ci]
+    lib.rfe_binarize_descriptors.argtypes = [vp, vp, ci, vp, vp]
+    lib.rfe_l2_best2.argtypes = [vp, vp, ci, vp, ci, vp, vp, cf, vp, vp, vp, vp]
     lib.rfe_lg_match.argtypes = [vp, vp, ci, vp, ci, vp, vp, ci, ci, cf, vp, vp, vp]
     lib.rfe_lg_match_slots.argtypes = [vp, ci, ci, ci, ci, cf, ci]
     lib.rfe_lg_match_slots_batch.argtypes = [vp, ci, vp, vp, ci, ci, cf]
@@ -157,6 +160,36 @@ class FrontEnd:
         self._check(self.lib.rfe_sp_read_slot(self.ctx, slot, _ptr(kp), _ptr(sc), _ptr(de), C.byref(n), cap))
         n = n.value
         return kp[:n].copy(), sc[:n].copy(), de[:n].copy() if want_desc else None
+
+    def read_slot_bin(self, slot: int) -> np.ndarray:
+        """Sign-binarised descriptors [N,256] uint8 (0/1) of a feature slot (Frame::binarize_descriptors)."""
+        out = np.empty((self.cap, DESC_DIM), np.uint8)
+        n = C.c_int(0)
+        self._check(self.lib.rfe_sp_read_slot_bin(self.ctx, slot, _ptr(out), C.byref(n), self.cap))
+        return out[:n.value].copy()
+
+    def binarize(self, desc: np.ndarray):
+        """(bin uint8 [N,256] 0/1, bits uint32 [N,8]) of host descriptors [N,256]."""
+        d = np.ascontiguousarray(desc, np.float32).reshape(-1, DESC_DIM)
+        n = len(d)
+        b = np.empty((n, DESC_DIM), np.uint8)
+        w = np.empty((n, 8), np.uint32)
+        self._check(self.lib.rfe_binarize_descriptors(self.ctx, _ptr(d), n, _ptr(b), _ptr(w)))
+        return b, w
+
+    def l2_best2(self, q: np.ndarray, db: np.ndarray, cand_off: np.ndarray, cand_idx: np.ndarray, init_dist: float = 256.0):
+        """Best / second-best L2 match of every query over its candidate list (SearchByProjection inner loop).
+        Returns (best_dist, best_idx, second_dist, second_idx)."""
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, DESC_DIM)
+        db = np.ascontiguousarray(db, np.float32).reshape(-1, DESC_DIM)
+        off = np.ascontiguousarray(cand_off, np.int32)
+        idx = np.ascontiguousarray(cand_idx, np.int32)
+        nq = len(q)
+        b1, b2 = np.empty(nq, np.float32), np.empty(nq, np.float32)
+        i1, i2 = np.empty(nq, np.int32), np.empty(nq, np.int32)
+        self._check(self.lib.rfe_l2_best2(self.ctx, _ptr(q), nq, _ptr(db), len(db), _ptr(off), _ptr(idx), init_dist,
+                                          _ptr(b1), _ptr(i1), _ptr(b2), _ptr(i2)))
+        return b1, i1, b2, i2
 
     # ---- LightGlue -------------------------------------------------------------------------------
     def match(self, kpts0, kpts1, desc0, desc1, norm_h: int, norm_w: int, thresh: float = 0.0):

@@ -13,7 +13,10 @@ void launch_nms(cudaStream_t s, const float* heat, float* out, int B, int H, int
 void launch_select(cudaStream_t s, const float* nms, int B, int H, int W, float thr, int cap, int* row_cnt,
                    int* row_off, int* counts, int* kpts, float* scores);
 void launch_desc_sample(cudaStream_t s, const float* dense, int h, int w, int B, const int* kpts, const int* counts,
-                        int cap, float* desc);
+                        int cap, float* desc, uint8_t* desc_bin);
+void launch_binarize(cudaStream_t s, const float* desc, int n, uint8_t* out, uint32_t* bits);
+void launch_l2_best2(cudaStream_t s, const float* q, int nq, const float* db, const int* cand_off, const int* cand_idx,
+                     float init_dist, float* best_dist, int* best_idx, float* second_dist, int* second_idx);
 
 // ---- LightGlue -------------------------------------------------------------------------------------------
 constexpr int kLgMaxImages = 32;          // images (2 per pair) handled by one batched launch

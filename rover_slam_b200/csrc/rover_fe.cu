@@ -71,6 +71,7 @@ struct rfe_ctx {
   int* kpts = nullptr;          // [max_batch][cap][2]
   float* kp_scores = nullptr;   // [max_batch][cap]
   float* desc = nullptr;        // [max_batch][cap][256]
+  uint8_t* desc_bin = nullptr;  // [2*max_batch][cap][256] sign-binarised descriptors (0/1 per element)
   int last_batch = 0, last_h = 0, last_w = 0;
   int* h_counts = nullptr;      // pinned [max_batch]
   // pipelined pair matching (rfe_pairs_submit / rfe_pairs_collect): two feature-slot sets (set k = slots
@@ -119,6 +120,8 @@ struct rfe_ctx {
   std::vector<ProfRec> prof;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pool;
 
+  void* scr[2] = {nullptr, nullptr};         // grow-on-demand scratch of the host-in / host-out helpers
+  size_t scr_bytes[2] = {0, 0};
   // debug scratch
   float* dbg = nullptr;
   size_t dbg_bytes = 0;
@@ -494,7 +497,8 @@ int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B, i
   float* desc = c->desc + static_cast<size_t>(slot_base) * c->cap * 256;
   { ProfScope ps_(c, "sp.select"); launch_select(s, c->nmsmap, B, h, w, kDetThreshold, c->cap, c->row_cnt, c->row_off, kp_counts, kpts,
                 kp_scores); }
-  { ProfScope ps_(c, "sp.desc_sample"); launch_desc_sample(s, c->dense, hc, wc, B, kpts, kp_counts, c->cap, desc); }
+  { ProfScope ps_(c, "sp.desc_sample"); launch_desc_sample(s, c->dense, hc, wc, B, kpts, kp_counts, c->cap, desc,
+                                                           c->desc_bin + static_cast<size_t>(slot_base) * c->cap * 256); }
   c->launches += 5;
   RFE_CUDA_CHECK(cudaGetLastError());
   c->last_batch = B;
@@ -889,6 +893,7 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   A_(dev_alloc(c, &c->kpts, 2 * B * cap * 2));
   A_(dev_alloc(c, &c->kp_scores, 2 * B * cap));
   A_(dev_alloc(c, &c->desc, 2 * B * cap * 256));
+  A_(dev_alloc(c, &c->desc_bin, 2 * B * cap * 256));
   RFE_CUDA_CHECK(cudaMallocHost(&c->h_counts, sizeof(int) * (2 * B + 2)));
   RFE_CUDA_CHECK(cudaMallocHost(&c->h_counts2, sizeof(int) * 2 * B));
   RFE_CUDA_CHECK(cudaMallocHost(&c->h_mcounts, sizeof(int) * B));
@@ -1000,6 +1005,119 @@ int rfe_sp_read_slot(rfe_ctx* c, int slot, int32_t* kpts_xy, float* scores, floa
     set_error("image slot %d has %d keypoints, capacity %d", slot, n, cap < c->cap ? cap : c->cap);
     return RFE_ERR_CAPACITY;
   }
+  return RFE_OK;
+}
+
+int rfe_sp_read_slot_bin(rfe_ctx* c, int slot, uint8_t* bin, int32_t* count, int cap) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (slot < 0 || slot >= c->last_batch || !bin || cap <= 0) {
+    set_error("rfe_sp_read_slot_bin: invalid argument (slot %d, last batch %d)", slot, c->last_batch);
+    return RFE_ERR_INVALID;
+  }
+  RFE_CUDA_CHECK(cudaMemcpyAsync(c->h_counts, c->kp_counts + slot, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  const int n = c->h_counts[0];
+  if (count) *count = n;
+  int m = n < c->cap ? n : c->cap;
+  if (cap < m) m = cap;
+  if (m > 0) {
+    RFE_CUDA_CHECK(cudaMemcpyAsync(bin, c->desc_bin + static_cast<size_t>(slot) * c->cap * 256, static_cast<size_t>(m) * 256,
+                                   cudaMemcpyDeviceToHost, c->stream));
+    RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  }
+  if (n > c->cap || n > cap) {
+    set_error("image slot %d has %d keypoints, capacity %d", slot, n, cap < c->cap ? cap : c->cap);
+    return RFE_ERR_CAPACITY;
+  }
+  return RFE_OK;
+}
+
+// scratch device buffer of the ctx, grown on demand (host-in / host-out helpers below)
+static int scratch(rfe_ctx* c, void** p, size_t* have, size_t need) {
+  if (*have >= need) return RFE_OK;
+  void* d = nullptr;
+  if (cudaMalloc(&d, need) != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes) failed", need);
+    return RFE_ERR_CUDA;
+  }
+  c->allocs.push_back(d);      // the old buffer is released with the ctx
+  *p = d;
+  *have = need;
+  return RFE_OK;
+}
+
+int rfe_binarize_descriptors(rfe_ctx* c, const float* desc, int n, uint8_t* bin, uint32_t* bits) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (n < 0 || (n > 0 && (!desc || (!bin && !bits)))) {
+    set_error("rfe_binarize_descriptors: null/invalid argument");
+    return RFE_ERR_INVALID;
+  }
+  if (n == 0) return RFE_OK;
+  const size_t nb = static_cast<size_t>(n) * 256;
+  if ((r = scratch(c, &c->scr[0], &c->scr_bytes[0], nb * 4))) return r;
+  if ((r = scratch(c, &c->scr[1], &c->scr_bytes[1], nb + static_cast<size_t>(n) * 32))) return r;
+  float* d_desc = static_cast<float*>(c->scr[0]);
+  uint8_t* d_bin = static_cast<uint8_t*>(c->scr[1]);
+  uint32_t* d_bits = reinterpret_cast<uint32_t*>(d_bin + nb);
+  RFE_CUDA_CHECK(cudaMemcpyAsync(d_desc, desc, nb * 4, cudaMemcpyHostToDevice, c->stream));
+  launch_binarize(c->stream, d_desc, n, d_bin, d_bits);
+  c->launches++;
+  if (bin) RFE_CUDA_CHECK(cudaMemcpyAsync(bin, d_bin, nb, cudaMemcpyDeviceToHost, c->stream));
+  if (bits) RFE_CUDA_CHECK(cudaMemcpyAsync(bits, d_bits, static_cast<size_t>(n) * 32, cudaMemcpyDeviceToHost, c->stream));
+  RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return RFE_OK;
+}
+
+int rfe_l2_best2(rfe_ctx* c, const float* q, int nq, const float* db, int nd, const int32_t* cand_off, const int32_t* cand_idx,
+                 float init_dist, float* best_dist, int32_t* best_idx, float* second_dist, int32_t* second_idx) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (nq < 0 || nd < 0 || (nq > 0 && (!q || !cand_off || !best_dist || !best_idx))) {
+    set_error("rfe_l2_best2: null/invalid argument");
+    return RFE_ERR_INVALID;
+  }
+  if (nq == 0) return RFE_OK;
+  const int total = cand_off[nq];
+  if (cand_off[0] != 0 || total < 0 || (total > 0 && (!cand_idx || !db))) {
+    set_error("rfe_l2_best2: malformed candidate lists");
+    return RFE_ERR_INVALID;
+  }
+  for (int i = 0; i < nq; ++i)
+    if (cand_off[i + 1] < cand_off[i]) {
+      set_error("rfe_l2_best2: candidate offsets must be non-decreasing");
+      return RFE_ERR_INVALID;
+    }
+  for (int i = 0; i < total; ++i)
+    if (cand_idx[i] < 0 || cand_idx[i] >= nd) {
+      set_error("rfe_l2_best2: candidate index %d out of range [0, %d)", cand_idx[i], nd);
+      return RFE_ERR_INVALID;
+    }
+  const size_t bq = static_cast<size_t>(nq) * 1024, bd = static_cast<size_t>(nd > 0 ? nd : 1) * 1024;
+  const size_t bo = static_cast<size_t>(nq + 1) * 4, bc = static_cast<size_t>(total > 0 ? total : 1) * 4, br = static_cast<size_t>(nq) * 16;
+  if ((r = scratch(c, &c->scr[0], &c->scr_bytes[0], bq + bd))) return r;
+  if ((r = scratch(c, &c->scr[1], &c->scr_bytes[1], bo + bc + br + 64))) return r;
+  float* d_q = static_cast<float*>(c->scr[0]);
+  float* d_db = d_q + static_cast<size_t>(nq) * 256;
+  int* d_off = static_cast<int*>(c->scr[1]);
+  int* d_idx = d_off + (nq + 1);
+  float* d_b1 = reinterpret_cast<float*>(d_idx + (total > 0 ? total : 1));
+  int* d_i1 = reinterpret_cast<int*>(d_b1 + nq);
+  float* d_b2 = reinterpret_cast<float*>(d_i1 + nq);
+  int* d_i2 = reinterpret_cast<int*>(d_b2 + nq);
+  cudaStream_t s = c->stream;
+  RFE_CUDA_CHECK(cudaMemcpyAsync(d_q, q, bq, cudaMemcpyHostToDevice, s));
+  if (nd > 0) RFE_CUDA_CHECK(cudaMemcpyAsync(d_db, db, static_cast<size_t>(nd) * 1024, cudaMemcpyHostToDevice, s));
+  RFE_CUDA_CHECK(cudaMemcpyAsync(d_off, cand_off, bo, cudaMemcpyHostToDevice, s));
+  if (total > 0) RFE_CUDA_CHECK(cudaMemcpyAsync(d_idx, cand_idx, static_cast<size_t>(total) * 4, cudaMemcpyHostToDevice, s));
+  launch_l2_best2(s, d_q, nq, d_db, d_off, d_idx, init_dist, d_b1, d_i1, d_b2, d_i2);
+  c->launches++;
+  RFE_CUDA_CHECK(cudaMemcpyAsync(best_dist, d_b1, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, s));
+  RFE_CUDA_CHECK(cudaMemcpyAsync(best_idx, d_i1, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, s));
+  if (second_dist) RFE_CUDA_CHECK(cudaMemcpyAsync(second_dist, d_b2, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, s));
+  if (second_idx) RFE_CUDA_CHECK(cudaMemcpyAsync(second_idx, d_i2, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, s));
+  RFE_CUDA_CHECK(cudaStreamSynchronize(s));
   return RFE_OK;
 }
 

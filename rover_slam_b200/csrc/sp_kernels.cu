@@ -340,7 +340,8 @@ void launch_select(cudaStream_t s, const float* nms, int B, int H, int W, float 
 __global__ void __launch_bounds__(256) desc_sample_kernel(const float* __restrict__ dense /*[B][h][w][256]*/, int h,
                                                           int w, int B, const int* __restrict__ kpts,
                                                           const int* __restrict__ counts, int cap,
-                                                          float* __restrict__ desc /*[B][cap][256]*/) {
+                                                          float* __restrict__ desc /*[B][cap][256]*/,
+                                                          uint8_t* __restrict__ desc_bin /*[B][cap][256] or null*/) {
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= B * cap) return;
@@ -384,14 +385,97 @@ __global__ void __launch_bounds__(256) desc_sample_kernel(const float* __restric
   for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float nrm = fmaxf(sqrtf(ss), 1e-12f);
   float4* o = reinterpret_cast<float4*>(desc + (static_cast<size_t>(b) * cap + i) * 256 + lane * 8);
-  o[0] = make_float4(acc[0] / nrm, acc[1] / nrm, acc[2] / nrm, acc[3] / nrm);
-  o[1] = make_float4(acc[4] / nrm, acc[5] / nrm, acc[6] / nrm, acc[7] / nrm);
+  const float4 d0 = make_float4(acc[0] / nrm, acc[1] / nrm, acc[2] / nrm, acc[3] / nrm);
+  const float4 d1 = make_float4(acc[4] / nrm, acc[5] / nrm, acc[6] / nrm, acc[7] / nrm);
+  o[0] = d0;
+  o[1] = d1;
+  if (desc_bin) {
+    // sign binarisation for the DBoW3 feed (Frame::binarize_descriptors, Frame.cc:1034-1043: cv::threshold(row, 0, 1,
+    // THRESH_BINARY) -> one uchar 0/1 per element), written while the descriptor is still in registers
+    const uint32_t b0 = (d0.x > 0.0f ? 1u : 0u) | (d0.y > 0.0f ? 0x100u : 0u) | (d0.z > 0.0f ? 0x10000u : 0u) | (d0.w > 0.0f ? 0x1000000u : 0u);
+    const uint32_t b1 = (d1.x > 0.0f ? 1u : 0u) | (d1.y > 0.0f ? 0x100u : 0u) | (d1.z > 0.0f ? 0x10000u : 0u) | (d1.w > 0.0f ? 0x1000000u : 0u);
+    *reinterpret_cast<uint2*>(desc_bin + (static_cast<size_t>(b) * cap + i) * 256 + lane * 8) = make_uint2(b0, b1);
+  }
 }
 
 void launch_desc_sample(cudaStream_t s, const float* dense, int h, int w, int B, const int* kpts, const int* counts,
-                        int cap, float* desc) {
+                        int cap, float* desc, uint8_t* desc_bin) {
   const int warps = B * cap;
-  desc_sample_kernel<<<(warps * 32 + 255) / 256, 256, 0, s>>>(dense, h, w, B, kpts, counts, cap, desc);
+  desc_sample_kernel<<<(warps * 32 + 255) / 256, 256, 0, s>>>(dense, h, w, B, kpts, counts, cap, desc, desc_bin);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone sign binarisation of fp32 descriptors [n][256] -> u8 0/1 [n][256] (+ optional 256-bit packing [n][8] u32,
+// bit j of word j/32 = element j): the same operation for descriptors that did not come out of desc_sample_kernel.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) binarize_kernel(const float* __restrict__ desc, int n, uint8_t* __restrict__ out,
+                                                       uint32_t* __restrict__ bits) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= n) return;
+  const float* r = desc + static_cast<size_t>(wid) * 256;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const bool on = r[j * 32 + lane] > 0.0f;
+    if (out) out[static_cast<size_t>(wid) * 256 + j * 32 + lane] = on ? 1 : 0;
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if (bits && lane == 0) bits[static_cast<size_t>(wid) * 8 + j] = m;
+  }
+}
+void launch_binarize(cudaStream_t s, const float* desc, int n, uint8_t* out, uint32_t* bits) {
+  if (n > 0) binarize_kernel<<<(n * 32 + 255) / 256, 256, 0, s>>>(desc, n, out, bits);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Best / second-best L2 descriptor match over per-query candidate lists: the inner loop of SPmatcher::SearchByProjection /
+// Fuse / Frame::ComputeStereoMatches (e.g. SPmatcher.cc:1225-1250 with DescriptorDistance_sp = cv::norm(a, b, NORM_L2),
+// SPmatcher.cc:2184-2189).  One warp per query; candidates are visited in list order with the reference's update rule
+// (strict <: the first of equal distances wins; both distances start at `init_dist`, 256 in the reference).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) l2_best2_kernel(const float* __restrict__ q, int nq, const float* __restrict__ db,
+                                                       const int* __restrict__ cand_off, const int* __restrict__ cand_idx,
+                                                       float init_dist, float* __restrict__ best_dist,
+                                                       int* __restrict__ best_idx, float* __restrict__ second_dist,
+                                                       int* __restrict__ second_idx) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= nq) return;
+  const float4* q4 = reinterpret_cast<const float4*>(q + static_cast<size_t>(wid) * 256);
+  const float4 qa = q4[lane], qb = q4[32 + lane];
+  float b1 = init_dist, b2 = init_dist;
+  int i1 = -1, i2 = -1;
+  const int c0 = cand_off[wid], c1 = cand_off[wid + 1];
+  for (int c = c0; c < c1; ++c) {
+    const int idx = cand_idx[c];
+    const float4* d4 = reinterpret_cast<const float4*>(db + static_cast<size_t>(idx) * 256);
+    const float4 da = __ldg(d4 + lane), dbv = __ldg(d4 + 32 + lane);
+    float t, acc = 0.0f;
+    t = qa.x - da.x; acc = fmaf(t, t, acc);  t = qa.y - da.y; acc = fmaf(t, t, acc);
+    t = qa.z - da.z; acc = fmaf(t, t, acc);  t = qa.w - da.w; acc = fmaf(t, t, acc);
+    t = qb.x - dbv.x; acc = fmaf(t, t, acc); t = qb.y - dbv.y; acc = fmaf(t, t, acc);
+    t = qb.z - dbv.z; acc = fmaf(t, t, acc); t = qb.w - dbv.w; acc = fmaf(t, t, acc);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const float dist = sqrtf(acc);
+    if (dist < b1) {
+      b2 = b1; i2 = i1;
+      b1 = dist; i1 = idx;
+    } else if (dist < b2) {
+      b2 = dist; i2 = idx;
+    }
+  }
+  if (lane == 0) {
+    best_dist[wid] = b1;
+    best_idx[wid] = i1;
+    if (second_dist) second_dist[wid] = b2;
+    if (second_idx) second_idx[wid] = i2;
+  }
+}
+void launch_l2_best2(cudaStream_t s, const float* q, int nq, const float* db, const int* cand_off, const int* cand_idx,
+                     float init_dist, float* best_dist, int* best_idx, float* second_dist, int* second_idx) {
+  if (nq > 0)
+    l2_best2_kernel<<<(nq * 32 + 255) / 256, 256, 0, s>>>(q, nq, db, cand_off, cand_idx, init_dist, best_dist, best_idx,
+                                                          second_dist, second_idx);
 }
 
 }  // namespace rfe

@@ -29,6 +29,10 @@ class SPextractor {
   std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
   std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
 
+  // DBoW3 feed: the CV_8UC1 N x 256 sign-binarised descriptors of the last operator() call, i.e. what
+  // Frame::binarize_descriptors (Frame.cc:1034-1043) would compute from the returned descriptors.
+  int GetBinaryDescriptors(cv::Mat& bin) { return featureExtractor ? featureExtractor->BinarizeLast(bin) : 1; }
+
   std::vector<cv::Mat> mvImagePyramid;
   SuperPointOnnxRunner* featureExtractor;
   std::string mModelstr = "onnx";

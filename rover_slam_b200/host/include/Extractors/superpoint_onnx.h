@@ -38,6 +38,10 @@ class SuperPointOnnxRunner {
   float GetMatchThresh();
   void SetMatchThresh(float thresh);
   double GetTimer(std::string name);                                               // superpoint_onnx.cc:268-277
+  // SURVEY.md 8(f).1 -- the DBoW3 feed.  Frame::binarize_descriptors (Frame.cc:1034-1043) thresholds mDescriptors at 0
+  // into a CV_8UC1 N x 256 matrix on every ComputeBoW3; the extractor already produced that matrix on the GPU.
+  int BinarizeLast(cv::Mat& bin);                             // descriptors of the last Extractor_Inference
+  int BinarizeDescriptors(const cv::Mat& desc, cv::Mat& bin); // any N x 256 CV_32F matrix (KeyFrame.cc:113-123)
   rfe_ctx* context() { return ctx_; }
 
  private:

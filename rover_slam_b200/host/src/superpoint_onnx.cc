@@ -100,6 +100,31 @@ void SuperPointOnnxRunner::Extractor_PostProcess(Configuration cfg, SuperPointRe
   }
 }
 
+int SuperPointOnnxRunner::BinarizeLast(cv::Mat& bin) {
+  if (!ctx_ || extractor_outputtensors.empty()) return EXIT_FAILURE;
+  const int n = extractor_outputtensors.back().count;
+  bin.create(n, RFE_DESC_DIM, CV_8UC1);
+  if (n == 0) return EXIT_SUCCESS;
+  int32_t count = 0;
+  const int rc = rfe_sp_read_slot_bin(ctx_, 0, bin.ptr<uint8_t>(0), &count, n);
+  if (rc != RFE_OK && rc != RFE_ERR_CAPACITY) {
+    std::cerr << "[ERROR] SuperPointOnnxRunner BinarizeLast failed : " << rfe_last_error() << std::endl;
+    return EXIT_FAILURE;
+  }
+  return EXIT_SUCCESS;
+}
+
+int SuperPointOnnxRunner::BinarizeDescriptors(const cv::Mat& desc, cv::Mat& bin) {
+  if (!ctx_ || desc.cols != RFE_DESC_DIM || desc.depth() != CV_32F) return EXIT_FAILURE;
+  bin.create(desc.rows, RFE_DESC_DIM, CV_8UC1);
+  if (desc.rows == 0) return EXIT_SUCCESS;
+  if (rfe_binarize_descriptors(ctx_, desc.ptr<float>(0), desc.rows, bin.ptr<uint8_t>(0), nullptr) != RFE_OK) {
+    std::cerr << "[ERROR] SuperPointOnnxRunner BinarizeDescriptors failed : " << rfe_last_error() << std::endl;
+    return EXIT_FAILURE;
+  }
+  return EXIT_SUCCESS;
+}
+
 float SuperPointOnnxRunner::GetMatchThresh() { return matchThresh; }
 void SuperPointOnnxRunner::SetMatchThresh(float thresh) { matchThresh = thresh; }
 double SuperPointOnnxRunner::GetTimer(std::string name) {

@@ -252,3 +252,54 @@ def test_pipelined_pairs_equal_one_shot_calls(fe):
         for (rm, rs), (om, os_) in zip(rr, orr):
             assert np.array_equal(rm, om) and np.array_equal(rs, os_)
             assert len(rm) > 20
+
+
+# ---- descriptor binarisation and L2 projection matching -------------------------------------------
+def test_binarized_descriptors_bit_exact(fe):
+    """8(f).1: the sampler's fused sign binarisation equals Frame::binarize_descriptors of the SAME descriptors (bit-exact),
+    and the stand-alone entry point equals the oracle on arbitrary descriptors including +-0 and denormals."""
+    from oracle import frontend_aux_ref as aux
+    imgs = np.stack([synth.frame(s, 240, 320) for s in (5, 6)])
+    fe.extract_device_from_host(imgs)
+    for slot in range(2):
+        k, s, d = fe.read_slot(slot)
+        b = fe.read_slot_bin(slot)
+        assert b.shape == (len(k), 256) and len(k) > 50
+        assert np.array_equal(b, aux.binarize_descriptors(d))
+    rng = np.random.RandomState(0)
+    d = rng.randn(1000, 256).astype(np.float32)
+    d[0, :4] = [0.0, -0.0, 1e-40, -1e-40]
+    b, w = fe.binarize(d)
+    assert np.array_equal(b, aux.binarize_descriptors(d))
+    assert np.array_equal(w, aux.pack_bits(aux.binarize_descriptors(d)))
+    b0, w0 = fe.binarize(np.zeros((0, 256), np.float32))
+    assert b0.shape == (0, 256)
+
+
+def test_l2_best2_vs_oracle(fe):
+    """8(f).2: best / second-best L2 match over ragged candidate lists (empty lists, exact ties, every db row)."""
+    from oracle import frontend_aux_ref as aux
+    rng = np.random.RandomState(11)
+    nq, nd = 300, 700
+    q = rng.randn(nq, 256).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    db = rng.randn(nd, 256).astype(np.float32)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    db[17] = db[5]
+    off, idx = [0], []
+    for i in range(nq):
+        k = 0 if i % 37 == 0 else (nd if i == 1 else rng.randint(1, 40))
+        c = rng.choice(nd, size=k, replace=False).tolist()
+        if i == 2:
+            c = [17, 5, 100, 3]
+        idx += c
+        off.append(len(idx))
+    off, idx = np.array(off, np.int32), np.array(idx, np.int32)
+    b1, i1, b2, i2 = fe.l2_best2(q, db, off, idx)
+    r1, j1, r2, j2 = aux.l2_best2(q, db, off, idx)
+    assert np.allclose(b1, r1, rtol=2e-6, atol=1e-6) and np.allclose(b2, r2, rtol=2e-6, atol=1e-6)
+    # indices identical except where two candidates are closer than the fp32 / fp64 accumulation difference
+    gap_ok = np.abs(r2 - r1) > 1e-5
+    assert np.array_equal(i1[gap_ok], j1[gap_ok])
+    assert i1[0] == -1 and b1[0] == 256.0                   # empty candidate list
+    assert i1[2] == 17 and i2[2] == 5                       # exact tie: list order wins (strict <)
