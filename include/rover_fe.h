@@ -74,6 +74,14 @@ int rfe_sp_extract_device(rfe_ctx* ctx, const uint8_t* d_gray, int h, int w, int
 /* Copy slot b's features to the host (synchronises).  Any output pointer may be NULL. */
 int rfe_sp_read_slot(rfe_ctx* ctx, int slot, int32_t* kpts_xy, float* scores, float* desc, int32_t* count, int cap);
 
+/* Upload features that are already on the host into slot b (synchronises): the inverse of rfe_sp_read_slot.  This is how a
+ * stored KeyFrame's keypoints + descriptors re-enter the device-resident path: the reference copies
+ * mDescriptors / mvKeysUn of BOTH frames host->device on every MatchingPoints_onnx call (src/Matchers/SPmatcher.cc:498-528,
+ * `new float[]` + Ort tensors); here a KeyFrame is uploaded once and matched against many frames with rfe_lg_match_slots*.
+ * slot < max_batch, n <= max_keypoints; scores may be NULL (stored as 0).  Slots below `slot` that were never written hold 0
+ * keypoints.  The next rfe_sp_extract_* call overwrites slots 0..batch-1. */
+int rfe_sp_write_slot(rfe_ctx* ctx, int slot, const int32_t* kpts_xy, const float* scores, const float* desc, int n);
+
 /* Sign-binarised descriptors of slot b: what Frame::binarize_descriptors (src/Frame.cc:1034-1043) and
  * KeyFrame::binarize_descriptors (src/KeyFrame.cc:113-123) compute on the host with cv::threshold(row, 0, 1, THRESH_BINARY)
  * before every DBoW3 transform -- here written by the descriptor sampler while the values are in registers.

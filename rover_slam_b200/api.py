@@ -60,6 +60,7 @@ def load_library():
     lib.rfe_sp_extract_device.argtypes = [vp, vp, ci, ci, ci, ci]
     lib.rfe_sp_read_slot.argtypes = [vp, ci, vp, vp, vp, vp, ci]
     lib.rfe_sp_read_slot_bin.argtypes = [vp, ci, vp, vp, ci]
+    lib.rfe_sp_write_slot.argtypes = [vp, ci, vp, vp, vp, ci]
     lib.rfe_binarize_descriptors.argtypes = [vp, vp, ci, vp, vp]
     lib.rfe_l2_best2.argtypes = [vp, vp, ci, vp, ci, vp, vp, cf, vp, vp, vp, vp]
     lib.rfe_lg_match.argtypes = [vp, vp, ci, vp, ci, vp, vp, ci, ci, cf, vp, vp, vp]
@@ -160,6 +161,17 @@ class FrontEnd:
         self._check(self.lib.rfe_sp_read_slot(self.ctx, slot, _ptr(kp), _ptr(sc), _ptr(de), C.byref(n), cap))
         n = n.value
         return kp[:n].copy(), sc[:n].copy(), de[:n].copy() if want_desc else None
+
+    def write_slot(self, slot: int, kpts_xy, desc, scores=None):
+        """Upload host features (e.g. a stored KeyFrame's) into a device slot for match_slots / match_slots_batch."""
+        kp = np.ascontiguousarray(np.rint(np.asarray(kpts_xy)), np.int32).reshape(-1, 2)
+        de = np.ascontiguousarray(desc, np.float32).reshape(-1, DESC_DIM)
+        if len(kp) != len(de):
+            raise ValueError("keypoints and descriptors differ in length")
+        sc = None if scores is None else np.ascontiguousarray(scores, np.float32).reshape(-1)
+        if sc is not None and len(sc) != len(kp):
+            raise ValueError("scores and keypoints differ in length")
+        self._check(self.lib.rfe_sp_write_slot(self.ctx, slot, _ptr(kp), _ptr(sc), _ptr(de), len(kp)))
 
     def read_slot_bin(self, slot: int) -> np.ndarray:
         """Sign-binarised descriptors [N,256] uint8 (0/1) of a feature slot (Frame::binarize_descriptors)."""

@@ -15,15 +15,25 @@
 // Tensor-core work per 64-key tile, using a [hi ; lo] concatenated B operand (the hi and lo planes of K and of V^T sit
 // next to each other in the stage, so one N=128 MMA computes a_hi*b_hi and a_hi*b_lo at once):
 //     S:  [S_hh | S_hl] = Q_hi [K_hi;K_lo]^T (N=128) ;  S_hl += Q_lo K_hi^T (N=64)        -> S = S_hh + 2^-11 S_hl
-//     O:  [O_hh | O_hl] += P_hi [V_hi;V_lo]^T (N=128);  O_hl += P_lo V_hi^T (N=64)
+//     O:  [O_hh | O_hl] += P_hi [V_hi;V_lo]^T (N=128);  O_hl += P_lo V_hi^T (N=64)        -> O = (O_hh + O_hl) / (256 sum E)
+// P and V^T carry their two planes at ONE scale each (common.cuh, RFE_ATTN_V_SCALE): P_hi = rn16(E), P_lo = rn16(E - P_hi)
+// with E = 2^11 exp(s - max) straight from the SFU (the 2^11 is added to the exponent argument), so the low part costs
+// one mixed-precision FHFMA and one convert per element: no unpack, subtract, multiply chain.
 //
-// CTA = 640 threads: warps 0..15 softmax/epilogue (the four warps with the same w%4 share a TMEM lane quarter and split
-// each tile's 64 columns 16/16/16/16: four warps per scheduler hide the SFU / convert latencies of the exponentials),
-// warp 16 K producer, warp 17 V producer, warp 19 MMA issuer (+ TMEM alloc).  The single-thread roles sit in the
-// HIGHEST warp ids on purpose: the warp scheduler arbitrates highest-warp-id-first, so the thread that feeds the
-// tensor pipe is never starved by the sixteen softmax warps sharing its schedulers.
-// TMEM: 3 score buffers x 128 columns + O 128 columns = 512.  The score MMAs run two key tiles ahead of the P V MMAs so
-// that the TMEM -> registers -> exp -> shared memory -> fence -> mbarrier latency of the softmax stage is hidden.
+// CTA = 640 threads: warps 0..15 softmax/epilogue, warp 16 K producer, warp 17 V producer, warp 18 issues the score
+// MMAs, warp 19 (+ TMEM alloc) issues the P V MMAs.
+//   * Pass 1 and the epilogue use all sixteen softmax warps on one tile (the four warps with the same w%4 share a TMEM
+//     lane quarter and split the columns).  In pass 2 they work as two groups of eight on alternate key tiles, so one
+//     group's SFU phase overlaps the other group's TMEM-load / shared-store / fence / barrier phase.
+//   * Two MMA-issuing threads feed the one tensor pipe: while one polls an mbarrier the other keeps the queue full.
+//     Ordering between the two instruction streams is carried by the mbarriers (S -> softmax -> P -> PV) alone.
+//   * The single-thread roles sit in the HIGHEST warp ids on purpose: the warp scheduler arbitrates highest-warp-id-
+//     first, so the threads that feed the tensor pipe are never starved by the softmax warps sharing their schedulers.
+// TMEM: 3 score buffers x 128 columns + O 128 columns = 512.  The score MMAs run up to three tiles ahead of the P V MMAs
+// so that the TMEM -> registers -> exp -> shared memory -> fence -> mbarrier latency of the softmax stage is hidden.
+// Measured on B200 (tools/gpu_probe.py, profiles/r01_role_breakdown.txt): 16 warps drain TMEM at 412 B/clk (not a
+// limit); ex2 8.2, cvt.f16x2.f32 ~5 cycles per warp-instruction per scheduler; kind::f16 rejects A = bf16 with B = fp16
+// (illegal instruction), so P_lo cannot be a free bf16 truncation.
 #pragma once
 
 #include <cuda/std/type_traits>
@@ -44,7 +54,8 @@ struct AttnParams {
 
 constexpr int kAttnSoftmaxWarps = 16;                             // 4 per TMEM lane quarter: 16 of a tile's 64 columns each
 constexpr int kAttnThreads = 128 + 32 * kAttnSoftmaxWarps;      // + warps 16..19: K producer, V producer, idle, MMA
-constexpr int kAttnWarpK = kAttnSoftmaxWarps, kAttnWarpV = kAttnSoftmaxWarps + 1, kAttnWarpMma = kAttnSoftmaxWarps + 3;
+constexpr int kAttnWarpK = kAttnSoftmaxWarps, kAttnWarpV = kAttnSoftmaxWarps + 1, kAttnWarpMmaS = kAttnSoftmaxWarps + 2,
+              kAttnWarpMma = kAttnSoftmaxWarps + 3;
 constexpr int kAttnKStages = 4;
 constexpr int kAttnVStages = 3;
 constexpr int kAttnSBufs = 3;                                   // score buffers in TMEM: S runs two tiles ahead of P V
@@ -101,7 +112,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
   uint64_t* k1_full = o_full + 1;                       // [7]
   uint64_t* k1_empty = k1_full + kAttnP1Stages;         // [7]
   uint64_t* p1_done = k1_empty + kAttnP1Stages;         // all pass-1 MMAs have retired: sP | sV may be rewritten
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(p1_done + 1);
+  uint64_t* s1_full = p1_done + 1;                      // [3] pass-1 score buffers (all 16 softmax warps drain each)
+  uint64_t* s1_empty = s1_full + kAttnSBufs;            // [3]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s1_empty + kAttnSBufs);
   float* stat = reinterpret_cast<float*>(tail + 512);   // [4][128] partial row max, then partial row sum
 
   auto tick = [&]() -> long long { return PROF ? clock64() : 0; };
@@ -121,8 +134,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
     mbar_init(q_full, 1);
     for (int s = 0; s < kAttnKStages; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
     for (int s = 0; s < kAttnVStages; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-    for (int s = 0; s < kAttnSBufs; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kAttnSoftmaxWarps); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&p_full[s], kAttnSoftmaxWarps); mbar_init(&p_empty[s], 1); }
+    // pass 2: the softmax warps work as two groups of eight on alternate key tiles (group = tile & 1 = P buffer)
+    for (int s = 0; s < kAttnSBufs; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kAttnSoftmaxWarps / 2); }
+    for (int s = 0; s < kAttnSBufs; ++s) { mbar_init(&s1_full[s], 1); mbar_init(&s1_empty[s], kAttnSoftmaxWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&p_full[s], kAttnSoftmaxWarps / 2); mbar_init(&p_empty[s], 1); }
     mbar_init(o_full, 1);
     for (int s = 0; s < kAttnP1Stages; ++s) { mbar_init(&k1_full[s], 1); mbar_init(&k1_empty[s], 1); }
     mbar_init(p1_done, 1);
@@ -174,24 +189,27 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
         tma_load_3d(sb + 8192, &tmV_lo, &v_full[st], krow + t * kAttnKeyTile, 0, head);
       }
     }
-  } else if (warp == kAttnWarpMma) {
-    // ===== MMA issuer ===========================================================================================
+  } else if (warp == kAttnWarpMmaS) {
+    // ===== MMA issuer 1: the score products (pass 1 and pass 2) ==========================================
+    // Two issuing threads feed the one tensor pipe: while this one polls a barrier (K tile landed? score buffer
+    // drained?) the other keeps the pipe's queue full, and vice versa.  With a single issuer every barrier round trip
+    // (~70-150 cycles, four per key tile) was a bubble in the pipe.  Ordering between the two instruction streams is
+    // carried by the mbarriers alone (S -> softmax -> P -> PV), never by issue order.
     if (elect_one()) {
       constexpr uint32_t idesc64 = make_idesc_f16(128, 64);
       constexpr uint32_t idesc128 = make_idesc_f16(128, 128);
       const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + 16384;
-      const uint32_t o_base = tmem_base + 384;
       const bool prof = PROF && p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-      long long w_k = 0, w_se = 0, w_v = 0, w_p = 0, w_k1 = 0, w_se1 = 0;
+      long long w_k = 0, w_se = 0, w_k1 = 0, w_se1 = 0;
       const long long t_begin = tick();
       mbar_wait(q_full, 0);
       const long long t_q = tick();
-      auto issue_s1 = [&](int g) {          // pass 1: S_hh of 128 keys, one N=128 MMA per k-step
+      for (int g = 0; g < T1; ++g) {           // pass 1: S_hh of 128 keys, one N=128 MMA per k-step
         const int st = g % kAttnP1Stages, b = g % kAttnSBufs;
         long long c0 = tick();
         mbar_wait(&k1_full[st], (g / kAttnP1Stages) & 1);
         long long c1 = tick();
-        mbar_wait(&s_empty[b], ((g / kAttnSBufs) & 1) ^ 1);
+        mbar_wait(&s1_empty[b], ((g / kAttnSBufs) & 1) ^ 1);
         w_k1 += c1 - c0;
         w_se1 += tick() - c1;
         tc_fence_after();
@@ -200,16 +218,20 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16(s_base, make_sw128_kmajor_desc(q_hi + k * 32), make_sw128_kmajor_desc(k_hi + k * 32), idesc128, k > 0);
-        umma_commit(&s_full[b]);
+        umma_commit(&s1_full[b]);
         umma_commit(&k1_empty[st]);
-      };
-      auto issue_s = [&](int t) {           // pass 2: fp32-equivalent scores of key tile t (S buffer index continues at T1)
+      }
+      umma_commit(p1_done);
+      const long long t_p1 = tick();
+      for (int t = 0; t < T; ++t) {            // pass 2: fp32-equivalent scores of key tile t (the buffer ring continues)
         const int g = T1 + t;
         const int st = t % kAttnKStages, b = g % kAttnSBufs;
         long long c0 = tick();
         mbar_wait(&k_full[st], (t / kAttnKStages) & 1);
         long long c1 = tick();
-        mbar_wait(&s_empty[b], ((g / kAttnSBufs) & 1) ^ 1);
+        // the first three pass-2 tiles wait for the pass-1 drain of their buffer
+        if (t < kAttnSBufs && g >= kAttnSBufs) mbar_wait(&s1_empty[b], ((g - kAttnSBufs) / kAttnSBufs) & 1);
+        mbar_wait(&s_empty[b], ((t / kAttnSBufs) & 1) ^ 1);
         w_k += c1 - c0;
         w_se += tick() - c1;
         tc_fence_after();
@@ -223,8 +245,27 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
         }
         umma_commit(&s_full[b]);
         umma_commit(&k_empty[st]);          // the K stage is free as soon as these MMAs retire
-      };
-      auto issue_pv = [&](int t) {          // consumes P buffer t&1 and V stage t%3
+      }
+      if (prof) {
+        const long long t_end = tick();
+        p.prof[0] = t_q - t_begin;      // wait for Q
+        p.prof[1] = t_p1 - t_q;         // pass 1 issue time
+        p.prof[2] = t_end - t_p1;       // pass 2 issue time (score issuer)
+        p.prof[3] = w_k;                // waiting for K tiles
+        p.prof[4] = w_se;               // waiting for a free score buffer
+        p.prof[8] = w_k1;               // pass 1: waiting for K tiles
+        p.prof[9] = w_se1;              // pass 1: waiting for a free score buffer
+      }
+    }
+  } else if (warp == kAttnWarpMma) {
+    // ===== MMA issuer 2: O += P V ===========================================================================
+    if (elect_one()) {
+      constexpr uint32_t idesc64 = make_idesc_f16(128, 64);
+      constexpr uint32_t idesc128 = make_idesc_f16(128, 128);
+      const uint32_t o_base = tmem_base + 384;
+      const bool prof = PROF && p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      long long w_v = 0, w_p = 0;
+      for (int t = 0; t < T; ++t) {            // consumes P buffer t&1 and V stage t%3
         const int st = t % kAttnVStages, pb = t & 1;
         long long c0 = tick();
         mbar_wait(&v_full[st], (t / kAttnVStages) & 1);
@@ -243,38 +284,21 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
         }
         umma_commit(&v_empty[st]);
         umma_commit(&p_empty[pb]);
-      };
-      // pass 1: hi*hi scores only
-      for (int g = 0; g < T1; ++g) issue_s1(g);
-      umma_commit(p1_done);
-      const long long t_p1 = tick();
-      // pass 2: the score MMAs run two tiles ahead of the P V MMAs
-      issue_s(0);
-      if (T > 1) issue_s(1);
-      for (int t = 0; t < T; ++t) {
-        if (t + 2 < T) issue_s(t + 2);
-        issue_pv(t);
       }
       umma_commit(o_full);
       if (prof) {
-        const long long t_end = tick();
-        p.prof[0] = t_q - t_begin;      // wait for Q
-        p.prof[1] = t_p1 - t_q;         // pass 1 issue time
-        p.prof[2] = t_end - t_p1;       // pass 2 issue time
-        p.prof[3] = w_k;                // waiting for K tiles
-        p.prof[4] = w_se;               // waiting for a free score buffer
         p.prof[5] = w_v;                // waiting for V tiles
         p.prof[6] = w_p;                // waiting for P (softmax)
         p.prof[7] = T;
-        p.prof[8] = w_k1;               // pass 1: waiting for K tiles
-        p.prof[9] = w_se1;              // pass 1: waiting for a free score buffer
       }
     }
   } else if (warp < kAttnSoftmaxWarps) {
     // ===== softmax / epilogue warps =========================================================================
     const int sw = warp;                     // 0..15
     const int q = warp & 3;                  // TMEM lane quarter
-    const int cq = sw >> 2;                  // which 16-column quarter of every 64-key tile
+    const int cq = sw >> 2;                  // pass 1 / epilogue: which quarter of the columns
+    const int grp = sw >> 3;                 // pass 2: the group that owns key tiles t with (t & 1) == grp
+    const int ch2 = (sw >> 2) & 1;           // pass 2: which 32-column half of the group's 64-key tile
     const int row = q * 32 + lane;
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float NEG = -INFINITY;
@@ -283,16 +307,21 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
 
     // ---- pass 1: row maximum of the hi*hi scores ----
     float mx = NEG;
+    const bool sprof = PROF && p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 0 && lane == 0;
+    long long sw_s1 = 0, sw_s = 0, sw_ld = 0, sw_p = 0;
+    const long long st_begin = tick();
     for (int g = 0; g < T1; ++g) {
       const int b = g % kAttnSBufs;
-      mbar_wait(&s_full[b], (g / kAttnSBufs) & 1);
+      const long long w0 = tick();
+      mbar_wait(&s1_full[b], (g / kAttnSBufs) & 1);
+      sw_s1 += tick() - w0;
       tc_fence_after();
       uint32_t a0[32];
       tmem_ld32(tlane + b * 128 + cq * 32, a0);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[b]);
+      if (lane == 0) mbar_arrive(&s1_empty[b]);
       const int c0 = g * 128 + cq * 32;
       if (c0 + 32 <= nk) {
 #pragma unroll
@@ -308,54 +337,78 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
     mx = fmaxf(fmaxf(stat[row], stat[128 + row]), fmaxf(stat[256 + row], stat[384 + row]));
     named_bar_sync(1, kSmThreads);
     const float mx_l2 = mx * kLog2e;
+    const long long st_p1 = tick();
 
     // ---- pass 2: P = exp(S - max) -> smem (K-major, 128-byte swizzle), row sum ----
-    // Packed fp32x2 arithmetic throughout (FFMA2 / FADD2 / FMUL2): the sixteen softmax warps share the SM's issue slots
-    // with the MMA thread, and this loop, not the tensor pipe, was the limiter of pass 2.  Only the last key tile can be
-    // ragged, so the column mask lives in a separate instantiation of the tile body.
+    // Two groups of eight warps take alternate key tiles, so one group's SFU phase overlaps the other group's
+    // TMEM-load / shared-store / fence / barrier phase (with all sixteen warps in lock step on one tile those phases
+    // serialised and the tile period was the sum of both).  A warp owns 32 rows x 32 key columns of its tile.
+    // Packed fp32x2 arithmetic (FFMA2 / FADD2); only the last key tile can be ragged, so the column mask lives in a
+    // separate instantiation of the tile body.
     f32x2 lsum = pk2(0.0f, 0.0f);
     const f32x2 kL2 = pk2(kLog2e, kLog2e), kL2s = pk2(kLog2e * RFE_SPLIT_INV, kLog2e * RFE_SPLIT_INV);
-    const f32x2 nmx = pk2(-mx_l2, -mx_l2);
+    const f32x2 nmx = pk2(11.0f - mx_l2, 11.0f - mx_l2);        // P is produced as E = 2^11 P
     auto tile_body = [&](int t, auto masked_tag) {
       constexpr bool kMasked = decltype(masked_tag)::value;
       const int g = T1 + t, b = g % kAttnSBufs, pb = t & 1;
-      mbar_wait(&s_full[b], (g / kAttnSBufs) & 1);
+      const long long w0 = tick();
+      mbar_wait(&s_full[b], (t / kAttnSBufs) & 1);
+      const long long w1 = tick();
       tc_fence_after();
-      uint32_t a0[16], x0[16];
-      const uint32_t base = tlane + b * 128 + cq * 16;
-      tmem_ld16(base, a0);
-      tmem_ld16(base + 64, x0);
+      uint32_t a0[2][16], x0[2][16];
+      const uint32_t base = tlane + b * 128 + ch2 * 32;
+      tmem_ld16(base, a0[0]);
+      tmem_ld16(base + 64, x0[0]);
+      tmem_ld16(base + 16, a0[1]);
+      tmem_ld16(base + 80, x0[1]);
       tmem_ld_wait();
+      sw_s += w1 - w0;
+      sw_ld += tick() - w1;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[b]);
-      const int c0 = t * kAttnKeyTile + cq * 16;
-      uint32_t ph[8], pl[8];
+      uint32_t ph[2][8], pl[2][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        // exp(s - max) through the SFU: ex2.approx(s*log2e - max*log2e); relative error ~2^-22 + |s-max|*2^-23, the
-        // same order as the 22-bit split-fp16 operand that carries P into the tensor core
-        f32x2 x = fma2(pk2u(a0[2 * j], a0[2 * j + 1]), kL2, nmx);
-        x = fma2(pk2u(x0[2 * j], x0[2 * j + 1]), kL2s, x);
-        float x_0, x_1;
-        upk2(x, x_0, x_1);
-        float e0 = fast_exp2(x_0), e1 = fast_exp2(x_1);
-        if (kMasked) {
-          if (c0 + 2 * j >= nk) e0 = 0.0f;
-          if (c0 + 2 * j + 1 >= nk) e1 = 0.0f;
+      for (int hf = 0; hf < 2; ++hf) {
+        const int c0 = t * kAttnKeyTile + ch2 * 32 + hf * 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // E = 2^11 exp(s - max) through the SFU: ex2.approx(s*log2e - max*log2e + 11); relative error ~2^-22 +
+          // |s-max|*2^-23, the same order as the split operand that carries P into the tensor core.  The 2^11 lives in
+          // the exponent, so E - rn16(E) IS the scaled low part: no unpack / subtract / multiply chain on the FMA
+          // pipe, one mixed-precision FHFMA per element instead.
+          f32x2 x = fma2(pk2u(a0[hf][2 * j], a0[hf][2 * j + 1]), kL2, nmx);
+          x = fma2(pk2u(x0[hf][2 * j], x0[hf][2 * j + 1]), kL2s, x);
+          float x_0, x_1;
+          upk2(x, x_0, x_1);
+          float e0 = fast_exp2(x_0), e1 = fast_exp2(x_1);
+          if (kMasked) {
+            if (c0 + 2 * j >= nk) e0 = 0.0f;
+            if (c0 + 2 * j + 1 >= nk) e1 = 0.0f;
+          }
+          lsum = add2(lsum, pk2(e0, e1));
+          uint32_t hE;
+          asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hE) : "f"(e1), "f"(e0));       // low half = e0
+          ph[hf][j] = hE;                                                          // P_hi = rn16(E)
+          float d0, d1;
+          asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\t"
+              "fma.rn.f32.f16 %0, l, %5, %3;\n\tfma.rn.f32.f16 %1, h, %5, %4;\n\t}"
+              : "=f"(d0), "=f"(d1)
+              : "r"(hE), "f"(e0), "f"(e1), "h"(static_cast<unsigned short>(0xBC00)));   // E - rn16(E), exact
+          asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pl[hf][j]) : "f"(d1), "f"(d0));
         }
-        const f32x2 e = pk2(e0, e1);
-        lsum = add2(lsum, e);
-        split2(e, ph[j], pl[j]);
       }
+      const long long w2 = tick();
       mbar_wait(&p_empty[pb], ((t >> 1) & 1) ^ 1);       // PV(t-2) has consumed this P buffer
+      sw_p += tick() - w2;
       uint8_t* prow_hi = sP + pb * kAttnPBytes + row * 128;
       uint8_t* prow_lo = prow_hi + 16384;
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        const int sc = ((cq * 2 + ch) ^ (row & 7)) << 4;
-        *reinterpret_cast<uint4*>(prow_hi + sc) = make_uint4(ph[4 * ch], ph[4 * ch + 1], ph[4 * ch + 2], ph[4 * ch + 3]);
-        *reinterpret_cast<uint4*>(prow_lo + sc) = make_uint4(pl[4 * ch], pl[4 * ch + 1], pl[4 * ch + 2], pl[4 * ch + 3]);
+      for (int ch = 0; ch < 4; ++ch) {
+        const int sc = ((ch2 * 4 + ch) ^ (row & 7)) << 4;
+        const int hf = ch >> 1, o = 4 * (ch & 1);
+        *reinterpret_cast<uint4*>(prow_hi + sc) = make_uint4(ph[hf][o], ph[hf][o + 1], ph[hf][o + 2], ph[hf][o + 3]);
+        *reinterpret_cast<uint4*>(prow_lo + sc) = make_uint4(pl[hf][o], pl[hf][o + 1], pl[hf][o + 2], pl[hf][o + 3]);
       }
       fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
@@ -363,15 +416,23 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
     };
     const int t_full = (nk % kAttnKeyTile) ? T - 1 : T;
 #pragma unroll 1
-    for (int t = 0; t < t_full; ++t) tile_body(t, cuda::std::false_type{});
-    if (t_full < T) tile_body(T - 1, cuda::std::true_type{});
+    for (int t = grp; t < t_full; t += 2) tile_body(t, cuda::std::false_type{});
+    if (t_full < T && ((T - 1) & 1) == grp) tile_body(T - 1, cuda::std::true_type{});
+    if (sprof) {
+      p.prof[10] = tick() - st_p1;    // softmax warp 0: pass-2 loop
+      p.prof[11] = sw_s;              //   waiting for scores
+      p.prof[12] = sw_p;              //   waiting for a free P buffer
+      p.prof[13] = st_p1 - st_begin;  // pass-1 loop (incl. the max exchange)
+      p.prof[14] = sw_s1;             //   waiting for scores
+      p.prof[15] = sw_ld;             // pass 2: tcgen05.ld + wait::ld
+    }
     float l;
     {
       float l0, l1;
       upk2(lsum, l0, l1);
       l = l0 + l1;
     }
-    stat[cq * 128 + row] = l;
+    stat[cq * 128 + row] = l;                // cq = 2 * grp + ch2: four partial sums per row
     named_bar_sync(1, kSmThreads);
     l = (stat[row] + stat[128 + row]) + (stat[256 + row] + stat[384 + row]);
 
@@ -386,10 +447,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       tmem_ld_wait();
       __align__(16) __half oh[16];
       __align__(16) __half ol[16];
-      const float inv_l = 1.0f / l;
+      const float inv_l = 1.0f / (RFE_ATTN_V_SCALE * l);   // l = sum E ; both operand scales cancel here
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        split_f32((__uint_as_float(a0[j]) + __uint_as_float(x0[j]) * RFE_SPLIT_INV) * inv_l, oh[j], ol[j]);
+        split_f32((__uint_as_float(a0[j]) + __uint_as_float(x0[j])) * inv_l, oh[j], ol[j]);
       if (m0 + row < nq) {
         const size_t o = static_cast<size_t>(qrow + row) * 256 + head * 64 + cq * 16;
 #pragma unroll

@@ -22,6 +22,13 @@ namespace rfe {
 // ------------------------------------------------------------------------------------------------
 // split-fp16
 // ------------------------------------------------------------------------------------------------
+// Attention operands (attn_kernel.cuh): P = exp(s - max) is produced as E = 2^11 P, P_hi = rn16(E), P_lo = rn16(E - P_hi)
+// (both planes at ONE scale: the low part needs no multiply), so V^T is stored the same way at scale RFE_ATTN_V_SCALE:
+// P_hi V_lo and P_lo V_hi then share an accumulator and O = (acc_hh + acc_hl) / (RFE_ATTN_V_SCALE * sum E).
+// |v| must stay below 65504 / 256 = 255 (largest LightGlue value seen: 46); the low plane keeps an absolute precision of
+// 2^-25 / 256 in units of v even where it is an fp16 denormal.
+#define RFE_ATTN_V_SCALE 256.0f
+
 __host__ __device__ inline void split_f32(float v, __half& hi, __half& lo) {
   hi = __float2half_rn(v);
   lo = __float2half_rn((v - __half2float(hi)) * RFE_SPLIT_SCALE);

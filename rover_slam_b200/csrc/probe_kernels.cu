@@ -306,4 +306,130 @@ int launch_probe_ts(cudaStream_t s, const __half* a, const __half* b, float* out
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+//  probe 3: what bounds the softmax role of the attention kernel.  640 threads like attn_kernel (16 worker warps + 4).
+//    out[0..2]  cycles per 16 KB drained from TMEM (128 lanes x 32 columns) with 4 / 8 / 16 warps issuing
+//               tcgen05.ld.32x32b.x32 back to back, tensor pipe idle
+//    out[3]     the same with 16 warps while warp 19 issues N = 128 MMAs back to back; out[4] = cycles per MMA then
+//    out[5..8]  cycles per warp-instruction per SM sub-partition (16 warps = 4 per scheduler, 8-way independent chains):
+//               ex2.approx.f32, cvt.rn.f16x2.f32 (F2FP), cvt.f32.f16 (HADD2.F32), fma.rn.f32x2
+__global__ void __launch_bounds__(640, 1) probe_softmax_role_kernel(float* __restrict__ out, int reps) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                 // 16 KB
+  uint8_t* sB = smem + 16384;         // 16 KB (128 rows)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 32768);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  long long* tstamp = reinterpret_cast<long long*>(smem + 32768 + 64);   // [2]
+  for (int i = threadIdx.x; i < 32768 / 4; i += 640) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 19) {
+    tmem_alloc(tptr, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tptr;
+  const uint32_t tlane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  uint32_t sink = 0;
+  int phase = 0;
+  for (int cfg = 0; cfg < 4; ++cfg) {
+    const int nw = cfg == 0 ? 4 : cfg == 1 ? 8 : 16;
+    const bool with_mma = cfg == 3;
+    __syncthreads();
+    long long t0 = clock64();
+    if (warp < nw) {
+      for (int i = 0; i < reps; ++i) {
+        uint32_t r[32];
+        tmem_ld32(tlane + ((i + (warp >> 2)) & 7) * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sink ^= r[j];
+      }
+      long long t1 = clock64();
+      if (warp == 0 && lane == 0) tstamp[0] = t1 - t0;
+    } else if (warp == 19 && with_mma && lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, 128);
+      for (int i = 0; i < reps; ++i)
+        umma_f16(tmem + 256, make_sw128_kmajor_desc(smem_u32(sA) + (i & 3) * 32),
+                 make_sw128_kmajor_desc(smem_u32(sB) + (i & 3) * 32), idesc, 1u);
+      umma_commit(bar);
+      mbar_wait(bar, phase);
+      tstamp[1] = clock64() - t0;
+    }
+    if (with_mma) phase ^= 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // each LDTM.x32 of one warp moves 32 lanes x 32 columns x 4 B = 4 KB; nw warps in parallel -> nw/4 x 16 KB per rep
+      out[cfg] = static_cast<float>(tstamp[0]) / reps / (nw / 4);
+      if (with_mma) out[4] = static_cast<float>(tstamp[1]) / reps;
+    }
+  }
+  // instruction issue rates, 16 warps, 8 independent chains per thread
+  for (int op = 0; op < 4; ++op) {
+    __syncthreads();
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = 0.001f * (threadIdx.x + j) - 0.3f;
+    long long t0 = clock64();
+    if (warp < 16) {
+      for (int i = 0; i < reps; ++i) {
+        if (op == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[j]));
+        } else if (op == 1) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            uint32_t h;
+            asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x[j]), "f"(x[j + 1]));
+            uint32_t h2;
+            asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(x[j + 1]), "f"(x[j]));
+            x[j] = __uint_as_float(h ^ 0x00010001u);
+            x[j + 1] = __uint_as_float(h2 ^ 0x00010001u);
+          }
+        } else if (op == 2) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            unsigned short hs = static_cast<unsigned short>(__float_as_uint(x[j]));
+            asm volatile("cvt.f32.f16 %0, %1;" : "=f"(x[j]) : "h"(hs));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            f32x2 v = pk2(x[j], x[j + 1]);
+            asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(v) : "l"(v));
+            asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(v) : "l"(v));
+            upk2(v, x[j], x[j + 1]);
+          }
+        }
+      }
+      long long t1 = clock64();
+      if (warp == 0 && lane == 0) tstamp[0] = t1 - t0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sink ^= __float_as_uint(x[j]);
+    __syncthreads();
+    // 4 warps per scheduler x 8 instructions per rep (op 3: 4 x 2)
+    if (threadIdx.x == 0) out[5 + op] = static_cast<float>(tstamp[0]) / reps / (4 * (op == 3 ? 4 : 8));
+  }
+  if (sink == 0x12345678u) out[15] = 1.0f;
+  __syncthreads();
+  if (warp == 19) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+int launch_probe_softmax_role(cudaStream_t s, float* out, int reps) {
+  const int smem = 32768 + 128 + 1024;
+  if (cudaFuncSetAttribute(probe_softmax_role_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+  probe_softmax_role_kernel<<<1, 640, smem, s>>>(out, reps);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 }  // namespace rfe

@@ -785,6 +785,7 @@ namespace rfe {
 int launch_probe_shift(cudaStream_t s, const __half* a, const __half* b, float* out);
 int launch_probe_mma_rate(cudaStream_t s, float* out, int reps);
 int launch_probe_ts(cudaStream_t s, const __half* a, const __half* b, float* out, int reps);
+int launch_probe_softmax_role(cudaStream_t s, float* out, int reps);
 }
 namespace {
 
@@ -1004,6 +1005,36 @@ int rfe_sp_read_slot(rfe_ctx* c, int slot, int32_t* kpts_xy, float* scores, floa
   if (n > c->cap || n > cap) {
     set_error("image slot %d has %d keypoints, capacity %d", slot, n, cap < c->cap ? cap : c->cap);
     return RFE_ERR_CAPACITY;
+  }
+  return RFE_OK;
+}
+
+int rfe_sp_write_slot(rfe_ctx* c, int slot, const int32_t* kpts_xy, const float* scores, const float* desc, int n) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (slot < 0 || slot >= c->max_batch || n < 0 || n > c->cap || (n > 0 && (!kpts_xy || !desc))) {
+    set_error("rfe_sp_write_slot: invalid argument (slot %d of %d, n %d, capacity %d)", slot, c->max_batch, n, c->cap);
+    return RFE_ERR_INVALID;
+  }
+  if (n > 0) {
+    const size_t so = static_cast<size_t>(slot) * c->cap;
+    RFE_CUDA_CHECK(cudaMemcpyAsync(c->kpts + so * 2, kpts_xy, sizeof(int) * 2 * n, cudaMemcpyHostToDevice, c->stream));
+    if (scores) RFE_CUDA_CHECK(cudaMemcpyAsync(c->kp_scores + so, scores, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    else RFE_CUDA_CHECK(cudaMemsetAsync(c->kp_scores + so, 0, sizeof(float) * n, c->stream));
+    RFE_CUDA_CHECK(cudaMemcpyAsync(c->desc + so * 256, desc, sizeof(float) * 256 * n, cudaMemcpyHostToDevice, c->stream));
+    // keep the slot's sign-binarised copy (rfe_sp_read_slot_bin) consistent with the uploaded descriptors
+    launch_binarize(c->stream, c->desc + so * 256, n, c->desc_bin + so * 256, nullptr);
+    c->launches++;
+    c->bytes_h2d += static_cast<unsigned long long>(n) * (8 + (scores ? 4 : 0) + 1024);
+  }
+  c->h_counts[0] = n;
+  RFE_CUDA_CHECK(cudaMemcpyAsync(c->kp_counts + slot, c->h_counts, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (slot >= c->last_batch) {
+    // slots between the old batch end and this one have never been written: give them zero keypoints
+    if (slot > c->last_batch)
+      RFE_CUDA_CHECK(cudaMemsetAsync(c->kp_counts + c->last_batch, 0, sizeof(int) * (slot - c->last_batch), c->stream));
+    c->last_batch = slot + 1;
   }
   return RFE_OK;
 }
@@ -1596,11 +1627,11 @@ int rfe_debug_gemm(rfe_ctx* c, const float* a, const float* b, const float* bias
 int rfe_debug_probe(rfe_ctx* c, int which, const float* a, const float* b, float* out) {
   int r = check_ctx(c);
   if (r) return r;
-  if (which == 1 && out) {      // MMA issue-rate probe: out[0..6] = cycles per MMA (see probe_kernels.cu)
+  if ((which == 1 || which == 3) && out) {      // MMA issue-rate probe / softmax-role probe: out[16] (see probe_kernels.cu)
     float* dout1;
     RFE_CUDA_CHECK(cudaMalloc(&dout1, 16 * 4));
     RFE_CUDA_CHECK(cudaMemset(dout1, 0, 16 * 4));
-    if (rfe::launch_probe_mma_rate(c->stream, dout1, 512)) {
+    if (which == 1 ? rfe::launch_probe_mma_rate(c->stream, dout1, 512) : rfe::launch_probe_softmax_role(c->stream, dout1, 512)) {
       set_error("probe launch failed");
       return RFE_ERR_CUDA;
     }

@@ -611,15 +611,30 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
         const bool is_v = (EPI == EPI_QKV) && (n0 >> 8) == 2;
         if (EPI == EPI_QKV || p.out_hi) {
           uint32_t ph[16], pl[16];
+          const bool vt_store = is_v || (EPI == EPI_LINEAR && p.transpose_h);
+          if (vt_store) {
+            // V^T feeds only the attention kernel, whose P operand carries both planes at one scale (attn_kernel.cuh):
+            // V is split the same way, hi = rn16(kAttnVScale v), lo = rn16(kAttnVScale v - hi) with NO 2^11 on lo
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const __half2 h2 = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-            const float2 hf = __half22float2(h2);
-            const __half2 l2 = __floats2half2_rn((v[2 * j] - hf.x) * RFE_SPLIT_SCALE, (v[2 * j + 1] - hf.y) * RFE_SPLIT_SCALE);
-            ph[j] = *reinterpret_cast<const uint32_t*>(&h2);
-            pl[j] = *reinterpret_cast<const uint32_t*>(&l2);
+            for (int j = 0; j < 16; ++j) {
+              const float s0 = v[2 * j] * RFE_ATTN_V_SCALE, s1 = v[2 * j + 1] * RFE_ATTN_V_SCALE;
+              const __half2 h2 = __floats2half2_rn(s0, s1);
+              const float2 hf = __half22float2(h2);
+              const __half2 l2 = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+              ph[j] = *reinterpret_cast<const uint32_t*>(&h2);
+              pl[j] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const __half2 h2 = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+              const float2 hf = __half22float2(h2);
+              const __half2 l2 = __floats2half2_rn((v[2 * j] - hf.x) * RFE_SPLIT_SCALE, (v[2 * j + 1] - hf.y) * RFE_SPLIT_SCALE);
+              ph[j] = *reinterpret_cast<const uint32_t*>(&h2);
+              pl[j] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
           }
-          if (is_v || (EPI == EPI_LINEAR && p.transpose_h)) {
+          if (vt_store) {
             // transposed planes [col][ld]: lanes are consecutive rows -> every store instruction writes 64 contiguous bytes
             if (valid) {
               __half* th = is_v ? p.vt_hi : p.out_hi + static_cast<size_t>(z) * p.bstride_h;

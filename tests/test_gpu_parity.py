@@ -216,6 +216,39 @@ def test_match_pairs_one_call_pipeline(fe):
         assert np.array_equal(res[p][0], m) and np.array_equal(res[p][1], ms)
 
 
+def test_write_slot_round_trip_and_match(fe):
+    """rfe_sp_write_slot (8(f).3: a stored KeyFrame re-enters the device-resident path): the slot reads back bit for bit,
+    its binarised copy follows, and matching uploaded slots == rfe_lg_match on the same host features, bit for bit --
+    also against a slot that a real extraction filled."""
+    from rover_slam_b200.api import RoverFeError
+    a, b = synth.frame_pair(61, 240, 320, shift=(6, 3))
+    fa, fb = fe.extract(np.stack([a, b]))
+    (ka, sa, da), (kb, sb, db) = [(x[0].copy(), x[1].copy(), x[2].copy()) for x in (fa, fb)]
+    m_ref, s_ref = fe.match(ka, kb, da, db, 240, 320)
+    assert len(m_ref) > 50
+    fe.extract_device_from_host(np.stack([a, b]))        # slots 0, 1 = the same two frames
+    fe.write_slot(3, kb, db, sb)                          # slot 2 is skipped: it must read as empty
+    k3, s3, d3 = fe.read_slot(3)
+    assert np.array_equal(k3, kb) and np.array_equal(s3, sb) and np.array_equal(d3, db)
+    assert np.array_equal(fe.read_slot_bin(3), (db > 0).astype(np.uint8))
+    assert len(fe.read_slot(2)[0]) == 0
+    fe.match_slots(0, 3, 240, 320, 0.0, 0)                # extracted slot vs uploaded slot
+    m, ms = fe.read_result(0)
+    assert np.array_equal(m, m_ref) and np.array_equal(ms, s_ref)
+    fe.write_slot(0, ka, da)                              # scores are optional
+    fe.match_slots_batch([0, 3], [3, 0], 240, 320)
+    m, ms = fe.read_result(0)
+    assert np.array_equal(m, m_ref) and np.array_equal(ms, s_ref)
+    m10, _ = fe.match(kb, ka, db, da, 240, 320)
+    assert np.array_equal(fe.read_result(1)[0], m10)
+    fe.write_slot(1, ka[:0], da[:0])                      # empty upload
+    assert len(fe.read_slot(1)[0]) == 0
+    with pytest.raises(RoverFeError):
+        fe.write_slot(8, ka, da)                          # slot >= max_batch
+    with pytest.raises(RoverFeError):
+        fe.write_slot(0, np.zeros((5000, 2)), np.zeros((5000, 256), np.float32))   # n > max_keypoints
+
+
 def test_gpu_path_launches_kernels(fe):
     before = fe.kernel_launches()
     fe.extract(synth.frame(1, 64, 64))

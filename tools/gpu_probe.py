@@ -26,6 +26,13 @@ print("  alternating A    : N=64 %.1f  N=128 %.1f  N=256 %.1f" % tuple(o[3:6]))
 print("  issue-loop only  : N=64 %.1f cycles per instruction issued" % o[6])
 print("  A start +128 B   : N=128 %.1f   A start +256 B: N=128 %.1f" % (o[8], o[9]))
 
+o3 = np.zeros(16, np.float32)
+fe._check(fe.lib.rfe_debug_probe(fe.ctx, 3, None, None, o3.ctypes.data_as(C.c_void_p)))
+print("probe 3: softmax-role limits (640-thread CTA, one SM)")
+print("  cycles per 16 KB drained from TMEM (tcgen05.ld.32x32b.x32): 4 warps %.1f  8 warps %.1f  16 warps %.1f" % tuple(o3[0:3]))
+print("  16 warps + concurrent N=128 MMAs: %.1f per 16 KB, %.1f cycles per MMA" % (o3[3], o3[4]))
+print("  cycles per warp-instruction per scheduler: ex2 %.2f  cvt.f16x2.f32 %.2f  cvt.f32.f16 %.2f  fma.f32x2 %.2f" % tuple(o3[5:9]))
+
 # attention role timing (cycles) on a 2000-keypoint pair
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
 from oracle import synth
@@ -38,7 +45,8 @@ names = ["wait Q", "pass1 issue loop", "pass2 issue loop", "wait K", "wait free 
 print("attention MMA-thread cycle breakdown (CTA 0 of the last launch):")
 for n, v in zip(names, pr[:8]): print(f"  {n:22s} {int(v)}")
 print(f"  pass 1 only: wait K {int(pr[8])}, wait free S buffer {int(pr[9])}")
-print(f"  softmax warp 0, pass 2: loop {int(pr[10])}, wait scores {int(pr[11])}, wait free P buffer {int(pr[12])}")
+print(f"  softmax warp 0, pass 2: loop {int(pr[10])}, wait scores {int(pr[11])}, wait free P buffer {int(pr[12])}, tcgen05.ld {int(pr[15])}")
+print(f"  softmax warp 0, pass 1: loop {int(pr[13])}, wait scores {int(pr[14])}")
 
 # strip conv (conv1b) MMA-thread breakdown on one 480x640 frame batch of 8
 fe3 = FrontEnd(max_batch=8, max_height=480, max_width=640, max_keypoints=4096)
