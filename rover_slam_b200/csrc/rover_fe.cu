@@ -266,13 +266,13 @@ struct ProfScope {   // records a CUDA event pair around one launch when profili
   }
 };
 
-template <int BLOCK_N, int AMODE, int EPI>
+template <int BLOCK_N, int AMODE, int EPI, bool BRES = false>
 int launch_umma(rfe_ctx* c, const char* tag, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                 const CUtensorMap& b_lo, const UmmaParams& p, dim3 grid, const EpiMaps* em = nullptr) {
   static bool configured[64] = {};
-  auto kern = umma_kernel<BLOCK_N, AMODE, EPI>;
+  auto kern = umma_kernel<BLOCK_N, AMODE, EPI, BRES>;
   if (!configured[c->device & 63]) {
-    RFE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, umma_smem_bytes(BLOCK_N)));
+    RFE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, umma_smem_bytes(BLOCK_N, BRES)));
     configured[c->device & 63] = true;
   }
   // persistent launch: `grid` holds the tile counts (m, n, z); one CTA per SM walks the tiles round-robin
@@ -281,10 +281,18 @@ int launch_umma(rfe_ctx* c, const char* tag, const CUtensorMap& a_hi, const CUte
   pp.tiles_n = static_cast<int>(grid.y);
   pp.num_tiles = static_cast<int>(grid.x * grid.y * grid.z);
   pp.prof = (c->attn_prof && c->prof_tag && !strcmp(tag, c->prof_tag)) ? c->attn_prof + 16 : nullptr;
-  const int ctas = pp.num_tiles < c->num_sms ? pp.num_tiles : c->num_sms;
+  int ctas = pp.num_tiles < c->num_sms ? pp.num_tiles : c->num_sms;
+  if (BRES) {   // B-resident: every CTA is bound to one n-tile, so launch a multiple of tiles_n (umma_kernel.cuh)
+    if (grid.z != 1 || pp.num_k_steps > kBresMaxKSteps || pp.tiles_n > c->num_sms) {
+      set_error("%s: B-resident GEMM needs an unbatched problem with K <= %d", tag, 64 * kBresMaxKSteps);
+      return RFE_ERR_INVALID;
+    }
+    const int per_n = c->num_sms / pp.tiles_n < pp.tiles_m ? c->num_sms / pp.tiles_n : pp.tiles_m;
+    ctas = per_n * pp.tiles_n;
+  }
   ProfScope ps(c, tag);
   static const EpiMaps kNoMaps = {};
-  kern<<<ctas, umma_threads(BLOCK_N, EPI), umma_smem_bytes(BLOCK_N), c->stream>>>(a_hi, a_lo, b_hi, b_lo, em ? *em : kNoMaps, pp);
+  kern<<<ctas, umma_threads(BLOCK_N, EPI), umma_smem_bytes(BLOCK_N, BRES), c->stream>>>(a_hi, a_lo, b_hi, b_lo, em ? *em : kNoMaps, pp);
   c->launches++;
   RFE_CUDA_CHECK(cudaGetLastError());
   return RFE_OK;
@@ -333,6 +341,13 @@ UmmaParams default_params() {
   return p;
 }
 
+// B-resident GEMM tiles (umma_kernel.cuh, BRES): RFE_BRES=0 in the environment falls back to the streamed-B kernel
+// everywhere (A/B measurements), RFE_BRES=2 uses them even below one wave of tiles (tests), default: from one wave up.
+static const int kBresMode = getenv("RFE_BRES") ? atoi(getenv("RFE_BRES")) : 1;
+static bool use_bres(const rfe_ctx* c, unsigned tiles) {
+  return kBresMode >= 2 || (kBresMode == 1 && tiles >= static_cast<unsigned>(c->num_sms));
+}
+
 // D = A * B^T with the LINEAR epilogue.  p carries the epilogue; M/N/K are filled here.
 int gemm_linear(rfe_ctx* c, const char* tag, const Operand& A, const Operand& B, UmmaParams p, int block_n) {
   if (A.rows == 0 || B.rows == 0) return RFE_OK;
@@ -361,6 +376,9 @@ int gemm_linear(rfe_ctx* c, const char* tag, const Operand& A, const Operand& B,
     }
   }
   if (block_n == 64) return launch_umma<64, A_GEMM, EPI_LINEAR>(c, tag, ah, al, bh, bl, p, grid, &em);
+  // K <= 256, one problem, enough m-tiles to amortise the weight load: keep the weights of one n-tile resident (BRES)
+  if (z == 1 && p.num_k_steps <= kBresMaxKSteps && use_bres(c, grid.x * grid.y))
+    return launch_umma<128, A_GEMM, EPI_LINEAR, true>(c, tag, ah, al, bh, bl, p, grid, &em);
   return launch_umma<128, A_GEMM, EPI_LINEAR>(c, tag, ah, al, bh, bl, p, grid, &em);
 }
 
@@ -643,6 +661,8 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
     cross_p.nq[2 * i + 1] = n1; cross_p.nk[2 * i + 1] = n0; cross_p.q_row0[2 * i + 1] = off1[i]; cross_p.k_row0[2 * i + 1] = off0[i];
   }
   const long long hs = static_cast<long long>(rows) * 64;
+  // the 256 -> 256 linears: 128-wide B-resident tiles once there are two waves of them, else 64-wide streamed tiles
+  const int lin_bn = use_bres(c, ((rows + 127) / 128) * 2) ? 128 : 64;
   for (int i = 0; i < kLayers; ++i) {
     const LgLayer& L = c->layers[i];
     // ---------------- self attention ----------------
@@ -673,7 +693,12 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
       if ((r = make_head_map(&em.h_hi, c->q.hi, rows, hs, 4)) || (r = make_head_map(&em.h_lo, c->q.lo, rows, hs, 4)) ||
           (r = make_head_map(&em.k_hi, c->k.hi, rows, hs, 4)) || (r = make_head_map(&em.k_lo, c->k.lo, rows, hs, 4)))
         return r;
-      if ((r = launch_umma<128, A_GEMM, EPI_QKV>(c, "lg.wqkv_rope", ah, al, bh, bl, p, dim3((rows + 127) / 128, 6, 1), &em))) return r;
+      const dim3 tiles((rows + 127) / 128, 6, 1);
+      if (use_bres(c, tiles.x * tiles.y))
+        r = launch_umma<128, A_GEMM, EPI_QKV, true>(c, "lg.wqkv_rope", ah, al, bh, bl, p, tiles, &em);
+      else
+        r = launch_umma<128, A_GEMM, EPI_QKV>(c, "lg.wqkv_rope", ah, al, bh, bl, p, tiles, &em);
+      if (r) return r;
     }
     if ((r = attention_fused(c, "lg.attn_self", c->q, c->k, rows, self_p, 2 * np, max_n))) return r;
     {
@@ -684,7 +709,7 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
       p.out_hi = c->cat.hi + 256;
       p.out_lo = c->cat.lo + 256;
       p.ld_h = 512;
-      if ((r = gemm_linear(c, "lg.out_proj", A, B, p, 64))) return r;
+      if ((r = gemm_linear(c, "lg.out_proj", A, B, p, lin_bn))) return r;
     }
     if ((r = ffn_block(c, rows, L.s_ffn0, L.s_ln_w, L.s_ln_b, L.s_ffn3))) return r;
     // ---------------- cross attention ----------------
@@ -698,7 +723,7 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
       p.out_lo = c->q.lo;
       p.head_major = 1;
       p.head_stride = hs;
-      if ((r = gemm_linear(c, "lg.to_qk", A, B, p, 64))) return r;
+      if ((r = gemm_linear(c, "lg.to_qk", A, B, p, lin_bn))) return r;
     }
     {
       Operand A{c->cat.hi, c->cat.lo, rows, 256, 512, 0, 1};
@@ -709,7 +734,7 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
       p.out_lo = c->vt.lo;
       p.transpose_h = 1;
       p.ld_h = c->lg_ldv;
-      if ((r = gemm_linear(c, "lg.to_v", A, B, p, 64))) return r;
+      if ((r = gemm_linear(c, "lg.to_v", A, B, p, lin_bn))) return r;
     }
     if ((r = attention_fused(c, "lg.attn_cross", c->q, c->q, rows, cross_p, 2 * np, max_n))) return r;
     {
@@ -720,7 +745,7 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
       p.out_hi = c->cat.hi + 256;
       p.out_lo = c->cat.lo + 256;
       p.ld_h = 512;
-      if ((r = gemm_linear(c, "lg.to_out", A, B, p, 64))) return r;
+      if ((r = gemm_linear(c, "lg.to_out", A, B, p, lin_bn))) return r;
     }
     if ((r = ffn_block(c, rows, L.c_ffn0, L.c_ln_w, L.c_ln_b, L.c_ffn3))) return r;
   }
@@ -734,7 +759,7 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
     p.out_hi = c->md.hi;
     p.out_lo = c->md.lo;
     p.ld_h = 256;
-    if ((r = gemm_linear(c, "lg.final_proj", A, B, p, 64))) return r;
+    if ((r = gemm_linear(c, "lg.final_proj", A, B, p, lin_bn))) return r;
   }
   { ProfScope ps_(c, "lg.matchability"); launch_matchability(s, c->x, rows, c->match_w, c->match_b, c->ls); }
   c->launches++;

@@ -89,9 +89,14 @@ __host__ __device__ constexpr int umma_num_stages(int block_n) {
 }
 constexpr int kEpiStageWarpBytes = 4096;     // per epilogue warp: 32 rows x 128 B (32 fp32 or 64 fp16 per row)
 __host__ __device__ constexpr int umma_num_stages(int block_n);
-__host__ __device__ constexpr int umma_smem_bytes(int block_n) {
-  return umma_num_stages(block_n) * umma_stage_bytes(block_n) + 8 * kEpiStageWarpBytes + 1024 /*align slack*/ +
-         256 /*barriers*/;
+// B-resident mode (BRES, K <= 256): the CTA keeps ONE n-tile of the weights (all k-steps, hi+lo: up to 4 x 2 x block_n x
+// 128 B) in shared memory for its whole life and streams only A, plane by plane, through kBresSlots 16 KB slots.
+constexpr int kBresSlots = 4;
+constexpr int kBresMaxKSteps = 4;
+__host__ __device__ constexpr int umma_smem_bytes(int block_n, bool bres = false) {
+  return (bres ? kBresSlots * kStageABytes + kBresMaxKSteps * 2 * block_n * 128
+               : umma_num_stages(block_n) * umma_stage_bytes(block_n)) +
+         8 * kEpiStageWarpBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 // Number of hi*hi accumulators.  The tensor core adds each K=16 partial sum into the fp32 accumulator with
 // truncation, so the error grows linearly with the number of accumulation steps (measured: 1.1e-4 abs at K=512 on
@@ -107,14 +112,18 @@ __host__ __device__ constexpr int umma_tmem_cols(int block_n, int amode) {
 
 #ifdef __CUDACC__
 
-template <int BLOCK_N, int AMODE, int EPI>
+template <int BLOCK_N, int AMODE, int EPI, bool BRES = false>
 __global__ void __launch_bounds__(umma_threads(BLOCK_N, EPI), 1)
 umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
             const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
             const __grid_constant__ EpiMaps em, const UmmaParams p) {
-  constexpr int STAGES = umma_num_stages(BLOCK_N);
-  constexpr int STAGE_BYTES = umma_stage_bytes(BLOCK_N);
+  // BRES: the "stages" are kBresSlots single-plane A slots (A_hi and A_lo of a k-step travel separately, so the hi MMAs
+  // start while the lo plane is still in flight) followed by the resident B region [k-step][B_hi | B_lo].
+  constexpr int STAGES = BRES ? kBresSlots : umma_num_stages(BLOCK_N);
+  constexpr int STAGE_BYTES = BRES ? kStageABytes : umma_stage_bytes(BLOCK_N);
   constexpr int STAGE_B = BLOCK_N * 128;
+  constexpr int BRES_BYTES = BRES ? kBresMaxKSteps * 2 * STAGE_B : 0;
+  static_assert(!BRES || (AMODE == A_GEMM && 2 * BLOCK_N <= 256), "B-resident mode: plain GEMM with the concatenated-B MMA");
   constexpr int NACC0 = umma_num_acc0(AMODE);
   constexpr int TILE_COLS = umma_tmem_cols(BLOCK_N, AMODE);  // TMEM columns of one output tile's accumulators
   constexpr int NBUF = TILE_COLS <= 256 ? 2 : 1;             // accumulator sets: the epilogue of tile i overlaps the MMAs of tile i+1
@@ -130,13 +139,15 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int EPI_WARPS = umma_epi_warps(BLOCK_N, EPI);
   constexpr int NHALF = EPI_WARPS / 4;                   // warps sharing a TMEM lane quarter
-  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;      // 8 x kEpiStageWarpBytes
+  uint8_t* bres = smem + STAGES * STAGE_BYTES;           // BRES: resident weights
+  uint8_t* epi_stage = bres + BRES_BYTES;                // 8 x kEpiStageWarpBytes
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + 8 * kEpiStageWarpBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;       // [NBUF]
   uint64_t* tmem_empty_bar = tmem_full_bar + NBUF;    // [NBUF]
   uint64_t* res_bar = tmem_empty_bar + NBUF;          // [8] one per epilogue warp: residual tile landed
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 8);
+  uint64_t* bres_bar = res_bar + 8;                   // BRES: the resident weights have landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -164,6 +175,13 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     return t;
   };
 
+  // BRES: a CTA is bound to one n-tile (blockIdx.x % tiles_n) and walks m-tiles with stride gridDim.x / tiles_n; the host
+  // launches a multiple of tiles_n CTAs.  Otherwise: round-robin over all tiles.
+  const int bres_n = BRES ? static_cast<int>(blockIdx.x) % p.tiles_n : 0;
+  const int tile_first = BRES ? bres_n * p.tiles_m + static_cast<int>(blockIdx.x) / p.tiles_n : static_cast<int>(blockIdx.x);
+  const int tile_step = BRES ? static_cast<int>(gridDim.x) / p.tiles_n : static_cast<int>(gridDim.x);
+  const int tile_end = BRES ? (bres_n + 1) * p.tiles_m : p.num_tiles;
+
   // ---- one-time setup ------------------------------------------------------------------------------
   if (warp == WARP_TMA && lane == 0) {
     tma_prefetch_desc(&tmA_hi);
@@ -179,6 +197,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       mbar_init(&tmem_empty_bar[b], EPI_WARPS);      // one arrival per epilogue warp
     }
     for (int w = 0; w < 8; ++w) mbar_init(&res_bar[w], 1);
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == WARP_MMA) {
@@ -195,10 +214,31 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      if constexpr (BRES) {
+        if (tile_first < tile_end) {
+          mbar_expect_tx(bres_bar, static_cast<uint32_t>(p.num_k_steps) * 2 * STAGE_B);
+          for (int ks = 0; ks < p.num_k_steps; ++ks) {
+            tma_load_3d(bres + ks * 2 * STAGE_B, &tmB_hi, bres_bar, ks * 64, bres_n * BLOCK_N, 0);
+            tma_load_3d(bres + ks * 2 * STAGE_B + STAGE_B, &tmB_lo, bres_bar, ks * 64, bres_n * BLOCK_N, 0);
+          }
+        }
+      }
+      for (int tile = tile_first; tile < tile_end; tile += tile_step) {
       const Tile tc = decode(tile);
       const int m0 = tc.m0, n0 = tc.n0, img = tc.img, x0 = tc.x0, y0 = tc.y0;
       (void)m0; (void)img; (void)x0; (void)y0;
+      if constexpr (BRES) {
+        for (int ks = 0; ks < p.num_k_steps; ++ks)
+          for (int pl = 0; pl < 2; ++pl) {       // A_hi then A_lo of this k-step, one slot each
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], kStageABytes);
+            tma_load_3d(smem + stage * STAGE_BYTES, pl ? &tmA_lo : &tmA_hi, &full_bar[stage], ks * 64, m0, 0);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+      } else {
       for (int ks = 0; ks < p.num_k_steps; ++ks) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = smem + stage * STAGE_BYTES;
@@ -223,6 +263,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
         }
       }
       }
+      }
     }
   } else if (warp == WARP_MMA) {
     // ===== MMA issuer ===========================================================================
@@ -235,7 +276,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       int it = 0;
       long long w_te = 0, w_full = 0;
       const long long t_begin = tick();
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
       const int buf = it % NBUF;
       const uint32_t tile_base = tmem_base + buf * TILE_COLS;
       const uint32_t acc1 = tile_base + ACC1_COL;
@@ -243,6 +284,49 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       mbar_wait(&tmem_empty_bar[buf], (((it / NBUF) & 1) ^ 1));     // the epilogue has drained this accumulator set
       w_te += tick() - c0;
       tc_fence_after();
+      if constexpr (BRES) {
+        if (it == 0) {
+          c0 = tick();
+          mbar_wait(bres_bar, 0);
+          w_full += tick() - c0;
+        }
+        for (int ks = 0; ks < p.num_k_steps; ++ks) {
+          const uint32_t b_hi = smem_u32(bres + ks * 2 * STAGE_B);     // B_lo follows B_hi: one N = 2*BLOCK_N operand
+          // slot with A_hi: [acc0 | acc1] (+)= A_hi [B_hi;B_lo]^T
+          c0 = tick();
+          mbar_wait(&full_bar[stage], phase);
+          w_full += tick() - c0;
+          tc_fence_after();
+          {
+            const uint32_t a = smem_u32(smem + stage * STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16(tile_base, make_sw128_kmajor_desc(a + k * 32), make_sw128_kmajor_desc(b_hi + k * 32), idesc2,
+                       (ks > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+          // slot with A_lo: acc1 += A_lo B_hi^T
+          c0 = tick();
+          mbar_wait(&full_bar[stage], phase);
+          w_full += tick() - c0;
+          tc_fence_after();
+          {
+            const uint32_t a = smem_u32(smem + stage * STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16(acc1, make_sw128_kmajor_desc(a + k * 32), make_sw128_kmajor_desc(b_hi + k * 32), idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      } else {
       for (int ks = 0; ks < p.num_k_steps; ++ks) {
         c0 = tick();
         mbar_wait(&full_bar[stage], phase);
@@ -285,6 +369,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
           phase ^= 1;
         }
       }
+      }
       umma_commit(&tmem_full_bar[buf]);
       }
       if (p.prof && blockIdx.x == 0) {
@@ -302,7 +387,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     uint32_t res_phase = 0;
     long long w_tf = 0;
     const long long e_begin = tick();
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
     const Tile tc = decode(tile);
     const int m0 = tc.m0, n0 = tc.n0, img = tc.img, x0 = tc.x0, y0 = tc.y0;
     (void)m0; (void)img; (void)x0; (void)y0;

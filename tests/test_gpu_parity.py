@@ -142,6 +142,69 @@ def test_lightglue_vs_oracle_ragged(fe, lg, n0, n1):
     parity.compare_matches(rm.numpy(), rms.numpy(), m, ms)
 
 
+_BRES_CHILD = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from oracle import synth
+from rover_slam_b200 import FrontEnd
+fe = FrontEnd(max_batch=2, max_height=64, max_width=64, max_keypoints=2048)
+out = {}
+for n0, n1 in ((1024, 1024), (300, 777), (1, 1)):
+    n = max(n0, n1)
+    k0, k1, d0, d1, _ = synth.lightglue_inputs(n, 300 + n)
+    m, ms = fe.match(k0[:n0], k1[:n1], d0[:n0], d1[:n1], 480, 640)
+    out[f"m_{n0}_{n1}"], out[f"s_{n0}_{n1}"] = m, ms
+np.savez(sys.argv[2], **out)
+"""
+
+
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_lightglue_gemm_tile_modes_vs_oracle(lg, tmp_path, mode):
+    """The 256 -> 256 linears and Wqkv have two tilings (umma_kernel.cuh): streamed 64-wide tiles below one wave of tiles,
+    128-wide B-resident tiles above.  RFE_BRES=0 / 2 (read when the library loads, hence the child process) forces either
+    one for every size; both must agree with the oracle."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "bres.npz")
+    env = dict(os.environ, RFE_BRES=mode)
+    subprocess.run([sys.executable, "-c", _BRES_CHILD, root, out], check=True, env=env, timeout=600)
+    got = np.load(out)
+    for n0, n1 in ((1024, 1024), (300, 777), (1, 1)):
+        n = max(n0, n1)
+        k0, k1, d0, d1, _ = synth.lightglue_inputs(n, 300 + n)
+        k0, d0, k1, d1 = k0[:n0], d0[:n0], k1[:n1], d1[:n1]
+        rm, rms = lg(lightglue_ref.normalize_keypoints(k0, 480, 640), lightglue_ref.normalize_keypoints(k1, 480, 640), d0, d1)
+        parity.compare_matches(rm.numpy(), rms.numpy(), got[f"m_{n0}_{n1}"], got[f"s_{n0}_{n1}"])
+
+
+def test_bench_shape_batch_vs_oracle(sp, lg):
+    """BASELINE config 5 shape: 8 pairs of 640x480 frames in ONE batched pass (16 frames extracted, 8 pairs matched: the
+    size at which the B-resident GEMM tiles and the 1024-CTA attention launches are used) -- first and last pair against
+    the oracle end to end."""
+    from rover_slam_b200 import FrontEnd
+    import bench
+    frames = bench.make_pairs(8, 3)
+    big = FrontEnd(max_batch=16, max_height=480, max_width=640, max_keypoints=4096)
+    try:
+        kpts, res = big.match_pairs(frames.reshape(16, 480, 640))
+        kpts = [k.copy() for k in kpts]
+        res = [(m.copy(), s.copy()) for m, s in res]
+    finally:
+        big.close()
+    for pi in (0, 7):
+        feats = []
+        for f in (0, 1):
+            rk, rs, rd = sp(frames[pi, f])
+            got_k = kpts[2 * pi + f]
+            assert len(got_k) >= len(rk) - 3 and len(got_k) <= len(rk) + 3
+            feats.append((rk.numpy(), rd))
+        if all(np.array_equal(kpts[2 * pi + f], feats[f][0]) for f in (0, 1)):     # identical keypoint sets (the usual case)
+            rm, rms = lg(lightglue_ref.normalize_keypoints(feats[0][0], 480, 640),
+                         lightglue_ref.normalize_keypoints(feats[1][0], 480, 640), feats[0][1], feats[1][1])
+            parity.compare_matches(rm.numpy(), rms.numpy(), res[pi][0], res[pi][1])
+        assert len(res[pi][0]) > 500
+
+
 def test_lightglue_empty_inputs(fe):
     k0, k1, d0, d1, _ = synth.lightglue_inputs(16, 1)
     m, ms = fe.match(k0[:0], k1, d0[:0], d1, 480, 640)
