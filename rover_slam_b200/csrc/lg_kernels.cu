@@ -400,9 +400,11 @@ __global__ void __launch_bounds__(256) row_lse_batch_kernel(const LgAssign a, fl
   if (i >= n0) return;
   const float* r = a.sim[pr] + static_cast<size_t>(i) * a.ld[pr];
   float mx = -INFINITY;
+#pragma unroll 8
   for (int j = lane; j < n1; j += 32) mx = fmaxf(mx, r[j]);
   mx = warp_max(mx);
   float sum = 0.0f;
+#pragma unroll 8
   for (int j = lane; j < n1; j += 32) sum += expf(r[j] - mx);
   sum = warp_sum(sum);
   if (lane == 0) {
@@ -420,8 +422,10 @@ __global__ void __launch_bounds__(1024) col_lse_batch_kernel(const LgAssign a, f
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + tx;
   float mx = -INFINITY;
-  if (j < n1)
+  if (j < n1) {
+#pragma unroll 8
     for (int i = ty; i < n0; i += 32) mx = fmaxf(mx, sim[static_cast<size_t>(i) * ld + j]);
+  }
   red[ty][tx] = mx;
   __syncthreads();
   if (ty == 0) {
@@ -433,8 +437,10 @@ __global__ void __launch_bounds__(1024) col_lse_batch_kernel(const LgAssign a, f
   mx = red[0][tx];
   __syncthreads();
   float sum = 0.0f;
-  if (j < n1)
+  if (j < n1) {
+#pragma unroll 8
     for (int i = ty; i < n0; i += 32) sum += expf(sim[static_cast<size_t>(i) * ld + j] - mx);
+  }
   red[ty][tx] = sum;
   __syncthreads();
   if (ty == 0 && j < n1) {
@@ -459,6 +465,7 @@ __global__ void __launch_bounds__(256) row_argmax_batch_kernel(const LgAssign a,
   const float rm = rmax[o0 + i], rl = rlog[o0 + i], a0 = ls[o0 + i];
   float best = -INFINITY;
   int bi = 0x7fffffff;
+#pragma unroll 4
   for (int j = lane; j < n1; j += 32) {
     const float sc = assign_score(r[j], rm, rl, cmax[o1 + j], clog[o1 + j], a0, ls[o1 + j]);
     if (S_dbg && pr == a.pairs - 1) S_dbg[static_cast<size_t>(i) * n1 + j] = sc;
@@ -499,6 +506,7 @@ __global__ void __launch_bounds__(1024) col_argmax_batch_kernel(const LgAssign a
   int bi = 0x7fffffff;
   if (j < n1) {
     const float cm = cmax[o1 + j], cl = clog[o1 + j], a1 = ls[o1 + j];
+#pragma unroll 8
     for (int i = ty; i < n0; i += 32) {
       const float sc = assign_score(sim[static_cast<size_t>(i) * ld + j], rmax[o0 + i], rlog[o0 + i], cm, cl, ls[o0 + i], a1);
       if (sc > best) {
