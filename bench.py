@@ -274,7 +274,7 @@ def main():
     barrier()
     tb0 = fe.transfer_bytes()
     t0 = time.perf_counter()
-    e_steps = max(3, args.steps // 2)
+    e_steps = max(3, args.steps)
     run_host(e_steps)
     barrier()
     tb1 = fe.transfer_bytes()

@@ -49,7 +49,8 @@ struct AttnParams {
   int q_row0[kAttnMaxProblems], k_row0[kAttnMaxProblems];  // row offsets inside the head-major Q / K tensors and the V^T columns
   __half* out_hi;            // split-fp16 [rows][256]
   __half* out_lo;
-  unsigned long long* prof;  // optional [16] cycle counters written by CTA (0,0,0): where the MMA / softmax roles wait
+  unsigned long long* prof;  // optional cycle counters written by CTA prof_cta: where the MMA / softmax roles wait
+  int prof_cta;              // linear CTA index (z, y, x) whose role counters are recorded (RFE_ATTN_PROF_CTA, default 0)
 };
 
 constexpr int kAttnSoftmaxWarps = 16;                             // 4 per TMEM lane quarter: 16 of a tile's 64 columns each
@@ -124,6 +125,16 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
   const int nq = p.nq[z], nk = p.nk[z];
   const int m0 = blockIdx.x * 128;
   if (m0 >= nq) return;                                 // uniform per CTA
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (PROF && p.prof && threadIdx.x == 0 && cta_lin < 4096) {      // per-CTA timeline (tools/gpu_attn_timeline.py)
+    unsigned long long t;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    p.prof[32 + 3 * cta_lin] = t;
+    p.prof[32 + 3 * cta_lin + 2] = smid;
+  }
+  const long long cta_c0 = PROF ? clock64() : 0;
   const int T = (nk + kAttnKeyTile - 1) / kAttnKeyTile;
   const int T1 = (nk + 127) / 128;                      // pass-1 tiles (128 keys)
   const int qrow = p.q_row0[z] + m0, krow = p.k_row0[z];
@@ -199,7 +210,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       constexpr uint32_t idesc64 = make_idesc_f16(128, 64);
       constexpr uint32_t idesc128 = make_idesc_f16(128, 128);
       const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + 16384;
-      const bool prof = PROF && p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      const bool prof = PROF && p.prof && cta_lin == p.prof_cta;
       long long w_k = 0, w_se = 0, w_k1 = 0, w_se1 = 0;
       const long long t_begin = tick();
       mbar_wait(q_full, 0);
@@ -263,7 +274,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
       constexpr uint32_t idesc64 = make_idesc_f16(128, 64);
       constexpr uint32_t idesc128 = make_idesc_f16(128, 128);
       const uint32_t o_base = tmem_base + 384;
-      const bool prof = PROF && p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      const bool prof = PROF && p.prof && cta_lin == p.prof_cta;
       long long w_v = 0, w_p = 0;
       for (int t = 0; t < T; ++t) {            // consumes P buffer t&1 and V stage t%3
         const int st = t % kAttnVStages, pb = t & 1;
@@ -307,7 +318,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
 
     // ---- pass 1: row maximum of the hi*hi scores ----
     float mx = NEG;
-    const bool sprof = PROF && p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 0 && lane == 0;
+    const bool sprof = PROF && p.prof && cta_lin == p.prof_cta && warp == 0 && lane == 0;
     long long sw_s1 = 0, sw_s = 0, sw_ld = 0, sw_p = 0;
     const long long st_begin = tick();
     for (int g = 0; g < T1; ++g) {
@@ -467,6 +478,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ 
   if (warp == kAttnWarpMma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+  if (PROF && p.prof && threadIdx.x == 0 && cta_lin < 4096) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.prof[32 + 3 * cta_lin + 1] = t;
+    p.prof[32 + 3 * cta_lin + 2] |= static_cast<unsigned long long>(clock64() - cta_c0) << 16;   // SM cycles of this CTA
   }
 }
 

@@ -583,6 +583,7 @@ int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitB
   p.out_hi = c->attn.hi;
   p.out_lo = c->attn.lo;
   p.prof = c->attn_prof;
+  p.prof_cta = getenv("RFE_ATTN_PROF_CTA") ? atoi(getenv("RFE_ATTN_PROF_CTA")) : 0;
   dim3 grid((max_nq + 127) / 128, 4, nprob);
   ProfScope ps(c, tag);
   if (p.prof) attn_kernel<true><<<grid, kAttnThreads, kAttnSmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
@@ -1570,11 +1571,13 @@ int rfe_debug_read(rfe_ctx* c, const char* name, void* dst, size_t capacity, siz
     n = static_cast<size_t>(c->dbg_n0) * c->dbg_n1;
   } else if (s == "lg.attn_prof") {   // 16 x u64 cycle counters of the last attention launch (first request arms it)
     if (!c->attn_prof) {
-      if ((r = dev_alloc(c, &c->attn_prof, 32))) return r;
+      // [0,32): role counters; [32, 32 + 3*4096): per-CTA {start ns, end ns, SM id} of the last attention launch
+      if ((r = dev_alloc(c, &c->attn_prof, 32 + 3 * 4096))) return r;
+      RFE_CUDA_CHECK(cudaMemsetAsync(c->attn_prof, 0, (32 + 3 * 4096) * sizeof(unsigned long long), c->stream));
       *bytes = 0;
       return RFE_OK;
     }
-    *bytes = 32 * sizeof(unsigned long long);
+    *bytes = (32 + 3 * 4096) * sizeof(unsigned long long);
     if (dst) {
       RFE_CUDA_CHECK(cudaMemcpyAsync(dst, c->attn_prof, *bytes < capacity ? *bytes : capacity, cudaMemcpyDeviceToHost, c->stream));
       RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));

@@ -16,9 +16,11 @@ namespace rfe {
 // (two IEEE fp32 FMAs per issue slot, same operation order as a scalar fmaf chain: bit-identical results).  The
 // 3 x 10 input window of the run is loaded and scaled once and slides along x, so a pixel costs 36 FFMA2 + the
 // bias / ReLU / split-fp16 epilogue instead of 72 FFMA + 9 guarded byte loads.  A warp covers 4 runs x 8 groups:
-// each store instruction writes 4 full 128-byte lines per plane.  Bound: HBM writes (256 B out per 1 B in).
+// each store instruction writes 4 full 128-byte lines per plane.  Bound: HBM writes (256 B out per 1 B in), so the number
+// of warps in flight matters: __launch_bounds__(256, 2) caps the kernel at 128 registers (17 words spilled) for two blocks per
+// SM: 577 -> 370 us per 16 frames.  (4 channels per thread at 80 registers / 3 blocks per SM: 456 us, more redundant loads.)
 constexpr int kConv1aRun = 8;
-__global__ void __launch_bounds__(256) conv1a_kernel(const uint8_t* __restrict__ img, int stride, int H, int W, int B,
+__global__ void __launch_bounds__(256, 2) conv1a_kernel(const uint8_t* __restrict__ img, int stride, int H, int W, int B,
                                                      const float* __restrict__ w /*[64][9]*/,
                                                      const float* __restrict__ bias, __half* __restrict__ out_hi,
                                                      __half* __restrict__ out_lo) {
@@ -88,7 +90,7 @@ namespace {
 constexpr int NT_W = 80, NT_H = 48, NHALO = 20, NR = 4;   // 640 = 8 x 80, 480 = 10 x 48: no ragged tiles; halo overhead 2.75x
 constexpr int RW = NT_W + 2 * NHALO;  // 104
 constexpr int RH = NT_H + 2 * NHALO;  // 72
-constexpr int NMS_THREADS = 512;
+constexpr int NMS_THREADS = 1024;
 
 // out[i] = max(v[i .. i+8]) for i = 0..7 with 44 max operations (log-step doubling) instead of 64
 __device__ __forceinline__ void max9_run8(const float (&v)[16], float (&out)[8]) {
