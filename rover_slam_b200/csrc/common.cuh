@@ -125,8 +125,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef RFE_DEBUG_WAIT   // debug builds (-DRFE_DEBUG_WAIT): a wait that never completes reports its barrier and traps instead of hanging
+  for (long long spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+    if (spins > (1ll << 24)) {
+      printf("mbar_wait timeout: block %d thread %d barrier smem 0x%x parity %u\n", static_cast<int>(blockIdx.x),
+             static_cast<int>(threadIdx.x), smem_u32(bar), parity);
+      __trap();
+    }
+  }
+#else
   while (!mbar_try_wait(bar, parity)) {
   }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
