@@ -25,7 +25,8 @@ sys.path.insert(0, ROOT)
 
 H, W = 480, 640
 SP_FLOPS_PER_FRAME = 52.10e9
-ATTN_DRAM_BYTES_PER_LAUNCH = None                          # filled from profiles/ once the ncu --set full capture exists
+ATTN_DRAM_BYTES_PER_LAUNCH = 119_990_528                   # dram__bytes_read.sum + dram__bytes_write.sum of ONE attention launch at 8 pairs
+                                                           # (profiles/r01_attn_full.ncu-rep: 101.6 MB + 18.4 MB; algorithmic bytes 131 MB)
 
 
 def peaks():
@@ -322,12 +323,12 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "attn_kernel (lg.attn_self / lg.attn_cross: fused 4-head attention of all pairs, 18 launches per step)",
                      "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak if tf_peak else None,
-                     "traffic": ATTN_DRAM_BYTES_PER_LAUNCH, "peak_source": peak_src, "launch_ms": per_launch_ms, "launches_timed": attn_n,
+                     "traffic": ATTN_DRAM_BYTES_PER_LAUNCH if P == 8 else None, "peak_source": peak_src, "launch_ms": per_launch_ms, "launches_timed": attn_n,
                      "algorithmic_flops_per_launch": attn_flops,
                      "executed_mma_flops_per_launch": 3.5 * attn_flops,
                      "share_of_step": attn_share,
                      "note": "split-fp16: 3 MMAs per algorithmic MAC for QK^T and PV plus a hi-only max pass = 3.5x: frac <= 0.286 by construction; "
-                             "traffic = dram bytes of one launch from the ncu --set full capture under profiles/ (4 pairs)"},
+                             "traffic = DRAM bytes of one launch from the ncu --set full capture profiles/r01_attn_full.ncu-rep (8 pairs per step)"},
         "kernel_us_per_step": breakdown,
     }
     if world == 1 and args.cpu_pairs > 0:

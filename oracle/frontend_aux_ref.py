@@ -45,3 +45,27 @@ def l2_best2(q, db, cand_off, cand_idx, init_dist=256.0):
             elif dist < b2[i]:
                 b2[i], i2[i] = dist, idx
     return b1, i1, b2, i2
+
+
+def adaptive_threshold(scores: np.ndarray, lastmatch: float) -> np.float32:
+    """the score filter the reference compiles out (src/Extractors/superpoint_onnx.cc:192-210,
+    `bool adaptivethresold = false`): threshold = mean - 0.6*sqrt(var) - 0.02 / (1 + exp(-0.02 (lastmatch - 270))).
+    float32 sum / mean / variance accumulated in index order, the last expression in double, narrowed to float32."""
+    s = np.asarray(scores, np.float32)
+    n = len(s)
+    acc = np.float32(0)
+    for v in s:                                   # :196-199
+        acc = np.float32(acc + v)
+    mean = np.float32(acc / np.float32(n))
+    var = np.float32(0)
+    for v in s:                                   # :202-206
+        d = np.float32(v - mean)
+        var = np.float32(var + np.float32(d * d))
+    var = np.float32(var / np.float32(n))
+    return np.float32(float(mean) - 0.6 * float(np.sqrt(var)) - 0.02 / (1.0 + np.exp(-0.02 * (float(lastmatch) - 270.0))))
+
+
+def adaptive_filter(scores: np.ndarray, lastmatch: float) -> np.ndarray:
+    """Indices Extractor_PostProcess keeps under the adaptive rule: `if (scores[i] < threshold) continue;` (:226)."""
+    s = np.asarray(scores, np.float32)
+    return np.nonzero(~(s < adaptive_threshold(s, lastmatch)))[0]

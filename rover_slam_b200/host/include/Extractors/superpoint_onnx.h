@@ -25,6 +25,11 @@ class SuperPointOnnxRunner {
   long long extractor_timer = 0;       // milliseconds, like the reference (superpoint_onnx.cc:138-140)
   long long matcher_timer = 0;
   float lastmatch = 0;
+  // the reference carries a score filter it compiles out (`bool adaptivethresold = false;`,
+  // superpoint_onnx.cc:192-210): threshold = mean - 0.6 sigma - 0.02 / (1 + exp(-0.02 (lastmatch - 270))) over the scores of
+  // the frame; keypoints below it are dropped in Extractor_PostProcess.  Off by default (= the reference's behaviour).
+  bool adaptive_threshold = false;
+  static float AdaptiveThreshold(const float* scores, int n, float lastmatch);
   std::vector<float> scales = {1.0f, 1.0f};
   std::vector<SuperPointResult> extractor_outputtensors;
 

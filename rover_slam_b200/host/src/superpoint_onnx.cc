@@ -87,17 +87,34 @@ void SuperPointOnnxRunner::Extractor_PostProcess(Configuration cfg, SuperPointRe
   // octave=0 (:222-236).  The reference reads response from scores[2*idx] (out-of-bounds bug, :227) -- waived:
   // response = scores[idx].
   const int n = tensor.count;
-  Descriptors.create(n, RFE_DESC_DIM, CV_32F);
+  const float threshold = adaptive_threshold ? AdaptiveThreshold(tensor.scores.data(), n, lastmatch) : 0.0f;
+  int keep = 0;
+  for (int i = 0; i < n; ++i) keep += !(tensor.scores[i] < threshold);     // superpoint_onnx.cc:212-217
+  Descriptors.create(keep, RFE_DESC_DIM, CV_32F);
+  int row = 0;
   for (int i = 0; i < n; ++i) {
+    if (tensor.scores[i] < threshold) continue;                            // superpoint_onnx.cc:226
     cv::KeyPoint kp;
     kp.pt = cv::Point2f(static_cast<float>(tensor.keypoints[2 * i]), static_cast<float>(tensor.keypoints[2 * i + 1]));
     kp.size = 10;
     kp.octave = 0;
     kp.response = tensor.scores[i];
     vKeyPoints.emplace_back(kp);
-    memcpy(Descriptors.ptr<float>(i), tensor.descriptors.data() + static_cast<size_t>(i) * RFE_DESC_DIM,
+    memcpy(Descriptors.ptr<float>(row++), tensor.descriptors.data() + static_cast<size_t>(i) * RFE_DESC_DIM,
            sizeof(float) * RFE_DESC_DIM);
   }
+}
+
+// The reference's disabled rule, operation for operation (superpoint_onnx.cc:194-209): float sum / mean / variance
+// accumulated in index order, the final expression in double, narrowed to float.
+float SuperPointOnnxRunner::AdaptiveThreshold(const float* scores, int n, float lastmatch) {
+  float sum = 0;
+  for (int i = 0; i < n; i++) sum = sum + scores[i];
+  float mean = sum / n;
+  float variance = 0.0;
+  for (int i = 0; i < n; i++) variance += (scores[i] - mean) * (scores[i] - mean);
+  variance /= n;
+  return static_cast<float>(mean - 0.6 * std::sqrt(variance) - 0.02 / (1.0 + std::exp(-0.02 * (lastmatch - 270))));
 }
 
 int SuperPointOnnxRunner::BinarizeLast(cv::Mat& bin) {

@@ -39,9 +39,16 @@ int main(int argc, char** argv) {
   std::vector<int> vn_frame, vn_kp;
   const int m_frame = matcher.MatchingPoints_onnx(fa, fb, vn_frame);
   const int m_kp = matcher.MatchingPoints_onnx(fa.mvKeys, fb.mvKeys, fa.mDescriptors, fb.mDescriptors, vn_kp);
+  // the reference's compiled-out adaptive score rule, switched on (LocalMapping.cc:951-952 writes lastmatchnum)
+  ORB_SLAM3::SPextractor ada(1000, 1.2f, 1, 20, 7);
+  ada.featureExtractor->adaptive_threshold = true;
+  ada.lastmatchnum = 150.0f;
+  std::vector<cv::KeyPoint> ka;
+  cv::Mat da;
+  const int n_ada = ada(fa.imgLeft, ka, da);
   FILE* f = fopen(argv[5], "wb");
   if (!f) return 4;
-  const int hdr[6] = {na, nb, nmulti, m_frame, m_kp, static_cast<int>(ext.featureExtractor->GetTimer("extractor"))};
+  const int hdr[6] = {na, nb, nmulti, m_frame, m_kp, n_ada};
   put(f, hdr, 6);
   for (const auto* fr : {&fa, &fb}) {
     for (const cv::KeyPoint& k : fr->mvKeys) {
@@ -52,6 +59,11 @@ int main(int argc, char** argv) {
   }
   put(f, vn_frame.data(), vn_frame.size());
   put(f, vn_kp.data(), vn_kp.size());
+  for (const cv::KeyPoint& k : ka) {
+    const float v[3] = {k.pt.x, k.pt.y, k.response};
+    put(f, v, 3);
+  }
+  for (int i = 0; i < da.rows; ++i) put(f, da.ptr<float>(i), 256);
   fclose(f);
   printf("host_driver: %d / %d keypoints, multi=%d, matches frame=%d kp=%d\n", na, nb, nmulti, m_frame, m_kp);
   return 0;

@@ -38,3 +38,21 @@ def test_l2_best2_matches_brute_force():
         if len(c) > 1:
             assert np.isclose(b2[i], d[order[1]])
     assert i1[4] == 7 and i2[4] == 3                         # tie broken by list order (strict <)
+
+
+def test_adaptive_threshold_known_answers():
+    """8(f).4: the reference's compiled-out adaptive score rule (superpoint_onnx.cc:192-210)."""
+    from oracle import frontend_aux_ref as aux
+    s = np.array([0.5, 0.25, 0.25, 0.0], np.float32)             # mean 0.25, variance 0.03125 (all exact in binary)
+    sig = 0.02 / (1.0 + np.exp(-0.02 * (270.0 - 270.0)))         # lastmatch = 270: the logistic term is 0.01
+    want = np.float32(0.25 - 0.6 * float(np.sqrt(np.float32(0.03125))) - sig)   # sqrt in float, the rest in double (C++ promotion)
+    assert aux.adaptive_threshold(s, 270.0) == want
+    assert list(aux.adaptive_filter(s, 270.0)) == [0, 1, 2]       # 0.0 < threshold (0.1339...) is dropped
+    # the logistic term grows with the previous frame's match count: more matches -> lower threshold -> more keypoints
+    t_lo, t_hi = aux.adaptive_threshold(s, 0.0), aux.adaptive_threshold(s, 1000.0)
+    assert t_hi < t_lo and abs(float(t_lo - t_hi) - 0.02 * (1 / (1 + np.exp(-14.6)) - 1 / (1 + np.exp(5.4)))) < 1e-6
+    rng = np.random.RandomState(0)
+    sc = (rng.rand(2000).astype(np.float32) ** 4) * np.float32(0.6)
+    keep = aux.adaptive_filter(sc, 150.0)
+    thr = aux.adaptive_threshold(sc, 150.0)
+    assert 0 < len(keep) <= 2000 and (sc[keep] >= thr).all() and (np.delete(sc, keep) < thr).all()

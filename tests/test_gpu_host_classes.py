@@ -33,7 +33,7 @@ def test_spextractor_spmatcher_classes():
         assert r.returncode == 0, r.stdout + r.stderr
         raw = np.fromfile(out, dtype=np.uint8)
     hdr = raw[:24].view(np.int32)
-    na, nb, nmulti, m_frame, m_kp = (int(v) for v in hdr[:5])
+    na, nb, nmulti, m_frame, m_kp, n_ada = (int(v) for v in hdr[:6])
     off = 24
     feats = []
     for n in (na, nb):
@@ -41,7 +41,9 @@ def test_spextractor_spmatcher_classes():
         de = raw[off:off + n * 1024].view(np.float32).reshape(n, 256); off += n * 1024
         feats.append((kp, de))
     vn_frame = raw[off:off + na * 4].view(np.int32); off += na * 4
-    vn_kp = raw[off:off + na * 4].view(np.int32)
+    vn_kp = raw[off:off + na * 4].view(np.int32); off += na * 4
+    kp_ada = raw[off:off + n_ada * 12].view(np.float32).reshape(n_ada, 3); off += n_ada * 12
+    de_ada = raw[off:off + n_ada * 1024].view(np.float32).reshape(n_ada, 256)
     assert nmulti == 0                                   # nLevels != 1 extracts nothing, like the reference
     fe = FrontEnd(max_batch=2, max_height=h, max_width=w)
     ref = fe.extract(np.stack([a, b]))
@@ -58,4 +60,10 @@ def test_spextractor_spmatcher_classes():
                                            lightglue_ref.normalize_keypoints(ref[1][0], h, w), ref[0][2], ref[1][2])
     m, ms = fe.match(ref[0][0], ref[1][0], ref[0][2], ref[1][2], h, w)
     parity.compare_matches(rm.numpy(), rms.numpy(), m, ms)
+    # 8(f).4: the adaptive score rule (superpoint_onnx.cc:192-210) switched on with lastmatch = 150: exactly the oracle's subset
+    from oracle import frontend_aux_ref as aux
+    keep = aux.adaptive_filter(ref[0][1], 150.0)
+    assert n_ada == len(keep), (n_ada, len(keep), na, float(aux.adaptive_threshold(ref[0][1], 150.0)))
+    assert np.array_equal(kp_ada[:, :2], ref[0][0][keep].astype(np.float32)) and np.array_equal(kp_ada[:, 2], ref[0][1][keep])
+    assert np.array_equal(de_ada, ref[0][2][keep])
     fe.close()
