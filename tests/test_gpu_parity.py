@@ -312,6 +312,39 @@ def test_write_slot_round_trip_and_match(fe):
         fe.write_slot(0, np.zeros((5000, 2)), np.zeros((5000, 256), np.float32))   # n > max_keypoints
 
 
+def test_concurrent_contexts_from_threads(fe):
+    """SURVEY 8(b) threading contract: one ctx per SLAM thread (Tracking, LocalMapping, LoopClosing each own an extractor and a
+    matcher), used concurrently.  Three threads with their own ctx (own stream, buffers, thread-local tensor-map cache and error
+    string) must return exactly what a single thread returns for the same frames, every repetition."""
+    import threading
+    from rover_slam_b200 import FrontEnd
+    pairs = [np.stack(synth.frame_pair(70 + i, 240, 320, shift=(3 + i, 2 - i))) for i in range(3)]
+    want = []
+    for imgs in pairs:
+        kp, res = fe.match_pairs(imgs)
+        want.append(([k.copy() for k in kp], res[0][0].copy(), res[0][1].copy()))
+    errors = []
+
+    def worker(i):
+        try:
+            ctx = FrontEnd(max_batch=2, max_height=240, max_width=320, max_keypoints=2048)
+            for _ in range(4):
+                kp, res = ctx.match_pairs(pairs[i])
+                assert all(np.array_equal(a, b) for a, b in zip(kp, want[i][0]))
+                assert np.array_equal(res[0][0], want[i][1]) and np.array_equal(res[0][1], want[i][2])
+            ctx.close()
+        except Exception as e:          # noqa: BLE001 -- reported by the main thread
+            errors.append((i, repr(e)))
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(3)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert not errors, errors
+    assert len(want[0][1]) > 50
+
+
 def test_gpu_path_launches_kernels(fe):
     before = fe.kernel_launches()
     fe.extract(synth.frame(1, 64, 64))
