@@ -72,3 +72,26 @@ def test_weight_blob_matches_reference_when_mounted():
     g2 = onnx_reader.load("/root/reference/onnxmodel/lightglue_sim.onnx")
     assert np.array_equal(blob["lg.l4.cross.to_v.b"], g2.initializers["transformers.4.cross_attn.to_v.bias"])
     assert blob["lg.l0.self.wqkv.w"].shape == (768, 256)
+
+
+def test_host_classes_without_device_follow_the_reference_error_convention(tmp_path):
+    """errors never cross the class surface as exceptions (the reference returns EXIT_FAILURE,
+    superpoint_onnx.cc:62-65,158-161): without a GPU SPextractor::operator() yields 0 keypoints and
+    SPmatcher::MatchingPoints_onnx 0 matches, each failure is reported on stderr, and nothing falls back to the CPU."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    drv = os.path.join(ROOT, "rover_slam_b200", "host_driver")
+    if not os.path.exists(drv):
+        subprocess.run(["make", "-C", ROOT, "host"], check=True, capture_output=True)
+    a, b, out = (str(tmp_path / n) for n in ("a.raw", "b.raw", "out.bin"))
+    img = (np.arange(240 * 320) % 251).astype(np.uint8)
+    img.tofile(a)
+    img.tofile(b)
+    r = subprocess.run([drv, "240", "320", a, b, out], capture_output=True, text=True, timeout=120,
+                       env=dict(os.environ, ROVER_FE_WEIGHTS=os.path.join(ROOT, "weights", "rover_fe.rfw")))
+    assert r.returncode == 0, r.stderr
+    assert "no CPU fallback" in r.stderr and "init failed" in r.stderr
+    hdr = np.fromfile(out, dtype=np.int32)
+    assert hdr.tolist() == [0, 0, 0, 0, 0, 0]            # keypoints a / b, multi-level, matches (Frame / KeyPoint overload), adaptive
