@@ -25,8 +25,8 @@ sys.path.insert(0, ROOT)
 
 H, W = 480, 640
 SP_FLOPS_PER_FRAME = 52.10e9
-ATTN_DRAM_BYTES_PER_LAUNCH = 119_990_528                   # dram__bytes_read.sum + dram__bytes_write.sum of ONE attention launch at 8 pairs
-                                                           # (profiles/r01_attn_full.ncu-rep: 101.6 MB + 18.4 MB; algorithmic bytes 131 MB)
+ATTN_DRAM_BYTES_PER_LAUNCH = 116_912_128                   # dram__bytes_read.sum + dram__bytes_write.sum of ONE attention launch at 8 pairs
+                                                           # (profiles/r01_attn_full.ncu-rep: 101.6 MB + 15.3 MB; algorithmic bytes 131 MB)
 
 
 def peaks():
