@@ -23,8 +23,8 @@ struct Configuration {
   std::string device;
 
   // --- carried for source compatibility, not interpreted -----------------------------------------------------------------
-  std::string extractorType;          // the reference logs it ("superpoint") and never branches on it
-  unsigned int image_size = 512;      // LightGlue-ONNX resize hint; the SLAM path never resizes (frames arrive at sensor size)
+  std::string extractorType;          // "superpoint"; only the reference's uncalled Extractor_PreProcess branches on it (superpoint_onnx.cc:78)
+  unsigned int image_size = 512;      // resize hint; the reference's only use is commented out (superpoint_onnx.cc:76): frames keep sensor size
   float threshold = 0.0f;             // initial match threshold; SPmatcher overrides it through SetMatchThresh (SPmatcher.cc:25)
   bool grayScale = false;             // NormalizeImage decides by channel count (transform.cpp:5), not by this flag
   bool isEndtoEnd = true;             // selects the fused-vs-decoupled ONNX export upstream; one implementation here
