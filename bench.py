@@ -24,6 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 H, W = 480, 640
+WORKLOAD = ("BASELINE config 5 shape: 640x480 synthetic frame pairs, SuperPoint on both frames + one LightGlue match per pair")
 SP_FLOPS_PER_FRAME = 52.10e9
 ATTN_DRAM_BYTES_PER_LAUNCH = 116_912_128                   # dram__bytes_read.sum + dram__bytes_write.sum of ONE attention launch at 8 pairs
                                                            # (profiles/r01_attn_full.ncu-rep: 101.6 MB + 15.3 MB; algorithmic bytes 131 MB)
@@ -148,8 +149,10 @@ def run_reference(args, rank, world):
     line = {"metric": "frames/sec (extract+match) on 640x480", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * t / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "640x480 synthetic frame pairs: SuperPoint on both frames + LightGlue per pair",
-                       "pairs_per_step": 1, "reference_kind": "torch-CPU restatement of superpoint.onnx / lightglue_sim.onnx "
+            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": 1, "frames_per_step_per_gpu": 2,
+                       "keypoints_per_frame": "about 2000 (no top-K, threshold 0.0005)",
+                       "sample": "bounded sample of the workload: one pair of the same synthetic stream per step",
+                       "reference_kind": "torch-CPU restatement of superpoint.onnx / lightglue_sim.onnx "
                        "(ONNXRuntime is not installable offline)"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": f"{args.steps} steps x 1 pair (2 extracts + 1 match); {threads} of {avail} host threads "
@@ -312,7 +315,7 @@ def main():
         "metric": "frames/sec (extract+match) on 640x480", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16x2-split (fp32-equivalent), f32 accumulate", "data": "synthetic",
-        "config": {"workload": "BASELINE config 5 shape: 640x480 synthetic frame pairs, SuperPoint on both frames + one LightGlue match per pair",
+        "config": {"workload": WORKLOAD,
                    "pairs_per_step_per_gpu": P, "frames_per_step_per_gpu": B, "keypoints_per_frame": "about 2000 (no top-K, threshold 0.0005)",
                    "parallelism": f"dp{world} (independent pairs per GPU; NCCL only scatters the input shards)",
                    "l2": f"per-step activation working set about {0.31 * B:.1f} GB >> 126 MB L2; 4 distinct input sets cycled",
