@@ -1,4 +1,6 @@
 """CPU tests of the section-8(f) helper oracles (binarisation, L2 best-two)."""
+import os
+
 import numpy as np
 
 from oracle import frontend_aux_ref as aux
@@ -56,3 +58,20 @@ def test_adaptive_threshold_known_answers():
     keep = aux.adaptive_filter(sc, 150.0)
     thr = aux.adaptive_threshold(sc, 150.0)
     assert 0 < len(keep) <= 2000 and (sc[keep] >= thr).all() and (np.delete(sc, keep) < thr).all()
+
+
+def test_algorithmic_flop_formulas_match_the_survey():
+    """LightGlue 9*(4 980 736 N + 4096 N^2) + 263 168 N + 512 N^2 FLOP per pair = 14.0 / 32.9 / 85.4 / 249.1 GFLOP
+    at N = 256 / 512 / 1024 / 2048, attention 9*4096 N^2 = 2.4 / 9.7 / 38.7 / 154.6; SuperPoint 52.10 GFLOP per 640x480 frame
+    (sum of 2 k^2 Cin Cout Hout Wout over the twelve convolutions).  bench.py and tools/lg_sweep.py divide by these."""
+    import bench
+    lg = lambda n: 9 * (4980736 * n + 4096 * n * n) + 263168 * n + 512 * n * n
+    assert [round(lg(n) / 1e9, 1) for n in (256, 512, 1024, 2048)] == [14.0, 32.9, 85.4, 249.1]
+    assert [round(9 * 4096 * n * n / 1e9, 1) for n in (256, 512, 1024, 2048)] == [2.4, 9.7, 38.7, 154.6]
+    h, w = 480, 640
+    convs = [(3, 1, 64, 1), (3, 64, 64, 1), (3, 64, 64, 2), (3, 64, 64, 2), (3, 64, 128, 4), (3, 128, 128, 4), (3, 128, 128, 8),
+             (3, 128, 128, 8), (3, 128, 256, 8), (1, 256, 65, 8), (3, 128, 256, 8), (1, 256, 256, 8)]     # (k, Cin, Cout, stride of the map)
+    sp = sum(2 * k * k * ci * co * (h // s) * (w // s) for k, ci, co, s in convs)
+    assert abs(sp - bench.SP_FLOPS_PER_FRAME) / sp < 2e-3, sp
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "lg_sweep.py")).read()
+    assert "9 * (4980736 * n + 4096 * n * n) + 263168 * n + 512 * n * n" in src and "9 * 4096 * n * n" in src
