@@ -1,0 +1,84 @@
+"""Numerics of the operand formats the tensor-core kernels use, restated in numpy (np.float16 conversion = cvt.rn.f16.f32):
+the bounds DESIGN.md section 4 and rover_slam_b200/csrc/common.cuh state for
+  * the general split  v = hi + lo / 2^11                       (split_f32: every GEMM / convolution operand),
+  * the attention probabilities  E = 2^11 p, P_hi = rn16(E), P_lo = rn16(E - P_hi)      (attn_kernel.cuh),
+  * the attention values  V_hi = rn16(256 v), V_lo = rn16(256 v - V_hi)                   (RFE_ATTN_V_SCALE),
+and that a split-fp16 dot product with three partial products reproduces the fp32 one to fp32 accuracy."""
+import numpy as np
+
+F16_MIN_NORMAL = 2.0 ** -14
+
+
+def rn16(x):
+    return np.asarray(x, np.float32).astype(np.float16).astype(np.float32)
+
+
+def split(v):
+    hi = rn16(v)
+    lo = rn16((np.asarray(v, np.float32) - hi) * np.float32(2048.0))
+    return hi, lo
+
+
+def test_general_split_is_22_bits():
+    rng = np.random.RandomState(0)
+    v = (rng.randn(200000) * np.exp(rng.uniform(-6, 4.8, 200000))).astype(np.float32)       # magnitudes down to denormal hi, up to ~400
+    hi, lo = split(v)
+    rec = hi.astype(np.float64) + lo.astype(np.float64) / 2048.0
+    err = np.abs(rec - v.astype(np.float64))
+    normal = np.abs(v) >= F16_MIN_NORMAL
+    assert np.abs(v).max() < 65504 and normal.sum() > 190000
+    assert (err[normal] <= 2.0 ** -22 * np.abs(v[normal])).all()                             # 22 significand bits while hi is a normal fp16
+    assert (err[~normal] <= 2.0 ** -36 * 1.0001).all()                                       # below 6.1e-5: absolute (half a denormal step of lo / 2^11)
+    assert (np.abs(lo[normal]) <= np.abs(hi[normal]) * 1.0001).all()                         # lo / 2^11 is at most half an ulp of hi
+
+
+def test_attention_probability_planes():
+    rng = np.random.RandomState(1)
+    p = np.exp(-rng.uniform(0, 30, 300000)).astype(np.float32)                               # softmax numerators exp(s - max) in (9e-14, 1]
+    p[:4] = [1.0, 0.5, 2.0 ** -14, 2.0 ** -30]
+    E = p * np.float32(2048.0)
+    hi = rn16(E)
+    lo = rn16(E - hi)                                                                        # E - hi is exact in fp32 (the FHFMA)
+    assert np.array_equal((E.astype(np.float64) - hi.astype(np.float64)).astype(np.float32), E - hi)
+    rec = (hi.astype(np.float64) + lo.astype(np.float64)) / 2048.0
+    err = np.abs(rec - p.astype(np.float64))
+    # 21 bits relative while the low plane is a normal fp16 (p >= 2^-15 = 3e-5); below that the error is ABSOLUTE, half a denormal
+    # step of the low plane = 2^-25 / 2^11 = 2^-36 of the row maximum (which is ~1): 2000 such keys perturb a row sum by < 3e-8
+    assert (err <= np.maximum(2.0 ** -21 * p.astype(np.float64), 2.0 ** -36 * 1.0001)).all()
+    big = p >= 2.0 ** -15
+    assert big.sum() > 90000 and (err[big] / p[big] <= 2.0 ** -21).all()
+    assert E.max() <= 2048.0 * 1.0 and 2048.0 * np.exp(3.4) < 65504                          # head-room: the hi-only max may be 3.4 too low
+
+
+def test_attention_value_planes():
+    rng = np.random.RandomState(2)
+    v = (rng.randn(300000) * np.exp(rng.uniform(-12, 3.8, 300000))).astype(np.float32)       # up to ~ +-150 (largest LightGlue value seen: 46)
+    v = v[np.abs(v) < 250]
+    s = v * np.float32(256.0)
+    hi = rn16(s)
+    lo = rn16(s - hi)
+    rec = (hi.astype(np.float64) + lo.astype(np.float64)) / 256.0
+    err = np.abs(rec - v.astype(np.float64))
+    assert np.isfinite(hi).all() and (err <= np.maximum(2.0 ** -21 * np.abs(v), 2.0 ** -25 / 256.0 * 1.0001)).all()
+
+
+def test_three_product_dot_is_fp32_equivalent():
+    """acc0 = a_hi.b_hi ; acc1 = a_hi.b_lo + a_lo.b_hi ; result acc0 + acc1 / 2^11 -- against the float64 dot product the error is
+    of the order of fp32's own rounding (the dropped a_lo.b_lo term is 2^-22 relative)."""
+    rng = np.random.RandomState(3)
+    worst = 0.0
+    for k in (64, 256, 512, 1152):
+        a = (rng.randn(64, k) * 3).astype(np.float32)
+        b = rng.randn(k, 32).astype(np.float32)
+        ah, al = split(a)
+        bh, bl = split(b)
+        acc0 = ah.astype(np.float64) @ bh.astype(np.float64)
+        acc1 = ah.astype(np.float64) @ bl.astype(np.float64) + al.astype(np.float64) @ bh.astype(np.float64)
+        got = acc0 + acc1 / 2048.0
+        ref = a.astype(np.float64) @ b.astype(np.float64)
+        scale = (np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64))                # sum of |terms|: the natural error scale
+        worst = max(worst, (np.abs(got - ref) / scale).max())
+        f32 = np.abs((a @ b).astype(np.float64) - ref) / scale
+        assert (np.abs(got - ref) / scale).max() <= 2.0 ** -21
+        assert (np.abs(got - ref) / scale).max() <= 4 * max(f32.max(), 2.0 ** -24)
+    assert worst > 0
