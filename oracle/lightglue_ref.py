@@ -37,12 +37,14 @@ def normalize_keypoints(kpts_px: np.ndarray, h: int, w: int) -> np.ndarray:
 
 
 class LightGlueRef:
-    def __init__(self, blob: dict | None = None, dtype=torch.float32, mm=None):
+    def __init__(self, blob: dict | None = None, dtype=torch.float32, mm=None, attn=None):
         blob = blob if blob is not None else _weights.load()
         self.dtype = dtype
         self.p = {k[3:]: torch.from_numpy(v).to(dtype) for k, v in blob.items() if k.startswith("lg.")}
         # blob stores [out,in]; x @ W^T == ONNX MatMul(x, W_onnx)
         self.mm = mm or (lambda name, x, wt: x @ wt.t())
+        # softmax(q k^T / 8) v per head, q and k each scaled by 64^-1/4 first (nodes 50-54); hook: numerics experiments
+        self.attn = attn or (lambda q, k, v: torch.softmax((q * ATTN_SCALE) @ (k.transpose(1, 2) * ATTN_SCALE), -1) @ v)
 
     def lin(self, name, x):
         y = self.mm(name, x, self.p[name + ".w"])
@@ -75,7 +77,7 @@ class LightGlueRef:
         qkv = self.lin(f"l{i}.self.wqkv", x).reshape(n, HEADS, HEAD_DIM, 3).permute(1, 0, 2, 3)   # [4,N,64,3]
         q, k, v = qkv[..., 0], qkv[..., 1], qkv[..., 2]
         q, k = self.rope(e, q), self.rope(e, k)
-        a = torch.softmax((q * ATTN_SCALE) @ (k.transpose(1, 2) * ATTN_SCALE), -1) @ v          # [4,N,64]
+        a = self.attn(q, k, v)                                                                   # [4,N,64]
         m = self.lin(f"l{i}.self.out_proj", a.permute(1, 0, 2).reshape(n, 256))
         return self.ffn(f"l{i}.self", x, m)
 
@@ -85,8 +87,8 @@ class LightGlueRef:
         pre = f"l{i}.cross"
         qk0, qk1 = heads(self.lin(pre + ".to_qk", x0)), heads(self.lin(pre + ".to_qk", x1))
         v0, v1 = heads(self.lin(pre + ".to_v", x0)), heads(self.lin(pre + ".to_v", x1))
-        m0 = torch.softmax((qk0 * ATTN_SCALE) @ (qk1.transpose(1, 2) * ATTN_SCALE), -1) @ v1
-        m1 = torch.softmax((qk1 * ATTN_SCALE) @ (qk0.transpose(1, 2) * ATTN_SCALE), -1) @ v0
+        m0 = self.attn(qk0, qk1, v1)
+        m1 = self.attn(qk1, qk0, v0)
         m0 = self.lin(pre + ".to_out", m0.permute(1, 0, 2).reshape(-1, 256))
         m1 = self.lin(pre + ".to_out", m1.permute(1, 0, 2).reshape(-1, 256))
         return self.ffn(pre, x0, m0), self.ffn(pre, x1, m1)

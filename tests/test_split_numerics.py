@@ -82,3 +82,52 @@ def test_three_product_dot_is_fp32_equivalent():
         assert (np.abs(got - ref) / scale).max() <= 2.0 ** -21
         assert (np.abs(got - ref) / scale).max() <= 4 * max(f32.max(), 2.0 ** -24)
     assert worst > 0
+
+
+def test_lightglue_with_emulated_split_fp16_everywhere_matches_fp32():
+    """End-to-end design check on the CPU: LightGlue with EVERY tensor-core contraction replaced by the arithmetic the kernels
+    perform -- three-product split-fp16 linears, attention with the hi-only row maximum, E = 2^11 exp(s - max) probability planes and
+    256-scaled value planes -- returns the fp32 oracle's match set with match scores within the stated tolerance."""
+    import torch
+    from oracle import lightglue_ref, synth
+    from tests import parity
+
+    def t16(x):                                   # fp32 tensor -> nearest fp16, back in float64
+        return x.to(torch.float32).to(torch.float16).to(torch.float64)
+
+    def split_t(x):
+        x = x.to(torch.float32)
+        hi = x.to(torch.float16).to(torch.float32)
+        lo = ((x - hi) * 2048.0).to(torch.float16).to(torch.float64)
+        return hi.to(torch.float64), lo
+
+    def mm(name, x, wt):
+        if name in ("posenc", "matchability"):    # CUDA-core fp32 kernels, not tensor-core contractions
+            return x @ wt.t()
+        xh, xl = split_t(x)
+        wh, wl = split_t(wt)
+        return (xh @ wh.t() + (xh @ wl.t() + xl @ wh.t()) / 2048.0).to(torch.float32)
+
+    def attn(q, k, v):
+        qs, ks = (q * lightglue_ref.ATTN_SCALE).to(torch.float32), (k * lightglue_ref.ATTN_SCALE).to(torch.float32)
+        qh, ql = split_t(qs)
+        kh, kl = split_t(ks)
+        s_hh = qh @ kh.transpose(1, 2)
+        s = (s_hh + (qh @ kl.transpose(1, 2) + ql @ kh.transpose(1, 2)) / 2048.0).to(torch.float32)
+        mx = s_hh.to(torch.float32).max(-1, keepdim=True).values          # pass 1: hi*hi products only
+        E = (2048.0 * torch.exp((s - mx).to(torch.float32))).to(torch.float32)
+        ph = E.to(torch.float16).to(torch.float32)
+        pl = t16(E - ph)
+        vs = (v * 256.0).to(torch.float32)
+        vh = vs.to(torch.float16).to(torch.float32)
+        vl = t16(vs - vh)
+        ph, vh = ph.to(torch.float64), vh.to(torch.float64)
+        o = (ph @ vh + (ph @ vl + pl @ vh)) / (256.0 * E.to(torch.float64).sum(-1, keepdim=True))
+        return o.to(torch.float32)
+
+    k0, k1, d0, d1, perm = synth.lightglue_inputs(256, 456)
+    kn0, kn1 = lightglue_ref.normalize_keypoints(k0, 480, 640), lightglue_ref.normalize_keypoints(k1, 480, 640)
+    rm, rs = lightglue_ref.LightGlueRef()(kn0, kn1, d0, d1)
+    em, es = lightglue_ref.LightGlueRef(mm=mm, attn=attn)(kn0, kn1, d0, d1)
+    r = parity.compare_matches(rm.numpy(), rs.numpy(), em.numpy(), es.numpy())
+    assert r["common"] == len(rm) == len(em) and len(rm) > 200 and r["mscore_maxabs"] < 2e-4, r      # measured: 254 / 254, 2.3e-5
