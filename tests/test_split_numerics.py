@@ -131,3 +131,33 @@ def test_lightglue_with_emulated_split_fp16_everywhere_matches_fp32():
     em, es = lightglue_ref.LightGlueRef(mm=mm, attn=attn)(kn0, kn1, d0, d1)
     r = parity.compare_matches(rm.numpy(), rs.numpy(), em.numpy(), es.numpy())
     assert r["common"] == len(rm) == len(em) and len(rm) > 200 and r["mscore_maxabs"] < 2e-4, r      # measured: 254 / 254, 2.3e-5
+
+
+def test_superpoint_with_emulated_split_fp16_convolutions_matches_fp32():
+    """The same design check for the extractor: every convolution except conv1a (exact fp32 FMA on CUDA cores) computed as the three
+    split-fp16 products, bias added in fp32 -- keypoint set identical to the fp32 oracle, scores and descriptors inside the tolerance."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import superpoint_ref, synth
+    from tests import parity
+
+    def split_t(x):
+        x = x.to(torch.float32)
+        hi = x.to(torch.float16).to(torch.float32)
+        lo = ((x - hi) * 2048.0).to(torch.float16).to(torch.float64)
+        return hi.to(torch.float64), lo
+
+    def conv_fn(name, x, w, b, pad):
+        if name == "conv1a":
+            return F.conv2d(x, w, b, padding=pad)
+        xh, xl = split_t(x)
+        wh, wl = split_t(w)
+        y = F.conv2d(xh, wh, None, padding=pad) + (F.conv2d(xh, wl, None, padding=pad) + F.conv2d(xl, wh, None, padding=pad)) / 2048.0
+        return y.to(torch.float32) + b.reshape(1, -1, 1, 1)
+
+    img = synth.frame(21, 120, 160)
+    rk, rs, rd = superpoint_ref.SuperPointRef()(img)
+    ek, es, ed = superpoint_ref.SuperPointRef(conv_fn=conv_fn)(img)
+    r = parity.compare_keypoints(rk.numpy(), rs.numpy(), ek.numpy(), es.numpy())
+    assert len(rk) > 50 and len(r["ref_idx"]) >= len(rk) - 1
+    parity.compare_descriptors(rd.numpy()[r["ref_idx"]], ed.numpy()[r["tst_idx"]])
