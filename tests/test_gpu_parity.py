@@ -383,6 +383,35 @@ def test_pipelined_pairs_equal_one_shot_calls(fe):
             assert len(rm) > 20
 
 
+
+# ---- against an independent runtime: OpenCV DNN executing the reference's ONNX files (tests/golden/cv2dnn_*.npz) ----------
+@pytest.mark.parametrize("name", ["sp_640x480_seed0", "sp_752x480_seed100_a"])
+def test_superpoint_vs_cv2dnn_golden(fe, golden_dir, name):
+    """Heat-map (softmax-65 + depth-to-space) and L2-normalised dense descriptors of the CUDA path against the tensors
+    cv2.dnn computed from superpoint.onnx (no code of this repository between the reference's graph and the fixture)."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    c = np.load(os.path.join(golden_dir, "cv2dnn_" + name + ".npz"))
+    fe.extract(g["image"])
+    h, w = g["image"].shape
+    heat = fe.debug_read("sp.heat").reshape(-1, h, w)[0]
+    assert np.abs(heat[c["heat_rows"]] - c["heat"]).max() <= parity.HEAT_ATOL
+    dense = fe.debug_read("sp.dense").reshape(h // 8, w // 8, 256)
+    assert np.abs(np.transpose(dense, (2, 0, 1))[:, ::8, ::8] - c["dense_desc_px"]).max() <= parity.DESC_ATOL
+
+
+@pytest.mark.parametrize("n", [256, 512])
+def test_lightglue_vs_cv2dnn_golden(fe, golden_dir, n):
+    """The N0 x N1 log-assignment matrix after all nine layers, and the match list, against cv2.dnn's execution of
+    lightglue_sim.onnx (TopK / mutual / filter applied in numpy to cv2.dnn's matrix by the fixture generator)."""
+    c = np.load(os.path.join(golden_dir, f"cv2dnn_lg_synth_n{n}.npz"))
+    k0, k1, d0, d1, _ = synth.lightglue_inputs(n, 200 + n)
+    fe.debug_read("lg.S")                                    # arms the capture
+    m, ms = fe.match(k0, k1, d0, d1, 480, 640)
+    S = fe.debug_read("lg.S").reshape(n, n)
+    assert np.abs(S[c["S_rows"]] - c["S"]).max() <= 5e-3 * max(1.0, np.abs(c["S"]).max() / 100)
+    r = parity.compare_matches(c["matches"], c["mscores"], m, ms)
+    assert r["only_ref"] == 0 and r["only_tst"] == 0
+
 # ---- SURVEY.md 8(f): descriptor binarisation and L2 projection matching -------------------------------------------
 def test_binarized_descriptors_bit_exact(fe):
     """8(f).1: the sampler's fused sign binarisation equals Frame::binarize_descriptors of the SAME descriptors (bit-exact),
