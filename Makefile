@@ -3,7 +3,13 @@ NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 CSRC := rover_slam_b200/csrc
 NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Iinclude -I$(CSRC) --expt-relaxed-constexpr
-OBJ := $(CSRC)/rover_fe.o $(CSRC)/sp_kernels.o $(CSRC)/lg_kernels.o $(CSRC)/probe_kernels.o $(CSRC)/tensormap.o $(CSRC)/weights.o
+OBJ := $(CSRC)/rover_fe.o $(CSRC)/sp_kernels.o $(CSRC)/lg_kernels.o $(CSRC)/tensormap.o $(CSRC)/weights.o
+# `make PROBES=1` adds the tcgen05 hardware probes (csrc/probe_kernels.cu, rfe_debug_probe) that tools/gpu_probe.py drives;
+# they are measurement scaffolding and stay out of the product library by default.
+ifeq ($(PROBES),1)
+OBJ += $(CSRC)/probe_kernels.o
+NVCCFLAGS += -DRFE_ENABLE_PROBES
+endif
 LIB := rover_slam_b200/librover_fe.so
 
 all: $(LIB)

@@ -51,7 +51,13 @@ typedef struct rfe_config {
   int max_height;           /* largest image height, multiple of 8 (0 = 480) */
   int max_width;            /* largest image width, multiple of 8  (0 = 768) */
   int max_keypoints;        /* per-image keypoint capacity         (0 = 4096) */
+  int flags;                /* RFE_FLAG_* (0 = a ctx that both extracts and matches) */
 } rfe_config;
+/* A runner that only ever extracts (SuperPointOnnxRunner) or only ever matches (LightGlueDecoupleOnnxRunner) skips the other
+ * half's device buffers: the LightGlue state of an 8192-keypoint ctx is ~0.6 GB, the SuperPoint activations of a 1024x1280
+ * ctx ~1.3 GB.  Calls into the disabled half return RFE_ERR_INVALID. */
+#define RFE_FLAG_NO_MATCHER 1
+#define RFE_FLAG_NO_EXTRACTOR 2
 
 int rfe_create(const rfe_config* cfg, rfe_ctx** out);
 void rfe_destroy(rfe_ctx* ctx);
@@ -111,6 +117,14 @@ int rfe_lg_match(rfe_ctx* ctx, const float* kpts0_px, int n0, const float* kpts1
                  const float* desc1, int norm_h, int norm_w, float match_thresh, int32_t* matches, float* mscores,
                  int* k);
 
+/* The same with keypoints the caller has ALREADY normalised -- exactly the tensors the reference feeds its session
+ * (LightGlueDecoupleOnnxRunner::Matcher_Inference takes the output of Matcher_PreProcess / NormalizeKeypoints,
+ * src/Matchers/lightglue_onnx.cpp:162-240 and :241-330; src/Matchers/transform.cpp:19-32).  The device applies no further
+ * normalisation, so the host runner is stateless between Matcher_PreProcess and Matcher_Inference like the reference's. */
+int rfe_lg_match_normalized(rfe_ctx* ctx, const float* kpts0_norm, int n0, const float* kpts1_norm, int n1,
+                            const float* desc0, const float* desc1, float match_thresh, int32_t* matches, float* mscores,
+                            int* k);
+
 /* Match two feature slots left on the device by rfe_sp_extract_device (asynchronous); the result
  * stays on the device in result slot `rslot` (0 .. max_batch-1). */
 int rfe_lg_match_slots(rfe_ctx* ctx, int slot0, int slot1, int norm_h, int norm_w, float match_thresh, int rslot);
@@ -167,8 +181,10 @@ int rfe_debug_read(rfe_ctx* ctx, const char* name, void* dst, size_t capacity, s
 /* Test hook: run one split-fp16 tensor-core GEMM D = A[M,K] * B[N,K]^T (+bias) on host fp32 data. */
 int rfe_debug_gemm(rfe_ctx* ctx, const float* a, const float* b, const float* bias, float* d, int m, int n, int kdim);
 
-/* Test hook: tcgen05 hardware probes used to pin down descriptor semantics (see csrc/probe_kernels.cu). */
+#ifdef RFE_ENABLE_PROBES
+/* Measurement scaffolding, only in a `make PROBES=1` build: tcgen05 hardware probes (csrc/probe_kernels.cu). */
 int rfe_debug_probe(rfe_ctx* ctx, int which, const float* a, const float* b, float* out);
+#endif
 
 #ifdef __cplusplus
 }

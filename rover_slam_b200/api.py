@@ -27,7 +27,9 @@ def lib_path() -> str:
 class _Config(C.Structure):
     _fields_ = [("device", C.c_int), ("stream", C.c_void_p), ("weights_path", C.c_char_p),
                 ("max_batch", C.c_int), ("max_height", C.c_int), ("max_width", C.c_int),
-                ("max_keypoints", C.c_int)]
+                ("max_keypoints", C.c_int), ("flags", C.c_int)]
+
+RFE_FLAG_NO_MATCHER, RFE_FLAG_NO_EXTRACTOR = 1, 2
 
 
 _lib = None
@@ -37,6 +39,7 @@ def exported_symbols() -> list:
     """Every function include/rover_fe.h declares (parsed from the header)."""
     with open(os.path.join(ROOT, "include", "rover_fe.h")) as f:
         src = f.read()
+    src = re.sub(r"#ifdef RFE_ENABLE_PROBES.*?#endif", "", src, flags=re.S)      # probe builds only (make PROBES=1)
     return sorted(set(re.findall(r"\b(rfe_[a-z0-9_]+)\s*\(", src)))
 
 
@@ -64,6 +67,7 @@ def load_library():
     lib.rfe_binarize_descriptors.argtypes = [vp, vp, ci, vp, vp]
     lib.rfe_l2_best2.argtypes = [vp, vp, ci, vp, ci, vp, vp, cf, vp, vp, vp, vp]
     lib.rfe_lg_match.argtypes = [vp, vp, ci, vp, ci, vp, vp, ci, ci, cf, vp, vp, vp]
+    lib.rfe_lg_match_normalized.argtypes = [vp, vp, ci, vp, ci, vp, vp, cf, vp, vp, vp]
     lib.rfe_lg_match_slots.argtypes = [vp, ci, ci, ci, ci, cf, ci]
     lib.rfe_lg_match_slots_batch.argtypes = [vp, ci, vp, vp, ci, ci, cf]
     lib.rfe_match_pairs_u8.argtypes = [vp, vp, ci, ci, ci, ci, cf, vp, vp, vp, vp, vp, ci]
@@ -82,7 +86,8 @@ def load_library():
     lib.rfe_profile_read.argtypes = [vp, C.c_char_p, P(C.c_double), P(C.c_longlong), ci]
     lib.rfe_debug_read.argtypes = [vp, C.c_char_p, vp, C.c_size_t, P(C.c_size_t)]
     lib.rfe_debug_gemm.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci]
-    lib.rfe_debug_probe.argtypes = [vp, ci, vp, vp, vp]
+    if hasattr(lib, "rfe_debug_probe"):
+        lib.rfe_debug_probe.argtypes = [vp, ci, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -95,10 +100,10 @@ class FrontEnd:
     """One rfe_ctx.  Mirrors what the reference's SuperPointOnnxRunner + LightGlueDecoupleOnnxRunner pair does."""
 
     def __init__(self, device: int = 0, stream: int | None = None, weights: str | None = None, max_batch: int = 8,
-                 max_height: int = 480, max_width: int = 768, max_keypoints: int = 4096):
+                 max_height: int = 480, max_width: int = 768, max_keypoints: int = 4096, flags: int = 0):
         self.lib = load_library()
         weights = weights or os.environ.get("ROVER_FE_WEIGHTS") or os.path.join(ROOT, "weights", "rover_fe.rfw")
-        cfg = _Config(device, stream, weights.encode(), max_batch, max_height, max_width, max_keypoints)
+        cfg = _Config(device, stream, weights.encode(), max_batch, max_height, max_width, max_keypoints, flags)
         h = C.c_void_p()
         self.ctx = None
         self._check(self.lib.rfe_create(C.byref(cfg), C.byref(h)))
@@ -216,6 +221,21 @@ class FrontEnd:
         k = C.c_int(0)
         self._check(self.lib.rfe_lg_match(self.ctx, _ptr(k0), n0, _ptr(k1), n1, _ptr(d0), _ptr(d1), norm_h, norm_w,
                                           thresh, _ptr(m), _ptr(s), C.byref(k)))
+        return m[:k.value].copy(), s[:k.value].copy()
+
+    def match_normalized(self, kn0, kn1, desc0, desc1, thresh: float = 0.0):
+        """Keypoints already normalised by the caller (NormalizeKeypoints, transform.cpp:19-32): what the reference's
+        Matcher_Inference receives."""
+        k0 = np.ascontiguousarray(kn0, np.float32).reshape(-1, 2)
+        k1 = np.ascontiguousarray(kn1, np.float32).reshape(-1, 2)
+        d0 = np.ascontiguousarray(desc0, np.float32).reshape(-1, DESC_DIM)
+        d1 = np.ascontiguousarray(desc1, np.float32).reshape(-1, DESC_DIM)
+        n0, n1 = len(k0), len(k1)
+        m = np.empty((max(n0, 1), 2), np.int32)
+        s = np.empty(max(n0, 1), np.float32)
+        k = C.c_int(0)
+        self._check(self.lib.rfe_lg_match_normalized(self.ctx, _ptr(k0), n0, _ptr(k1), n1, _ptr(d0), _ptr(d1), thresh,
+                                                     _ptr(m), _ptr(s), C.byref(k)))
         return m[:k.value].copy(), s[:k.value].copy()
 
     def match_slots(self, slot0: int, slot1: int, norm_h: int, norm_w: int, thresh: float = 0.0, rslot: int = 0):

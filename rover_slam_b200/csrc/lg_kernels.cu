@@ -352,7 +352,26 @@ __global__ void __launch_bounds__(256) lg_prepare_kernel(const LgImages im, floa
   const int img = blockIdx.y;
   const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (k >= im.n[img]) return;
+  const int n = im.n[img];
+  if (k >= ((n + 7) & ~7)) return;
+  if (k >= n) {
+    // Padding rows (every image starts at a multiple of 8 rows): every GEMM and FFN runs over them, and the last key tile
+    // of the attention kernel loads their K / V^T columns (with P = 0).  Left uninitialised they would carry their state
+    // from call to call through 18 more residual updates each time and eventually overflow the fp16 planes
+    // (0 * inf = NaN for every query of the image): reset them to zero on every call.
+    const size_t row = static_cast<size_t>(im.row0[img]) + k;
+    cs[row * 32 + lane] = 0.0f;
+    sn[row * 32 + lane] = 0.0f;
+    const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4* x4 = reinterpret_cast<float4*>(x + row * 256);
+    x4[lane] = z4;
+    x4[32 + lane] = z4;
+    *reinterpret_cast<uint2*>(cat_hi + row * 512 + 4 * lane) = make_uint2(0u, 0u);
+    *reinterpret_cast<uint2*>(cat_lo + row * 512 + 4 * lane) = make_uint2(0u, 0u);
+    *reinterpret_cast<uint2*>(cat_hi + row * 512 + 128 + 4 * lane) = make_uint2(0u, 0u);
+    *reinterpret_cast<uint2*>(cat_lo + row * 512 + 128 + 4 * lane) = make_uint2(0u, 0u);
+    return;
+  }
   float px, py;
   if (im.kpts_i[img]) {
     px = static_cast<float>(im.kpts_i[img][2 * k]);
@@ -385,8 +404,10 @@ __global__ void __launch_bounds__(256) lg_prepare_kernel(const LgImages im, floa
 void launch_lg_prepare(cudaStream_t s, const LgImages& im, int max_n, int norm_h, int norm_w, const float* wr, float* cs,
                        float* sn, float* x, __half* cat_hi, __half* cat_lo) {
   if (im.count == 0 || max_n == 0) return;
-  const float sx = static_cast<float>(norm_w) / 2.0f, sy = static_cast<float>(norm_h) / 2.0f;
-  const float sc = static_cast<float>(norm_w > norm_h ? norm_w : norm_h) / 2.0f;
+  // norm_h = norm_w = 0: the keypoints are ALREADY normalised by the caller (rfe_lg_match_normalized): (k - 0) / 1 is exact
+  const bool ident = norm_h <= 0 || norm_w <= 0;
+  const float sx = ident ? 0.0f : static_cast<float>(norm_w) / 2.0f, sy = ident ? 0.0f : static_cast<float>(norm_h) / 2.0f;
+  const float sc = ident ? 1.0f : static_cast<float>(norm_w > norm_h ? norm_w : norm_h) / 2.0f;
   lg_prepare_kernel<<<dim3((max_n + 7) / 8, im.count), 256, 0, s>>>(im, sx, sy, sc, wr, cs, sn, x, cat_hi, cat_lo);
 }
 

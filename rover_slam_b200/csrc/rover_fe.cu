@@ -49,6 +49,7 @@ struct rfe_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int max_batch = 8, max_h = 480, max_w = 768, cap = 4096;
+  bool no_sp = false, no_lg = false;     // RFE_FLAG_NO_EXTRACTOR / RFE_FLAG_NO_MATCHER
   std::vector<void*> allocs;
   long long launches = 0;
   double timer_extract_ms = 0.0, timer_match_ms = 0.0;
@@ -203,6 +204,7 @@ int load_weights(rfe_ctx* c, const char* path) {
   WeightBlob blob;
   if (blob.load(path)) return RFE_ERR_IO;
   int r;
+  if (!c->no_sp) {     // a matcher-only ctx (RFE_FLAG_NO_EXTRACTOR) uploads no SuperPoint weights, and vice versa
   if ((r = load_vec(c, blob, "sp.conv1a.w", &c->conv1a_w))) return r;
   if ((r = load_vec(c, blob, "sp.conv1a.b", &c->conv1a_b))) return r;
   struct { const char* n; SplitW* w; } convs[] = {
@@ -211,6 +213,8 @@ int load_weights(rfe_ctx* c, const char* path) {
       {"sp.convPb", &c->cPb}, {"sp.convDa", &c->cDa}, {"sp.convDb", &c->cDb}};
   for (auto& e : convs)
     if ((r = load_linear(c, blob, e.n, e.w))) return r;   // OHWI flattens to [Cout][9*Cin]
+  }
+  if (c->no_lg) return RFE_OK;
   if ((r = load_vec(c, blob, "lg.posenc.w", &c->posenc_w))) return r;
   // Wqkv rows: ONNX column c = h*192 + d*3 + t  ->  ours t*256 + h*64 + d
   std::vector<int> perm(768);
@@ -458,6 +462,10 @@ int conv64_strip(rfe_ctx* c, const char* tag, const SplitBuf& in, int B, int H, 
 int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B, int slot_base = 0) {
   cudaStream_t s = c->stream;
   int r;
+  if (c->no_sp) {
+    set_error("this ctx was created with RFE_FLAG_NO_EXTRACTOR");
+    return RFE_ERR_INVALID;
+  }
   { ProfScope ps_(c, "sp.conv1a"); launch_conv1a(s, d_gray, stride, h, w, B, c->conv1a_w, c->conv1a_b, c->a1a.hi, c->a1a.lo); }
   c->launches++;
   if (c->use_strip_conv) {
@@ -609,6 +617,10 @@ struct PairDesc {      // one LightGlue problem: device-resident pixel keypoints
 int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm_w, float thresh) {
   cudaStream_t s = c->stream;
   int r;
+  if (c->no_lg) {
+    set_error("this ctx was created with RFE_FLAG_NO_MATCHER");
+    return RFE_ERR_INVALID;
+  }
   PairDesc pairs[kMaxPairs];
   int off0[kMaxPairs], off1[kMaxPairs];
   int np = 0, rows = 0;
@@ -807,12 +819,14 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
 }
 
 }  // namespace
+#ifdef RFE_ENABLE_PROBES
 namespace rfe {
 int launch_probe_shift(cudaStream_t s, const __half* a, const __half* b, float* out);
 int launch_probe_mma_rate(cudaStream_t s, float* out, int reps);
 int launch_probe_ts(cudaStream_t s, const __half* a, const __half* b, float* out, int reps);
 int launch_probe_softmax_role(cudaStream_t s, float* out, int reps);
 }
+#endif
 namespace {
 
 int check_ctx(rfe_ctx* c) {
@@ -868,19 +882,32 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   c->max_h = cfg->max_height > 0 ? cfg->max_height : 480;
   c->max_w = cfg->max_width > 0 ? cfg->max_width : 768;
   c->cap = cfg->max_keypoints > 0 ? cfg->max_keypoints : 4096;
+  c->no_sp = (cfg->flags & RFE_FLAG_NO_EXTRACTOR) != 0;
+  c->no_lg = (cfg->flags & RFE_FLAG_NO_MATCHER) != 0;
+  if (c->no_sp) c->max_h = c->max_w = 8;      // the activation buffers shrink to nothing; the feature slots stay (rfe_sp_write_slot)
   if (c->max_h % 8 || c->max_w % 8) {
     set_error("max_height/max_width must be multiples of 8");
     delete c;
     return RFE_ERR_INVALID;
   }
+  // every failure below releases what was built so far
+#define C_(expr)                                                                                  \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));            \
+      rfe_destroy(c);                                                                             \
+      return RFE_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
   if (cfg->stream) {
     c->stream = static_cast<cudaStream_t>(cfg->stream);
   } else {
-    RFE_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    C_(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
   }
-  RFE_CUDA_CHECK(cudaEventCreate(&c->ev0));
-  RFE_CUDA_CHECK(cudaEventCreate(&c->ev1));
+  C_(cudaEventCreate(&c->ev0));
+  C_(cudaEventCreate(&c->ev1));
   c->prof_tag = getenv("RFE_PROF_TAG");
   if (getenv("RFE_CONV_STRIP")) c->use_strip_conv = atoi(getenv("RFE_CONV_STRIP")) != 0;
   const char* path = cfg->weights_path;
@@ -921,18 +948,20 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   A_(dev_alloc(c, &c->kp_scores, 2 * B * cap));
   A_(dev_alloc(c, &c->desc, 2 * B * cap * 256));
   A_(dev_alloc(c, &c->desc_bin, 2 * B * cap * 256));
-  RFE_CUDA_CHECK(cudaMallocHost(&c->h_counts, sizeof(int) * (2 * B + 2)));
-  RFE_CUDA_CHECK(cudaMallocHost(&c->h_counts2, sizeof(int) * 2 * B));
-  RFE_CUDA_CHECK(cudaMallocHost(&c->h_mcounts, sizeof(int) * B));
-  RFE_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_counts[0], cudaEventDisableTiming));
-  RFE_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_counts[1], cudaEventDisableTiming));
-  RFE_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+  C_(cudaMallocHost(&c->h_counts, sizeof(int) * (2 * B + 2)));
+  C_(cudaMallocHost(&c->h_counts2, sizeof(int) * 2 * B));
+  C_(cudaMallocHost(&c->h_mcounts, sizeof(int) * B));
+  C_(cudaEventCreateWithFlags(&c->ev_counts[0], cudaEventDisableTiming));
+  C_(cudaEventCreateWithFlags(&c->ev_counts[1], cudaEventDisableTiming));
+  C_(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
   // ---- LightGlue buffers ----
   c->lg_pairs = c->max_batch < kMaxPairs ? c->max_batch : kMaxPairs;   // pairs per rfe_lg_match_slots_batch
+  if (c->no_lg) c->lg_pairs = 0;
   c->lg_rows = 2 * c->lg_pairs * (c->cap + 8);
   c->lg_ld = round_up(c->cap, 8);
   c->lg_ldv = round_up(c->lg_rows, 8);
   const size_t R = c->lg_rows, LD = c->lg_ld;
+  if (!c->no_lg) {
   A_(dev_alloc(c, &c->in_kpts, R * 2));
   A_(dev_alloc(c, &c->in_desc, R * 256));
   A_(dev_alloc(c, &c->cs, R * 32));
@@ -955,11 +984,13 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   A_(dev_alloc(c, &c->max0, R));
   A_(dev_alloc(c, &c->m0, R));
   A_(dev_alloc(c, &c->m1, R));
+  }
   A_(dev_alloc(c, &c->res_matches, B * cap * 2));
   A_(dev_alloc(c, &c->res_scores, B * cap));
   A_(dev_alloc(c, &c->res_count, B));
 #undef A_
-  RFE_CUDA_CHECK(cudaDeviceSynchronize());
+  C_(cudaDeviceSynchronize());
+#undef C_
   *out = c;
   return RFE_OK;
 }
@@ -1093,14 +1124,26 @@ int rfe_sp_read_slot_bin(rfe_ctx* c, int slot, uint8_t* bin, int32_t* count, int
 // scratch device buffer of the ctx, grown on demand (host-in / host-out helpers below)
 static int scratch(rfe_ctx* c, void** p, size_t* have, size_t need) {
   if (*have >= need) return RFE_OK;
+  // per-frame callers (rfe_l2_best2, rfe_binarize_descriptors) see sizes that drift upward with the local map: grow
+  // geometrically and release the old buffer (it may still be read by work in flight on the stream: synchronise first)
+  const size_t want = need > 2 * *have ? need : 2 * *have;
   void* d = nullptr;
-  if (cudaMalloc(&d, need) != cudaSuccess) {
-    set_error("cudaMalloc(%zu bytes) failed", need);
+  if (cudaMalloc(&d, want) != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes) failed", want);
     return RFE_ERR_CUDA;
   }
-  c->allocs.push_back(d);      // the old buffer is released with the ctx
+  if (*p) {
+    cudaStreamSynchronize(c->stream);
+    for (size_t i = 0; i < c->allocs.size(); ++i)
+      if (c->allocs[i] == *p) {
+        c->allocs.erase(c->allocs.begin() + i);
+        break;
+      }
+    cudaFree(*p);
+  }
+  c->allocs.push_back(d);
   *p = d;
-  *have = need;
+  *have = want;
   return RFE_OK;
 }
 
@@ -1297,9 +1340,7 @@ int rfe_pairs_collect_begin(rfe_ctx* c, float thresh, int32_t* kpts_xy, int32_t*
     set_error("rfe_pairs_collect_begin: nothing was submitted, or the previous collect was not ended");
     return RFE_ERR_INVALID;
   }
-  const rfe_ctx::Pending pd0 = c->pending[0];
-  c->pending[0] = c->pending[1];
-  --c->n_pending;
+  const rfe_ctx::Pending pd0 = c->pending[0];     // dequeued below, once the matcher has been enqueued successfully
   cudaStream_t s = c->stream;
   const int B = 2 * pd0.n_pairs, base = pd0.set * c->max_batch;
   // the keypoint counts size the LightGlue launches: wait for THIS batch's SuperPoint only -- a batch submitted after it
@@ -1315,7 +1356,9 @@ int rfe_pairs_collect_begin(rfe_ctx* c, float thresh, int32_t* kpts_xy, int32_t*
     pd[i] = PairDesc{nullptr, nullptr, c->kpts + static_cast<size_t>(s0) * c->cap * 2, c->kpts + static_cast<size_t>(s1) * c->cap * 2,
                      c->desc + static_cast<size_t>(s0) * c->cap * 256, c->desc + static_cast<size_t>(s1) * c->cap * 256, n0, n1, i};
   }
-  if ((r = lg_run(c, pd, pd0.n_pairs, pd0.h, pd0.w, thresh))) return r;
+  if ((r = lg_run(c, pd, pd0.n_pairs, pd0.h, pd0.w, thresh))) return r;   // the batch stays queued: collect can be retried
+  c->pending[0] = c->pending[1];
+  --c->n_pending;
   // Results go back in as few copies as possible (a small device-to-host copy costs ~10 us of stream time, and a batch
   // has 3 arrays per pair): when the caller's capacity equals the ctx capacity the slot arrays are copied whole.
   const bool bulk = (cap == c->cap);
@@ -1447,16 +1490,17 @@ int rfe_lg_read_result(rfe_ctx* c, int rslot, int32_t* matches, float* mscores, 
   return RFE_OK;
 }
 
-int rfe_lg_match(rfe_ctx* c, const float* kpts0, int n0, const float* kpts1, int n1, const float* desc0,
-                 const float* desc1, int norm_h, int norm_w, float thresh, int32_t* matches, float* mscores, int* k) {
+static int lg_match_host(rfe_ctx* c, const char* who, const float* kpts0, int n0, const float* kpts1, int n1,
+                         const float* desc0, const float* desc1, int norm_h, int norm_w, float thresh, int32_t* matches,
+                         float* mscores, int* k) {
   int r = check_ctx(c);
   if (r) return r;
-  if (!k || n0 < 0 || n1 < 0 || (n0 > 0 && (!kpts0 || !desc0)) || (n1 > 0 && (!kpts1 || !desc1)) || norm_h <= 0 || norm_w <= 0) {
-    set_error("rfe_lg_match: null/invalid argument");
+  if (!k || n0 < 0 || n1 < 0 || (n0 > 0 && (!kpts0 || !desc0)) || (n1 > 0 && (!kpts1 || !desc1))) {
+    set_error("%s: null/invalid argument", who);
     return RFE_ERR_INVALID;
   }
   if (n0 > c->cap || n1 > c->cap) {
-    set_error("rfe_lg_match: %d/%d keypoints exceed the ctx capacity %d", n0, n1, c->cap);
+    set_error("%s: %d/%d keypoints exceed the ctx capacity %d", who, n0, n1, c->cap);
     return RFE_ERR_CAPACITY;
   }
   *k = 0;
@@ -1478,6 +1522,20 @@ int rfe_lg_match(rfe_ctx* c, const float* kpts0, int n0, const float* kpts1, int
   cudaEventElapsedTime(&ms, c->ev0, c->ev1);
   c->timer_match_ms += ms;
   return r;
+}
+
+int rfe_lg_match(rfe_ctx* c, const float* kpts0, int n0, const float* kpts1, int n1, const float* desc0,
+                 const float* desc1, int norm_h, int norm_w, float thresh, int32_t* matches, float* mscores, int* k) {
+  if (norm_h <= 0 || norm_w <= 0) {
+    set_error("rfe_lg_match: norm_h / norm_w must be positive");
+    return RFE_ERR_INVALID;
+  }
+  return lg_match_host(c, "rfe_lg_match", kpts0, n0, kpts1, n1, desc0, desc1, norm_h, norm_w, thresh, matches, mscores, k);
+}
+
+int rfe_lg_match_normalized(rfe_ctx* c, const float* kn0, int n0, const float* kn1, int n1, const float* desc0,
+                            const float* desc1, float thresh, int32_t* matches, float* mscores, int* k) {
+  return lg_match_host(c, "rfe_lg_match_normalized", kn0, n0, kn1, n1, desc0, desc1, 0, 0, thresh, matches, mscores, k);
 }
 
 double rfe_get_timer_ms(rfe_ctx* c, const char* name) {
@@ -1651,6 +1709,7 @@ int rfe_debug_gemm(rfe_ctx* c, const float* a, const float* b, const float* bias
 }
 
 
+#ifdef RFE_ENABLE_PROBES
 // Hardware probe 0 (see probe_kernels.cu): a [136][64], b [64][64] fp32 in (rounded to fp16), out [9][3][128][64] fp32.
 int rfe_debug_probe(rfe_ctx* c, int which, const float* a, const float* b, float* out) {
   int r = check_ctx(c);
@@ -1725,5 +1784,6 @@ int rfe_debug_probe(rfe_ctx* c, int which, const float* a, const float* b, float
   cudaFree(da); cudaFree(db); cudaFree(dout);
   return RFE_OK;
 }
+#endif  // RFE_ENABLE_PROBES
 
 }  // extern "C"

@@ -16,6 +16,11 @@ int WeightBlob::load(const char* path) {
   fseek(f, 0, SEEK_END);
   const long sz = ftell(f);
   fseek(f, 0, SEEK_SET);
+  if (sz < 16) {                       // also a failing ftell (-1): never resize((size_t)-1) across the C ABI
+    fclose(f);
+    set_error("'%s' is not an RFW1 weight blob (size %ld)", path, sz);
+    return 1;
+  }
   buf_.resize(static_cast<size_t>(sz));
   const size_t rd = fread(buf_.data(), 1, buf_.size(), f);
   fclose(f);
@@ -40,12 +45,20 @@ int WeightBlob::load(const char* path) {
     memcpy(d, e + 84, 16);
     memcpy(&off, e + 100, 8);
     memcpy(&nb, e + 108, 8);
-    if (nd > 4 || off + nb > buf_.size()) {
+    if (nd > 4 || off > buf_.size() || nb > buf_.size() - off || (off & 3)) {    // overflow-safe bounds
       set_error("'%s': bad entry %s", path, name);
       return 1;
     }
     HostTensor t;
-    for (uint32_t k = 0; k < nd; ++k) t.dims.push_back(static_cast<int>(d[k]));
+    bool zero_dim = false;
+    for (uint32_t k = 0; k < nd; ++k) {
+      t.dims.push_back(static_cast<int>(d[k]));
+      zero_dim |= d[k] == 0 || d[k] > 0x7fffffffu;
+    }
+    if (zero_dim) {
+      set_error("'%s': zero / oversized dimension in %s", path, name);
+      return 1;
+    }
     t.data = reinterpret_cast<const float*>(buf_.data() + off);
     if (t.size() * 4 != nb) {
       set_error("'%s': size mismatch in %s", path, name);

@@ -32,17 +32,20 @@ class SuperPointOnnxRunner {
   static float AdaptiveThreshold(const float* scores, int n, float lastmatch);
   std::vector<float> scales = {1.0f, 1.0f};
   std::vector<SuperPointResult> extractor_outputtensors;
+  std::pair<std::vector<cv::Point2f>, std::vector<cv::Point2f>> keypoints_result;           // superpoint_onnx.h:38
 
   explicit SuperPointOnnxRunner(unsigned int num_threads = 1);
   ~SuperPointOnnxRunner();
 
   int InitOrtEnv(Configuration cfg);                                               // superpoint_onnx.cc:4-66
+  cv::Mat Extractor_PreProcess(Configuration cfg, const cv::Mat& Image, float& scale);    // superpoint_onnx.cc:68-86 (dead in the reference)
   int Extractor_Inference(Configuration cfg, const cv::Mat& image);                // superpoint_onnx.cc:88-162 (CV_32F [0,1] or CV_8UC1)
   void Extractor_PostProcess(Configuration cfg, SuperPointResult tensor, std::vector<cv::KeyPoint>& vKeyPoints,
                              cv::Mat& Descriptors);                                // superpoint_onnx.cc:165-255
   float GetMatchThresh();
   void SetMatchThresh(float thresh);
   double GetTimer(std::string name);                                               // superpoint_onnx.cc:268-277
+  std::pair<std::vector<cv::Point2f>, std::vector<cv::Point2f>> GetKeypointsResult();   // superpoint_onnx.cc:279-282
   // SURVEY.md 8(f).1 -- the DBoW3 feed.  Frame::binarize_descriptors (Frame.cc:1034-1043) thresholds mDescriptors at 0
   // into a CV_8UC1 N x 256 matrix on every ComputeBoW3; the extractor already produced that matrix on the GPU.
   int BinarizeLast(cv::Mat& bin);                             // descriptors of the last Extractor_Inference

@@ -25,8 +25,7 @@ class Frame;
 
 class SPmatcher {
  public:
-  SPmatcher(float thre);
-  ~SPmatcher();
+  SPmatcher(float thre);        // no destructor, like the reference's header (SPmatcher.h:44-142): featureMatcher lives as long as the process
   int MatchingPoints_onnx(Frame& f1, Frame& f2, std::vector<int>& vnMatches12);
   int MatchingPoints_onnx(std::vector<cv::KeyPoint> kpts0, const std::vector<cv::KeyPoint> kpts1, cv::Mat desc0,
                           const cv::Mat desc1, std::vector<int>& vnMatches12);

@@ -89,6 +89,38 @@ class Mat {
   std::shared_ptr<uint8_t> buf_;
 };
 
+enum ColorConversionCodes { COLOR_BGR2RGB = 4, COLOR_RGB2GRAY = 7 };
+// the two conversions transform.cpp uses; RGB2GRAY with OpenCV's weights (0.299, 0.587, 0.114)
+inline void cvtColor(const Mat& src, Mat& dst, int code) {
+  if (src.channels() != 3) throw std::invalid_argument("shim cvtColor: 3-channel input expected");
+  const bool f32 = src.depth() == CV_32F;
+  if (code == COLOR_BGR2RGB) {
+    Mat out(src.rows, src.cols, src.type());
+    for (int r = 0; r < src.rows; ++r)
+      for (int c = 0; c < src.cols; ++c)
+        for (int k = 0; k < 3; ++k) {
+          if (f32) out.ptr<float>(r)[3 * c + k] = src.ptr<float>(r)[3 * c + 2 - k];
+          else out.ptr<uint8_t>(r)[3 * c + k] = src.ptr<uint8_t>(r)[3 * c + 2 - k];
+        }
+    dst = out;
+  } else if (code == COLOR_RGB2GRAY) {
+    Mat out(src.rows, src.cols, CV_MAKETYPE(src.depth(), 1));
+    for (int r = 0; r < src.rows; ++r)
+      for (int c = 0; c < src.cols; ++c) {
+        if (f32) {
+          const float* p = src.ptr<float>(r) + 3 * c;
+          out.ptr<float>(r)[c] = p[0] * 0.299f + p[1] * 0.587f + p[2] * 0.114f;
+        } else {
+          const uint8_t* p = src.ptr<uint8_t>(r) + 3 * c;
+          out.ptr<uint8_t>(r)[c] = static_cast<uint8_t>((p[0] * 4899 + p[1] * 9617 + p[2] * 1868 + 8192) >> 14);
+        }
+      }
+    dst = out;
+  } else {
+    throw std::invalid_argument("shim cvtColor: unsupported code");
+  }
+}
+
 class _InputArray {
  public:
   _InputArray(const Mat& m) : m_(m) {}

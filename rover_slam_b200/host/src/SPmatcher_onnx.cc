@@ -27,8 +27,6 @@ SPmatcher::SPmatcher(float thre) {
   featureMatcher->SetMatchThresh(thre);
 }
 
-SPmatcher::~SPmatcher() { delete featureMatcher; }
-
 namespace {
 // contiguous [rows][cols] copy of a CV_32F descriptor matrix (the reference copies into a leaked new float[])
 std::vector<float> flatten(const cv::Mat& m) {

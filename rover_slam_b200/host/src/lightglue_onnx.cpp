@@ -23,6 +23,7 @@ int LightGlueDecoupleOnnxRunner::InitOrtEnv(Configuration cfg) {
   rc.max_height = 8;     // the matcher ctx does not extract: keep the SuperPoint buffers minimal
   rc.max_width = 8;
   rc.max_keypoints = cap_;
+  rc.flags = RFE_FLAG_NO_EXTRACTOR;       // a matcher never extracts: no SuperPoint weights or activation buffers
   if (rfe_create(&rc, &ctx_) != RFE_OK) {
     std::cerr << "[ERROR] rover_fe matcher init failed : " << rfe_last_error() << std::endl;
     ctx_ = nullptr;
@@ -31,17 +32,10 @@ int LightGlueDecoupleOnnxRunner::InitOrtEnv(Configuration cfg) {
   return EXIT_SUCCESS;
 }
 
-namespace {
-int g_norm_h = 0, g_norm_w = 0;   // remembered per thread: Matcher_PreProcess(h, w) precedes Matcher_Inference
-thread_local int t_norm_h = 0, t_norm_w = 0;
-thread_local std::vector<cv::Point2f> t_px0, t_px1;
-thread_local int t_which = 0;
-}  // namespace
-
+// Matcher_PreProcess is the reference's pure function (lightglue_onnx.cpp:140-159): it only normalises.  Nothing is remembered
+// between it and Matcher_Inference: the runner hands the NORMALISED keypoints to the device (rfe_lg_match_normalized), which
+// is exactly the tensor the reference feeds its session, so any interleaving of the two calls behaves like the reference.
 std::vector<cv::Point2f> LightGlueDecoupleOnnxRunner::Matcher_PreProcess(std::vector<cv::Point2f> kpts, int h, int w) {
-  t_norm_h = h;
-  t_norm_w = w;
-  (t_which++ % 2 == 0 ? t_px0 : t_px1) = kpts;     // keep the pixel coordinates: the device normalises them itself
   return NormalizeKeypoints(kpts, h, w);
 }
 
@@ -49,40 +43,25 @@ std::vector<cv::Point2f> LightGlueDecoupleOnnxRunner::Matcher_PreProcess(std::ve
   std::vector<cv::Point2f> pf;
   pf.reserve(kpts.size());
   for (const cv::KeyPoint& k : kpts) pf.emplace_back(k.pt);
-  return Matcher_PreProcess(pf, h, w);
+  return NormalizeKeypoints(pf, h, w);
 }
 
-LightGlueResult LightGlueDecoupleOnnxRunner::Matcher_Inference(std::vector<cv::Point2f> kpts0, std::vector<cv::Point2f> kpts1,
-                                                               float* desc0, float* desc1) {
+LightGlueResult LightGlueDecoupleOnnxRunner::RunNormalized(const std::vector<float>& k0, const std::vector<float>& k1,
+                                                           float* desc0, float* desc1) {
   LightGlueResult out;
-  (void)g_norm_h; (void)g_norm_w;
-  if (!ctx_ || t_norm_h <= 0 || t_norm_w <= 0) {
+  if (!ctx_) {
     std::cerr << "[ERROR] LightGlueDecoupleOnnxRunner Matcher inference failed : not initialised" << std::endl;
     return out;
   }
-  // Recover pixel coordinates: prefer the ones remembered by Matcher_PreProcess (exact); otherwise invert
-  // (kpt - shift) / scale.
-  auto to_px = [&](const std::vector<cv::Point2f>& nk, const std::vector<cv::Point2f>& px) {
-    std::vector<float> v(nk.size() * 2);
-    if (px.size() == nk.size()) {
-      for (size_t i = 0; i < nk.size(); ++i) { v[2 * i] = px[i].x; v[2 * i + 1] = px[i].y; }
-    } else {
-      const float sx = static_cast<float>(t_norm_w) / 2, sy = static_cast<float>(t_norm_h) / 2;
-      const float sc = static_cast<float>(std::max(t_norm_w, t_norm_h)) / 2;
-      for (size_t i = 0; i < nk.size(); ++i) { v[2 * i] = nk[i].x * sc + sx; v[2 * i + 1] = nk[i].y * sc + sy; }
-    }
-    return v;
-  };
-  const std::vector<float> p0 = to_px(kpts0, t_px0), p1 = to_px(kpts1, t_px1);
-  const int n0 = static_cast<int>(kpts0.size()), n1 = static_cast<int>(kpts1.size());
+  const int n0 = static_cast<int>(k0.size() / 2), n1 = static_cast<int>(k1.size() / 2);
   out.matches.resize(static_cast<size_t>(std::max(n0, 1)) * 2);
   out.mscores.resize(std::max(n0, 1));
   int k = 0;
   auto t0 = std::chrono::high_resolution_clock::now();
   // threshold 0 here: the graph's own 0.1 filter applies; matchThresh is applied in Matcher_PostProcess_fused,
   // exactly where the reference applies it (lightglue_onnx.cpp:437-453)
-  const int rc = rfe_lg_match(ctx_, p0.data(), n0, p1.data(), n1, desc0, desc1, t_norm_h, t_norm_w, 0.0f,
-                              out.matches.data(), out.mscores.data(), &k);
+  const int rc = rfe_lg_match_normalized(ctx_, k0.data(), n0, k1.data(), n1, desc0, desc1, 0.0f, out.matches.data(),
+                                         out.mscores.data(), &k);
   auto t1 = std::chrono::high_resolution_clock::now();
   matcher_timer += std::chrono::duration_cast<std::chrono::milliseconds>(t1 - t0).count();
   if (rc != RFE_OK) {
@@ -92,6 +71,25 @@ LightGlueResult LightGlueDecoupleOnnxRunner::Matcher_Inference(std::vector<cv::P
   out.count = k;
   out.ok = true;
   return out;
+}
+
+// kpts: the output of Matcher_PreProcess (normalised), as in the reference (lightglue_onnx.cpp:162-240)
+LightGlueResult LightGlueDecoupleOnnxRunner::Matcher_Inference(std::vector<cv::Point2f> kpts0, std::vector<cv::Point2f> kpts1,
+                                                               float* desc0, float* desc1) {
+  std::vector<float> k0(kpts0.size() * 2), k1(kpts1.size() * 2);
+  for (size_t i = 0; i < kpts0.size(); ++i) { k0[2 * i] = kpts0[i].x; k0[2 * i + 1] = kpts0[i].y; }
+  for (size_t i = 0; i < kpts1.size(); ++i) { k1[2 * i] = kpts1[i].x; k1[2 * i + 1] = kpts1[i].y; }
+  return RunNormalized(k0, k1, desc0, desc1);
+}
+
+// The KeyPoint twin feeds kpts[i].pt to the session AS IS (lightglue_onnx.cpp:241-330, :268-275): no normalisation
+// happens inside; the caller is expected to have done it.  Reproduced.
+LightGlueResult LightGlueDecoupleOnnxRunner::Matcher_Inference(std::vector<cv::KeyPoint> kpts0, std::vector<cv::KeyPoint> kpts1,
+                                                               float* desc0, float* desc1) {
+  std::vector<float> k0(kpts0.size() * 2), k1(kpts1.size() * 2);
+  for (size_t i = 0; i < kpts0.size(); ++i) { k0[2 * i] = kpts0[i].pt.x; k0[2 * i + 1] = kpts0[i].pt.y; }
+  for (size_t i = 0; i < kpts1.size(); ++i) { k1[2 * i] = kpts1[i].pt.x; k1[2 * i + 1] = kpts1[i].pt.y; }
+  return RunNormalized(k0, k1, desc0, desc1);
 }
 
 int LightGlueDecoupleOnnxRunner::Matcher_PostProcess_fused(LightGlueResult& output, std::vector<cv::Point2f> kpts0,
@@ -113,6 +111,9 @@ int LightGlueDecoupleOnnxRunner::Matcher_PostProcess_fused(LightGlueResult& outp
 
 float LightGlueDecoupleOnnxRunner::GetMatchThresh() { return matchThresh; }
 void LightGlueDecoupleOnnxRunner::SetMatchThresh(float thresh) { matchThresh = thresh; }
+std::pair<std::vector<cv::Point2f>, std::vector<cv::Point2f>> LightGlueDecoupleOnnxRunner::GetKeypointsResult() {
+  return keypoints_result;                 // lightglue_onnx.cpp:505-508
+}
 double LightGlueDecoupleOnnxRunner::GetTimer(std::string name) {
   if (name == "extractor") return static_cast<double>(extractor_timer);
   return static_cast<double>(matcher_timer);

@@ -27,12 +27,23 @@ int SuperPointOnnxRunner::InitOrtEnv(Configuration cfg) {
   rc.max_height = 1024;
   rc.max_width = 1280;
   rc.max_keypoints = cap_;
+  rc.flags = RFE_FLAG_NO_MATCHER;         // an extractor never matches: no LightGlue weights or state buffers
   if (rfe_create(&rc, &ctx_) != RFE_OK) {
     std::cerr << "[ERROR] rover_fe extractor init failed : " << rfe_last_error() << std::endl;
     ctx_ = nullptr;
     return EXIT_FAILURE;
   }
   return EXIT_SUCCESS;
+}
+
+// Public but never called by the reference (superpoint_onnx.cc:68-86): normalise, then RGB -> gray for "superpoint".
+// Like the reference it only works on a 3-channel image (cvtColor RGB2GRAY rejects 1 channel, transform.cpp:87).
+cv::Mat SuperPointOnnxRunner::Extractor_PreProcess(Configuration cfg, const cv::Mat& Image, float& scale) {
+  (void)scale;
+  cv::Mat tempImage = Image.clone();
+  cv::Mat resultImage = NormalizeImage(tempImage);
+  if (cfg.extractorType == "superpoint") resultImage = RGB2Grayscale(resultImage);
+  return resultImage;
 }
 
 int SuperPointOnnxRunner::Extractor_Inference(Configuration cfg, const cv::Mat& image) {
@@ -72,6 +83,9 @@ int SuperPointOnnxRunner::Extractor_Inference(Configuration cfg, const cv::Mat& 
     std::cerr << "[ERROR] SuperPointOnnxRunner Extractor inference failed : " << rfe_last_error() << std::endl;
     return EXIT_FAILURE;
   }
+  if (rc == RFE_ERR_CAPACITY)     // the reference returns every keypoint; say so when the fixed capacity truncates
+    std::cerr << "[WARN] SuperPointOnnxRunner : " << count << " keypoints exceed the capacity " << cap_
+              << "; the first " << cap_ << " in row-major order are returned" << std::endl;
   res.count = count < cap_ ? count : cap_;
   res.keypoints.resize(static_cast<size_t>(res.count) * 2);
   res.scores.resize(res.count);
@@ -142,6 +156,9 @@ int SuperPointOnnxRunner::BinarizeDescriptors(const cv::Mat& desc, cv::Mat& bin)
   return EXIT_SUCCESS;
 }
 
+std::pair<std::vector<cv::Point2f>, std::vector<cv::Point2f>> SuperPointOnnxRunner::GetKeypointsResult() {
+  return keypoints_result;                 // superpoint_onnx.cc:279-282
+}
 float SuperPointOnnxRunner::GetMatchThresh() { return matchThresh; }
 void SuperPointOnnxRunner::SetMatchThresh(float thresh) { matchThresh = thresh; }
 double SuperPointOnnxRunner::GetTimer(std::string name) {

@@ -6,14 +6,25 @@
 #include <algorithm>
 #include <stdexcept>
 
+// Same branches and the same exception as the reference (transform.cpp:3-17 throws std::invalid_argument for anything
+// but 1 or 3 channels; SPextractor::operator() asserts CV_8UC1 before it gets here, SPextractor.cc:525).
 cv::Mat NormalizeImage(cv::Mat& Image) {
-  cv::Mat normalizedImage;
-  if (Image.channels() == 1) {
+  cv::Mat normalizedImage = Image.clone();
+  if (Image.channels() == 3) {
+    cv::cvtColor(normalizedImage, normalizedImage, cv::COLOR_BGR2RGB);
+    normalizedImage.convertTo(normalizedImage, CV_32F, 1.0 / 255.0);
+  } else if (Image.channels() == 1) {
     Image.convertTo(normalizedImage, CV_32F, 1.0 / 255.0);
   } else {
-    throw std::invalid_argument("[ERROR] NormalizeImage: the SuperPoint front end takes 1-channel images");
+    throw std::invalid_argument("[ERROR] Not an image");
   }
   return normalizedImage;
+}
+
+cv::Mat RGB2Grayscale(cv::Mat& Image) {            // transform.cpp:85-89
+  cv::Mat resultImage;
+  cv::cvtColor(Image, resultImage, cv::COLOR_RGB2GRAY);
+  return resultImage;
 }
 
 std::vector<cv::Point2f> NormalizeKeypoints(std::vector<cv::Point2f> kpts, int h, int w) {

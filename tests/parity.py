@@ -24,11 +24,15 @@ THRESHOLD = 0.0005
 FILTER = 0.1
 
 
-def compare_keypoints(k_ref, s_ref, k_tst, s_tst, strict=False):
+def compare_keypoints(k_ref, s_ref, k_tst, s_tst, strict=False, heat=None):
     """k_*: [N,2] int (x,y) row-major ordered; s_*: [N].  Returns dict with common index arrays.
 
-    Raises AssertionError when the sets differ by anything other than threshold-marginal points
-    (or, for NMS near-ties, points whose score differs from a suppressing neighbour by < SCORE_MARGIN).
+    strict=True: the two sets must be identical (the goldens: DESIGN.md section 4 reports identical sets).
+    Otherwise a keypoint present in only one set is accepted only if
+      * its score is within SCORE_MARGIN of the 0.0005 threshold, or
+      * `heat` (a heat-map [H,W] of either side) is given and the 9x9 neighbourhood of the point really holds a rival
+        whose score is within SCORE_MARGIN of the point's (an NMS near-tie: `==` against the 9x9 maximum on exact floats).
+    Anything else raises AssertionError: there is no allowance for unexplained differences.
     """
     k_ref, k_tst = np.asarray(k_ref).astype(np.int64), np.asarray(k_tst).astype(np.int64)
     key_r = k_ref[:, 1] * 100000 + k_ref[:, 0]
@@ -40,13 +44,20 @@ def compare_keypoints(k_ref, s_ref, k_tst, s_tst, strict=False):
     only_t = np.setdiff1d(np.arange(len(key_t)), it)
     if strict:
         assert len(only_r) == 0 and len(only_t) == 0, (len(only_r), len(only_t))
-    marginal_r = np.abs(np.asarray(s_ref)[only_r] - THRESHOLD) < SCORE_MARGIN
-    marginal_t = np.abs(np.asarray(s_tst)[only_t] - THRESHOLD) < SCORE_MARGIN
-    # anything non-marginal must be an NMS near-tie: allow at most a handful and report them
-    hard = int((~marginal_r).sum() + (~marginal_t).sum())
-    assert hard <= max(2, len(key_r) // 500), (
-        f"{hard} keypoints differ beyond the threshold margin "
-        f"(only_ref={len(only_r)}, only_test={len(only_t)})")
+
+    def explained(k, s):
+        if abs(float(s) - THRESHOLD) < SCORE_MARGIN:
+            return True
+        if heat is None:
+            return False
+        x, y = int(k[0]), int(k[1])
+        win = np.asarray(heat)[max(0, y - 4):y + 5, max(0, x - 4):x + 5].astype(np.float64).copy()
+        win[min(4, y), min(4, x)] = -np.inf               # the point itself
+        return bool((np.abs(win - float(np.asarray(heat)[y, x])) < SCORE_MARGIN).any())
+
+    bad = [("ref", tuple(k_ref[i]), float(np.asarray(s_ref)[i])) for i in only_r if not explained(k_ref[i], np.asarray(s_ref)[i])]
+    bad += [("tst", tuple(k_tst[i]), float(np.asarray(s_tst)[i])) for i in only_t if not explained(k_tst[i], np.asarray(s_tst)[i])]
+    assert not bad, f"keypoints differ without a threshold margin or an NMS near-tie to explain it: {bad[:8]}"
     ds = np.abs(np.asarray(s_ref)[ir] - np.asarray(s_tst)[it])
     assert ds.size == 0 or ds.max() <= SCORE_ATOL, f"score diff {ds.max()}"
     return {"ref_idx": ir, "tst_idx": it, "only_ref": only_r, "only_tst": only_t,

@@ -60,16 +60,47 @@ def test_product_does_not_import_oracle():
 
 
 def test_weight_blob_matches_reference_when_mounted():
-    ref = "/root/reference/onnxmodel/superpoint.onnx"
-    if not os.path.exists(ref):
+    """EVERY tensor of weights/rover_fe.rfw against the initialisers of the reference's two ONNX files:
+    (1) layout-independent: the multiset of values of each blob tensor (hash of the sorted values) is the multiset of exactly one
+        ONNX float initialiser and vice versa -- nothing missing, nothing invented, nothing altered;
+    (2) layout: every tensor equals what the documented repacking (OIHW -> OHWI, [in,out] -> [out,in]) yields."""
+    ref = "/root/reference/onnxmodel"
+    if not os.path.exists(ref + "/superpoint.onnx"):
         pytest.skip("reference not mounted")
+    import hashlib
+    import sys
     import numpy as np
     from oracle import onnx_reader, weights
     blob = weights.load()
-    g = onnx_reader.load(ref)
-    w = g.initializers["conv3b.weight"]
-    assert np.array_equal(blob["sp.conv3b.w"], w.transpose(0, 2, 3, 1))
-    g2 = onnx_reader.load("/root/reference/onnxmodel/lightglue_sim.onnx")
+
+    def h(a):
+        return hashlib.sha1(np.sort(np.asarray(a, np.float32).reshape(-1)).tobytes()).hexdigest()
+
+    blob_h = {h(v): k for k, v in blob.items()}
+    onnx_h, n_params = {}, 0
+    for f in ("superpoint.onnx", "lightglue_sim.onnx"):
+        g = onnx_reader.load(os.path.join(ref, f))
+        for k, v in g.initializers.items():
+            if v.dtype == np.float32 and v.size >= 2:
+                onnx_h[h(v)] = f + ":" + k
+                n_params += v.size
+    assert len(blob) == 227 and len(blob_h) == 227
+    assert not [v for k, v in onnx_h.items() if k not in blob_h]                       # every reference weight is in the blob
+    extra = [v for k, v in blob_h.items() if k not in onnx_h]
+    assert extra == ["lg.matchability.b"]                                              # the one scalar initialiser (size 1)
+    g2 = onnx_reader.load(os.path.join(ref, "lightglue_sim.onnx"))
+    assert np.array_equal(blob["lg.matchability.b"].reshape(-1), g2.initializers["log_assignment.8.matchability.bias"].reshape(-1))
+    assert sum(v.size for v in blob.values()) == n_params + 1
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import pack_weights
+    want = {}
+    want.update(pack_weights.superpoint_tensors(os.path.join(ref, "superpoint.onnx")))
+    want.update(pack_weights.lightglue_tensors(os.path.join(ref, "lightglue_sim.onnx")))
+    assert sorted(want) == sorted(blob)
+    for k, v in want.items():
+        assert np.array_equal(blob[k], np.asarray(v, np.float32)), k
+    g = onnx_reader.load(os.path.join(ref, "superpoint.onnx"))
+    assert np.array_equal(blob["sp.conv3b.w"], g.initializers["conv3b.weight"].transpose(0, 2, 3, 1))
     assert np.array_equal(blob["lg.l4.cross.to_v.b"], g2.initializers["transformers.4.cross_attn.to_v.bias"])
     assert blob["lg.l0.self.wqkv.w"].shape == (768, 256)
 
@@ -93,5 +124,5 @@ def test_host_classes_without_device_follow_the_reference_error_convention(tmp_p
                        env=dict(os.environ, ROVER_FE_WEIGHTS=os.path.join(ROOT, "weights", "rover_fe.rfw")))
     assert r.returncode == 0, r.stderr
     assert "no CPU fallback" in r.stderr and "init failed" in r.stderr
-    hdr = np.fromfile(out, dtype=np.int32)
+    hdr = np.fromfile(out, dtype=np.int32)[:6]
     assert hdr.tolist() == [0, 0, 0, 0, 0, 0]            # keypoints a / b, multi-level, matches (Frame / KeyPoint overload), adaptive

@@ -43,7 +43,11 @@ def test_spextractor_spmatcher_classes():
     vn_frame = raw[off:off + na * 4].view(np.int32); off += na * 4
     vn_kp = raw[off:off + na * 4].view(np.int32); off += na * 4
     kp_ada = raw[off:off + n_ada * 12].view(np.float32).reshape(n_ada, 3); off += n_ada * 12
-    de_ada = raw[off:off + n_ada * 1024].view(np.float32).reshape(n_ada, 256)
+    de_ada = raw[off:off + n_ada * 1024].view(np.float32).reshape(n_ada, 256); off += n_ada * 1024
+    m_pf, m_fp, n_app_ret, n_app_ok, m_kpinf, n_vn_pf = (int(v) for v in raw[off:off + 24].view(np.int32)); off += 24
+    vn_pf = raw[off:off + n_vn_pf * 4].view(np.int32); off += n_vn_pf * 4
+    vn_kpinf = raw[off:off + na * 4].view(np.int32); off += na * 4
+    px0 = raw[off:off + 16].view(np.float32)
     assert nmulti == 0                                   # nLevels != 1 extracts nothing, like the reference
     fe = FrontEnd(max_batch=2, max_height=h, max_width=w)
     ref = fe.extract(np.stack([a, b]))
@@ -56,6 +60,19 @@ def test_spextractor_spmatcher_classes():
         m, ms = fe.match(ref[0][0], ref[1][0], ref[0][2], ref[1][2], nh, nw)
         exp, c = lightglue_ref.scatter_matches(m, ms, na, 0.0)
         assert c == cnt and np.array_equal(exp, vn)
+    # the other overloads (SPmatcher.cc:359-410): all three normalise with 300 x 400; the Point2f + Mat one was handed a
+    # NON-EMPTY vector (5 x 77): resize(n, -1) keeps those five entries unless a match overwrites them (SPmatcher.cc:375)
+    m, ms = fe.match(ref[0][0], ref[1][0], ref[0][2], ref[1][2], 300, 400)
+    exp, c = lightglue_ref.scatter_matches(m, ms, na, 0.0)
+    assert m_pf == c and m_fp == c and m_kpinf == c and n_vn_pf == na
+    stale = exp.copy()
+    stale[:5] = np.where(exp[:5] >= 0, exp[:5], 77)
+    assert np.array_equal(vn_pf, stale)
+    assert np.array_equal(vn_kpinf, exp)                 # Matcher_Inference(KeyPoint...) fed normalised points, after an odd PreProcess call
+    assert n_app_ret == na + 3 and n_app_ok == 1         # operator() appends and returns the vector's size (superpoint_onnx.cc:230)
+    # NormalizeImage on BGR bytes (5, 25, 45): RGB order, 1/255; RGB2Grayscale with OpenCV's weights
+    assert np.allclose(px0[:3], np.float32([45, 25, 5]) * np.float32(1 / 255.0), atol=1e-7)
+    assert abs(px0[3] - float(np.float32([45, 25, 5]) @ np.float32([0.299, 0.587, 0.114])) / 255.0) < 1e-6
     rm, rms = lightglue_ref.LightGlueRef()(lightglue_ref.normalize_keypoints(ref[0][0], h, w),
                                            lightglue_ref.normalize_keypoints(ref[1][0], h, w), ref[0][2], ref[1][2])
     m, ms = fe.match(ref[0][0], ref[1][0], ref[0][2], ref[1][2], h, w)

@@ -52,7 +52,7 @@ def test_split_fp16_gemm_is_fp32_equivalent(fe, m, n, k):
 def test_superpoint_vs_golden(fe, golden_dir, name):
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     (k, s, d), = fe.extract(g["image"])
-    r = parity.compare_keypoints(g["keypoints"], g["scores"], k, s)
+    r = parity.compare_keypoints(g["keypoints"], g["scores"], k, s, strict=True)      # identical sets on the goldens
     h, w = g["image"].shape
     heat = fe.debug_read("sp.heat").reshape(-1, h, w)[0]
     assert np.abs(heat[g["heat_rows"]] - g["heat"]).max() <= parity.HEAT_ATOL
@@ -69,10 +69,11 @@ def test_superpoint_batch8_vs_oracle(fe, sp):
     """BASELINE config 2: batch of 8 synthetic 640x480 frames."""
     imgs = np.stack([synth.frame(s, 480, 640) for s in range(8)])
     feats = fe.extract(imgs)
+    heat = fe.debug_read("sp.heat").reshape(8, 480, 640)
     for i in range(8):
         rk, rs, rd = sp(imgs[i])
         k, s, d = feats[i]
-        r = parity.compare_keypoints(rk.numpy(), rs.numpy(), k, s)
+        r = parity.compare_keypoints(rk.numpy(), rs.numpy(), k, s, heat=heat[i])
         parity.compare_descriptors(rd.numpy()[r["ref_idx"]], d[r["tst_idx"]])
         assert np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-5)
 
@@ -108,7 +109,7 @@ def test_superpoint_sizes_and_blank(fe, sp, hw):
     for img in (np.zeros((h, w), np.uint8), synth.frame(9, h, w) if min(h, w) >= 16 else np.full((h, w), 200, np.uint8)):
         (k, s, d), = fe.extract(img)
         rk, rs, rd = sp(img)
-        r = parity.compare_keypoints(rk.numpy(), rs.numpy(), k, s)
+        r = parity.compare_keypoints(rk.numpy(), rs.numpy(), k, s, heat=fe.debug_read("sp.heat").reshape(-1, h, w)[0])
         if len(r["ref_idx"]):
             parity.compare_descriptors(rd.numpy()[r["ref_idx"]], d[r["tst_idx"]])
 
@@ -128,7 +129,7 @@ def test_lightglue_vs_golden_synth(fe, golden_dir, n):
     k0, k1, d0, d1, perm = synth.lightglue_inputs(n, 200 + n)
     m, ms = fe.match(k0, k1, d0, d1, 480, 640)
     r = parity.compare_matches(g["matches"], g["mscores"], m, ms)
-    assert r["common"] >= len(g["matches"]) - 2
+    assert r["only_ref"] == 0 and r["only_tst"] == 0          # identical pairs on the goldens
 
 
 @pytest.mark.parametrize("n0,n1", [(1024, 1024), (300, 777), (5, 1000), (1, 1), (2048, 2048)])
@@ -179,8 +180,9 @@ def test_lightglue_gemm_tile_modes_vs_oracle(lg, tmp_path, mode):
 
 def test_bench_shape_batch_vs_oracle(sp, lg):
     """BASELINE config 5 shape: 8 pairs of 640x480 frames in ONE batched pass (16 frames extracted, 8 pairs matched: the
-    size at which the B-resident GEMM tiles and the 1024-CTA attention launches are used) -- first and last pair against
-    the oracle end to end."""
+    size at which the B-resident GEMM tiles and the persistent attention launches are used).  ALL 8 pairs against the
+    oracle: the 16 keypoint sets, then the matches of the oracle run on OUR features (so a keypoint near-tie cannot
+    excuse a matcher difference)."""
     from rover_slam_b200 import FrontEnd
     import bench
     frames = bench.make_pairs(8, 3)
@@ -189,19 +191,20 @@ def test_bench_shape_batch_vs_oracle(sp, lg):
         kpts, res = big.match_pairs(frames.reshape(16, 480, 640))
         kpts = [k.copy() for k in kpts]
         res = [(m.copy(), s.copy()) for m, s in res]
+        heat = big.debug_read("sp.heat").reshape(16, 480, 640)
+        feats = [big.read_slot(b) for b in range(16)]          # the features the batched matcher consumed
     finally:
         big.close()
-    for pi in (0, 7):
-        feats = []
+    for pi in range(8):
         for f in (0, 1):
             rk, rs, rd = sp(frames[pi, f])
-            got_k = kpts[2 * pi + f]
-            assert len(got_k) >= len(rk) - 3 and len(got_k) <= len(rk) + 3
-            feats.append((rk.numpy(), rd))
-        if all(np.array_equal(kpts[2 * pi + f], feats[f][0]) for f in (0, 1)):     # identical keypoint sets (the usual case)
-            rm, rms = lg(lightglue_ref.normalize_keypoints(feats[0][0], 480, 640),
-                         lightglue_ref.normalize_keypoints(feats[1][0], 480, 640), feats[0][1], feats[1][1])
-            parity.compare_matches(rm.numpy(), rms.numpy(), res[pi][0], res[pi][1])
+            k, s, d = feats[2 * pi + f]
+            assert np.array_equal(k, kpts[2 * pi + f])
+            r = parity.compare_keypoints(rk.numpy(), rs.numpy(), k, s, heat=heat[2 * pi + f])
+            parity.compare_descriptors(rd.numpy()[r["ref_idx"]], d[r["tst_idx"]])
+        (k0, _, d0), (k1, _, d1) = feats[2 * pi], feats[2 * pi + 1]
+        rm, rms = lg(lightglue_ref.normalize_keypoints(k0, 480, 640), lightglue_ref.normalize_keypoints(k1, 480, 640), d0, d1)
+        parity.compare_matches(rm.numpy(), rms.numpy(), res[pi][0], res[pi][1])
         assert len(res[pi][0]) > 500
 
 
@@ -382,6 +385,31 @@ def test_pipelined_pairs_equal_one_shot_calls(fe):
             assert np.array_equal(rm, om) and np.array_equal(rs, os_)
             assert len(rm) > 20
 
+
+
+def test_padding_rows_do_not_drift_over_many_calls(fe):
+    """Images start at multiples of 8 rows; the padding rows go through every GEMM / FFN of every call.  They are reset by
+    lg_prepare on each call: 3000 matches with n % 8 != 0 return exactly what the first one returned, and the residual
+    stream of a padding row stays bounded (it would otherwise grow by ~11 per call until the fp16 planes overflow)."""
+    k0, k1, d0, d1, _ = synth.lightglue_inputs(64, 77)
+    k0, d0, k1, d1 = k0[:13], d0[:13], k1[:27], d1[:27]
+    first = fe.match(k0, k1, d0, d1, 480, 640)
+    assert len(first[0]) > 3
+    for _ in range(3000):
+        m, ms = fe.match(k0, k1, d0, d1, 480, 640)
+    assert np.array_equal(m, first[0]) and np.array_equal(ms, first[1])
+    x = fe.debug_read("lg.x").reshape(-1, 256)            # rows [0, 13) image 0, [13, 16) padding, [16, 43) image 1
+    assert np.isfinite(x).all() and np.abs(x[13:16]).max() < 1e3
+
+
+def test_match_normalized_equals_match(fe):
+    """rfe_lg_match_normalized (the host runner's path: keypoints normalised on the host exactly like
+    NormalizeKeypoints, transform.cpp:19-32) == rfe_lg_match (pixels, normalised on the device)."""
+    k0, k1, d0, d1, _ = synth.lightglue_inputs(300, 5)
+    for nh, nw in ((480, 640), (300, 400)):
+        m, ms = fe.match(k0, k1, d0, d1, nh, nw)
+        m2, ms2 = fe.match_normalized(lightglue_ref.normalize_keypoints(k0, nh, nw), lightglue_ref.normalize_keypoints(k1, nh, nw), d0, d1)
+        assert np.array_equal(m, m2) and np.array_equal(ms, ms2)
 
 
 # ---- against an independent runtime: OpenCV DNN executing the reference's ONNX files (tests/golden/cv2dnn_*.npz) ----------
