@@ -43,3 +43,13 @@ $(HOSTDRV): $(HOST)/test/host_driver.cpp $(HOSTLIB)
 	g++ $(HOSTFLAGS) -o $@ $< -Lrover_slam_b200 -lrover_slam_frontend -lrover_fe -Wl,-rpath,'$$ORIGIN'
 
 all: host
+
+# ---- debug build: every mbarrier wait is bounded and traps with a message instead of hanging (common.cuh, RFE_DEBUG_WAIT).
+# Select it at run time with ROVER_FE_LIB=rover_slam_b200/librover_fe_dbg.so; used for the first GPU run of a new kernel.
+DBGOBJ := $(patsubst $(CSRC)/%.o,$(CSRC)/dbg_%.o,$(OBJ))
+$(CSRC)/dbg_%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/rover_fe.h
+	$(NVCC) $(NVCCFLAGS) -DRFE_DEBUG_WAIT -c $< -o $@
+$(CSRC)/dbg_%.o: $(CSRC)/%.cc $(wildcard $(CSRC)/*.h)
+	$(NVCC) $(NVCCFLAGS) -DRFE_DEBUG_WAIT -x cu -c $< -o $@
+dbg: $(DBGOBJ)
+	$(NVCC) $(ARCH) -shared -o rover_slam_b200/librover_fe_dbg.so $(DBGOBJ) -lcudart

@@ -48,6 +48,8 @@ constexpr int kAttnMaxProblems = 32;   // 16 pairs x 2 directions per launch
 struct AttnParams {
   int nq[kAttnMaxProblems], nk[kAttnMaxProblems];          // per problem (blockIdx.z): query rows, key rows
   int q_row0[kAttnMaxProblems], k_row0[kAttnMaxProblems];  // row offsets inside the head-major Q / K tensors and the V^T columns
+  int item_prefix[kAttnMaxProblems + 1];   // attn2_kernel: work items (4 heads x 128-query tiles) before problem z; [nprob] = total
+  int nprob;
   __half* out_hi;            // split-fp16 [rows][256]
   __half* out_lo;
   unsigned long long* prof;  // optional cycle counters written by CTA prof_cta: where the MMA / softmax roles wait

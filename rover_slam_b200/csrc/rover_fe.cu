@@ -11,6 +11,7 @@
 #include "kernels.h"
 #include "tensormap.h"
 #include "attn_kernel.cuh"
+#include "attn2_kernel.cuh"
 #include "conv_strip.cuh"
 #include "umma_kernel.cuh"
 #include "weights.h"
@@ -571,9 +572,13 @@ int ffn_block(rfe_ctx* c, int rows, const SplitW& ffn0, const float* ln_w, const
 int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitBuf& K, int rows_total,
                     const AttnParams& problems, int nprob, int max_nq) {
   static bool configured[64] = {};
+  // RFE_ATTN=1 selects the one-item-per-CTA kernel of round 1 (A/B measurements); default: the persistent kernel
+  static const int kAttnMode = getenv("RFE_ATTN") ? atoi(getenv("RFE_ATTN")) : 2;
   if (!configured[c->device & 63]) {
     RFE_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
     RFE_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    RFE_CUDA_CHECK(cudaFuncSetAttribute(attn2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2SmemBytes));
+    RFE_CUDA_CHECK(cudaFuncSetAttribute(attn2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2SmemBytes));
     configured[c->device & 63] = true;
   }
   CUtensorMap qh, ql, kh, kl, vh, vl;
@@ -593,8 +598,16 @@ int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitB
   p.prof = c->attn_prof;
   p.prof_cta = getenv("RFE_ATTN_PROF_CTA") ? atoi(getenv("RFE_ATTN_PROF_CTA")) : 0;
   dim3 grid((max_nq + 127) / 128, 4, nprob);
+  p.nprob = nprob;
+  p.item_prefix[0] = 0;
+  for (int z = 0; z < nprob; ++z) p.item_prefix[z + 1] = p.item_prefix[z] + 4 * ((p.nq[z] + 127) / 128);
   ProfScope ps(c, tag);
-  if (p.prof) attn_kernel<true><<<grid, kAttnThreads, kAttnSmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
+  if (kAttnMode == 2) {
+    const int items = p.item_prefix[nprob];
+    const int ctas = items < c->num_sms ? items : c->num_sms;
+    if (p.prof) attn2_kernel<true><<<ctas, kAttnThreads, kAttn2SmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
+    else attn2_kernel<false><<<ctas, kAttnThreads, kAttn2SmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
+  } else if (p.prof) attn_kernel<true><<<grid, kAttnThreads, kAttnSmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
   else attn_kernel<false><<<grid, kAttnThreads, kAttnSmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
   c->launches++;
   RFE_CUDA_CHECK(cudaGetLastError());

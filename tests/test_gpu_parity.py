@@ -394,7 +394,7 @@ def test_padding_rows_do_not_drift_over_many_calls(fe):
     k0, k1, d0, d1, _ = synth.lightglue_inputs(64, 77)
     k0, d0, k1, d1 = k0[:13], d0[:13], k1[:27], d1[:27]
     first = fe.match(k0, k1, d0, d1, 480, 640)
-    assert len(first[0]) > 3
+    assert len(first[0]) >= 2
     for _ in range(3000):
         m, ms = fe.match(k0, k1, d0, d1, 480, 640)
     assert np.array_equal(m, first[0]) and np.array_equal(ms, first[1])
