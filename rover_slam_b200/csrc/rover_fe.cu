@@ -12,6 +12,7 @@
 #include "tensormap.h"
 #include "attn_kernel.cuh"
 #include "attn2_kernel.cuh"
+#include "attn3_kernel.cuh"
 #include "conv_strip.cuh"
 #include "umma_kernel.cuh"
 #include "weights.h"
@@ -572,13 +573,16 @@ int ffn_block(rfe_ctx* c, int rows, const SplitW& ffn0, const float* ln_w, const
 int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitBuf& K, int rows_total,
                     const AttnParams& problems, int nprob, int max_nq) {
   static bool configured[64] = {};
-  // RFE_ATTN=1 selects the one-item-per-CTA kernel of round 1 (A/B measurements); default: the persistent kernel
-  static const int kAttnMode = getenv("RFE_ATTN") ? atoi(getenv("RFE_ATTN")) : 2;
+  // RFE_ATTN=1: the one-item-per-CTA two-pass kernel of round 1; 2: its persistent form; 3 (default): the persistent
+  // single-pass (online-softmax) kernel.  The older two stay for A/B measurements.
+  static const int kAttnMode = getenv("RFE_ATTN") ? atoi(getenv("RFE_ATTN")) : 3;
   if (!configured[c->device & 63]) {
     RFE_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
     RFE_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
     RFE_CUDA_CHECK(cudaFuncSetAttribute(attn2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2SmemBytes));
     RFE_CUDA_CHECK(cudaFuncSetAttribute(attn2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2SmemBytes));
+    RFE_CUDA_CHECK(cudaFuncSetAttribute(attn3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes));
+    RFE_CUDA_CHECK(cudaFuncSetAttribute(attn3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes));
     configured[c->device & 63] = true;
   }
   CUtensorMap qh, ql, kh, kl, vh, vl;
@@ -602,7 +606,12 @@ int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitB
   p.item_prefix[0] = 0;
   for (int z = 0; z < nprob; ++z) p.item_prefix[z + 1] = p.item_prefix[z] + 4 * ((p.nq[z] + 127) / 128);
   ProfScope ps(c, tag);
-  if (kAttnMode == 2) {
+  if (kAttnMode == 3) {
+    const int items = p.item_prefix[nprob];
+    const int ctas = items < c->num_sms ? items : c->num_sms;
+    if (p.prof) attn3_kernel<true><<<ctas, kAttnThreads, kA3SmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
+    else attn3_kernel<false><<<ctas, kAttnThreads, kA3SmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
+  } else if (kAttnMode == 2) {
     const int items = p.item_prefix[nprob];
     const int ctas = items < c->num_sms ? items : c->num_sms;
     if (p.prof) attn2_kernel<true><<<ctas, kAttnThreads, kAttn2SmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);

@@ -161,3 +161,25 @@ def test_superpoint_with_emulated_split_fp16_convolutions_matches_fp32():
     r = parity.compare_keypoints(rk.numpy(), rs.numpy(), ek.numpy(), es.numpy())
     assert len(rk) > 50 and len(r["ref_idx"]) >= len(rk) - 1
     parity.compare_descriptors(rd.numpy()[r["ref_idx"]], ed.numpy()[r["tst_idx"]])
+
+
+def test_gelu_erfc_formulation_is_fp32_equivalent():
+    """ln_gelu_split_kernel computes GELU through erfc(|x|) = t (a1 + t (... a5)) exp(-x^2), t = 1 / (1 + p |x|)
+    (Abramowitz & Stegun 7.1.26) instead of erff(): restated here in fp32 and compared with float64 -- it must stay inside
+    the error envelope of the graph's own fp32 formulation 0.5 y (1 + erff(y / sqrt 2))."""
+    import math
+    import torch
+    from scipy.special import erf as erf64
+    f = np.float32
+    y = np.concatenate([np.linspace(-12, 12, 400001), np.random.RandomState(0).randn(400000) * 2]).astype(f)
+    ref = 0.5 * y.astype(np.float64) * (1 + erf64(y.astype(np.float64) / math.sqrt(2)))
+    yt = torch.from_numpy(y)
+    g_erff = ((yt * (torch.erf(yt / f(1.4142135381698608)) + 1)) * f(0.5)).numpy()          # lightglue_ref.py / the ONNX nodes
+    x = np.abs(y) * f(0.70710678118654752)
+    t = f(1) / (f(1) + f(0.3275911) * x)
+    p = ((((f(1.061405429) * t + f(-1.453152027)) * t + f(1.421413741)) * t + f(-0.284496736)) * t + f(0.254829592)) * t
+    c = (p * np.exp2((x * x * f(-1.4426950408889634)).astype(f)).astype(f)).astype(f)
+    g = (f(0.5) * y * np.where(y < 0, c, f(2) - c)).astype(f)
+    e_new, e_old = np.abs(g - ref).max(), np.abs(g_erff - ref).max()
+    assert e_new <= 5e-7 and e_new <= 1.25 * e_old, (e_new, e_old)             # measured 4.2e-7 vs 4.4e-7
+    assert np.abs(g - g_erff).max() <= 6e-7

@@ -28,8 +28,16 @@ print(f"CTAs {len(tl)}  SMs {len(np.unique(sm))}  launch span {end.max() / 1e3:.
       f"; clock {np.median(cyc / np.maximum(end - start, 1)) * 1e3:.0f} MHz")
 items, tiles = int(pr[17]), int(pr[7])
 print(f"CTA {os.environ.get('RFE_ATTN_PROF_CTA', '0')}: {items} items, {tiles} pass-2 key tiles")
-for name, i in (("score issuer: wait Q", 0), ("score issuer: pass-1 loops", 1), ("score issuer: pass-2 loops", 2), ("  pass 2 wait K", 3),
-                ("  pass 2 wait free S", 4), ("  pass 1 wait K", 8), ("  pass 1 wait free S", 9), ("PV issuer: wait V", 5), ("PV issuer: wait P", 6),
-                ("PV issuer: wait O hand-back", 16), ("softmax w0: pass-1 loops", 13), ("  wait scores", 14), ("softmax w0: pass-2 loops", 10),
-                ("  wait scores", 11), ("  wait free P", 12), ("softmax w0: l exchange + epilogue", 15), ("  wait o_full", 18)):
+mode = os.environ.get("RFE_ATTN", "3")
+if mode == "3":
+    rows = (("score issuer: wait Q", 0), ("score issuer: issue loops", 2), ("  wait K", 3), ("  wait group's score buffer", 4),
+            ("PV issuer: wait V", 5), ("PV issuer: wait P", 6), ("PV issuer: wait O hand-back", 16),
+            ("softmax w0: key-tile loops", 10), ("  wait scores", 11), ("  wait free P", 12), ("  pair-max exchange", 13),
+            ("  O corrections (count)", 14), ("softmax w0: merge + epilogue", 15), ("  wait o_full", 18))
+else:
+    rows = (("score issuer: wait Q", 0), ("score issuer: pass-1 loops", 1), ("score issuer: pass-2 loops", 2), ("  pass 2 wait K", 3),
+            ("  pass 2 wait free S", 4), ("  pass 1 wait K", 8), ("  pass 1 wait free S", 9), ("PV issuer: wait V", 5), ("PV issuer: wait P", 6),
+            ("PV issuer: wait O hand-back", 16), ("softmax w0: pass-1 loops", 13), ("  wait scores", 14), ("softmax w0: pass-2 loops", 10),
+            ("  wait scores", 11), ("  wait free P", 12), ("softmax w0: l exchange + epilogue", 15), ("  wait o_full", 18))
+for name, i in rows:
     print(f"  {name:36s} {int(pr[i]):9d}  ({int(pr[i]) / max(items, 1):9.0f} per item)")
