@@ -74,6 +74,12 @@ int rfe_sync(rfe_ctx* ctx);
 int rfe_sp_extract_u8(rfe_ctx* ctx, const uint8_t* gray, int h, int w, int stride_bytes, int batch,
                       int32_t* kpts_xy, float* scores, float* desc, int32_t* counts, int cap);
 
+/* Optional cap on the keypoints per image: the reference's SPextractor stores `nfeatures` and never uses
+ * it (src/Extractors/SPextractor.cc:84-146; the ONNX graph has no top-K).  k > 0: every later extraction keeps the k
+ * highest-scoring keypoints of each image, still in the graph's row-major order (among equal scores the earlier keypoint
+ * stays); descriptors are sampled for the kept ones only.  k <= 0 (default): every keypoint, i.e. the reference's behaviour. */
+int rfe_sp_set_topk(rfe_ctx* ctx, int k);
+
 /* Device in / device-resident out (asynchronous on the ctx stream).  d_gray: device pointer, layout as
  * above.  Features stay in the ctx ("slots" 0..batch-1) for rfe_lg_match_slots / rfe_sp_read_slot. */
 int rfe_sp_extract_device(rfe_ctx* ctx, const uint8_t* d_gray, int h, int w, int stride_bytes, int batch);
@@ -107,6 +113,14 @@ int rfe_binarize_descriptors(rfe_ctx* ctx, const float* desc, int n, uint8_t* bi
 int rfe_l2_best2(rfe_ctx* ctx, const float* q, int nq, const float* db, int nd, const int32_t* cand_off,
                  const int32_t* cand_idx, float init_dist, float* best_dist, int32_t* best_idx, float* second_dist,
                  int32_t* second_idx);
+
+/* The slot-resident form: queries = the first nq descriptors of feature slot q_slot, database = feature slot db_slot (both
+ * left on the device by rfe_sp_extract_device / rfe_pairs_submit, or uploaded once with rfe_sp_write_slot).  Only the
+ * candidate lists cross PCIe: the current frame against the last frame / a KeyFrame in SearchByProjection1
+ * (SPmatcher.cc:1170-1352), left against right in Frame::ComputeStereoMatches (Frame.cc:1159-1340).  INTEGRATION.md shows
+ * SearchByProjection1 written on it. */
+int rfe_l2_best2_slots(rfe_ctx* ctx, int q_slot, int db_slot, int nq, const int32_t* cand_off, const int32_t* cand_idx,
+                       float init_dist, float* best_dist, int32_t* best_idx, float* second_dist, int32_t* second_idx);
 
 /* ---- LightGlue -------------------------------------------------------------------------------- */
 /* Host in / host out.  kpts*_px: [n][2] pixel coordinates (x, y); desc*: [n][256].  Keypoints are

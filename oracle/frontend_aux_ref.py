@@ -69,3 +69,14 @@ def adaptive_filter(scores: np.ndarray, lastmatch: float) -> np.ndarray:
     """Indices Extractor_PostProcess keeps under the adaptive rule: `if (scores[i] < threshold) continue;` (:226)."""
     s = np.asarray(scores, np.float32)
     return np.nonzero(~(s < adaptive_threshold(s, lastmatch)))[0]
+
+
+def topk_keep_order(scores: np.ndarray, k: int) -> np.ndarray:
+    """SURVEY.md 8(f).4 -- the `nfeatures` cap the reference stores and never applies (SPextractor.cc:84-146): indices of the k
+    highest scores, returned in ascending (= the graph's row-major keypoint) order; among equal scores the earlier one stays
+    (stable sort).  k <= 0 or k >= len(scores): everything."""
+    s = np.asarray(scores, np.float32)
+    if k <= 0 or k >= len(s):
+        return np.arange(len(s))
+    order = np.argsort(-s.astype(np.float64), kind="stable")[:k]
+    return np.sort(order)

@@ -61,11 +61,13 @@ def load_library():
     lib.rfe_sync.argtypes = [vp]
     lib.rfe_sp_extract_u8.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp, vp, vp, ci]
     lib.rfe_sp_extract_device.argtypes = [vp, vp, ci, ci, ci, ci]
+    lib.rfe_sp_set_topk.argtypes = [vp, ci]
     lib.rfe_sp_read_slot.argtypes = [vp, ci, vp, vp, vp, vp, ci]
     lib.rfe_sp_read_slot_bin.argtypes = [vp, ci, vp, vp, ci]
     lib.rfe_sp_write_slot.argtypes = [vp, ci, vp, vp, vp, ci]
     lib.rfe_binarize_descriptors.argtypes = [vp, vp, ci, vp, vp]
     lib.rfe_l2_best2.argtypes = [vp, vp, ci, vp, ci, vp, vp, cf, vp, vp, vp, vp]
+    lib.rfe_l2_best2_slots.argtypes = [vp, ci, ci, ci, vp, vp, cf, vp, vp, vp, vp]
     lib.rfe_lg_match.argtypes = [vp, vp, ci, vp, ci, vp, vp, ci, ci, cf, vp, vp, vp]
     lib.rfe_lg_match_normalized.argtypes = [vp, vp, ci, vp, ci, vp, vp, cf, vp, vp, vp]
     lib.rfe_lg_match_slots.argtypes = [vp, ci, ci, ci, ci, cf, ci]
@@ -144,6 +146,10 @@ class FrontEnd:
         return [(kp[i, :cnt[i]].copy(), sc[i, :cnt[i]].copy(), de[i, :cnt[i]].copy() if want_desc else None)
                 for i in range(b)]
 
+    def set_topk(self, k: int):
+        """Keep the k best keypoints per image in later extractions (k <= 0: all of them, the reference's behaviour)."""
+        self._check(self.lib.rfe_sp_set_topk(self.ctx, int(k)))
+
     def extract_device(self, d_ptr: int, h: int, w: int, stride: int, batch: int):
         self._check(self.lib.rfe_sp_extract_device(self.ctx, C.c_void_p(d_ptr), h, w, stride, batch))
 
@@ -206,6 +212,17 @@ class FrontEnd:
         i1, i2 = np.empty(nq, np.int32), np.empty(nq, np.int32)
         self._check(self.lib.rfe_l2_best2(self.ctx, _ptr(q), nq, _ptr(db), len(db), _ptr(off), _ptr(idx), init_dist,
                                           _ptr(b1), _ptr(i1), _ptr(b2), _ptr(i2)))
+        return b1, i1, b2, i2
+
+    def l2_best2_slots(self, q_slot: int, db_slot: int, cand_off: np.ndarray, cand_idx: np.ndarray, init_dist: float = 256.0):
+        """l2_best2 with both descriptor sets taken from device-resident feature slots; only the candidate lists are uploaded."""
+        off = np.ascontiguousarray(cand_off, np.int32)
+        idx = np.ascontiguousarray(cand_idx, np.int32)
+        nq = len(off) - 1
+        b1, b2 = np.empty(nq, np.float32), np.empty(nq, np.float32)
+        i1, i2 = np.empty(nq, np.int32), np.empty(nq, np.int32)
+        self._check(self.lib.rfe_l2_best2_slots(self.ctx, q_slot, db_slot, nq, _ptr(off), _ptr(idx), init_dist,
+                                                _ptr(b1), _ptr(i1), _ptr(b2), _ptr(i2)))
         return b1, i1, b2, i2
 
     # ---- LightGlue -------------------------------------------------------------------------------

@@ -12,6 +12,8 @@ int nms_prepare();
 void launch_nms(cudaStream_t s, const float* heat, float* out, int B, int H, int W);
 void launch_select(cudaStream_t s, const float* nms, int B, int H, int W, float thr, int cap, int* row_cnt,
                    int* row_off, int* counts, int* kpts, float* scores);
+// optional top-K cap on the compacted keypoint lists (K <= 0: off = the reference's behaviour)
+void launch_topk(cudaStream_t s, int B, int cap, int K, int* counts, int* kpts, float* scores);
 void launch_desc_sample(cudaStream_t s, const float* dense, int h, int w, int B, const int* kpts, const int* counts,
                         int cap, float* desc, uint8_t* desc_bin);
 void launch_binarize(cudaStream_t s, const float* desc, int n, uint8_t* out, uint32_t* bits);

@@ -52,6 +52,7 @@ struct rfe_ctx {
   bool own_stream = false;
   int max_batch = 8, max_h = 480, max_w = 768, cap = 4096;
   bool no_sp = false, no_lg = false;     // RFE_FLAG_NO_EXTRACTOR / RFE_FLAG_NO_MATCHER
+  int topk = 0;                          // rfe_sp_set_topk: keep the K best keypoints per image (0 = all, the reference)
   std::vector<void*> allocs;
   long long launches = 0;
   double timer_extract_ms = 0.0, timer_match_ms = 0.0;
@@ -525,6 +526,11 @@ int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B, i
   float* desc = c->desc + static_cast<size_t>(slot_base) * c->cap * 256;
   { ProfScope ps_(c, "sp.select"); launch_select(s, c->nmsmap, B, h, w, kDetThreshold, c->cap, c->row_cnt, c->row_off, kp_counts, kpts,
                 kp_scores); }
+  if (c->topk > 0) {
+    ProfScope ps_(c, "sp.topk");
+    launch_topk(s, B, c->cap, c->topk, kp_counts, kpts, kp_scores);
+    c->launches++;
+  }
   { ProfScope ps_(c, "sp.desc_sample"); launch_desc_sample(s, c->dense, hc, wc, B, kpts, kp_counts, c->cap, desc,
                                                            c->desc_bin + static_cast<size_t>(slot_base) * c->cap * 256); }
   c->launches += 5;
@@ -1062,6 +1068,17 @@ int rfe_sp_extract_device(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int s
   return sp_run(c, d_gray, h, w, stride, batch);
 }
 
+int rfe_sp_set_topk(rfe_ctx* c, int k) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (k > c->cap) {
+    set_error("rfe_sp_set_topk: %d exceeds the ctx keypoint capacity %d", k, c->cap);
+    return RFE_ERR_INVALID;
+  }
+  c->topk = k > 0 ? k : 0;
+  return RFE_OK;
+}
+
 int rfe_sp_read_slot(rfe_ctx* c, int slot, int32_t* kpts_xy, float* scores, float* desc, int32_t* count, int cap) {
   int r = check_ctx(c);
   if (r) return r;
@@ -1234,6 +1251,58 @@ int rfe_l2_best2(rfe_ctx* c, const float* q, int nq, const float* db, int nd, co
   RFE_CUDA_CHECK(cudaMemcpyAsync(d_off, cand_off, bo, cudaMemcpyHostToDevice, s));
   if (total > 0) RFE_CUDA_CHECK(cudaMemcpyAsync(d_idx, cand_idx, static_cast<size_t>(total) * 4, cudaMemcpyHostToDevice, s));
   launch_l2_best2(s, d_q, nq, d_db, d_off, d_idx, init_dist, d_b1, d_i1, d_b2, d_i2);
+  c->launches++;
+  RFE_CUDA_CHECK(cudaMemcpyAsync(best_dist, d_b1, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, s));
+  RFE_CUDA_CHECK(cudaMemcpyAsync(best_idx, d_i1, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, s));
+  if (second_dist) RFE_CUDA_CHECK(cudaMemcpyAsync(second_dist, d_b2, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, s));
+  if (second_idx) RFE_CUDA_CHECK(cudaMemcpyAsync(second_idx, d_i2, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, s));
+  RFE_CUDA_CHECK(cudaStreamSynchronize(s));
+  return RFE_OK;
+}
+
+int rfe_l2_best2_slots(rfe_ctx* c, int q_slot, int db_slot, int nq, const int32_t* cand_off, const int32_t* cand_idx,
+                       float init_dist, float* best_dist, int32_t* best_idx, float* second_dist, int32_t* second_idx) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (q_slot < 0 || db_slot < 0 || q_slot >= c->last_batch || db_slot >= c->last_batch || nq < 0 ||
+      (nq > 0 && (!cand_off || !best_dist || !best_idx))) {
+    set_error("rfe_l2_best2_slots: null/invalid argument (slots %d, %d of %d)", q_slot, db_slot, c->last_batch);
+    return RFE_ERR_INVALID;
+  }
+  if (nq == 0) return RFE_OK;
+  cudaStream_t s = c->stream;
+  RFE_CUDA_CHECK(cudaMemcpyAsync(c->h_counts, c->kp_counts, sizeof(int) * c->last_batch, cudaMemcpyDeviceToHost, s));
+  RFE_CUDA_CHECK(cudaStreamSynchronize(s));
+  const int have_q = c->h_counts[q_slot] < c->cap ? c->h_counts[q_slot] : c->cap;
+  const int nd = c->h_counts[db_slot] < c->cap ? c->h_counts[db_slot] : c->cap;
+  const int total = cand_off[nq];
+  if (nq > have_q || cand_off[0] != 0 || total < 0 || (total > 0 && !cand_idx)) {
+    set_error("rfe_l2_best2_slots: %d queries but slot %d holds %d descriptors, or malformed candidate lists", nq, q_slot, have_q);
+    return RFE_ERR_INVALID;
+  }
+  for (int i = 0; i < nq; ++i)
+    if (cand_off[i + 1] < cand_off[i]) {
+      set_error("rfe_l2_best2_slots: candidate offsets must be non-decreasing");
+      return RFE_ERR_INVALID;
+    }
+  for (int i = 0; i < total; ++i)
+    if (cand_idx[i] < 0 || cand_idx[i] >= nd) {
+      set_error("rfe_l2_best2_slots: candidate index %d out of range [0, %d)", cand_idx[i], nd);
+      return RFE_ERR_INVALID;
+    }
+  // only the candidate lists travel: the descriptors of both sets are already in the slots
+  const size_t bo = static_cast<size_t>(nq + 1) * 4, bc = static_cast<size_t>(total > 0 ? total : 1) * 4, br = static_cast<size_t>(nq) * 16;
+  if ((r = scratch(c, &c->scr[1], &c->scr_bytes[1], bo + bc + br + 64))) return r;
+  int* d_off = static_cast<int*>(c->scr[1]);
+  int* d_idx = d_off + (nq + 1);
+  float* d_b1 = reinterpret_cast<float*>(d_idx + (total > 0 ? total : 1));
+  int* d_i1 = reinterpret_cast<int*>(d_b1 + nq);
+  float* d_b2 = reinterpret_cast<float*>(d_i1 + nq);
+  int* d_i2 = reinterpret_cast<int*>(d_b2 + nq);
+  RFE_CUDA_CHECK(cudaMemcpyAsync(d_off, cand_off, bo, cudaMemcpyHostToDevice, s));
+  if (total > 0) RFE_CUDA_CHECK(cudaMemcpyAsync(d_idx, cand_idx, static_cast<size_t>(total) * 4, cudaMemcpyHostToDevice, s));
+  launch_l2_best2(s, c->desc + static_cast<size_t>(q_slot) * c->cap * 256, nq, c->desc + static_cast<size_t>(db_slot) * c->cap * 256,
+                  d_off, d_idx, init_dist, d_b1, d_i1, d_b2, d_i2);
   c->launches++;
   RFE_CUDA_CHECK(cudaMemcpyAsync(best_dist, d_b1, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, s));
   RFE_CUDA_CHECK(cudaMemcpyAsync(best_idx, d_i1, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, s));

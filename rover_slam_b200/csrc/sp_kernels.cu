@@ -336,6 +336,105 @@ void launch_select(cudaStream_t s, const float* nms, int B, int H, int W, float 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Optional top-K cap (the `nfeatures` argument the reference stores and ignores, SPextractor.cc:84-146):
+// keep the K highest-scoring keypoints of an image, in the reference's row-major order; among equal scores the earlier
+// keypoint wins.  One block per image on the compacted list: a 4 x 8-bit radix select over the score bits finds the K-th
+// largest score (scores are positive floats: their bit patterns order like the values), then an in-place stable compaction.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) kp_topk_kernel(int* __restrict__ counts, int* __restrict__ kpts,
+                                                       float* __restrict__ scores, int cap, int K) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned sel_prefix, sel_remaining;
+  __shared__ int warp_sums[2][32];
+  __shared__ int carry[2];
+  const int b = blockIdx.x;
+  const int n = min(counts[b], cap);
+  if (n <= K) return;
+  int2* kp = reinterpret_cast<int2*>(kpts) + static_cast<size_t>(b) * cap;
+  float* sc = scores + static_cast<size_t>(b) * cap;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  // ---- radix select: after the loop sel_prefix = bits of the K-th largest score, sel_remaining = how many keypoints with
+  // exactly that score are kept
+  if (tid == 0) { sel_prefix = 0; sel_remaining = static_cast<unsigned>(K); }
+  __syncthreads();
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    const unsigned prefix = sel_prefix;
+    const unsigned himask = shift == 24 ? 0u : 0xFFFFFFFFu << (shift + 8);
+    for (int i = tid; i < n; i += 1024) {
+      const unsigned u = __float_as_uint(sc[i]);
+      if ((u & himask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned rem = sel_remaining;
+      int d = 255;
+      for (; d > 0; --d) {                 // walk down from the largest digit
+        if (hist[d] >= rem) break;
+        rem -= hist[d];
+      }
+      sel_prefix = prefix | (static_cast<unsigned>(d) << shift);
+      sel_remaining = rem;
+    }
+    __syncthreads();
+  }
+  const unsigned thr = sel_prefix;
+  const int keep_eq = static_cast<int>(sel_remaining);
+  // ---- stable in-place compaction, 1024 entries per round: keep (score > thr) and the first keep_eq with score == thr
+  if (tid == 0) { carry[0] = 0; carry[1] = 0; }
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + tid;
+    int2 k = make_int2(0, 0);
+    float v = 0.0f;
+    int eq = 0, gt = 0;
+    if (i < n) {
+      k = kp[i];
+      v = sc[i];
+      const unsigned u = __float_as_uint(v);
+      gt = u > thr;
+      eq = u == thr;
+    }
+    // two inclusive block scans at once: equals (to rank them) and kept-so-far is derived below
+    int ie = eq, ig = gt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int te = __shfl_up_sync(0xffffffffu, ie, o), tg = __shfl_up_sync(0xffffffffu, ig, o);
+      if (lane >= o) { ie += te; ig += tg; }
+    }
+    if (lane == 31) { warp_sums[0][w] = ie; warp_sums[1][w] = ig; }
+    __syncthreads();
+    if (w == 0) {
+      int se = warp_sums[0][lane], sg = warp_sums[1][lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int te = __shfl_up_sync(0xffffffffu, se, o), tg = __shfl_up_sync(0xffffffffu, sg, o);
+        if (lane >= o) { se += te; sg += tg; }
+      }
+      warp_sums[0][lane] = se;
+      warp_sums[1][lane] = sg;
+    }
+    __syncthreads();
+    const int eq_before = carry[0] + (w ? warp_sums[0][w - 1] : 0) + ie - eq;     // equals strictly before me
+    const int gt_before = carry[1] + (w ? warp_sums[1][w - 1] : 0) + ig - gt;
+    const bool keep = gt || (eq && eq_before < keep_eq);
+    const int pos = gt_before + min(eq_before, keep_eq);                           // kept entries before me
+    __syncthreads();                        // every read of this round is done before anything is overwritten
+    if (keep) {
+      kp[pos] = k;
+      sc[pos] = v;
+    }
+    if (tid == 1023) { carry[0] = eq_before + eq; carry[1] = gt_before + gt; }
+    __syncthreads();
+  }
+  if (tid == 0) counts[b] = K;
+}
+void launch_topk(cudaStream_t s, int B, int cap, int K, int* counts, int* kpts, float* scores) {
+  if (K > 0 && B > 0) kp_topk_kernel<<<B, 1024, 0, s>>>(counts, kpts, scores, cap, K);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Descriptor sampling: one warp per keypoint, lane = 8 channels.
 // grid = 2 * ((kp - 4 + 0.5) / (8*dim - 4 - 0.5)) - 1 ; grid_sample(bilinear, zeros, align_corners=True) ; L2 norm.
 // ------------------------------------------------------------------------------------------------

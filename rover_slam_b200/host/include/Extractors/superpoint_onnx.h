@@ -30,6 +30,10 @@ class SuperPointOnnxRunner {
   // the frame; keypoints below it are dropped in Extractor_PostProcess.  Off by default (= the reference's behaviour).
   bool adaptive_threshold = false;
   static float AdaptiveThreshold(const float* scores, int n, float lastmatch);
+  // the `nfeatures` cap.  SPextractor stores nfeatures and never applies it (SPextractor.cc:84-146; the graph has
+  // no top-K).  > 0: keep that many best-scoring keypoints per frame, in the graph's row-major order (rfe_sp_set_topk).
+  // 0 (default) = the reference's behaviour: every keypoint.
+  int max_keypoints_topk = 0;
   std::vector<float> scales = {1.0f, 1.0f};
   std::vector<SuperPointResult> extractor_outputtensors;
   std::pair<std::vector<cv::Point2f>, std::vector<cv::Point2f>> keypoints_result;           // superpoint_onnx.h:38

@@ -69,6 +69,7 @@ int SuperPointOnnxRunner::Extractor_Inference(Configuration cfg, const cv::Mat& 
     std::cerr << "[ERROR] SuperPointOnnxRunner Extractor inference failed : expected a 1-channel image" << std::endl;
     return EXIT_FAILURE;
   }
+  if (rfe_sp_set_topk(ctx_, max_keypoints_topk < cap_ ? max_keypoints_topk : cap_) != RFE_OK) return EXIT_FAILURE;
   SuperPointResult res;
   res.keypoints.resize(static_cast<size_t>(cap_) * 2);
   res.scores.resize(cap_);

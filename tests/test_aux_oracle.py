@@ -75,3 +75,13 @@ def test_algorithmic_flop_formulas_match_the_survey():
     assert abs(sp - bench.SP_FLOPS_PER_FRAME) / sp < 2e-3, sp
     src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "lg_sweep.py")).read()
     assert "9 * (4980736 * n + 4096 * n * n) + 263168 * n + 512 * n * n" in src and "9 * 4096 * n * n" in src
+
+
+def test_topk_keep_order():
+    from oracle import frontend_aux_ref as aux
+    s = np.float32([0.5, 0.9, 0.5, 0.1, 0.9, 0.5])
+    assert aux.topk_keep_order(s, 0).tolist() == [0, 1, 2, 3, 4, 5]
+    assert aux.topk_keep_order(s, 9).tolist() == [0, 1, 2, 3, 4, 5]
+    assert aux.topk_keep_order(s, 2).tolist() == [1, 4]
+    assert aux.topk_keep_order(s, 3).tolist() == [0, 1, 4]           # ties at the cut: the earliest 0.5 stays
+    assert aux.topk_keep_order(s, 4).tolist() == [0, 1, 2, 4]

@@ -412,6 +412,36 @@ def test_match_normalized_equals_match(fe):
         assert np.array_equal(m, m2) and np.array_equal(ms, ms2)
 
 
+def test_topk_cap_keeps_the_best_in_row_major_order(fe):
+    """8(f).4: rfe_sp_set_topk(k) == the oracle's order-preserving top-k of the uncapped extraction, bit for bit (keypoints,
+    scores, descriptors), including exact score ties at the cut; k >= N and k <= 0 leave everything."""
+    from oracle import frontend_aux_ref as aux
+    imgs = np.stack([synth.frame(s, 240, 320) for s in (8, 9)])
+    full = fe.extract(imgs)
+    try:
+        for k in (1, 100, 257, len(full[0][0]) - 1, len(full[0][0]), 4000):
+            fe.set_topk(k)
+            got = fe.extract(imgs)
+            for (fk, fs, fd), (gk, gs, gd) in zip(full, got):
+                keep = aux.topk_keep_order(fs, k)
+                assert np.array_equal(gk, fk[keep]) and np.array_equal(gs, fs[keep]) and np.array_equal(gd, fd[keep]), k
+        # exact ties at the cut: a flat image region gives many identical scores? use the scores themselves: pick k so that
+        # the k-th and (k+1)-th best scores are equal when such a pair exists
+        fs = full[0][1]
+        order = np.sort(fs)[::-1]
+        ties = np.nonzero(order[:-1] == order[1:])[0]
+        if len(ties):
+            k = int(ties[0]) + 1
+            fe.set_topk(k)
+            gk, gs, gd = fe.extract(imgs[:1])[0]
+            keep = aux.topk_keep_order(fs, k)
+            assert np.array_equal(gk, full[0][0][keep]) and np.array_equal(gs, fs[keep])
+    finally:
+        fe.set_topk(0)
+    again = fe.extract(imgs)
+    assert all(np.array_equal(a[0], b[0]) for a, b in zip(full, again))
+
+
 # ---- against an independent runtime: OpenCV DNN executing the reference's ONNX files (tests/golden/cv2dnn_*.npz) ----------
 @pytest.mark.parametrize("name", ["sp_640x480_seed0", "sp_752x480_seed100_a"])
 def test_superpoint_vs_cv2dnn_golden(fe, golden_dir, name):
@@ -489,3 +519,23 @@ def test_l2_best2_vs_oracle(fe):
     assert np.array_equal(i1[gap_ok], j1[gap_ok])
     assert i1[0] == -1 and b1[0] == 256.0                   # empty candidate list
     assert i1[2] == 17 and i2[2] == 5                       # exact tie: list order wins (strict <)
+
+
+def test_l2_best2_slots_equals_host_form(fe):
+    """8(f).2, slot-resident: the same answer as rfe_l2_best2 on the descriptors read back from the slots, bit for bit."""
+    imgs = np.stack(synth.frame_pair(90, 240, 320, shift=(5, 2)))
+    fe.extract_device_from_host(imgs)
+    (k0, _, d0), (k1, _, d1) = fe.read_slot(0), fe.read_slot(1)
+    rng = np.random.RandomState(3)
+    off, idx = [0], []
+    for i in range(len(k0)):
+        # candidates = keypoints of the other frame inside a 40-px window (the shape of SearchByProjection's GetFeaturesInArea)
+        near = np.nonzero(np.abs(k1 - k0[i]).max(1) <= 20)[0]
+        idx += rng.permutation(near).tolist()
+        off.append(len(idx))
+    off, idx = np.array(off, np.int32), np.array(idx, np.int32)
+    a = fe.l2_best2_slots(0, 1, off, idx)
+    b = fe.l2_best2(d0, d1, off, idx)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert (a[1] >= 0).sum() > 50
