@@ -114,13 +114,15 @@ int rfe_l2_best2(rfe_ctx* ctx, const float* q, int nq, const float* db, int nd, 
                  const int32_t* cand_idx, float init_dist, float* best_dist, int32_t* best_idx, float* second_dist,
                  int32_t* second_idx);
 
-/* The slot-resident form: queries = the first nq descriptors of feature slot q_slot, database = feature slot db_slot (both
- * left on the device by rfe_sp_extract_device / rfe_pairs_submit, or uploaded once with rfe_sp_write_slot).  Only the
- * candidate lists cross PCIe: the current frame against the last frame / a KeyFrame in SearchByProjection1
- * (SPmatcher.cc:1170-1352), left against right in Frame::ComputeStereoMatches (Frame.cc:1159-1340).  INTEGRATION.md shows
- * SearchByProjection1 written on it. */
-int rfe_l2_best2_slots(rfe_ctx* ctx, int q_slot, int db_slot, int nq, const int32_t* cand_off, const int32_t* cand_idx,
-                       float init_dist, float* best_dist, int32_t* best_idx, float* second_dist, int32_t* second_idx);
+/* The slot-resident form: the database is feature slot db_slot (left on the device by rfe_sp_extract_device /
+ * rfe_pairs_submit, or uploaded once with rfe_sp_write_slot); the queries are either the first nq descriptors of feature
+ * slot q_slot (q_host == NULL: frame against frame, e.g. left against right in Frame::ComputeStereoMatches,
+ * src/Frame.cc:1159-1340) or nq host descriptors q_host [nq][256] (MapPoint descriptors against the current frame in
+ * SPmatcher::SearchByProjection1, src/Matchers/SPmatcher.cc:1170-1352; q_slot is ignored).  The frame's descriptors never
+ * cross PCIe again.  INTEGRATION.md shows SearchByProjection1 written on it. */
+int rfe_l2_best2_slots(rfe_ctx* ctx, const float* q_host, int q_slot, int db_slot, int nq, const int32_t* cand_off,
+                       const int32_t* cand_idx, float init_dist, float* best_dist, int32_t* best_idx, float* second_dist,
+                       int32_t* second_idx);
 
 /* ---- LightGlue -------------------------------------------------------------------------------- */
 /* Host in / host out.  kpts*_px: [n][2] pixel coordinates (x, y); desc*: [n][256].  Keypoints are
@@ -147,6 +149,18 @@ int rfe_lg_match_slots(rfe_ctx* ctx, int slot0, int slot1, int norm_h, int norm_
  * goes to result slot i.  Asynchronous apart from one small device->host read of the keypoint counts. */
 int rfe_lg_match_slots_batch(rfe_ctx* ctx, int n_pairs, const int* slot0, const int* slot1, int norm_h, int norm_w,
                              float match_thresh);
+/* One feature slot against many: pair i = (slot, others[i]), result slot i -- LocalMapping's
+ * CreateNewMapPoints matches ONE KeyFrame against up to ten covisible neighbours (src/LocalMapping.cc:522-634 ->
+ * SPmatcher::SearchForTriangulation -> MatchingPoints_onnx per neighbour, src/Matchers/SPmatcher.cc:1355-1399), re-uploading
+ * and re-projecting that KeyFrame every time.  Here everything that depends on an image alone -- positional encoding and the
+ * whole first self-attention block of LightGlue -- is computed once per (slot contents, norm_h, norm_w) and cached on the
+ * device; the cache entry is rebuilt when the slot is overwritten (extraction, rfe_sp_write_slot) or matched with another
+ * normalisation size.  Results equal rfe_lg_match_slots_batch on the same pairs.  n_others <= max_batch. */
+int rfe_lg_match_one_to_many(rfe_ctx* ctx, int slot, const int* others, int n_others, int norm_h, int norm_w,
+                             float match_thresh);
+/* How many slot states rfe_lg_match_one_to_many found cached / had to build so far. */
+int rfe_lg_cache_stats(rfe_ctx* ctx, long long* hits, long long* builds);
+
 /* The whole hot path in one call, host in / host out: n_pairs pairs of images (pair p = images 2p and 2p+1 of `gray`,
  * layout as rfe_sp_extract_u8), SuperPoint on all 2*n_pairs images, LightGlue on every pair (keypoints normalised with
  * the image size, i.e. the semantics of MatchingPoints_onnx(Frame&, Frame&, ...), SPmatcher.cc:457-542).  Descriptors

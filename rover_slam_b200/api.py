@@ -67,11 +67,13 @@ def load_library():
     lib.rfe_sp_write_slot.argtypes = [vp, ci, vp, vp, vp, ci]
     lib.rfe_binarize_descriptors.argtypes = [vp, vp, ci, vp, vp]
     lib.rfe_l2_best2.argtypes = [vp, vp, ci, vp, ci, vp, vp, cf, vp, vp, vp, vp]
-    lib.rfe_l2_best2_slots.argtypes = [vp, ci, ci, ci, vp, vp, cf, vp, vp, vp, vp]
+    lib.rfe_l2_best2_slots.argtypes = [vp, vp, ci, ci, ci, vp, vp, cf, vp, vp, vp, vp]
     lib.rfe_lg_match.argtypes = [vp, vp, ci, vp, ci, vp, vp, ci, ci, cf, vp, vp, vp]
     lib.rfe_lg_match_normalized.argtypes = [vp, vp, ci, vp, ci, vp, vp, cf, vp, vp, vp]
     lib.rfe_lg_match_slots.argtypes = [vp, ci, ci, ci, ci, cf, ci]
     lib.rfe_lg_match_slots_batch.argtypes = [vp, ci, vp, vp, ci, ci, cf]
+    lib.rfe_lg_match_one_to_many.argtypes = [vp, ci, vp, ci, ci, ci, cf]
+    lib.rfe_lg_cache_stats.argtypes = [vp, P(C.c_longlong), P(C.c_longlong)]
     lib.rfe_match_pairs_u8.argtypes = [vp, vp, ci, ci, ci, ci, cf, vp, vp, vp, vp, vp, ci]
     lib.rfe_pairs_submit.argtypes = [vp, vp, ci, ci, ci, ci]
     lib.rfe_pairs_collect.argtypes = [vp, cf, vp, vp, vp, vp, vp, ci]
@@ -214,14 +216,15 @@ class FrontEnd:
                                           _ptr(b1), _ptr(i1), _ptr(b2), _ptr(i2)))
         return b1, i1, b2, i2
 
-    def l2_best2_slots(self, q_slot: int, db_slot: int, cand_off: np.ndarray, cand_idx: np.ndarray, init_dist: float = 256.0):
-        """l2_best2 with both descriptor sets taken from device-resident feature slots; only the candidate lists are uploaded."""
+    def l2_best2_slots(self, q_slot, db_slot: int, cand_off: np.ndarray, cand_idx: np.ndarray, init_dist: float = 256.0, q=None):
+        """l2_best2 with the database (and, when q is None, the queries) taken from device-resident feature slots."""
+        qh = None if q is None else np.ascontiguousarray(q, np.float32).reshape(-1, DESC_DIM)
         off = np.ascontiguousarray(cand_off, np.int32)
         idx = np.ascontiguousarray(cand_idx, np.int32)
         nq = len(off) - 1
         b1, b2 = np.empty(nq, np.float32), np.empty(nq, np.float32)
         i1, i2 = np.empty(nq, np.int32), np.empty(nq, np.int32)
-        self._check(self.lib.rfe_l2_best2_slots(self.ctx, q_slot, db_slot, nq, _ptr(off), _ptr(idx), init_dist,
+        self._check(self.lib.rfe_l2_best2_slots(self.ctx, _ptr(qh), -1 if q_slot is None else q_slot, db_slot, nq, _ptr(off), _ptr(idx), init_dist,
                                                 _ptr(b1), _ptr(i1), _ptr(b2), _ptr(i2)))
         return b1, i1, b2, i2
 
@@ -262,6 +265,16 @@ class FrontEnd:
         s0 = np.ascontiguousarray(slots0, np.int32)
         s1 = np.ascontiguousarray(slots1, np.int32)
         self._check(self.lib.rfe_lg_match_slots_batch(self.ctx, len(s0), _ptr(s0), _ptr(s1), norm_h, norm_w, thresh))
+
+    def match_one_to_many(self, slot: int, others, norm_h: int, norm_w: int, thresh: float = 0.0):
+        """Slot `slot` against every slot of `others` (result slot i = pair i), layer-0 state of every slot cached."""
+        o = np.ascontiguousarray(others, np.int32)
+        self._check(self.lib.rfe_lg_match_one_to_many(self.ctx, slot, _ptr(o), len(o), norm_h, norm_w, thresh))
+
+    def cache_stats(self):
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        self._check(self.lib.rfe_lg_cache_stats(self.ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def match_pairs(self, images: np.ndarray, thresh: float = 0.0, want_kpts: bool = True):
         """images: uint8 [2*P, H, W] host array, pair p = images 2p, 2p+1.  One call = extract all + match all.

@@ -284,6 +284,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
     constexpr int kSmThreads = 32 * kAttnSoftmaxWarps;
     const bool sprof = prof_cta && warp == 0 && lane == 0;
     long long sw_s1 = 0, sw_s = 0, sw_p = 0, sw_o = 0, t_sm1 = 0, t_sm2 = 0, t_epi = 0;
+    long long ph_ld = 0, ph_math = 0, ph_sts = 0, ph_fence = 0;     // pass-2 phases of one warp (PROF build)
     uint32_t n_base = 0, v_base = 0, it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const AttnItem a = attn_decode(p, item);
@@ -344,7 +345,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
         const int b = n % kAttnSBufs, pb = v & 1;
         const long long w0 = tick();
         mbar_wait(&s_full[b], (n / kAttnSBufs) & 1);
-        sw_s += tick() - w0;
+        const long long w0b = tick();
+        sw_s += w0b - w0;
         tc_fence_after();
         uint32_t a0[2][16], x0[2][16];
         const uint32_t base = tlane + b * 128 + ch2 * 32;
@@ -356,6 +358,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[b]);
+        const long long w1b = tick();
+        ph_ld += w1b - w0b;
         uint32_t ph[2][8], pl[2][8];
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -385,8 +389,10 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
           }
         }
         const long long w2 = tick();
+        ph_math += w2 - w1b;
         mbar_wait(&p_empty[pb], ((v >> 1) & 1) ^ 1);       // the P V product two tiles back has consumed this P buffer
-        sw_p += tick() - w2;
+        const long long w2b = tick();
+        sw_p += w2b - w2;
         uint8_t* prow_hi = sP + pb * kAttnPBytes + row * 128;
         uint8_t* prow_lo = prow_hi + 16384;
 #pragma unroll
@@ -396,9 +402,13 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
           *reinterpret_cast<uint4*>(prow_hi + sc) = make_uint4(ph[hf][o], ph[hf][o + 1], ph[hf][o + 2], ph[hf][o + 3]);
           *reinterpret_cast<uint4*>(prow_lo + sc) = make_uint4(pl[hf][o], pl[hf][o + 1], pl[hf][o + 2], pl[hf][o + 3]);
         }
+        const long long w3b = tick();
         fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[pb]);
+        const long long w4b = tick();
+        ph_sts += w3b - w2b;
+        ph_fence += w4b - w3b;
       };
       const int t_full = (nk % kAttnKeyTile) ? T - 1 : T;
 #pragma unroll 1
@@ -461,6 +471,10 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
       p.prof[14] = sw_s1;     //   waiting for scores
       p.prof[15] = t_epi;     // l exchange + wait for O + epilogue
       p.prof[18] = sw_o;      //   of which waiting for o_full
+      p.prof[19] = ph_ld;     // pass 2: tcgen05.ld + wait + score-buffer release
+      p.prof[20] = ph_math;   // pass 2: exp / split arithmetic
+      p.prof[21] = ph_sts;    // pass 2: shared-memory stores of P
+      p.prof[22] = ph_fence;  // pass 2: fence.proxy.async + arrive
     }
     tc_fence_before();
   }

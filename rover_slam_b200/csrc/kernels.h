@@ -39,6 +39,15 @@ struct LgAssign {                         // the assignment stage of all pairs o
   int* count[kLgMaxImages / 2];
   int pairs, max_n0, max_n1;
 };
+struct LgCacheMove {                      // batch state <-> per-slot layer-0 cache, one entry per image
+  float* x; __half* cat_hi; __half* cat_lo; float* cs; float* sn;            // batch state ([rows][256] / [rows][512] / [rows][32])
+  float* cx; __half* ccat_hi; __half* ccat_lo; float* ccs; float* csn;       // cache ([slot][cap][256] / [256] / [32])
+  int slot[kLgMaxImages], n[kLgMaxImages], row0[kLgMaxImages];
+  int count, cap, to_cache;
+};
+// to_cache = 1: store rows [row0, row0 + n) of every image into its slot's cache entry; 0: load them back (and zero the
+// image's padding rows, as lg_prepare does)
+void launch_lg_cache_move(cudaStream_t s, const LgCacheMove& mv, int max_n);
 // positional encoding + residual-stream initialisation (x = desc, cat[:, :256] = split(desc)) for every image
 void launch_lg_prepare(cudaStream_t s, const LgImages& im, int max_n, int norm_h, int norm_w, const float* wr, float* cs,
                        float* sn, float* x, __half* cat_hi, __half* cat_lo);

@@ -431,6 +431,52 @@ void launch_lg_prepare(cudaStream_t s, const LgImages& im, int max_n, int norm_h
   lg_prepare_kernel<<<dim3((max_n + 7) / 8, im.count), 256, 0, s>>>(im, sx, sy, sc, wr, cs, sn, x, cat_hi, cat_lo);
 }
 
+// Per-slot layer-0 cache (rover_fe.cu, lg_build_cache): one warp per keypoint row copies x (1 KB), the split copy of x
+// (2 x 512 B) and cos / sin (2 x 128 B) between the batch state and the slot's cache entry.  grid = (ceil(max_n / 8), images).
+__global__ void __launch_bounds__(256) lg_cache_move_kernel(const LgCacheMove mv) {
+  const int img = blockIdx.y;
+  const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int n = mv.n[img];
+  if (k >= ((n + 7) & ~7)) return;
+  const size_t row = static_cast<size_t>(mv.row0[img]) + k;
+  const size_t crow = static_cast<size_t>(mv.slot[img]) * mv.cap + k;
+  float4* bx = reinterpret_cast<float4*>(mv.x + row * 256);
+  uint4* bh = reinterpret_cast<uint4*>(mv.cat_hi + row * 512);
+  uint4* bl = reinterpret_cast<uint4*>(mv.cat_lo + row * 512);
+  if (k >= n) {                          // padding rows of the batch state: zero, like lg_prepare (never stored)
+    if (!mv.to_cache) {
+      const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      bx[lane] = z4; bx[32 + lane] = z4;
+      bh[lane] = make_uint4(0u, 0u, 0u, 0u);
+      bl[lane] = make_uint4(0u, 0u, 0u, 0u);
+      mv.cs[row * 32 + lane] = 0.0f;
+      mv.sn[row * 32 + lane] = 0.0f;
+    }
+    return;
+  }
+  float4* cx = reinterpret_cast<float4*>(mv.cx + crow * 256);
+  uint4* ch = reinterpret_cast<uint4*>(mv.ccat_hi + crow * 256);
+  uint4* cl = reinterpret_cast<uint4*>(mv.ccat_lo + crow * 256);
+  if (mv.to_cache) {
+    cx[lane] = bx[lane]; cx[32 + lane] = bx[32 + lane];
+    ch[lane] = bh[lane];
+    cl[lane] = bl[lane];
+    mv.ccs[crow * 32 + lane] = mv.cs[row * 32 + lane];
+    mv.csn[crow * 32 + lane] = mv.sn[row * 32 + lane];
+  } else {
+    bx[lane] = cx[lane]; bx[32 + lane] = cx[32 + lane];
+    bh[lane] = ch[lane];
+    bl[lane] = cl[lane];
+    mv.cs[row * 32 + lane] = mv.ccs[crow * 32 + lane];
+    mv.sn[row * 32 + lane] = mv.csn[crow * 32 + lane];
+  }
+}
+void launch_lg_cache_move(cudaStream_t s, const LgCacheMove& mv, int max_n) {
+  if (mv.count == 0 || max_n == 0) return;
+  lg_cache_move_kernel<<<dim3((max_n + 7) / 8, mv.count), 256, 0, s>>>(mv);
+}
+
 // Row statistics / row arg-max: one warp per row, blockIdx.y = pair.  Column statistics / arg-max: block = 32 columns x
 // 32 row-lanes.  Per-row vectors are indexed by the row's position in the concatenated LightGlue state.
 __global__ void __launch_bounds__(256) row_lse_batch_kernel(const LgAssign a, float* __restrict__ rmax,

@@ -52,6 +52,13 @@ struct rfe_ctx {
   bool own_stream = false;
   int max_batch = 8, max_h = 480, max_w = 768, cap = 4096;
   bool no_sp = false, no_lg = false;     // RFE_FLAG_NO_EXTRACTOR / RFE_FLAG_NO_MATCHER
+  // layer-0 cache of the feature slots (rfe_lg_match_one_to_many): allocated on first use
+  float* cache_x = nullptr;
+  SplitBuf cache_cat;
+  float *cache_cs = nullptr, *cache_sn = nullptr;
+  std::vector<long long> slot_gen, cache_gen;   // contents generation of every slot / generation its cache entry was built from
+  std::vector<int> cache_nh, cache_nw;          // normalisation size the entry was built with
+  long long cache_hits = 0, cache_builds = 0;
   int topk = 0;                          // rfe_sp_set_topk: keep the K best keypoints per image (0 = all, the reference)
   std::vector<void*> allocs;
   long long launches = 0;
@@ -341,6 +348,15 @@ int make_head_map(CUtensorMap* m, const void* base, int rows, long long head_str
   return make_tmap(m, 0, 2, base, 3, dims, strides, box) ? RFE_ERR_CUDA : RFE_OK;
 }
 
+// transposed planes [cols][ld] (V^T): (rows contiguous, cols, batch) with a 32 x 32 box, 64-byte swizzle
+int make_vt_map(CUtensorMap* m, const void* base, int rows, int cols, long long ld, int batch, long long bstride) {
+  const uint64_t dims[3] = {static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), static_cast<uint64_t>(batch > 1 ? batch : 1)};
+  const uint64_t strides[2] = {static_cast<uint64_t>(ld) * 2,
+                               static_cast<uint64_t>(batch > 1 ? bstride : static_cast<long long>(cols) * ld) * 2};
+  const uint32_t box[3] = {32, 32, 1};
+  return make_tmap(m, 0, 2, base, 3, dims, strides, box) ? RFE_ERR_CUDA : RFE_OK;
+}
+
 UmmaParams default_params() {
   UmmaParams p;
   memset(&p, 0, sizeof(p));
@@ -373,6 +389,10 @@ int gemm_linear(rfe_ctx* c, const char* tag, const Operand& A, const Operand& B,
   memset(&em, 0, sizeof(em));
   if (p.out_f32 && (r = make_out_map(&em.f32, p.out_f32, true, p.N, p.M, p.ld_f32, z, p.bstride_f32))) return r;
   if (p.residual && (r = make_out_map(&em.res, p.residual, true, p.N, p.M, p.ld_res, z, p.bstride_res))) return r;
+  if (p.out_hi && p.transpose_h) {
+    if ((r = make_vt_map(&em.vt_hi, p.out_hi, p.M, p.N, p.ld_h, z, p.bstride_h))) return r;
+    if ((r = make_vt_map(&em.vt_lo, p.out_lo, p.M, p.N, p.ld_h, z, p.bstride_h))) return r;
+  }
   if (p.out_hi && !p.transpose_h) {
     if (p.head_major) {
       if ((r = make_head_map(&em.h_hi, p.out_hi, p.M, p.head_stride, p.N / 64))) return r;
@@ -535,6 +555,7 @@ int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B, i
                                                            c->desc_bin + static_cast<size_t>(slot_base) * c->cap * 256); }
   c->launches += 5;
   RFE_CUDA_CHECK(cudaGetLastError());
+  for (int b = 0; b < B; ++b) c->slot_gen[slot_base + b]++;     // cached layer-0 state of these slots is stale now
   c->last_batch = B;
   c->last_h = h;
   c->last_w = w;
@@ -579,9 +600,11 @@ int ffn_block(rfe_ctx* c, int rows, const SplitW& ffn0, const float* ln_w, const
 int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitBuf& K, int rows_total,
                     const AttnParams& problems, int nprob, int max_nq) {
   static bool configured[64] = {};
-  // RFE_ATTN=1: the one-item-per-CTA two-pass kernel of round 1; 2: its persistent form; 3 (default): the persistent
-  // single-pass (online-softmax) kernel.  The older two stay for A/B measurements.
-  static const int kAttnMode = getenv("RFE_ATTN") ? atoi(getenv("RFE_ATTN")) : 3;
+  // RFE_ATTN=1: the one-item-per-CTA two-pass kernel of round 1; 2 (default): its persistent form; 3: the persistent
+  // single-pass (online-softmax) kernel -- correct, but measured slower (profiles/r02_attn3_online_softmax_prof.txt: the
+  // softmax warps, not the tensor pipe, bound this kernel, and the per-tile maximum + pair exchange costs them more than the
+  // separate maximum pass did).  Kept for A/B measurements.
+  static const int kAttnMode = getenv("RFE_ATTN") ? atoi(getenv("RFE_ATTN")) : 2;
   if (!configured[c->device & 63]) {
     RFE_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
     RFE_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
@@ -629,6 +652,129 @@ int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitB
   return RFE_OK;
 }
 
+// One self-attention block (Wqkv + rotary, fused attention of every image against itself, out_proj, FFN) over `rows` rows.
+int lg_self_block(rfe_ctx* c, const LgLayer& L, int rows, const AttnParams& self_p, int nprob, int max_n, int lin_bn) {
+  int r;
+  const long long hs = static_cast<long long>(rows) * 64;
+  // ---------------- self attention ----------------
+  {   // qkv = x Wqkv^T + b ; rotary on q,k ; head split ; V transposed -- all in the GEMM epilogue
+    Operand A{c->cat.hi, c->cat.lo, rows, 256, 512, 0, 1};
+    Operand B{L.wqkv.w.hi, L.wqkv.w.lo, 768, 256, 256, 0, 1};
+    CUtensorMap ah, al, bh, bl;
+    if ((r = make_operand_maps(A, kBlockM, &ah, &al))) return r;
+    if ((r = make_operand_maps(B, 128, &bh, &bl))) return r;
+    UmmaParams p = default_params();
+    p.num_k_steps = 4;
+    p.M = rows;
+    p.N = 768;
+    p.bias = L.wqkv.bias;
+    p.scale = kAttnScale;
+    p.cs = c->cs;
+    p.sn = c->sn;
+    p.out_hi = c->q.hi;
+    p.out_lo = c->q.lo;
+    p.k_hi = c->k.hi;
+    p.k_lo = c->k.lo;
+    p.vt_hi = c->vt.hi;
+    p.vt_lo = c->vt.lo;
+    p.ldv = c->lg_ldv;
+    p.head_stride = hs;
+    EpiMaps em;
+    memset(&em, 0, sizeof(em));
+    if ((r = make_head_map(&em.h_hi, c->q.hi, rows, hs, 4)) || (r = make_head_map(&em.h_lo, c->q.lo, rows, hs, 4)) ||
+        (r = make_head_map(&em.k_hi, c->k.hi, rows, hs, 4)) || (r = make_head_map(&em.k_lo, c->k.lo, rows, hs, 4)) ||
+        (r = make_vt_map(&em.vt_hi, c->vt.hi, rows, 256, c->lg_ldv, 1, 0)) || (r = make_vt_map(&em.vt_lo, c->vt.lo, rows, 256, c->lg_ldv, 1, 0)))
+      return r;
+    const dim3 tiles((rows + 127) / 128, 6, 1);
+    if (use_bres(c, tiles.x * tiles.y))
+      r = launch_umma<128, A_GEMM, EPI_QKV, true>(c, "lg.wqkv_rope", ah, al, bh, bl, p, tiles, &em);
+    else
+      r = launch_umma<128, A_GEMM, EPI_QKV>(c, "lg.wqkv_rope", ah, al, bh, bl, p, tiles, &em);
+    if (r) return r;
+  }
+  if ((r = attention_fused(c, "lg.attn_self", c->q, c->k, rows, self_p, nprob, max_n))) return r;
+  {
+    Operand A{c->attn.hi, c->attn.lo, rows, 256, 256, 0, 1};
+    Operand B{L.out_proj.w.hi, L.out_proj.w.lo, 256, 256, 256, 0, 1};
+    UmmaParams p = default_params();
+    p.bias = L.out_proj.bias;
+    p.out_hi = c->cat.hi + 256;
+    p.out_lo = c->cat.lo + 256;
+    p.ld_h = 512;
+    if ((r = gemm_linear(c, "lg.out_proj", A, B, p, lin_bn))) return r;
+  }
+  if ((r = ffn_block(c, rows, L.s_ffn0, L.s_ln_w, L.s_ln_b, L.s_ffn3))) return r;
+  return RFE_OK;
+}
+
+// ---- per-slot layer-0 cache ----------------------------------------------------------------------
+// LocalMapping matches ONE KeyFrame against up to ten neighbours (LocalMapping.cc:522-634 -> SearchForTriangulation ->
+// MatchingPoints_onnx per neighbour), the reference re-uploading and re-projecting the same KeyFrame every time.  What
+// depends on an image alone -- positional encoding, x = desc, and the whole first self-attention block -- is computed once
+// per (slot contents, normalisation size) and kept: x after the block, its split copy, cos / sin.
+int cache_alloc(rfe_ctx* c) {
+  if (c->cache_x) return RFE_OK;
+  const size_t slots = 2 * static_cast<size_t>(c->max_batch), cap = c->cap;
+  int r;
+  if ((r = dev_alloc(c, &c->cache_x, slots * cap * 256)) || (r = split_alloc(c, &c->cache_cat, slots * cap * 256)) ||
+      (r = dev_alloc(c, &c->cache_cs, slots * cap * 32)) || (r = dev_alloc(c, &c->cache_sn, slots * cap * 32)))
+    return r;
+  c->cache_gen.assign(slots, -1);
+  c->cache_nh.assign(slots, 0);
+  c->cache_nw.assign(slots, 0);
+  return RFE_OK;
+}
+void cache_move(rfe_ctx* c, LgCacheMove& mv, int max_n, int to_cache) {
+  mv.x = c->x; mv.cat_hi = c->cat.hi; mv.cat_lo = c->cat.lo; mv.cs = c->cs; mv.sn = c->sn;
+  mv.cx = c->cache_x; mv.ccat_hi = c->cache_cat.hi; mv.ccat_lo = c->cache_cat.lo; mv.ccs = c->cache_cs; mv.csn = c->cache_sn;
+  mv.cap = c->cap;
+  mv.to_cache = to_cache;
+  ProfScope ps_(c, to_cache ? "lg.cache_store" : "lg.cache_load");
+  launch_lg_cache_move(c->stream, mv, max_n);
+  c->launches++;
+}
+// Build the cache entries of `count` slots (n[i] keypoints each) in one pass: prepare + layer-0 self block over all of them.
+int lg_build_cache(rfe_ctx* c, const int* slots, const int* n, int count, int norm_h, int norm_w) {
+  int r;
+  if ((r = cache_alloc(c))) return r;
+  LgImages im;
+  LgCacheMove mv;
+  AttnParams self_p;
+  memset(&im, 0, sizeof(im));
+  memset(&mv, 0, sizeof(mv));
+  memset(&self_p, 0, sizeof(self_p));
+  int rows = 0, mx = 0;
+  for (int i = 0; i < count; ++i) {
+    im.kpts_i[i] = c->kpts + static_cast<size_t>(slots[i]) * c->cap * 2;
+    im.desc[i] = c->desc + static_cast<size_t>(slots[i]) * c->cap * 256;
+    im.n[i] = n[i];
+    im.row0[i] = rows;
+    mv.slot[i] = slots[i]; mv.n[i] = n[i]; mv.row0[i] = rows;
+    self_p.nq[i] = n[i]; self_p.nk[i] = n[i]; self_p.q_row0[i] = rows; self_p.k_row0[i] = rows;
+    rows += round_up(n[i], 8);
+    mx = n[i] > mx ? n[i] : mx;
+  }
+  im.count = mv.count = count;
+  if (rows > c->lg_rows) {
+    set_error("layer-0 cache build needs %d rows, ctx capacity %d", rows, c->lg_rows);
+    return RFE_ERR_CAPACITY;
+  }
+  {
+    ProfScope ps_(c, "lg.prepare");
+    launch_lg_prepare(c->stream, im, mx, norm_h, norm_w, c->posenc_w, c->cs, c->sn, c->x, c->cat.hi, c->cat.lo);
+    c->launches++;
+  }
+  const int lin_bn = use_bres(c, ((rows + 127) / 128) * 2) ? 128 : 64;
+  if ((r = lg_self_block(c, c->layers[0], rows, self_p, count, mx, lin_bn))) return r;
+  cache_move(c, mv, mx, /*to_cache=*/1);
+  for (int i = 0; i < count; ++i) {
+    c->cache_gen[slots[i]] = c->slot_gen[slots[i]];
+    c->cache_nh[slots[i]] = norm_h;
+    c->cache_nw[slots[i]] = norm_w;
+  }
+  return RFE_OK;
+}
+
 struct PairDesc {      // one LightGlue problem: device-resident pixel keypoints [n][2] and descriptors [n][256]
   const float* kpts0;  // fp32 keypoints (host API) ...
   const float* kpts1;
@@ -638,11 +784,12 @@ struct PairDesc {      // one LightGlue problem: device-resident pixel keypoints
   const float* desc1;
   int n0, n1;
   int rslot;
+  int slot0 = -1, slot1 = -1;   // feature slots the two images came from (needed by the layer-0 cache only)
 };
 
 // Match `np` independent pairs in one pass.  All images' rows are concatenated (each image starts at a multiple of
 // 8 rows), so every linear layer is ONE GEMM over all pairs; attention runs as 2*np problems of one fused launch.
-int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm_w, float thresh) {
+int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm_w, float thresh, bool cache_slots = false) {
   cudaStream_t s = c->stream;
   int r;
   if (c->no_lg) {
@@ -670,7 +817,19 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
     set_error("LightGlue batch needs %d rows, ctx capacity %d", rows, c->lg_rows);
     return RFE_ERR_CAPACITY;
   }
-  {   // positional encodings + residual-stream initialisation of every image: ONE launch
+  if (cache_slots) {   // every image's state after layer 0's self block comes out of its slot's cache: ONE launch
+    LgCacheMove mv;
+    memset(&mv, 0, sizeof(mv));
+    int mx = 0;
+    for (int i = 0; i < np; ++i) {
+      mv.slot[2 * i] = pairs[i].slot0;      mv.n[2 * i] = pairs[i].n0;      mv.row0[2 * i] = off0[i];
+      mv.slot[2 * i + 1] = pairs[i].slot1;  mv.n[2 * i + 1] = pairs[i].n1;  mv.row0[2 * i + 1] = off1[i];
+      mx = pairs[i].n0 > mx ? pairs[i].n0 : mx;
+      mx = pairs[i].n1 > mx ? pairs[i].n1 : mx;
+    }
+    mv.count = 2 * np;
+    cache_move(c, mv, mx, /*to_cache=*/0);
+  } else {   // positional encodings + residual-stream initialisation of every image: ONE launch
     LgImages im;
     memset(&im, 0, sizeof(im));
     int mx = 0;
@@ -707,52 +866,9 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
   for (int i = 0; i < kLayers; ++i) {
     const LgLayer& L = c->layers[i];
     // ---------------- self attention ----------------
-    {   // qkv = x Wqkv^T + b ; rotary on q,k ; head split ; V transposed -- all in the GEMM epilogue
-      Operand A{c->cat.hi, c->cat.lo, rows, 256, 512, 0, 1};
-      Operand B{L.wqkv.w.hi, L.wqkv.w.lo, 768, 256, 256, 0, 1};
-      CUtensorMap ah, al, bh, bl;
-      if ((r = make_operand_maps(A, kBlockM, &ah, &al))) return r;
-      if ((r = make_operand_maps(B, 128, &bh, &bl))) return r;
-      UmmaParams p = default_params();
-      p.num_k_steps = 4;
-      p.M = rows;
-      p.N = 768;
-      p.bias = L.wqkv.bias;
-      p.scale = kAttnScale;
-      p.cs = c->cs;
-      p.sn = c->sn;
-      p.out_hi = c->q.hi;
-      p.out_lo = c->q.lo;
-      p.k_hi = c->k.hi;
-      p.k_lo = c->k.lo;
-      p.vt_hi = c->vt.hi;
-      p.vt_lo = c->vt.lo;
-      p.ldv = c->lg_ldv;
-      p.head_stride = hs;
-      EpiMaps em;
-      memset(&em, 0, sizeof(em));
-      if ((r = make_head_map(&em.h_hi, c->q.hi, rows, hs, 4)) || (r = make_head_map(&em.h_lo, c->q.lo, rows, hs, 4)) ||
-          (r = make_head_map(&em.k_hi, c->k.hi, rows, hs, 4)) || (r = make_head_map(&em.k_lo, c->k.lo, rows, hs, 4)))
-        return r;
-      const dim3 tiles((rows + 127) / 128, 6, 1);
-      if (use_bres(c, tiles.x * tiles.y))
-        r = launch_umma<128, A_GEMM, EPI_QKV, true>(c, "lg.wqkv_rope", ah, al, bh, bl, p, tiles, &em);
-      else
-        r = launch_umma<128, A_GEMM, EPI_QKV>(c, "lg.wqkv_rope", ah, al, bh, bl, p, tiles, &em);
-      if (r) return r;
-    }
-    if ((r = attention_fused(c, "lg.attn_self", c->q, c->k, rows, self_p, 2 * np, max_n))) return r;
-    {
-      Operand A{c->attn.hi, c->attn.lo, rows, 256, 256, 0, 1};
-      Operand B{L.out_proj.w.hi, L.out_proj.w.lo, 256, 256, 256, 0, 1};
-      UmmaParams p = default_params();
-      p.bias = L.out_proj.bias;
-      p.out_hi = c->cat.hi + 256;
-      p.out_lo = c->cat.lo + 256;
-      p.ld_h = 512;
-      if ((r = gemm_linear(c, "lg.out_proj", A, B, p, lin_bn))) return r;
-    }
-    if ((r = ffn_block(c, rows, L.s_ffn0, L.s_ln_w, L.s_ln_b, L.s_ffn3))) return r;
+    // layer 0's self block depends on the image alone: with cached slots (rfe_lg_match_one_to_many) it was computed when
+    // the cache was built and the gathered state already holds its output
+    if (!(i == 0 && cache_slots) && (r = lg_self_block(c, L, rows, self_p, 2 * np, max_n, lin_bn))) return r;
     // ---------------- cross attention ----------------
     {
       Operand A{c->cat.hi, c->cat.lo, rows, 256, 512, 0, 1};
@@ -910,6 +1026,7 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   c->max_h = cfg->max_height > 0 ? cfg->max_height : 480;
   c->max_w = cfg->max_width > 0 ? cfg->max_width : 768;
   c->cap = cfg->max_keypoints > 0 ? cfg->max_keypoints : 4096;
+  c->slot_gen.assign(2 * static_cast<size_t>(c->max_batch), 0);
   c->no_sp = (cfg->flags & RFE_FLAG_NO_EXTRACTOR) != 0;
   c->no_lg = (cfg->flags & RFE_FLAG_NO_MATCHER) != 0;
   if (c->no_sp) c->max_h = c->max_w = 8;      // the activation buffers shrink to nothing; the feature slots stay (rfe_sp_write_slot)
@@ -1123,6 +1240,7 @@ int rfe_sp_write_slot(rfe_ctx* c, int slot, const int32_t* kpts_xy, const float*
     c->launches++;
     c->bytes_h2d += static_cast<unsigned long long>(n) * (8 + (scores ? 4 : 0) + 1024);
   }
+  c->slot_gen[slot]++;
   c->h_counts[0] = n;
   RFE_CUDA_CHECK(cudaMemcpyAsync(c->kp_counts + slot, c->h_counts, sizeof(int), cudaMemcpyHostToDevice, c->stream));
   RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -1260,10 +1378,12 @@ int rfe_l2_best2(rfe_ctx* c, const float* q, int nq, const float* db, int nd, co
   return RFE_OK;
 }
 
-int rfe_l2_best2_slots(rfe_ctx* c, int q_slot, int db_slot, int nq, const int32_t* cand_off, const int32_t* cand_idx,
-                       float init_dist, float* best_dist, int32_t* best_idx, float* second_dist, int32_t* second_idx) {
+int rfe_l2_best2_slots(rfe_ctx* c, const float* q_host, int q_slot, int db_slot, int nq, const int32_t* cand_off,
+                       const int32_t* cand_idx, float init_dist, float* best_dist, int32_t* best_idx, float* second_dist,
+                       int32_t* second_idx) {
   int r = check_ctx(c);
   if (r) return r;
+  if (q_host) q_slot = db_slot;          // queries come from the host: only the database slot is looked at
   if (q_slot < 0 || db_slot < 0 || q_slot >= c->last_batch || db_slot >= c->last_batch || nq < 0 ||
       (nq > 0 && (!cand_off || !best_dist || !best_idx))) {
     set_error("rfe_l2_best2_slots: null/invalid argument (slots %d, %d of %d)", q_slot, db_slot, c->last_batch);
@@ -1273,7 +1393,7 @@ int rfe_l2_best2_slots(rfe_ctx* c, int q_slot, int db_slot, int nq, const int32_
   cudaStream_t s = c->stream;
   RFE_CUDA_CHECK(cudaMemcpyAsync(c->h_counts, c->kp_counts, sizeof(int) * c->last_batch, cudaMemcpyDeviceToHost, s));
   RFE_CUDA_CHECK(cudaStreamSynchronize(s));
-  const int have_q = c->h_counts[q_slot] < c->cap ? c->h_counts[q_slot] : c->cap;
+  const int have_q = q_host ? nq : (c->h_counts[q_slot] < c->cap ? c->h_counts[q_slot] : c->cap);
   const int nd = c->h_counts[db_slot] < c->cap ? c->h_counts[db_slot] : c->cap;
   const int total = cand_off[nq];
   if (nq > have_q || cand_off[0] != 0 || total < 0 || (total > 0 && !cand_idx)) {
@@ -1301,8 +1421,13 @@ int rfe_l2_best2_slots(rfe_ctx* c, int q_slot, int db_slot, int nq, const int32_
   int* d_i2 = reinterpret_cast<int*>(d_b2 + nq);
   RFE_CUDA_CHECK(cudaMemcpyAsync(d_off, cand_off, bo, cudaMemcpyHostToDevice, s));
   if (total > 0) RFE_CUDA_CHECK(cudaMemcpyAsync(d_idx, cand_idx, static_cast<size_t>(total) * 4, cudaMemcpyHostToDevice, s));
-  launch_l2_best2(s, c->desc + static_cast<size_t>(q_slot) * c->cap * 256, nq, c->desc + static_cast<size_t>(db_slot) * c->cap * 256,
-                  d_off, d_idx, init_dist, d_b1, d_i1, d_b2, d_i2);
+  const float* d_q = c->desc + static_cast<size_t>(q_slot) * c->cap * 256;
+  if (q_host) {          // e.g. MapPoint descriptors (SearchByProjection1): uploaded; the frame's descriptors stay in their slot
+    if ((r = scratch(c, &c->scr[0], &c->scr_bytes[0], static_cast<size_t>(nq) * 1024))) return r;
+    RFE_CUDA_CHECK(cudaMemcpyAsync(c->scr[0], q_host, static_cast<size_t>(nq) * 1024, cudaMemcpyHostToDevice, s));
+    d_q = static_cast<const float*>(c->scr[0]);
+  }
+  launch_l2_best2(s, d_q, nq, c->desc + static_cast<size_t>(db_slot) * c->cap * 256, d_off, d_idx, init_dist, d_b1, d_i1, d_b2, d_i2);
   c->launches++;
   RFE_CUDA_CHECK(cudaMemcpyAsync(best_dist, d_b1, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, s));
   RFE_CUDA_CHECK(cudaMemcpyAsync(best_idx, d_i1, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, s));
@@ -1391,6 +1516,58 @@ int rfe_lg_match_slots(rfe_ctx* c, int slot0, int slot1, int norm_h, int norm_w,
   PairDesc pd{nullptr, nullptr, c->kpts + static_cast<size_t>(slot0) * c->cap * 2, c->kpts + static_cast<size_t>(slot1) * c->cap * 2,
               c->desc + static_cast<size_t>(slot0) * c->cap * 256, c->desc + static_cast<size_t>(slot1) * c->cap * 256, n0, n1, rslot};
   return lg_run(c, &pd, 1, norm_h, norm_w, thresh);
+}
+
+int rfe_lg_match_one_to_many(rfe_ctx* c, int slot, const int* others, int n_others, int norm_h, int norm_w, float thresh) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (n_others <= 0 || n_others > c->lg_pairs || !others || slot < 0 || slot >= c->last_batch || norm_h <= 0 || norm_w <= 0) {
+    set_error("rfe_lg_match_one_to_many: invalid argument (at most %d partners per call)", c->lg_pairs);
+    return RFE_ERR_INVALID;
+  }
+  for (int i = 0; i < n_others; ++i)
+    if (others[i] < 0 || others[i] >= c->last_batch) {
+      set_error("rfe_lg_match_one_to_many: slot out of range");
+      return RFE_ERR_INVALID;
+    }
+  if ((r = cache_alloc(c))) return r;
+  RFE_CUDA_CHECK(cudaMemcpyAsync(c->h_counts, c->kp_counts, sizeof(int) * c->last_batch, cudaMemcpyDeviceToHost, c->stream));
+  RFE_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  auto count_of = [&](int sl) { return c->h_counts[sl] < c->cap ? c->h_counts[sl] : c->cap; };
+  // cache entries that are missing or stale (slot rewritten, other normalisation size): built in ONE pass
+  int need[kMaxPairs + 1], need_n[kMaxPairs + 1], n_need = 0;
+  auto want = [&](int sl) {
+    if (count_of(sl) == 0) return;
+    if (c->cache_gen[sl] == c->slot_gen[sl] && c->cache_nh[sl] == norm_h && c->cache_nw[sl] == norm_w) {
+      c->cache_hits++;
+      return;
+    }
+    for (int k = 0; k < n_need; ++k)
+      if (need[k] == sl) return;
+    need[n_need] = sl;
+    need_n[n_need++] = count_of(sl);
+  };
+  want(slot);
+  for (int i = 0; i < n_others; ++i) want(others[i]);
+  if (n_need) {
+    c->cache_builds += n_need;
+    if ((r = lg_build_cache(c, need, need_n, n_need, norm_h, norm_w))) return r;
+  }
+  PairDesc pd[kMaxPairs];
+  for (int i = 0; i < n_others; ++i) {
+    const int s0 = slot, s1 = others[i];
+    pd[i] = PairDesc{nullptr, nullptr, c->kpts + static_cast<size_t>(s0) * c->cap * 2, c->kpts + static_cast<size_t>(s1) * c->cap * 2,
+                     c->desc + static_cast<size_t>(s0) * c->cap * 256, c->desc + static_cast<size_t>(s1) * c->cap * 256,
+                     count_of(s0), count_of(s1), i, s0, s1};
+  }
+  return lg_run(c, pd, n_others, norm_h, norm_w, thresh, /*cache_slots=*/true);
+}
+
+int rfe_lg_cache_stats(rfe_ctx* c, long long* hits, long long* builds) {
+  if (!c) return RFE_ERR_INVALID;
+  if (hits) *hits = c->cache_hits;
+  if (builds) *builds = c->cache_builds;
+  return RFE_OK;
 }
 
 int rfe_pairs_submit(rfe_ctx* c, const uint8_t* gray, int h, int w, int stride, int n_pairs) {

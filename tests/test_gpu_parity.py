@@ -539,3 +539,54 @@ def test_l2_best2_slots_equals_host_form(fe):
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
     assert (a[1] >= 0).sum() > 50
+    # host queries (MapPoint descriptors in SearchByProjection1) against the slot-resident frame
+    q = d0[::3] + np.float32(0.01) * rng.randn(*d0[::3].shape).astype(np.float32)
+    off3 = np.concatenate([[0], np.cumsum(np.diff(off)[::3])]).astype(np.int32)
+    idx3 = np.concatenate([idx[off[i]:off[i + 1]] for i in range(0, len(k0), 3)] + [np.zeros(0, np.int32)]).astype(np.int32)
+    a = fe.l2_best2_slots(None, 1, off3, idx3, q=q)
+    b = fe.l2_best2(q, d1, off3, idx3)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_one_to_many_with_layer0_cache_equals_batched_matching(fe):
+    """8(f).3: one KeyFrame against several neighbours with the per-slot layer-0 cache == rfe_lg_match_slots_batch on the same
+    pairs (same GEMM tilings at this size: bit for bit); the cache is reused on the second call, rebuilt after the slot is
+    overwritten or when the normalisation size changes, and a stale entry is never used."""
+    h, w = 240, 320
+    imgs = np.stack([synth.frame_pair(100 + i, h, w, shift=(3 * i - 4, 2 * i - 3))[i % 2] for i in range(5)]
+                    + [synth.frame_pair(100, h, w, shift=(6, -5))[1]])
+    fe.extract_device_from_host(imgs)                       # slots 0..5
+    others = [1, 2, 3, 5]
+    fe.match_slots_batch([0] * 4, others, h, w)
+    want = [fe.read_result(i) for i in range(4)]
+    h0, b0 = fe.cache_stats()
+    fe.match_one_to_many(0, others, h, w)
+    got = [fe.read_result(i) for i in range(4)]
+    h1, b1 = fe.cache_stats()
+    assert b1 - b0 == 5 and h1 == h0                        # five distinct slots built, none found
+    for (wm, ws), (gm, gs) in zip(want, got):
+        assert np.array_equal(wm, gm) and np.array_equal(ws, gs)
+    assert max(len(m) for m, _ in want) > 30
+    fe.match_one_to_many(0, [5, 3], h, w)                   # all three states come from the cache
+    h2, b2 = fe.cache_stats()
+    assert b2 == b1 and h2 - h1 == 3
+    assert np.array_equal(fe.read_result(0)[0], want[3][0]) and np.array_equal(fe.read_result(1)[0], want[2][0])
+    # other normalisation size (the KeyPoint overloads' 300 x 400): entries rebuilt, results follow
+    fe.match_slots_batch([0, 0], [1, 2], 300, 400)
+    w34 = [fe.read_result(i) for i in range(2)]
+    fe.match_one_to_many(0, [1, 2], 300, 400)
+    h3, b3 = fe.cache_stats()
+    assert b3 - b2 == 3
+    for i in range(2):
+        assert np.array_equal(fe.read_result(i)[0], w34[i][0]) and np.array_equal(fe.read_result(i)[1], w34[i][1])
+    # overwrite slot 2 with slot 5's features: its cache entry must be rebuilt, not reused
+    k5, s5, d5 = fe.read_slot(5)
+    fe.write_slot(2, k5, d5, s5)
+    fe.match_one_to_many(0, [2], 300, 400)
+    h4, b4 = fe.cache_stats()
+    assert b4 - b3 == 1 and h4 - h3 == 1
+    fe.match_slots_batch([0], [5], 300, 400)
+    m_ref, s_ref = fe.read_result(0)
+    fe.match_one_to_many(0, [2], 300, 400)
+    assert np.array_equal(fe.read_result(0)[0], m_ref) and np.array_equal(fe.read_result(0)[1], s_ref)

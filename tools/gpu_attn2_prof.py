@@ -38,6 +38,7 @@ else:
     rows = (("score issuer: wait Q", 0), ("score issuer: pass-1 loops", 1), ("score issuer: pass-2 loops", 2), ("  pass 2 wait K", 3),
             ("  pass 2 wait free S", 4), ("  pass 1 wait K", 8), ("  pass 1 wait free S", 9), ("PV issuer: wait V", 5), ("PV issuer: wait P", 6),
             ("PV issuer: wait O hand-back", 16), ("softmax w0: pass-1 loops", 13), ("  wait scores", 14), ("softmax w0: pass-2 loops", 10),
-            ("  wait scores", 11), ("  wait free P", 12), ("softmax w0: l exchange + epilogue", 15), ("  wait o_full", 18))
+            ("  wait scores", 11), ("  wait free P", 12), ("  phase: tmem ld + release", 19), ("  phase: exp / split math", 20), ("  phase: P stores", 21),
+            ("  phase: fence + arrive", 22), ("softmax w0: l exchange + epilogue", 15), ("  wait o_full", 18))
 for name, i in rows:
     print(f"  {name:36s} {int(pr[i]):9d}  ({int(pr[i]) / max(items, 1):9.0f} per item)")
