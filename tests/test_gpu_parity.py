@@ -551,8 +551,13 @@ def test_l2_best2_slots_equals_host_form(fe):
 
 def test_one_to_many_with_layer0_cache_equals_batched_matching(fe):
     """8(f).3: one KeyFrame against several neighbours with the per-slot layer-0 cache == rfe_lg_match_slots_batch on the same
-    pairs (same GEMM tilings at this size: bit for bit); the cache is reused on the second call, rebuilt after the slot is
-    overwritten or when the normalisation size changes, and a stale entry is never used."""
+    pairs: identical match lists, scores within 1e-5 (the cache is built in a pass with fewer rows, whose GEMMs may use the
+    other tiling: the lo-product accumulation order differs in the last bit); the cache is reused on the second call,
+    rebuilt after the slot is overwritten or when the normalisation size changes, and a stale entry is never used."""
+
+    def same(a, b):
+        return np.array_equal(a[0], b[0]) and (len(a[1]) == 0 or np.abs(a[1] - b[1]).max() <= 1e-5)
+
     h, w = 240, 320
     imgs = np.stack([synth.frame_pair(100 + i, h, w, shift=(3 * i - 4, 2 * i - 3))[i % 2] for i in range(5)]
                     + [synth.frame_pair(100, h, w, shift=(6, -5))[1]])
@@ -565,13 +570,13 @@ def test_one_to_many_with_layer0_cache_equals_batched_matching(fe):
     got = [fe.read_result(i) for i in range(4)]
     h1, b1 = fe.cache_stats()
     assert b1 - b0 == 5 and h1 == h0                        # five distinct slots built, none found
-    for (wm, ws), (gm, gs) in zip(want, got):
-        assert np.array_equal(wm, gm) and np.array_equal(ws, gs)
+    for w_, g_ in zip(want, got):
+        assert same(w_, g_)
     assert max(len(m) for m, _ in want) > 30
     fe.match_one_to_many(0, [5, 3], h, w)                   # all three states come from the cache
     h2, b2 = fe.cache_stats()
     assert b2 == b1 and h2 - h1 == 3
-    assert np.array_equal(fe.read_result(0)[0], want[3][0]) and np.array_equal(fe.read_result(1)[0], want[2][0])
+    assert same(fe.read_result(0), want[3]) and same(fe.read_result(1), want[2])
     # other normalisation size (the KeyPoint overloads' 300 x 400): entries rebuilt, results follow
     fe.match_slots_batch([0, 0], [1, 2], 300, 400)
     w34 = [fe.read_result(i) for i in range(2)]
@@ -579,7 +584,7 @@ def test_one_to_many_with_layer0_cache_equals_batched_matching(fe):
     h3, b3 = fe.cache_stats()
     assert b3 - b2 == 3
     for i in range(2):
-        assert np.array_equal(fe.read_result(i)[0], w34[i][0]) and np.array_equal(fe.read_result(i)[1], w34[i][1])
+        assert same(fe.read_result(i), w34[i])
     # overwrite slot 2 with slot 5's features: its cache entry must be rebuilt, not reused
     k5, s5, d5 = fe.read_slot(5)
     fe.write_slot(2, k5, d5, s5)
@@ -589,4 +594,4 @@ def test_one_to_many_with_layer0_cache_equals_batched_matching(fe):
     fe.match_slots_batch([0], [5], 300, 400)
     m_ref, s_ref = fe.read_result(0)
     fe.match_one_to_many(0, [2], 300, 400)
-    assert np.array_equal(fe.read_result(0)[0], m_ref) and np.array_equal(fe.read_result(0)[1], s_ref)
+    assert same(fe.read_result(0), (m_ref, s_ref))
