@@ -41,10 +41,18 @@ struct StripParams {
   __half* out_hi;           // NHWC [B][Ho][Wo][64]
   __half* out_lo;
   unsigned long long* prof;   // optional [8] cycle counters of CTA 0's MMA thread
+  // FUSE1A (conv1a computed in the kernel): the u8 image and the fp32 conv1a weights replace the activation tensor maps
+  const uint8_t* img;       // [B][H][img_stride]
+  int img_stride;
+  const float* w1a;         // [64][9]
+  const float* b1a;         // [64]
 };
 
 constexpr int kStripThreads = 384;
 constexpr int kStripWarpRows = 8, kStripWarpW = 9, kStripWarpMma = 11;
+// FUSE1A: warps 8, 10, 12, 13 compute the input rows (conv1a + ReLU + split of the u8 image) instead of fetching them
+constexpr int kStripThreadsFused = 448;
+constexpr int kStripRowProducerWarps = 4;
 constexpr int kStripRowBytes = 130 * 128;        // one plane of one input row of the strip (with 1-px halo each side)
 constexpr int kStripSlotBytes = 17 * 1024;       // slot pitch (1024-aligned for the swizzle)
 constexpr int kStripRowSlots = 4;
@@ -55,11 +63,17 @@ constexpr int kStripSmemBytes =
 
 #ifdef __CUDACC__
 
+// FUSE1A = true is SuperPoint's conv1 group (u8 -> 1/255 -> conv1a 1->64 + ReLU -> conv1b 64->64 + ReLU ->
+// 2x2 max-pool, superpoint.onnx nodes 1-5) in ONE kernel: the 480 x 640 x 64 conv1a activation (1.26 GB per 16 frames as
+// split fp16) is never written to or read from HBM.  Four producer warps compute each input row of the strip on the CUDA
+// cores -- K = 9 and |w| <= 197: exact fp32 FMAs in the order of conv1a_kernel, bit-identical to it -- and write it straight
+// into the row slot in the 128-byte-swizzled layout the TMA box would have produced (pixel p = one 128-byte row, 16-byte
+// chunk c at (c ^ (p & 7)); pixels outside the image are zeros = conv1b's padding), then fence.proxy.async + arrive.
 // tmA_*: 4-D (C=64, W, H, B) box (64, 130, 1, 1);  tmW_*: 3-D (K=576, 64, 1) box (64, 64, 1)
-__global__ void __launch_bounds__(kStripThreads, 1)
-conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                    const StripParams p) {
+template <bool FUSE1A>
+__device__ __forceinline__ void conv64_strip_body(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo,
+                                                  const CUtensorMap& tmW_hi, const CUtensorMap& tmW_lo,
+                                                  const StripParams& p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by offsetting the __shared__ array itself (keeps the shared address space: STS/LDS, not generic)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -82,7 +96,7 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 
   if (warp == kStripWarpRows && lane == 0) {
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmW_hi); tma_prefetch_desc(&tmW_lo);
-    for (int s = 0; s < kStripRowSlots; ++s) { mbar_init(&row_full[s], 1); mbar_init(&row_empty[s], 1); }
+    for (int s = 0; s < kStripRowSlots; ++s) { mbar_init(&row_full[s], FUSE1A ? kStripRowProducerWarps : 1); mbar_init(&row_empty[s], 1); }
     for (int s = 0; s < kStripWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 8);
@@ -109,7 +123,105 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     iters = rows >> 1;
   };
 
-  if (warp == kStripWarpRows) {
+  const int prod_rank = warp == 8 ? 0 : warp == 10 ? 1 : warp == 12 ? 2 : warp == 13 ? 3 : -1;
+  if (FUSE1A && prod_rank >= 0) {
+    // ===== input-row producers (FUSE1A): conv1a + ReLU + split of the u8 image, written as the TMA box would land ======
+    // thread = (run of 8 pixels, group of 8 output channels); 16 runs x 8 groups = the 128 threads cover pixels 0..127 of
+    // the 130-pixel row in one pass, pixels 128 / 129 are a second, one-pixel pass of 16 threads
+    const int tid = prod_rank * 32 + lane;
+    const int cg = tid & 7, run = tid >> 3;
+    f32x2 wr[4][9], br[4];
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      const int c = cg * 8 + 2 * jp;
+      br[jp] = pk2(__ldg(p.b1a + c), __ldg(p.b1a + c + 1));
+#pragma unroll
+      for (int t = 0; t < 9; ++t) wr[jp][t] = pk2(__ldg(p.w1a + c * 9 + t), __ldg(p.w1a + (c + 1) * 9 + t));
+    }
+    // one output pixel (8 channels) from its 3 x 3 window, as conv1a_kernel computes it (same FMA order: bit-identical)
+    auto pixel = [&](const float (&w0)[3], const float (&w1)[3], const float (&w2)[3], uint4& hi4, uint4& lo4) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        f32x2 acc = pk2(0.0f, 0.0f);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) acc = fma2(pk2(w0[dx], w0[dx]), wr[jp][dx], acc);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) acc = fma2(pk2(w1[dx], w1[dx]), wr[jp][3 + dx], acc);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) acc = fma2(pk2(w2[dx], w2[dx]), wr[jp][6 + dx], acc);
+        acc = add2(acc, br[jp]);
+        float a0, a1;
+        upk2(acc, a0, a1);
+        split2(pk2(fmaxf(a0, 0.0f), fmaxf(a1, 0.0f)), hi[jp], lo[jp]);
+      }
+      hi4 = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      lo4 = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    };
+    uint32_t n = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int b, x0, y_begin, iters;
+      item_coords(item, b, x0, y_begin, iters);
+      const uint8_t* im = p.img + static_cast<size_t>(b) * p.H * p.img_stride;
+      const int nrows = 2 * iters + 2;
+      for (int k = 0; k < nrows; ++k, ++n) {
+        const int slot = n & 3;
+        mbar_wait(&row_empty[slot], ((n >> 2) & 1) ^ 1);
+        uint8_t* dh = sRowHi + slot * kStripSlotBytes;
+        uint8_t* dl = sRowLo + slot * kStripSlotBytes;
+        const int y = y_begin - 1 + k;                          // row of the conv1a output map = image row
+        const bool row_in = y >= 0 && y < p.H;
+        // pixel pp of the slot is image column x0 - 1 + pp
+        auto load_px = [&](int yy, int xx) -> float {           // u8 * (1/255) with conv1a's zero padding (transform.cpp:8)
+          return (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
+                     ? static_cast<float>(__ldg(im + static_cast<size_t>(yy) * p.img_stride + xx)) * 0.003921568859368563f
+                     : 0.0f;
+        };
+        {
+          const int pp0 = run * 8, xs = x0 - 1 + pp0;           // pixels pp0 .. pp0 + 7
+          float in[3][10];
+          if (row_in) {
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+              for (int i = 0; i < 10; ++i) in[dy][i] = load_px(y + dy - 1, xs - 1 + i);
+          }
+#pragma unroll
+          for (int px = 0; px < 8; ++px) {
+            const int pp = pp0 + px, x = xs + px;
+            uint4 hi4 = make_uint4(0u, 0u, 0u, 0u), lo4 = hi4;
+            if (row_in && x >= 0 && x < p.W) {
+              const float w0[3] = {in[0][px], in[0][px + 1], in[0][px + 2]};
+              const float w1[3] = {in[1][px], in[1][px + 1], in[1][px + 2]};
+              const float w2[3] = {in[2][px], in[2][px + 1], in[2][px + 2]};
+              pixel(w0, w1, w2, hi4, lo4);
+            }
+            const int o = pp * 128 + ((cg ^ (pp & 7)) << 4);
+            *reinterpret_cast<uint4*>(dh + o) = hi4;
+            *reinterpret_cast<uint4*>(dl + o) = lo4;
+          }
+        }
+        if (tid < 16) {                                         // pixels 128, 129
+          const int pp = 128 + (tid >> 3), x = x0 - 1 + pp;
+          uint4 hi4 = make_uint4(0u, 0u, 0u, 0u), lo4 = hi4;
+          if (row_in && x >= 0 && x < p.W) {
+            float w[3][3];
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) w[dy][dx] = load_px(y + dy - 1, x + dx - 1);
+            pixel(w[0], w[1], w[2], hi4, lo4);
+          }
+          const int o = pp * 128 + ((cg ^ (pp & 7)) << 4);
+          *reinterpret_cast<uint4*>(dh + o) = hi4;
+          *reinterpret_cast<uint4*>(dl + o) = lo4;
+        }
+        fence_proxy_async();                                    // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&row_full[slot]);
+      }
+    }
+  } else if (!FUSE1A && warp == kStripWarpRows) {
     // ===== input-row producer: row sequence number n -> slot n & 3 =====================================================
     if (elect_one()) {
       uint32_t n = 0;
@@ -307,6 +419,21 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+__global__ void __launch_bounds__(kStripThreads, 1)
+conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                    const __grid_constant__ StripParams p) {
+  conv64_strip_body<false>(tmA_hi, tmA_lo, tmW_hi, tmW_lo, p);
+}
+// 448 threads: 65536 / 448 = 146 registers per thread; ask for 144 explicitly (ptxas otherwise settles on 128 and spills
+// the epilogue's 64 accumulator values)
+__global__ void __maxnreg__(144)
+conv64_strip_fused_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                          const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                          const __grid_constant__ StripParams p) {
+  conv64_strip_body<true>(tmA_hi, tmA_lo, tmW_hi, tmW_lo, p);
 }
 
 #endif  // __CUDACC__

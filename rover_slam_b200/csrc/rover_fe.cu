@@ -126,6 +126,7 @@ struct rfe_ctx {
   // optional per-kernel CUDA-event profiling (rfe_profile)
   struct ProfRec { std::string tag; cudaEvent_t a, b; };
   bool use_strip_conv = true;   // RFE_CONV_STRIP=0 falls back to the 9-box implicit GEMM for the 64->64 layers
+  bool fuse_conv1a = true;      // RFE_FUSE_CONV1A=0: stand-alone conv1a kernel + activation round trip (round-1 behaviour)
   bool profiling = false;
   std::string prof_prefix;                   // rfe_profile_select
   std::vector<ProfRec> prof;
@@ -442,11 +443,13 @@ int conv3x3(rfe_ctx* c, const char* tag, const SplitBuf& in, int B, int H, int W
 }
 
 // 3x3 conv 64 -> 64 (+ReLU, + optional 2x2 max-pool) with the strip kernel (conv_strip.cuh).
+// img != nullptr: conv1a is computed inside the kernel from the u8 image (conv_strip.cuh, FUSE1A) and `in` is not read.
 int conv64_strip(rfe_ctx* c, const char* tag, const SplitBuf& in, int B, int H, int W, const SplitW& w, const SplitBuf& out,
-                 bool pool) {
+                 bool pool, const uint8_t* img = nullptr, int img_stride = 0) {
   static bool configured[64] = {};
   if (!configured[c->device & 63]) {
     RFE_CUDA_CHECK(cudaFuncSetAttribute(conv64_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStripSmemBytes));
+    RFE_CUDA_CHECK(cudaFuncSetAttribute(conv64_strip_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStripSmemBytes));
     configured[c->device & 63] = true;
   }
   const uint64_t dims[4] = {64, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
@@ -473,7 +476,12 @@ int conv64_strip(rfe_ctx* c, const char* tag, const SplitBuf& in, int B, int H, 
   p.prof = (c->attn_prof && !strcmp(tag, "sp.conv1b")) ? c->attn_prof + 8 : nullptr;
   const int ctas = p.num_items < c->num_sms ? p.num_items : c->num_sms;
   ProfScope ps(c, tag);
-  conv64_strip_kernel<<<ctas, kStripThreads, kStripSmemBytes, c->stream>>>(ah, al, wh, wl, p);
+  p.img = img;
+  p.img_stride = img_stride;
+  p.w1a = c->conv1a_w;
+  p.b1a = c->conv1a_b;
+  if (img) conv64_strip_fused_kernel<<<ctas, kStripThreadsFused, kStripSmemBytes, c->stream>>>(ah, al, wh, wl, p);
+  else conv64_strip_kernel<<<ctas, kStripThreads, kStripSmemBytes, c->stream>>>(ah, al, wh, wl, p);
   c->launches++;
   RFE_CUDA_CHECK(cudaGetLastError());
   return RFE_OK;
@@ -489,10 +497,16 @@ int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B, i
     set_error("this ctx was created with RFE_FLAG_NO_EXTRACTOR");
     return RFE_ERR_INVALID;
   }
-  { ProfScope ps_(c, "sp.conv1a"); launch_conv1a(s, d_gray, stride, h, w, B, c->conv1a_w, c->conv1a_b, c->a1a.hi, c->a1a.lo); }
-  c->launches++;
+  // conv1 group (K1): with the strip kernel, conv1a is computed inside conv1b's row producers and its activation never
+  // touches HBM.  RFE_FUSE_CONV1A=0 (or the 9-box fallback) runs the stand-alone conv1a kernel first, as round 1 did.
+  const bool fuse1a = c->use_strip_conv && c->fuse_conv1a;
+  if (!fuse1a) {
+    ProfScope ps_(c, "sp.conv1a");
+    launch_conv1a(s, d_gray, stride, h, w, B, c->conv1a_w, c->conv1a_b, c->a1a.hi, c->a1a.lo);
+    c->launches++;
+  }
   if (c->use_strip_conv) {
-    if ((r = conv64_strip(c, "sp.conv1b", c->a1a, B, h, w, c->c1b, c->a1, true))) return r;
+    if ((r = conv64_strip(c, "sp.conv1b", c->a1a, B, h, w, c->c1b, c->a1, true, fuse1a ? d_gray : nullptr, stride))) return r;
     if ((r = conv64_strip(c, "sp.conv2a", c->a1, B, h / 2, w / 2, c->c2a, c->a2a, false))) return r;
     if ((r = conv64_strip(c, "sp.conv2b", c->a2a, B, h / 2, w / 2, c->c2b, c->a2, true))) return r;
   } else {
@@ -1055,6 +1069,7 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   C_(cudaEventCreate(&c->ev1));
   c->prof_tag = getenv("RFE_PROF_TAG");
   if (getenv("RFE_CONV_STRIP")) c->use_strip_conv = atoi(getenv("RFE_CONV_STRIP")) != 0;
+  if (getenv("RFE_FUSE_CONV1A")) c->fuse_conv1a = atoi(getenv("RFE_FUSE_CONV1A")) != 0;
   const char* path = cfg->weights_path;
   if (!path) path = getenv("ROVER_FE_WEIGHTS");
   if (!path) path = "weights/rover_fe.rfw";
@@ -1073,7 +1088,7 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   const size_t full = B * H * W, half_ = full / 4, quarter = full / 16, coarse = full / 64;
 #define A_(expr) if ((r = (expr))) { rfe_destroy(c); return r; }
   A_(dev_alloc(c, &c->img, full));
-  A_(split_alloc(c, &c->a1a, full * 64));
+  if (!(c->use_strip_conv && c->fuse_conv1a)) A_(split_alloc(c, &c->a1a, full * 64));   // fused: conv1a's activation never exists
   A_(split_alloc(c, &c->a1, half_ * 64));
   A_(split_alloc(c, &c->a2a, half_ * 64));
   A_(split_alloc(c, &c->a2, quarter * 64));
@@ -1872,7 +1887,13 @@ int rfe_debug_read(rfe_ctx* c, const char* name, void* dst, size_t capacity, siz
   const float* fb = nullptr;
   size_t n = 0;
   const std::string s(name);
-  if (s == "sp.a1a") { sb = &c->a1a; n = B * H * W * 64; }
+  if (s == "sp.a1a") {
+    if (!c->a1a.hi) {
+      set_error("rfe_debug_read: sp.a1a is never materialised when conv1a is fused into conv1b (run with RFE_FUSE_CONV1A=0)");
+      return RFE_ERR_INVALID;
+    }
+    sb = &c->a1a; n = B * H * W * 64;
+  }
   else if (s == "sp.pool1") { sb = &c->a1; n = B * H * W / 4 * 64; }
   else if (s == "sp.a2a") { sb = &c->a2a; n = B * H * W / 4 * 64; }
   else if (s == "sp.pool2") { sb = &c->a2; n = B * H * W / 16 * 64; }

@@ -83,7 +83,8 @@ def test_superpoint_intermediates(fe, sp):
     fe.extract(img)
     taps = {}
     sp(img, taps)
-    for name, key, c, div, tol in [("sp.a1a", "relu1a", 64, 1, 2e-4), ("sp.pool1", "pool1", 64, 2, 2e-4),
+    # conv1a's activation ("relu1a") is never materialised: it is computed inside conv1b's row producers; pool1 checks both
+    for name, key, c, div, tol in [("sp.pool1", "pool1", 64, 2, 2e-4),
                                    ("sp.pool2", "pool2", 64, 4, 2e-4), ("sp.pool3", "pool3", 128, 8, 2e-4),
                                    ("sp.feat", "feat", 128, 8, 2e-4)]:
         got = np.transpose(fe.debug_read(name).reshape(96 // div, 160 // div, c), (2, 0, 1))
@@ -440,6 +441,38 @@ def test_topk_cap_keeps_the_best_in_row_major_order(fe):
         fe.set_topk(0)
     again = fe.extract(imgs)
     assert all(np.array_equal(a[0], b[0]) for a, b in zip(full, again))
+
+
+_FUSE_CHILD = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from oracle import synth
+from rover_slam_b200 import FrontEnd
+fe = FrontEnd(max_batch=2, max_height=240, max_width=328, max_keypoints=4096)
+out = {}
+for i, (h, w) in enumerate(((240, 328), (16, 24), (96, 136))):
+    imgs = np.stack([synth.frame(60 + i, h, w), np.zeros((h, w), np.uint8)])
+    for b, (k, s, d) in enumerate(fe.extract(imgs)):
+        out[f"k{i}{b}"], out[f"s{i}{b}"], out[f"d{i}{b}"] = k, s, d
+    out[f"p{i}"] = fe.debug_read("sp.pool1")
+np.savez(sys.argv[2], **out)
+"""
+
+
+def test_fused_conv1a_is_bit_identical_to_the_two_kernel_path(tmp_path):
+    """K1 fusion: conv1a computed inside conv1b's row producers (no activation round trip) == stand-alone conv1a kernel +
+    conv1b, bit for bit (same fp32 FMA order, same split), on widths that are not multiples of 128 and on tiny images."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ("0", "1"):
+        out = str(tmp_path / f"fuse{mode}.npz")
+        subprocess.run([sys.executable, "-c", _FUSE_CHILD, root, out], check=True, env=dict(os.environ, RFE_FUSE_CONV1A=mode), timeout=600)
+        res[mode] = np.load(out)
+    assert sorted(res["0"].files) == sorted(res["1"].files)
+    for k in res["0"].files:
+        assert np.array_equal(res["0"][k], res["1"][k]), k
+    assert len(res["1"]["k00"]) > 100
 
 
 # ---- against an independent runtime: OpenCV DNN executing the reference's ONNX files (tests/golden/cv2dnn_*.npz) ----------
