@@ -50,9 +50,11 @@ struct StripParams {
 
 constexpr int kStripThreads = 384;
 constexpr int kStripWarpRows = 8, kStripWarpW = 9, kStripWarpMma = 11;
-// FUSE1A: warps 8, 10, 12, 13 compute the input rows (conv1a + ReLU + split of the u8 image) instead of fetching them
-constexpr int kStripThreadsFused = 448;
-constexpr int kStripRowProducerWarps = 4;
+// FUSE1A: warps 8 and 10 (the TMA row producer and the spare warp) compute the input rows -- conv1a + ReLU + split of the
+// u8 image -- instead of fetching them.  The CTA stays at 12 warps: registers are per scheduler (16 K each), so a 13th
+// warp would cap every thread at 128 registers and spill the epilogue's 64 accumulator values.
+constexpr int kStripThreadsFused = kStripThreads;
+constexpr int kStripRowProducerWarps = 2;
 constexpr int kStripRowBytes = 130 * 128;        // one plane of one input row of the strip (with 1-px halo each side)
 constexpr int kStripSlotBytes = 17 * 1024;       // slot pitch (1024-aligned for the swizzle)
 constexpr int kStripRowSlots = 4;
@@ -123,13 +125,13 @@ __device__ __forceinline__ void conv64_strip_body(const CUtensorMap& tmA_hi, con
     iters = rows >> 1;
   };
 
-  const int prod_rank = warp == 8 ? 0 : warp == 10 ? 1 : warp == 12 ? 2 : warp == 13 ? 3 : -1;
+  const int prod_rank = warp == 8 ? 0 : warp == 10 ? 1 : -1;
   if (FUSE1A && prod_rank >= 0) {
     // ===== input-row producers (FUSE1A): conv1a + ReLU + split of the u8 image, written as the TMA box would land ======
-    // thread = (run of 8 pixels, group of 8 output channels); 16 runs x 8 groups = the 128 threads cover pixels 0..127 of
-    // the 130-pixel row in one pass, pixels 128 / 129 are a second, one-pixel pass of 16 threads
+    // work item = (run of 8 pixels, group of 8 output channels): 16 runs x 8 groups cover pixels 0..127 of the 130-pixel
+    // row in two passes of the 64 producer threads; pixels 128 / 129 are a one-pixel pass of 16 threads
     const int tid = prod_rank * 32 + lane;
-    const int cg = tid & 7, run = tid >> 3;
+    const int cg = tid & 7;
     f32x2 wr[4][9], br[4];
 #pragma unroll
     for (int jp = 0; jp < 4; ++jp) {
@@ -177,7 +179,9 @@ __device__ __forceinline__ void conv64_strip_body(const CUtensorMap& tmA_hi, con
                      ? static_cast<float>(__ldg(im + static_cast<size_t>(yy) * p.img_stride + xx)) * 0.003921568859368563f
                      : 0.0f;
         };
-        {
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          const int run = pass * 8 + (tid >> 3);
           const int pp0 = run * 8, xs = x0 - 1 + pp0;           // pixels pp0 .. pp0 + 7
           float in[3][10];
           if (row_in) {
@@ -427,9 +431,7 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                     const __grid_constant__ StripParams p) {
   conv64_strip_body<false>(tmA_hi, tmA_lo, tmW_hi, tmW_lo, p);
 }
-// 448 threads: 65536 / 448 = 146 registers per thread; ask for 144 explicitly (ptxas otherwise settles on 128 and spills
-// the epilogue's 64 accumulator values)
-__global__ void __maxnreg__(144)
+__global__ void __launch_bounds__(kStripThreadsFused, 1)
 conv64_strip_fused_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                           const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                           const __grid_constant__ StripParams p) {

@@ -10,8 +10,11 @@ void launch_conv1a(cudaStream_t s, const uint8_t* img, int stride, int H, int W,
                    const float* bias, __half* out_hi, __half* out_lo);
 int nms_prepare();
 void launch_nms(cudaStream_t s, const float* heat, float* out, int B, int H, int W);
+int nms2_prepare();
+// bit-plane NMS that also produces the per-row keypoint counts of the ordered compaction
+void launch_nms2(cudaStream_t s, const float* heat, float* out, int* row_cnt, int B, int H, int W, float thr);
 void launch_select(cudaStream_t s, const float* nms, int B, int H, int W, float thr, int cap, int* row_cnt,
-                   int* row_off, int* counts, int* kpts, float* scores);
+                   int* row_off, int* counts, int* kpts, float* scores, bool have_counts);
 // optional top-K cap on the compacted keypoint lists (K <= 0: off = the reference's behaviour)
 void launch_topk(cudaStream_t s, int B, int cap, int K, int* counts, int* kpts, float* scores);
 void launch_desc_sample(cudaStream_t s, const float* dense, int h, int w, int B, const int* kpts, const int* counts,

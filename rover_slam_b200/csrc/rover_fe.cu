@@ -553,13 +553,19 @@ int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B, i
     p.ld_f32 = 256;
     if ((r = launch_umma<256, A_GEMM, EPI_DESC>(c, "sp.convDb_l2norm", ah, al, bh, bl, p, dim3((npix + 127) / 128, 1, 1)))) return r;
   }
-  { ProfScope ps_(c, "sp.nms"); launch_nms(s, c->heat, c->nmsmap, B, h, w); }
+  // RFE_NMS=1: the five-plane fp32 kernel of round 1 + a separate counting pass (A/B); default: bit-plane kernel with counts
+  static const int kNmsMode = getenv("RFE_NMS") ? atoi(getenv("RFE_NMS")) : 2;
+  {
+    ProfScope ps_(c, "sp.nms");
+    if (kNmsMode == 2) launch_nms2(s, c->heat, c->nmsmap, c->row_cnt, B, h, w, kDetThreshold);
+    else launch_nms(s, c->heat, c->nmsmap, B, h, w);
+  }
   int* kp_counts = c->kp_counts + slot_base;
   int* kpts = c->kpts + static_cast<size_t>(slot_base) * c->cap * 2;
   float* kp_scores = c->kp_scores + static_cast<size_t>(slot_base) * c->cap;
   float* desc = c->desc + static_cast<size_t>(slot_base) * c->cap * 256;
   { ProfScope ps_(c, "sp.select"); launch_select(s, c->nmsmap, B, h, w, kDetThreshold, c->cap, c->row_cnt, c->row_off, kp_counts, kpts,
-                kp_scores); }
+                kp_scores, kNmsMode == 2); }
   if (c->topk > 0) {
     ProfScope ps_(c, "sp.topk");
     launch_topk(s, B, c->cap, c->topk, kp_counts, kpts, kp_scores);
@@ -567,7 +573,7 @@ int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B, i
   }
   { ProfScope ps_(c, "sp.desc_sample"); launch_desc_sample(s, c->dense, hc, wc, B, kpts, kp_counts, c->cap, desc,
                                                            c->desc_bin + static_cast<size_t>(slot_base) * c->cap * 256); }
-  c->launches += 5;
+  c->launches += kNmsMode == 2 ? 4 : 5;      // nms, (count), scan, write, desc_sample
   RFE_CUDA_CHECK(cudaGetLastError());
   for (int b = 0; b < B; ++b) c->slot_gen[slot_base + b]++;     // cached layer-0 state of these slots is stale now
   c->last_batch = B;
@@ -1078,7 +1084,7 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
     rfe_destroy(c);
     return r;
   }
-  if (nms_prepare()) {
+  if (nms_prepare() || nms2_prepare()) {
     set_error("cudaFuncSetAttribute(nms) failed");
     rfe_destroy(c);
     return RFE_ERR_CUDA;

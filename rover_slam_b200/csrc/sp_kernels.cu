@@ -233,6 +233,182 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const float* __rest
 
 int nms_smem_bytes() { return 5 * RW * RH * static_cast<int>(sizeof(float)); }
 
+// ------------------------------------------------------------------------------------------------
+// NMS, second form (default): the same graph nodes 58-359 on bit-planes.
+//   * Only pixels above the detection threshold can become keypoints, and a pixel at or below it can neither suppress nor
+//     out-score one above it (a maximum only ever suppresses pixels of lower-or-equal score, and `ss == maxpool(ss)` is only
+//     lost to a higher unsuppressed score): the three max-pools therefore run on s_act = (s > thr ? s : 0) and the keypoints,
+//     their scores and their order are exactly the graph's.  (The output map holds 0 instead of the score at sub-threshold
+//     maxima, which the graph's own `s > 0.0005` selection never looks at.)
+//   * max_mask / supp_mask are bit-planes (one word per 32 pixels): the two 9x9 pools of 0/1 planes become shifts and ORs;
+//     only s_act and one row-pass plane are fp32 in shared memory (2 planes instead of 5).
+//   * separable 9-wide maxima with FMNMX3: a1[i] = max3(v[i..i+2]), out[i] = max3(a1[i], a1[i+3], a1[i+6]): 22 operations
+//     per 8 outputs; the row pass reads 16-byte vectors, the column pass one column per lane (conflict free) and packs its
+//     verdicts with ballots.
+//   * the per-row keypoint counts of the ordered compaction come out of this kernel (atomicAdd per tile row), so the separate
+//     counting launch is gone.
+// Tile 128 x 64 outputs + 20-pixel halo = 168 x 104 region, 512 threads, ~150 KB of shared memory.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int N2_W = 128, N2_H = 64, N2_HALO = 20;
+constexpr int N2_RW = N2_W + 2 * N2_HALO;   // 168 = 21 runs of 8
+constexpr int N2_RH = N2_H + 2 * N2_HALO;   // 104 = 13 runs of 8
+constexpr int N2_PITCH = N2_RW + 8;         // 4 zero pad floats on either side of a row (16-byte aligned rows)
+constexpr int N2_WORDS = 8;                 // bit-plane row: [0] = pad, [1..6] = 168 bits, [7] = pad
+constexpr int N2_THREADS = 512;
+constexpr int N2_SMEM = 2 * N2_RH * N2_PITCH * 4 + 4 * N2_RH * N2_WORDS * 4;
+
+__device__ __forceinline__ float max3f(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+// out[i] = max(v[i .. i+8]), i = 0..7
+__device__ __forceinline__ void max9_run8_v3(const float (&v)[16], float (&out)[8]) {
+  float a1[14];
+#pragma unroll
+  for (int i = 0; i < 14; ++i) a1[i] = max3f(v[i], v[i + 1], v[i + 2]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[i] = max3f(a1[i], a1[i + 3], a1[i + 6]);
+}
+}  // namespace
+
+__global__ void __launch_bounds__(N2_THREADS, 1) nms2_kernel(const float* __restrict__ heat, float* __restrict__ out,
+                                                            int* __restrict__ row_cnt, int H, int W, float thr) {
+  extern __shared__ __align__(16) float sm2[];
+  float* S = sm2;                                   // s_act, [RH][PITCH], pixel (r, c) at r*PITCH + 4 + c
+  float* T = S + N2_RH * N2_PITCH;                  // row-pass result
+  uint32_t* ACT = reinterpret_cast<uint32_t*>(T + N2_RH * N2_PITCH);    // [RH][WORDS]
+  uint32_t* MX = ACT + N2_RH * N2_WORDS;
+  uint32_t* SUP = MX + N2_RH * N2_WORDS;
+  uint32_t* HD = SUP + N2_RH * N2_WORDS;            // horizontal dilation scratch
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * N2_W - N2_HALO, y0 = blockIdx.y * N2_H - N2_HALO;
+  const float* hb = heat + static_cast<size_t>(b) * H * W;
+
+  // ---- load: s_act and the active bit-plane; pads and the other planes start at zero ----
+  for (int i = tid; i < N2_RH * N2_WORDS; i += N2_THREADS) { MX[i] = 0; SUP[i] = 0; HD[i] = 0; ACT[i] = 0; }
+  for (int i = tid; i < N2_RH * 8; i += N2_THREADS) {
+    const int r = i >> 3, j = i & 7;
+    S[r * N2_PITCH + (j < 4 ? j : N2_RW + j)] = 0.0f;
+  }
+  __syncthreads();
+  for (int t = warp; t < N2_RH * 6; t += N2_THREADS / 32) {
+    const int r = t / 6, w = t - r * 6;
+    const int c = 32 * w + lane;
+    const int y = y0 + r, x = x0 + c;
+    float v = 0.0f;
+    if (c < N2_RW && y >= 0 && y < H && x >= 0 && x < W) v = __ldg(hb + static_cast<size_t>(y) * W + x);
+    v = v > thr ? v : 0.0f;
+    if (c < N2_RW) S[r * N2_PITCH + 4 + c] = v;
+    const unsigned m = __ballot_sync(0xffffffffu, v > 0.0f);
+    if (lane == 0) ACT[r * N2_WORDS + 1 + w] = m;
+  }
+  __syncthreads();
+
+#pragma unroll 1
+  for (int stage = 0; stage < 3; ++stage) {
+    if (stage > 0) {
+      // ---- supp = 9x9 dilation of max_mask (nodes MaxPool(float(mask)) > 0): horizontal, then vertical ----
+      for (int i = tid; i < N2_RH * 6; i += N2_THREADS) {
+        const int r = i / 6, w = 1 + (i - r * 6);
+        const uint32_t* row = MX + r * N2_WORDS;
+        const uint32_t cur = row[w], L = row[w - 1], R = row[w + 1];
+        uint32_t d = cur;
+#pragma unroll
+        for (int sft = 1; sft <= 4; ++sft) d |= (cur << sft) | (L >> (32 - sft)) | (cur >> sft) | (R << (32 - sft));
+        HD[r * N2_WORDS + w] = d;
+      }
+      __syncthreads();
+      for (int i = tid; i < N2_RH * 6; i += N2_THREADS) {
+        const int r = i / 6, w = 1 + (i - r * 6);
+        uint32_t d = 0;
+#pragma unroll
+        for (int dr = -4; dr <= 4; ++dr) {
+          const int rr = r + dr;
+          if (rr >= 0 && rr < N2_RH) d |= HD[rr * N2_WORDS + w];
+        }
+        SUP[r * N2_WORDS + w] = d;
+      }
+      __syncthreads();
+    }
+    // ---- row pass: T = 9-wide running maximum of ss = (supp ? 0 : s_act) ----
+    for (int i = tid; i < N2_RH * 21; i += N2_THREADS) {
+      const int r = i / 21, run = i - r * 21;
+      const float4* src = reinterpret_cast<const float4*>(S + r * N2_PITCH + 8 * run);      // pixels 8run-4 .. 8run+11
+      float v[16];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const float4 t4 = src[q4];
+        v[4 * q4] = t4.x; v[4 * q4 + 1] = t4.y; v[4 * q4 + 2] = t4.z; v[4 * q4 + 3] = t4.w;
+      }
+      if (stage > 0) {
+        const int pos = 32 + 8 * run - 4;               // bit position of v[0] in the padded row (word 1 = pixels 0..31)
+        const uint32_t* row = SUP + r * N2_WORDS;
+        const uint32_t bits = __funnelshift_r(row[pos >> 5], row[(pos >> 5) + 1], pos & 31);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if ((bits >> j) & 1u) v[j] = 0.0f;
+      }
+      float o[8];
+      max9_run8_v3(v, o);
+      float4* dst = reinterpret_cast<float4*>(T + r * N2_PITCH + 4 + 8 * run);
+      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    __syncthreads();
+    // ---- column pass + verdict: new maxima = active & ~supp & (ss == 9x9 max of ss) ----
+    for (int t = warp; t < 13 * 6; t += N2_THREADS / 32) {
+      const int rr = t / 6, w = t - rr * 6;
+      const int c = 32 * w + lane, r0 = 8 * rr;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int r = r0 - 4 + j;
+        v[j] = (c < N2_RW && r >= 0 && r < N2_RH) ? T[r * N2_PITCH + 4 + c] : 0.0f;
+      }
+      float o[8];
+      max9_run8_v3(v, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = r0 + j;
+        const uint32_t act = ACT[r * N2_WORDS + 1 + w], sup = SUP[r * N2_WORDS + 1 + w];
+        const bool cand = ((act & ~sup) >> lane) & 1u;                 // active, not suppressed: ss = s_act there
+        const bool is_max = cand && (c < N2_RW) && S[r * N2_PITCH + 4 + c] == o[j];
+        const unsigned m = __ballot_sync(0xffffffffu, is_max);
+        if (lane == 0 && m) MX[r * N2_WORDS + 1 + w] |= m;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- output: where(max_mask, scores, 0), borders -1, per-row keypoint counts ----
+  float* ob = out + static_cast<size_t>(b) * H * W;
+  for (int t = warp; t < N2_H * 4; t += N2_THREADS / 32) {
+    const int ty = t >> 2, q = t & 3;
+    const int tx = 32 * q + lane;
+    const int y = blockIdx.y * N2_H + ty, x = blockIdx.x * N2_W + tx;
+    const int r = ty + N2_HALO, c = tx + N2_HALO;
+    bool kp = false;
+    if (y < H && x < W) {
+      const bool is_max = (MX[r * N2_WORDS + 1 + (c >> 5)] >> (c & 31)) & 1u;
+      float v = is_max ? S[r * N2_PITCH + 4 + c] : 0.0f;
+      if (y < 4 || x < 4 || y >= H - 4 || x >= W - 4) v = -1.0f;
+      ob[static_cast<size_t>(y) * W + x] = v;
+      kp = v > thr;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, kp);
+    if (lane == 0 && m) atomicAdd(row_cnt + b * H + y, __popc(m));
+  }
+}
+
+int nms2_prepare() {
+  return cudaFuncSetAttribute(nms2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, N2_SMEM) == cudaSuccess ? 0 : 1;
+}
+// heat -> NMS map + per-row keypoint counts (row_cnt [B*H], zeroed here)
+void launch_nms2(cudaStream_t s, const float* heat, float* out, int* row_cnt, int B, int H, int W, float thr) {
+  cudaMemsetAsync(row_cnt, 0, sizeof(int) * static_cast<size_t>(B) * H, s);
+  dim3 grid((W + N2_W - 1) / N2_W, (H + N2_H - 1) / N2_H, B);
+  nms2_kernel<<<grid, N2_THREADS, N2_SMEM, s>>>(heat, out, row_cnt, H, W, thr);
+}
+
 void launch_nms(cudaStream_t s, const float* heat, float* out, int B, int H, int W) {
   dim3 grid((W + NT_W - 1) / NT_W, (H + NT_H - 1) / NT_H, B);
   nms_kernel<<<grid, NMS_THREADS, nms_smem_bytes(), s>>>(heat, out, H, W);
@@ -327,10 +503,10 @@ __global__ void __launch_bounds__(256) kp_write_kernel(const float* __restrict__
 }
 
 void launch_select(cudaStream_t s, const float* nms, int B, int H, int W, float thr, int cap, int* row_cnt,
-                   int* row_off, int* counts, int* kpts, float* scores) {
+                   int* row_off, int* counts, int* kpts, float* scores, bool have_counts) {
   const int warps = B * H;
   const int blocks = (warps * 32 + 255) / 256;
-  kp_count_kernel<<<blocks, 256, 0, s>>>(nms, H, W, B, row_cnt, thr);
+  if (!have_counts) kp_count_kernel<<<blocks, 256, 0, s>>>(nms, H, W, B, row_cnt, thr);    // nms2_kernel already counted
   kp_scan_kernel<<<B, 1024, 0, s>>>(row_cnt, H, row_off, counts);
   kp_write_kernel<<<blocks, 256, 0, s>>>(nms, H, W, B, row_off, thr, cap, kpts, scores);
 }
