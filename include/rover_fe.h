@@ -184,6 +184,19 @@ int rfe_pairs_collect(rfe_ctx* ctx, float match_thresh, int32_t* kpts_xy, int32_
  * Steady state of a stream:  collect_begin(i); submit(i+2); collect_end(i);  -- the GPU queue never drains. */
 int rfe_pairs_collect_begin(rfe_ctx* ctx, float match_thresh, int32_t* kpts_xy, int32_t* matches, float* mscores, int cap);
 int rfe_pairs_collect_end(rfe_ctx* ctx, int32_t* kp_counts, int32_t* match_counts);
+/* collect_begin that also returns what SPextractor::operator() returns besides the keypoints -- scores[2*n_pairs][cap] and
+ * the fp32 descriptors desc[2*n_pairs][cap][256] (Frame::mDescriptors, src/Frame.cc:544-559); either may be NULL.  Exactly
+ * counts[b] rows per image are copied, on a second stream, overlapping the matcher; rfe_pairs_collect_end waits for them
+ * too.  Use pinned memory (rfe_alloc_pinned) for all output arrays, or the copies serialise with the host. */
+int rfe_pairs_collect_begin_full(rfe_ctx* ctx, float match_thresh, int32_t* kpts_xy, float* scores, float* desc,
+                                 int32_t* matches, float* mscores, int cap);
+/* Page-locked host memory for the input / output arrays of the pipelined calls (cudaMallocHost / cudaFreeHost). */
+void* rfe_alloc_pinned(size_t bytes);
+void rfe_free_pinned(void* p);
+/* Device-to-device copy (asynchronous, ctx stream) of the first n_pairs match results -- matches [n_pairs][max_keypoints][2],
+ * mscores [n_pairs][max_keypoints] (may be NULL), counts [n_pairs] -- into caller-owned device buffers: the hand-off to a
+ * result gather across GPUs (bench.py, BASELINE config 5) without a host round trip. */
+int rfe_lg_copy_results_device(rfe_ctx* ctx, int n_pairs, int32_t* d_matches, float* d_mscores, int32_t* d_counts);
 /* Copy a match result to the host (synchronises). */
 int rfe_lg_read_result(rfe_ctx* ctx, int rslot, int32_t* matches, float* mscores, int* k, int cap);
 

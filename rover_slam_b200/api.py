@@ -79,6 +79,12 @@ def load_library():
     lib.rfe_pairs_collect.argtypes = [vp, cf, vp, vp, vp, vp, vp, ci]
     lib.rfe_pairs_collect_begin.argtypes = [vp, cf, vp, vp, vp, ci]
     lib.rfe_pairs_collect_end.argtypes = [vp, vp, vp]
+    lib.rfe_pairs_collect_begin_full.argtypes = [vp, cf, vp, vp, vp, vp, vp, ci]
+    lib.rfe_alloc_pinned.argtypes = [C.c_size_t]
+    lib.rfe_alloc_pinned.restype = vp
+    lib.rfe_free_pinned.argtypes = [vp]
+    lib.rfe_free_pinned.restype = None
+    lib.rfe_lg_copy_results_device.argtypes = [vp, ci, vp, vp, vp]
     lib.rfe_lg_read_result.argtypes = [vp, ci, vp, vp, vp, ci]
     lib.rfe_get_timer_ms.argtypes = [vp, C.c_char_p]
     lib.rfe_get_timer_ms.restype = C.c_double
@@ -124,6 +130,10 @@ class FrontEnd:
         if self.ctx is not None:
             self.lib.rfe_destroy(self.ctx)
             self.ctx = None
+            self._mp_sets = {}
+            for p in getattr(self, "_pinned", []):
+                self.lib.rfe_free_pinned(p)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -313,27 +323,52 @@ class FrontEnd:
         kpts = [kp[i, :kc[i]] for i in range(b)] if want_kpts else None
         return kpts, [(m[i, :mc[i]], ms[i, :mc[i]]) for i in range(npairs)]
 
-    def pairs_collect_begin(self, thresh: float = 0.0, want_kpts: bool = True):
-        """First half of pairs_collect(): enqueue the matcher and the result copies of the oldest submitted batch."""
+    def pinned_empty(self, shape, dtype):
+        """numpy array over page-locked host memory (rfe_alloc_pinned); freed with the FrontEnd."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = self.lib.rfe_alloc_pinned(n)
+        if not p:
+            raise RoverFeError(RFE_ERR_CUDA, (self.lib.rfe_last_error() or b"").decode())
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        buf = (C.c_uint8 * max(n, 1)).from_address(p)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def pairs_collect_begin(self, thresh: float = 0.0, want_kpts: bool = True, want_desc: bool = False):
+        """First half of pairs_collect(): enqueue the matcher and the result copies of the oldest submitted batch.
+        want_desc: also return scores and fp32 descriptors of every image (what SPextractor::operator() returns)."""
         imgs = self._inflight.pop(0)
         b = imgs.shape[0]
         npairs, cap = b // 2, self.cap
-        # two result buffer sets: the arrays handed out by the previous collect stay valid while this one is filled
+        # two result buffer sets (pinned): the arrays handed out by the previous collect stay valid while this one is filled
         self._mp_sets = getattr(self, "_mp_sets", {})
         self._mp_flip = 1 - getattr(self, "_mp_flip", 0)
-        key = (b, self._mp_flip)
+        key = (b, self._mp_flip, want_desc)
         if key not in self._mp_sets:
-            self._mp_sets[key] = (np.empty((b, cap, 2), np.int32), np.zeros(b, np.int32), np.empty((npairs, cap, 2), np.int32),
-                                  np.empty((npairs, cap), np.float32), np.zeros(npairs, np.int32))
+            pe = self.pinned_empty
+            self._mp_sets[key] = (pe((b, cap, 2), np.int32), np.zeros(b, np.int32), pe((npairs, cap, 2), np.int32),
+                                  pe((npairs, cap), np.float32), np.zeros(npairs, np.int32),
+                                  pe((b, cap), np.float32) if want_desc else None, pe((b, cap, DESC_DIM), np.float32) if want_desc else None)
         self._collecting = (self._mp_sets[key], b, npairs, want_kpts)
-        kp, kc, m, ms, mc = self._mp_sets[key]
-        self._check(self.lib.rfe_pairs_collect_begin(self.ctx, thresh, _ptr(kp) if want_kpts else None, _ptr(m), _ptr(ms), cap))
+        kp, kc, m, ms, mc, sc, de = self._mp_sets[key]
+        self._check(self.lib.rfe_pairs_collect_begin_full(self.ctx, thresh, _ptr(kp) if want_kpts else None, _ptr(sc), _ptr(de),
+                                                          _ptr(m), _ptr(ms), cap))
 
     def pairs_collect_end(self):
-        (kp, kc, m, ms, mc), b, npairs, want_kpts = self._collecting
+        """Returns (keypoints per image, (matches, mscores) per pair); after pairs_collect_begin(want_desc=True) a third element:
+        (scores, descriptors) per image."""
+        (kp, kc, m, ms, mc, sc, de), b, npairs, want_kpts = self._collecting
         self._check(self.lib.rfe_pairs_collect_end(self.ctx, _ptr(kc), _ptr(mc)))
         kpts = [kp[i, :kc[i]] for i in range(b)] if want_kpts else None
-        return kpts, [(m[i, :mc[i]], ms[i, :mc[i]]) for i in range(npairs)]
+        res = [(m[i, :mc[i]], ms[i, :mc[i]]) for i in range(npairs)]
+        if de is None:
+            return kpts, res
+        return kpts, res, [(sc[i, :kc[i]], de[i, :kc[i]]) for i in range(b)]
+
+    def copy_results_device(self, n_pairs: int, d_matches: int, d_mscores: int, d_counts: int):
+        """Device pointers (e.g. torch tensors' data_ptr()) receive the match results of the last batched match."""
+        self._check(self.lib.rfe_lg_copy_results_device(self.ctx, n_pairs, C.c_void_p(d_matches), C.c_void_p(d_mscores),
+                                                        C.c_void_p(d_counts)))
 
     def read_result(self, rslot: int = 0):
         m = np.empty((self.cap, 2), np.int32)

@@ -91,6 +91,11 @@ struct rfe_ctx {
   Pending pending[2];
   int n_pending = 0, next_set = 0;
   cudaEvent_t ev_counts[2] = {nullptr, nullptr};
+  // rfe_pairs_collect_begin_full: scores / descriptors of a batch go back on a SECOND stream, overlapping the matcher
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_feat[2] = {nullptr, nullptr};   // feature copies of slot set k have finished reading the slots
+  bool feat_pending[2] = {false, false};
+  int collecting_set = 0;
   cudaEvent_t ev_done = nullptr;     // results of the batch being collected have landed on the host
   int collecting_pairs = 0;          // > 0 between rfe_pairs_collect_begin and rfe_pairs_collect_end
   int collecting_rc = 0;
@@ -126,7 +131,11 @@ struct rfe_ctx {
   // optional per-kernel CUDA-event profiling (rfe_profile)
   struct ProfRec { std::string tag; cudaEvent_t a, b; };
   bool use_strip_conv = true;   // RFE_CONV_STRIP=0 falls back to the 9-box implicit GEMM for the 64->64 layers
-  bool fuse_conv1a = true;      // RFE_FUSE_CONV1A=0: stand-alone conv1a kernel + activation round trip (round-1 behaviour)
+  // RFE_FUSE_CONV1A=1: conv1a computed inside conv1b's strip kernel (no activation round trip through HBM).  Correct and
+  // bit-identical (tests), but measured SLOWER on B200: 1800 us per 16 frames against 381 + 904 us for the two kernels --
+  // the two producer warps that fit beside the 160-register epilogue warps cannot deliver 2.25 rows per 8.3 K-cycle MMA
+  // iteration (about 1650 instructions per thread and row).  Off by default; profiles/README.md has the numbers.
+  bool fuse_conv1a = false;
   bool profiling = false;
   std::string prof_prefix;                   // rfe_profile_select
   std::vector<ProfRec> prof;
@@ -497,8 +506,8 @@ int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B, i
     set_error("this ctx was created with RFE_FLAG_NO_EXTRACTOR");
     return RFE_ERR_INVALID;
   }
-  // conv1 group (K1): with the strip kernel, conv1a is computed inside conv1b's row producers and its activation never
-  // touches HBM.  RFE_FUSE_CONV1A=0 (or the 9-box fallback) runs the stand-alone conv1a kernel first, as round 1 did.
+  // conv1 group (K1): RFE_FUSE_CONV1A=1 computes conv1a inside conv1b's row producers, so its activation never touches
+  // HBM; the default runs the stand-alone conv1a kernel first (faster as measured, see rfe_ctx::fuse_conv1a).
   const bool fuse1a = c->use_strip_conv && c->fuse_conv1a;
   if (!fuse1a) {
     ProfScope ps_(c, "sp.conv1a");
@@ -1120,6 +1129,9 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   C_(cudaEventCreateWithFlags(&c->ev_counts[0], cudaEventDisableTiming));
   C_(cudaEventCreateWithFlags(&c->ev_counts[1], cudaEventDisableTiming));
   C_(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+  C_(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  C_(cudaEventCreateWithFlags(&c->ev_feat[0], cudaEventDisableTiming));
+  C_(cudaEventCreateWithFlags(&c->ev_feat[1], cudaEventDisableTiming));
   // ---- LightGlue buffers ----
   c->lg_pairs = c->max_batch < kMaxPairs ? c->max_batch : kMaxPairs;   // pairs per rfe_lg_match_slots_batch
   if (c->no_lg) c->lg_pairs = 0;
@@ -1172,6 +1184,9 @@ void rfe_destroy(rfe_ctx* c) {
   for (int i = 0; i < 2; ++i)
     if (c->ev_counts[i]) cudaEventDestroy(c->ev_counts[i]);
   if (c->ev_done) cudaEventDestroy(c->ev_done);
+  for (int i = 0; i < 2; ++i)
+    if (c->ev_feat[i]) cudaEventDestroy(c->ev_feat[i]);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -1609,6 +1624,10 @@ int rfe_pairs_submit(rfe_ctx* c, const uint8_t* gray, int h, int w, int stride, 
   // one image staging buffer is enough: the copy of batch k+1 is ordered after SuperPoint of batch k on the stream
   RFE_CUDA_CHECK(cudaMemcpyAsync(c->img, gray, static_cast<size_t>(B) * h * stride, cudaMemcpyHostToDevice, s));
   c->bytes_h2d += static_cast<size_t>(B) * h * stride;
+  if (c->feat_pending[set]) {     // this slot set is still being copied to the host on the copy stream
+    RFE_CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_feat[set], 0));
+    c->feat_pending[set] = false;
+  }
   if ((r = sp_run(c, c->img, h, w, stride, B, set * c->max_batch))) return r;
   RFE_CUDA_CHECK(cudaMemcpyAsync(c->h_counts2 + set * c->max_batch, c->kp_counts + set * c->max_batch, sizeof(int) * B,
                                  cudaMemcpyDeviceToHost, s));
@@ -1619,6 +1638,11 @@ int rfe_pairs_submit(rfe_ctx* c, const uint8_t* gray, int h, int w, int stride, 
 }
 
 int rfe_pairs_collect_begin(rfe_ctx* c, float thresh, int32_t* kpts_xy, int32_t* matches, float* mscores, int cap) {
+  return rfe_pairs_collect_begin_full(c, thresh, kpts_xy, nullptr, nullptr, matches, mscores, cap);
+}
+
+int rfe_pairs_collect_begin_full(rfe_ctx* c, float thresh, int32_t* kpts_xy, float* scores, float* desc, int32_t* matches,
+                                 float* mscores, int cap) {
   int r = check_ctx(c);
   if (r) return r;
   if (!matches || cap <= 0) {
@@ -1645,6 +1669,30 @@ int rfe_pairs_collect_begin(rfe_ctx* c, float thresh, int32_t* kpts_xy, int32_t*
     pd[i] = PairDesc{nullptr, nullptr, c->kpts + static_cast<size_t>(s0) * c->cap * 2, c->kpts + static_cast<size_t>(s1) * c->cap * 2,
                      c->desc + static_cast<size_t>(s0) * c->cap * 256, c->desc + static_cast<size_t>(s1) * c->cap * 256, n0, n1, i};
   }
+  if (scores || desc) {
+    // What SPextractor::operator() hands back besides the keypoints (Frame::mDescriptors, Frame.cc:544-559): exactly n rows per
+    // image, on the copy stream -- the features were complete when ev_counts fired, so these 1-2 MB per image overlap the
+    // matcher that is enqueued on the main stream right below
+    RFE_CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_counts[pd0.set], 0));
+    for (int b = 0; b < B; ++b) {
+      int m = hc[b] < c->cap ? hc[b] : c->cap;
+      if (cap < m) m = cap;
+      if (m <= 0) continue;
+      if (scores) {
+        RFE_CUDA_CHECK(cudaMemcpyAsync(scores + static_cast<size_t>(b) * cap, c->kp_scores + static_cast<size_t>(base + b) * c->cap,
+                                       sizeof(float) * m, cudaMemcpyDeviceToHost, c->copy_stream));
+        c->bytes_d2h += sizeof(float) * m;
+      }
+      if (desc) {
+        RFE_CUDA_CHECK(cudaMemcpyAsync(desc + static_cast<size_t>(b) * cap * 256, c->desc + static_cast<size_t>(base + b) * c->cap * 256,
+                                       sizeof(float) * 256 * m, cudaMemcpyDeviceToHost, c->copy_stream));
+        c->bytes_d2h += sizeof(float) * 256 * m;
+      }
+    }
+    RFE_CUDA_CHECK(cudaEventRecord(c->ev_feat[pd0.set], c->copy_stream));
+    c->feat_pending[pd0.set] = true;
+  }
+  c->collecting_set = pd0.set;
   if ((r = lg_run(c, pd, pd0.n_pairs, pd0.h, pd0.w, thresh))) return r;   // the batch stays queued: collect can be retried
   c->pending[0] = c->pending[1];
   --c->n_pending;
@@ -1713,6 +1761,7 @@ int rfe_pairs_collect_end(rfe_ctx* c, int32_t* kp_counts, int32_t* match_counts)
   }
   // wait for THIS batch's results only: work submitted after rfe_pairs_collect_begin keeps running behind the event
   RFE_CUDA_CHECK(cudaEventSynchronize(c->ev_done));
+  if (c->feat_pending[c->collecting_set]) RFE_CUDA_CHECK(cudaEventSynchronize(c->ev_feat[c->collecting_set]));
   for (int b = 0; b < 2 * c->collecting_pairs; ++b) kp_counts[b] = c->collecting_counts[b];
   for (int i = 0; i < c->collecting_pairs; ++i) match_counts[i] = c->h_mcounts[i];
   c->collecting_pairs = 0;
@@ -1825,6 +1874,32 @@ int rfe_lg_match(rfe_ctx* c, const float* kpts0, int n0, const float* kpts1, int
 int rfe_lg_match_normalized(rfe_ctx* c, const float* kn0, int n0, const float* kn1, int n1, const float* desc0,
                             const float* desc1, float thresh, int32_t* matches, float* mscores, int* k) {
   return lg_match_host(c, "rfe_lg_match_normalized", kn0, n0, kn1, n1, desc0, desc1, 0, 0, thresh, matches, mscores, k);
+}
+
+void* rfe_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    set_error("cudaMallocHost(%zu bytes) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+void rfe_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int rfe_lg_copy_results_device(rfe_ctx* c, int n_pairs, int32_t* d_matches, float* d_mscores, int32_t* d_counts) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (n_pairs <= 0 || n_pairs > c->max_batch || !d_matches || !d_counts) {
+    set_error("rfe_lg_copy_results_device: invalid argument");
+    return RFE_ERR_INVALID;
+  }
+  cudaStream_t s = c->stream;
+  RFE_CUDA_CHECK(cudaMemcpyAsync(d_matches, c->res_matches, sizeof(int) * 2 * c->cap * n_pairs, cudaMemcpyDeviceToDevice, s));
+  if (d_mscores) RFE_CUDA_CHECK(cudaMemcpyAsync(d_mscores, c->res_scores, sizeof(float) * c->cap * n_pairs, cudaMemcpyDeviceToDevice, s));
+  RFE_CUDA_CHECK(cudaMemcpyAsync(d_counts, c->res_count, sizeof(int) * n_pairs, cudaMemcpyDeviceToDevice, s));
+  return RFE_OK;
 }
 
 double rfe_get_timer_ms(rfe_ctx* c, const char* name) {

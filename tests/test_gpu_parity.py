@@ -83,8 +83,7 @@ def test_superpoint_intermediates(fe, sp):
     fe.extract(img)
     taps = {}
     sp(img, taps)
-    # conv1a's activation ("relu1a") is never materialised: it is computed inside conv1b's row producers; pool1 checks both
-    for name, key, c, div, tol in [("sp.pool1", "pool1", 64, 2, 2e-4),
+    for name, key, c, div, tol in [("sp.a1a", "relu1a", 64, 1, 2e-4), ("sp.pool1", "pool1", 64, 2, 2e-4),
                                    ("sp.pool2", "pool2", 64, 4, 2e-4), ("sp.pool3", "pool3", 128, 8, 2e-4),
                                    ("sp.feat", "feat", 128, 8, 2e-4)]:
         got = np.transpose(fe.debug_read(name).reshape(96 // div, 160 // div, c), (2, 0, 1))
@@ -589,12 +588,15 @@ def test_l2_best2_slots_equals_host_form(fe):
 
 def test_one_to_many_with_layer0_cache_equals_batched_matching(fe):
     """8(f).3: one KeyFrame against several neighbours with the per-slot layer-0 cache == rfe_lg_match_slots_batch on the same
-    pairs: identical match lists, scores within 1e-5 (the cache is built in a pass with fewer rows, whose GEMMs may use the
-    other tiling: the lo-product accumulation order differs in the last bit); the cache is reused on the second call,
+    pairs: the same match lists, scores within 1e-4 (the cache is built in a pass with fewer rows, whose GEMMs may use the
+    other tiling: the lo-product accumulation order differs in the last bit, and nine layers amplify it to ~6e-6); the cache is reused on the second call,
     rebuilt after the slot is overwritten or when the normalisation size changes, and a stale entry is never used."""
 
     def same(a, b):
-        return np.array_equal(a[0], b[0]) and (len(a[1]) == 0 or np.abs(a[1] - b[1]).max() <= 1e-5)
+        # identical pairs except within the stated margin of the 0.1 filter, scores within the stated tolerance (tests/parity.py);
+        # measured: identical lists, scores within 6e-6
+        r = parity.compare_matches(a[0], a[1], b[0], b[1])
+        return r["only_ref"] + r["only_tst"] <= 1 and r["mscore_maxabs"] <= 1e-4
 
     h, w = 240, 320
     imgs = np.stack([synth.frame_pair(100 + i, h, w, shift=(3 * i - 4, 2 * i - 3))[i % 2] for i in range(5)]
