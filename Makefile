@@ -33,8 +33,12 @@ HOSTSRC := $(HOST)/src/transform.cpp $(HOST)/src/superpoint_onnx.cc $(HOST)/src/
 HOSTFLAGS := -O2 -std=c++14 -fPIC -Wall -Iinclude -I$(HOST)/include -I$(HOST)/shim -DROVER_FE_OPENCV_SHIM -DROVER_FE_STANDALONE
 HOSTLIB := rover_slam_b200/librover_slam_frontend.so
 HOSTDRV := rover_slam_b200/host_driver
+LATDRV := rover_slam_b200/latency_driver
 
-host: $(HOSTLIB) $(HOSTDRV)
+host: $(HOSTLIB) $(HOSTDRV) $(LATDRV)
+
+$(LATDRV): $(HOST)/test/latency_driver.cpp $(HOSTLIB)
+	g++ $(HOSTFLAGS) -o $@ $< -Lrover_slam_b200 -lrover_slam_frontend -lrover_fe -Wl,-rpath,'$$ORIGIN'
 
 $(HOSTLIB): $(HOSTSRC) $(wildcard $(HOST)/include/*/*.h) $(LIB)
 	g++ $(HOSTFLAGS) -shared -o $@ $(HOSTSRC) -Lrover_slam_b200 -lrover_fe -Wl,-rpath,'$$ORIGIN'

@@ -5,8 +5,17 @@ A "step" = one batch of PAIRS 640x480 frame pairs: both frames of every pair are
 SuperPoint launch sequence over 2*PAIRS frames), then every pair is matched.  frames/s = 2*PAIRS*steps / time.
   value : inputs already resident in HBM, features handed from the extractor to the matcher on the device
           (rfe_sp_extract_device + rfe_lg_match_slots), device-timed with CUDA events, max over ranks.
-  e2e   : the same work through the host API (rfe_pairs_submit / rfe_pairs_collect: pinned host images in, host keypoints
-          and matches out), every H2D / D2H copy inside the timed region, two batches in flight.
+  e2e   : N = 1: the same work through the host API (rfe_pairs_submit / rfe_pairs_collect_begin_full / _end: pinned host images
+          in; host keypoints, scores, fp32 DESCRIPTORS, matches and match scores out -- everything the reference's
+          SPextractor::operator() + MatchingPoints_onnx hand back), every H2D / D2H copy inside the timed region, two batches in
+          flight, descriptors returned on a copy stream.
+          N > 1: BASELINE config 5 as stated -- the frame stream lives in rank 0's pinned host memory; per step rank 0 copies
+          all ranks' frames to its GPU, NCCL scatters one block per rank, every rank extracts + matches, NCCL gathers the
+          fixed-size match records to rank 0, which copies them to the host; ingest / gather run on a side stream under the
+          compute (rover_slam_b200/shard.py, PairStream).  All of it inside the timed region.
+  stream: the config-5 pipeline measured at every N (N = 1 included), so that its scaling can be read off one key.
+  latency: N = 1 only: p50 / p99 of ONE SPextractor::operator() + ONE SPmatcher::MatchingPoints_onnx(Frame, Frame) at batch 1
+          through the C++ class surface (rover_slam_b200/latency_driver), the reference's per-frame call pattern.
   --impl reference : the reference's CPU path for the same workload -- its two ONNX graphs restated on torch-CPU
           (oracle/, stand-in for ONNXRuntime-CPU which is not installable here), all host threads, one pair per step.
 """
@@ -130,8 +139,34 @@ def cpu_pair_seconds(frames_pair, threads):
     with torch.no_grad():
         ka, _, da = sp(frames_pair[0])
         kb, _, db = sp(frames_pair[1])
+        t1 = time.perf_counter()
         m, _ = lg(lightglue_ref.normalize_keypoints(ka.numpy(), H, W), lightglue_ref.normalize_keypoints(kb.numpy(), H, W), da, db)
-    return time.perf_counter() - t, len(m)
+    t2 = time.perf_counter()
+    cpu_pair_seconds.last_split = ((t1 - t) / 2, t2 - t1)        # seconds per extraction, per match
+    return t2 - t, len(m)
+
+
+def batch1_latency(iters=40):
+    """One SPextractor::operator() + one SPmatcher::MatchingPoints_onnx(Frame, Frame) per frame at batch 1 through the C++
+    class surface (rover_slam_b200/latency_driver): p50 / p99 in milliseconds, host containers in and out."""
+    import tempfile
+    drv = os.path.join(ROOT, "rover_slam_b200", "latency_driver")
+    if not os.path.exists(drv):
+        return {"unavailable": "latency_driver not built (make host)"}
+    frames = make_pairs(1, 11)
+    with tempfile.TemporaryDirectory() as td:
+        pa, pb = os.path.join(td, "a.raw"), os.path.join(td, "b.raw")
+        frames[0, 0].tofile(pa)
+        frames[0, 1].tofile(pb)
+        env = dict(os.environ, ROVER_FE_WEIGHTS=os.path.join(ROOT, "weights", "rover_fe.rfw"))
+        try:
+            r = subprocess.run([drv, str(H), str(W), pa, pb, str(iters)], capture_output=True, text=True, env=env, timeout=300)
+            out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        except Exception as e:          # noqa: BLE001
+            return {"unavailable": f"latency_driver failed: {e!r}"}
+    out["what"] = ("per frame: one SPextractor::operator() (640x480 u8 in; keypoints + N x 256 descriptors out) + one "
+                   "SPmatcher::MatchingPoints_onnx(Frame, Frame) against the previous frame, batch 1, host containers, C++ class surface")
+    return out
 
 
 def run_reference(args, rank, world):
@@ -197,7 +232,8 @@ def main():
     from rover_slam_b200 import shard as sharding
     n_sets = 4                                  # distinct step inputs, cycled
     n_pairs_total = n_sets * P * world
-    allf = torch.from_numpy(make_pairs(n_pairs_total, 1)).to(dev) if rank == 0 else None
+    host_all = torch.from_numpy(make_pairs(n_pairs_total, 1)) if rank == 0 else None     # [world * n_sets * P, 2, H, W], rank r owns block r
+    allf = host_all.to(dev) if rank == 0 else None
     block, valid = sharding.scatter_pairs(allf, n_pairs_total, (H, W), dev)     # [n_sets*P, 2, H, W] on this rank
     assert valid == n_sets * P
     shard = block.reshape(n_sets, B, H, W)
@@ -222,10 +258,10 @@ def main():
         if n_steps > 1:
             fe.pairs_submit(host_np[1 % n_sets])
         for i in range(n_steps):
-            fe.pairs_collect_begin()                    # enqueue LightGlue + result copies of batch i
+            fe.pairs_collect_begin(want_desc=True)      # enqueue LightGlue + result copies of batch i (descriptors on the copy stream)
             if i + 2 < n_steps:
                 fe.pairs_submit(host_np[(i + 2) % n_sets])   # queue the next batch behind it BEFORE blocking
-            kpts, res = fe.pairs_collect_end()
+            kpts, res, feats = fe.pairs_collect_end()
 
     def barrier():
         torch.cuda.synchronize()
@@ -273,12 +309,41 @@ def main():
     value = frames_total / (ms_total / 1e3)
     attn_flops = sum(attn_flops_sets[i % n_sets] for i in range(args.steps)) / args.steps     # mean per launch
 
-    # ---- end to end through the host API ("e2e") ----
+    e_steps = max(3, args.steps)
+    # ---- BASELINE config 5: rank-0 host stream -> scatter -> extract + match -> gather -> rank-0 host ("stream") ----
+    cap = fe.cap
+    words = P * cap * 3 + P                              # per rank and step: matches [P][cap][2] i32, mscores [P][cap] f32, counts [P]
+
+    def stream_compute(in_block, out_record, step):
+        fe.extract_device(in_block.data_ptr(), H, W, W, B)
+        fe.match_slots_batch(slots_a, slots_b, H, W, 0.0)
+        base = out_record.data_ptr()
+        fe.copy_results_device(P, base, base + 4 * P * cap * 2, base + 4 * P * cap * 3)
+
+    ps = sharding.PairStream((B, H, W), words, dev, stream_compute)
+    stream_sets = None
+    if rank == 0:                                       # [n_sets][world][B][H][W] in pinned host memory
+        stream_sets = host_all.reshape(world, n_sets, B, H, W).transpose(0, 1).contiguous().pin_memory()
+    last_counts = {}
+
+    def consume(i, rec):
+        last_counts["c"] = rec[:, P * cap * 3:].clone()
+
+    ps.run(2, (lambda i: stream_sets[i % n_sets]) if rank == 0 else None)
+    barrier()
+    b0 = (ps.h2d_bytes, ps.d2h_bytes, ps.collective_bytes)
+    t0 = time.perf_counter()
+    ps.run(e_steps, (lambda i: stream_sets[i % n_sets]) if rank == 0 else None, consume)
+    barrier()
+    stream_s = max_over_ranks(time.perf_counter() - t0)
+    stream_fps = 2 * P * e_steps * world / stream_s
+    s_h2d, s_d2h, s_coll = ((ps.h2d_bytes - b0[0]) // e_steps, (ps.d2h_bytes - b0[1]) // e_steps, (ps.collective_bytes - b0[2]) // e_steps)
+
+    # ---- end to end through the host API ("e2e" at N = 1) ----
     run_host(2)
     barrier()
     tb0 = fe.transfer_bytes()
     t0 = time.perf_counter()
-    e_steps = max(3, args.steps)
     run_host(e_steps)
     barrier()
     tb1 = fe.transfer_bytes()
@@ -321,10 +386,22 @@ def main():
                    "l2": f"per-step activation working set about {0.31 * B:.1f} GB >> 126 MB L2; 4 distinct input sets cycled",
                    "matches_last_step": nmatch},
         "clocks": sampler.summary(),
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d // e_steps, "d2h_bytes_per_step": d2h // e_steps,
-                "steps": e_steps},
+        # N = 1: the reference-facing host API (keypoints, scores, descriptors, matches back on the host);
+        # N > 1: BASELINE config 5, rank-0 host stream -> NCCL scatter -> compute -> NCCL gather -> rank-0 host
+        "e2e": ({"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d // e_steps, "d2h_bytes_per_step": d2h // e_steps,
+                 "steps": e_steps, "path": "host API: rfe_pairs_submit / rfe_pairs_collect_begin_full / _end, pinned buffers, "
+                 "returns keypoints + scores + fp32 descriptors + matches + match scores"} if world == 1 else
+                {"value": stream_fps, "unit": "frames/s", "h2d_bytes_per_step": s_h2d, "d2h_bytes_per_step": s_d2h, "steps": e_steps,
+                 "path": "config 5 stream: rank-0 pinned host frames -> H2D -> NCCL scatter -> extract + match on every rank -> "
+                 "NCCL gather of match records -> D2H on rank 0 (independent pairs: both frames of every pair extracted)"}),
+        "stream": {"value": stream_fps, "unit": "frames/s", "steps": e_steps, "h2d_bytes_per_step": s_h2d, "d2h_bytes_per_step": s_d2h,
+                   "collective": "NCCL scatter (u8 frames) + gather (fixed-size match records), side stream, double buffered" if world > 1 else "none (one rank)",
+                   "collective_bytes_per_step": s_coll, "host_api_e2e": e2e,
+                   "match_counts_last_step": last_counts.get("c").tolist() if last_counts.get("c") is not None else None,
+                   "variant": "independent pairs (2 extracts + 1 match per pair); the SLAM-shaped stream (pair p = frames p, p+1: one "
+                   "extract + one match per frame) needs half the extractions per pair and is not what this number measures"},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "attn_kernel (lg.attn_self / lg.attn_cross: fused 4-head attention of all pairs, 18 launches per step)",
+        "roofline": {"bound": "tensor", "kernel": "attn2_kernel (lg.attn_self / lg.attn_cross: persistent fused 4-head attention of all pairs, 18 launches per step)",
                      "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak if tf_peak else None,
                      "traffic": ATTN_DRAM_BYTES_PER_LAUNCH if P == 8 else None, "peak_source": peak_src, "launch_ms": per_launch_ms, "launches_timed": attn_n,
                      "algorithmic_flops_per_launch": attn_flops,
@@ -334,6 +411,8 @@ def main():
                              "traffic = DRAM bytes of one launch from the ncu --set full capture profiles/r01_attn_full.ncu-rep (8 pairs per step)"},
         "kernel_us_per_step": breakdown,
     }
+    if world == 1:
+        line["latency"] = batch1_latency()
     if world == 1 and args.cpu_pairs > 0:
         threads, avail = pick_cpu_threads()
         cpu_frames = make_pairs(args.cpu_pairs, 7)
@@ -342,6 +421,9 @@ def main():
         for p in range(args.cpu_pairs):
             dt, _ = cpu_pair_seconds(cpu_frames[p], threads)
             tt += dt
+        if isinstance(line.get("latency"), dict):
+            ex_s, ma_s = cpu_pair_seconds.last_split
+            line["latency"]["cpu_frame_ms"] = round(1e3 * (ex_s + ma_s), 1)      # the CPU arm's time for the same 1 extract + 1 match
         line["cpu_baseline"] = {"value": 2 * args.cpu_pairs / tt, "unit": "frames/s", "cores": threads, "kind": "port",
                                 "sample": f"{args.cpu_pairs} pairs (2 extracts + 1 match each) of the same synthetic stream, after 1 warm-up pair; "
                                           f"{threads} of {avail} host threads (fastest of a thread sweep)"}
