@@ -413,6 +413,9 @@ int gemm_linear(rfe_ctx* c, const char* tag, const Operand& A, const Operand& B,
     }
   }
   if (block_n == 64) return launch_umma<64, A_GEMM, EPI_LINEAR>(c, tag, ah, al, bh, bl, p, grid, &em);
+  // 128 x 256 tiles (K = 512 FFN GEMMs): one accumulator set (no MMA / epilogue overlap) but every A tile crosses L2 -> SM
+  // once per 256 instead of once per 128 output columns -- these GEMMs are bound by operand ingest, not by the tensor pipe
+  if (block_n == 256) return launch_umma<256, A_GEMM, EPI_LINEAR>(c, tag, ah, al, bh, bl, p, grid, &em);
   // K <= 256, one problem, enough m-tiles to amortise the weight load: keep the weights of one n-tile resident (BRES)
   if (z == 1 && p.num_k_steps <= kBresMaxKSteps && use_bres(c, grid.x * grid.y))
     return launch_umma<128, A_GEMM, EPI_LINEAR, true>(c, tag, ah, al, bh, bl, p, grid, &em);
@@ -604,7 +607,8 @@ int ffn_block(rfe_ctx* c, int rows, const SplitW& ffn0, const float* ln_w, const
     p.bias = ffn0.bias;
     p.out_f32 = c->hid;
     p.ld_f32 = 512;
-    if ((r = gemm_linear(c, "lg.ffn0", A, B, p, 128))) return r;
+    static const int kFfn0Bn = getenv("RFE_FFN0_BN") ? atoi(getenv("RFE_FFN0_BN")) : 128;
+    if ((r = gemm_linear(c, "lg.ffn0", A, B, p, kFfn0Bn))) return r;
   }
   { ProfScope ps_(c, "lg.ln_gelu"); launch_ln_gelu_split(c->stream, c->hid, rows, ln_w, ln_b, c->hs.hi, c->hs.lo); }
   c->launches++;
@@ -620,7 +624,8 @@ int ffn_block(rfe_ctx* c, int rows, const SplitW& ffn0, const float* ln_w, const
     p.out_hi = c->cat.hi;
     p.out_lo = c->cat.lo;
     p.ld_h = 512;
-    if ((r = gemm_linear(c, "lg.ffn3", A, B, p, 128))) return r;
+    static const int kFfn3Bn = getenv("RFE_FFN3_BN") ? atoi(getenv("RFE_FFN3_BN")) : 128;
+    if ((r = gemm_linear(c, "lg.ffn3", A, B, p, kFfn3Bn))) return r;
   }
   return RFE_OK;
 }
