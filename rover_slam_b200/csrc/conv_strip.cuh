@@ -50,11 +50,13 @@ struct StripParams {
 
 constexpr int kStripThreads = 384;
 constexpr int kStripWarpRows = 8, kStripWarpW = 9, kStripWarpMma = 11;
-// FUSE1A: warps 8 and 10 (the TMA row producer and the spare warp) compute the input rows -- conv1a + ReLU + split of the
-// u8 image -- instead of fetching them.  The CTA stays at 12 warps: registers are per scheduler (16 K each), so a 13th
-// warp would cap every thread at 128 registers and spill the epilogue's 64 accumulator values.
-constexpr int kStripThreadsFused = kStripThreads;
-constexpr int kStripRowProducerWarps = 2;
+// FUSE1A: a fourth warpgroup (warps 12..15) computes the input rows -- conv1a + ReLU + split of the u8 image -- instead of
+// the TMA row producer fetching them.  Registers are per scheduler (16 K each, four warps per scheduler at 16 warps): the
+// kernel is compiled for 128 registers per thread and re-balances at run time with setmaxnreg -- the two epilogue
+// warpgroups grow to 160 (their 64 accumulator values), the single-thread role warpgroup (TMA, MMA issue) shrinks to 40,
+// the row producers grow to 152 (72 of them hold the conv1a weights): 160 + 160 + 40 + 152 = 512 per scheduler.
+constexpr int kStripThreadsFused = 512;
+constexpr int kStripRowProducerWarps = 4;
 constexpr int kStripRowBytes = 130 * 128;        // one plane of one input row of the strip (with 1-px halo each side)
 constexpr int kStripSlotBytes = 17 * 1024;       // slot pitch (1024-aligned for the swizzle)
 constexpr int kStripRowSlots = 4;
@@ -125,11 +127,12 @@ __device__ __forceinline__ void conv64_strip_body(const CUtensorMap& tmA_hi, con
     iters = rows >> 1;
   };
 
-  const int prod_rank = warp == 8 ? 0 : warp == 10 ? 1 : -1;
+  const int prod_rank = warp >= 12 ? warp - 12 : -1;
   if (FUSE1A && prod_rank >= 0) {
     // ===== input-row producers (FUSE1A): conv1a + ReLU + split of the u8 image, written as the TMA box would land ======
-    // work item = (run of 8 pixels, group of 8 output channels): 16 runs x 8 groups cover pixels 0..127 of the 130-pixel
-    // row in two passes of the 64 producer threads; pixels 128 / 129 are a one-pixel pass of 16 threads
+    // thread = (run of 8 pixels, group of 8 output channels): 16 runs x 8 groups = the 128 producer threads cover pixels
+    // 0..127 of the 130-pixel row in one pass; pixels 128 / 129 are a one-pixel pass of 16 threads
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     const int tid = prod_rank * 32 + lane;
     const int cg = tid & 7;
     f32x2 wr[4][9], br[4];
@@ -179,9 +182,8 @@ __device__ __forceinline__ void conv64_strip_body(const CUtensorMap& tmA_hi, con
                      ? static_cast<float>(__ldg(im + static_cast<size_t>(yy) * p.img_stride + xx)) * 0.003921568859368563f
                      : 0.0f;
         };
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-          const int run = pass * 8 + (tid >> 3);
+        {
+          const int run = tid >> 3;
           const int pp0 = run * 8, xs = x0 - 1 + pp0;           // pixels pp0 .. pp0 + 7
           float in[3][10];
           if (row_in) {
@@ -242,7 +244,10 @@ __device__ __forceinline__ void conv64_strip_body(const CUtensorMap& tmA_hi, con
         }
       }
     }
-  } else if (warp == kStripWarpW) {
+  } else if (warp >= 8 && warp < 12) {
+    // the single-thread roles (one warpgroup: the register hand-over below is a warpgroup-wide instruction)
+    if (FUSE1A) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == kStripWarpW) {
     // ===== weight producer: tap sequence number m -> stage m & 3 ======================================================
     if (elect_one()) {
       uint32_t m = 0;
@@ -260,7 +265,7 @@ __device__ __forceinline__ void conv64_strip_body(const CUtensorMap& tmA_hi, con
           }
       }
     }
-  } else if (warp == kStripWarpMma) {
+    } else if (warp == kStripWarpMma) {
     // ===== MMA issuer ==================================================================================================
     if (elect_one()) {
       constexpr uint32_t idesc64 = make_idesc_f16(128, 64);
@@ -338,8 +343,10 @@ __device__ __forceinline__ void conv64_strip_body(const CUtensorMap& tmA_hi, con
         p.prof[4] = gi;                    // iterations
       }
     }
+    }
   } else if (warp < 8) {
     // ===== epilogue warps ==============================================================================================
+    if (FUSE1A) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
     const int q = warp & 3;
     const int half = warp >> 2;                     // channels [32*half, 32*half + 32)
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);

@@ -13,3 +13,12 @@ k = d["kernel_us_per_step"]
 print("ffn0 bn", sys.argv[1], "ffn3 bn", sys.argv[2], "| ffn0", k["lg.ffn0"], "ffn3", k["lg.ffn3"], "| ms/step", round(d["ms_per_step"], 3), "clk", d["clocks"]["sm_mhz"])
 PY
 done
+echo "== fused conv1a (setmaxnreg, four producer warps)"
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "fused_conv1a" 2>&1 | tail -3
+RFE_FUSE_CONV1A=1 timeout 300 python bench.py --steps 10 --warmup 3 --cpu-pairs 0 > gpurun_out/r02_fuse1a.json 2> gpurun_out/r02_fuse1a.err
+python - <<'PY'
+import json
+d = json.load(open("gpurun_out/r02_fuse1a.json"))
+k = d["kernel_us_per_step"]
+print("fused: conv1a", k.get("sp.conv1a"), "conv1b", k["sp.conv1b"], "| ms/step", round(d["ms_per_step"], 3), "clk", d["clocks"]["sm_mhz"])
+PY
