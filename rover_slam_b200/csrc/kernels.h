@@ -57,6 +57,10 @@ void launch_lg_prepare(cudaStream_t s, const LgImages& im, int max_n, int norm_h
 // dual log-softmax statistics, both arg-maxes and the mutual-match compaction for all pairs
 void launch_lg_assign(cudaStream_t s, const LgAssign& a, float* rmax, float* rlog, float* cmax, float* clog,
                       const float* ls, float* max0, int* m0, int* m1, float filter, float thresh, float* S_dbg);
+// the same in two passes over sim (32-row bands; part_a / part_b: [pairs][part_bands][part_ld] scratch)
+void launch_lg_assign_banded(cudaStream_t s, const LgAssign& a, float* rmax, float* rlog, float* cmax, float* clog,
+                             const float* ls, float* max0, int* m0, int* m1, float filter, float thresh, float* S_dbg,
+                             float* part_a, float* part_b, int part_ld, int part_bands);
 void launch_posenc(cudaStream_t s, const float* kpts_px, int n, int norm_h, int norm_w, const float* wr, float* cs,
                    float* sn);
 void launch_kpts_to_float(cudaStream_t s, const int* k, int n, float* o);

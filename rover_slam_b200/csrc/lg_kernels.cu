@@ -669,6 +669,194 @@ __global__ void __launch_bounds__(1024) match_compact_batch_kernel(const LgAssig
   }
   if (threadIdx.x == 0) *a.count[pr] = carry;
 }
+// ---- assignment in two passes over sim (default) ------------------------------------------------------------------
+// The five kernels above read the N0 x N1 similarity matrix six times (row statistics 2, column statistics 2, row arg-max 1,
+// column arg-max 1; 576 MB of DRAM reads per 8 pairs).  Here a block owns a BAND of 32 rows of one pair and walks the
+// columns in chunks of 256 (thread = column, 32 independent coalesced loads per chunk):
+//   pass 1 (assign_stats_band): per-row (max, sum exp) -- a warp reduces its 32 columns with shuffles, lane i keeps row i's
+//           running pair, the 8 warps merge through shared memory -- AND the band's per-column partial (max, sum exp);
+//           assign_col_merge folds the bands' partials into cmax / clog;
+//   pass 2 (assign_argmax_band): S = log-assignment score, row arg-max the same way, per-column partial arg-max of the
+//           band; assign_colarg_merge folds them into m1.
+// Ties resolve to the lowest index exactly as TopK(k = 1) does (strict > in ascending index order, explicit index rule in the
+// shuffles).  sim is read twice.
+constexpr int kBandRows = 32;
+__global__ void __launch_bounds__(256) assign_stats_band_kernel(const LgAssign a, float* __restrict__ rmax,
+                                                                float* __restrict__ rlog, float* __restrict__ part_a,
+                                                                float* __restrict__ part_b, int part_ld, int part_bands) {
+  __shared__ float sm_m[8][kBandRows], sm_s[8][kBandRows];
+  const int pr = blockIdx.y, band = blockIdx.x;
+  const int n0 = a.n0[pr], n1 = a.n1[pr], ld = a.ld[pr];
+  const int r0 = band * kBandRows;
+  if (r0 >= n0) return;
+  const int rows = min(kBandRows, n0 - r0);
+  const float* sim = a.sim[pr] + static_cast<size_t>(r0) * ld;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* pa = part_a + (static_cast<size_t>(pr) * part_bands + band) * part_ld;
+  float* pb = part_b + (static_cast<size_t>(pr) * part_bands + band) * part_ld;
+  float run_m = -INFINITY, run_s = 0.0f;            // lane i: running (max, sum) of row r0 + i over this warp's columns
+  for (int c0 = 0; c0 < n1; c0 += 256) {
+    const int j = c0 + threadIdx.x;
+    const bool in = j < n1;
+    float v[kBandRows];
+#pragma unroll
+    for (int i = 0; i < kBandRows; ++i) v[i] = (in && i < rows) ? sim[static_cast<size_t>(i) * ld + j] : -INFINITY;
+    // column partial of the band
+    float cm = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kBandRows; ++i) cm = fmaxf(cm, v[i]);
+    float cs = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kBandRows; ++i) cs += (i < rows) ? expf(v[i] - cm) : 0.0f;
+    if (in) { pa[j] = cm; pb[j] = cs; }
+    // row statistics of this warp's 32 columns
+#pragma unroll
+    for (int i = 0; i < kBandRows; ++i) {
+      const float wm = warp_max(v[i]);                            // -inf when the whole warp is beyond n1 (or the row beyond n0)
+      const float e = (in && wm > -INFINITY) ? expf(v[i] - wm) : 0.0f;
+      const float ws = warp_sum(e);
+      if (lane == i && wm > -INFINITY) {
+        const float nm = fmaxf(run_m, wm);
+        run_s = run_s * expf(run_m - nm) + ws * expf(wm - nm);    // exp(-inf) = 0 on the first chunk
+        run_m = nm;
+      }
+    }
+  }
+  sm_m[w][lane] = run_m;
+  sm_s[w][lane] = run_s;
+  __syncthreads();
+  if (w == 0 && lane < rows) {
+    float m = sm_m[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) m = fmaxf(m, sm_m[k][lane]);
+    float sacc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sacc += sm_m[k][lane] > -INFINITY ? sm_s[k][lane] * expf(sm_m[k][lane] - m) : 0.0f;
+    rmax[a.off0[pr] + r0 + lane] = m;
+    rlog[a.off0[pr] + r0 + lane] = logf(sacc);
+  }
+}
+__global__ void __launch_bounds__(256) assign_col_merge_kernel(const LgAssign a, const float* __restrict__ part_a,
+                                                               const float* __restrict__ part_b, int part_ld, int part_bands,
+                                                               float* __restrict__ cmax, float* __restrict__ clog) {
+  const int pr = blockIdx.y;
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  const int n0 = a.n0[pr], n1 = a.n1[pr];
+  if (j >= n1) return;
+  const int bands = (n0 + kBandRows - 1) / kBandRows;
+  const float* pa = part_a + static_cast<size_t>(pr) * part_bands * part_ld + j;
+  const float* pb = part_b + static_cast<size_t>(pr) * part_bands * part_ld + j;
+  float m = -INFINITY;
+  for (int b = 0; b < bands; ++b) m = fmaxf(m, pa[static_cast<size_t>(b) * part_ld]);
+  float sacc = 0.0f;
+  for (int b = 0; b < bands; ++b) sacc += pb[static_cast<size_t>(b) * part_ld] * expf(pa[static_cast<size_t>(b) * part_ld] - m);
+  cmax[a.off1[pr] + j] = m;
+  clog[a.off1[pr] + j] = logf(sacc);
+}
+__global__ void __launch_bounds__(256) assign_argmax_band_kernel(const LgAssign a, const float* __restrict__ rmax,
+                                                                 const float* __restrict__ rlog, const float* __restrict__ cmax,
+                                                                 const float* __restrict__ clog, const float* __restrict__ ls,
+                                                                 float* __restrict__ max0, int* __restrict__ m0,
+                                                                 float* __restrict__ part_a, float* __restrict__ part_b,
+                                                                 int part_ld, int part_bands, float* __restrict__ S_dbg) {
+  __shared__ float sm_b[8][kBandRows];
+  __shared__ int sm_i[8][kBandRows];
+  __shared__ float s_rm[kBandRows], s_rl[kBandRows], s_a0[kBandRows];
+  const int pr = blockIdx.y, band = blockIdx.x;
+  const int n0 = a.n0[pr], n1 = a.n1[pr], ld = a.ld[pr];
+  const int r0 = band * kBandRows;
+  if (r0 >= n0) return;
+  const int rows = min(kBandRows, n0 - r0);
+  const int o0 = a.off0[pr], o1 = a.off1[pr];
+  const float* sim = a.sim[pr] + static_cast<size_t>(r0) * ld;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x < kBandRows) {
+    const bool ok = threadIdx.x < rows;
+    s_rm[threadIdx.x] = ok ? rmax[o0 + r0 + threadIdx.x] : 0.0f;
+    s_rl[threadIdx.x] = ok ? rlog[o0 + r0 + threadIdx.x] : 0.0f;
+    s_a0[threadIdx.x] = ok ? ls[o0 + r0 + threadIdx.x] : 0.0f;
+  }
+  __syncthreads();
+  float* pa = part_a + (static_cast<size_t>(pr) * part_bands + band) * part_ld;
+  int* pb = reinterpret_cast<int*>(part_b) + (static_cast<size_t>(pr) * part_bands + band) * part_ld;
+  float run_b = -INFINITY;                        // lane i: running best of row r0 + i over this warp's columns
+  int run_i = 0x7fffffff;
+  for (int c0 = 0; c0 < n1; c0 += 256) {
+    const int j = c0 + threadIdx.x;
+    const bool in = j < n1;
+    const float cm = in ? cmax[o1 + j] : 0.0f, cl = in ? clog[o1 + j] : 0.0f, a1 = in ? ls[o1 + j] : 0.0f;
+    float v[kBandRows];
+#pragma unroll
+    for (int i = 0; i < kBandRows; ++i) v[i] = (in && i < rows) ? sim[static_cast<size_t>(i) * ld + j] : 0.0f;
+    float cb = -INFINITY;
+    int ci = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < kBandRows; ++i) {
+      float sc = -INFINITY;
+      if (in && i < rows) {
+        sc = assign_score(v[i], s_rm[i], s_rl[i], cm, cl, s_a0[i], a1);
+        if (S_dbg && pr == a.pairs - 1) S_dbg[static_cast<size_t>(r0 + i) * n1 + j] = sc;
+        if (sc > cb) { cb = sc; ci = r0 + i; }      // ascending rows: the first of equal scores stays
+      }
+      // row arg-max over this warp's 32 columns (ties -> lowest column)
+      float ob = sc;
+      int oi = in ? j : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const float tb = __shfl_xor_sync(0xffffffffu, ob, o);
+        const int ti = __shfl_xor_sync(0xffffffffu, oi, o);
+        if (tb > ob || (tb == ob && ti < oi)) { ob = tb; oi = ti; }
+      }
+      if (lane == i && (ob > run_b || (ob == run_b && oi < run_i))) { run_b = ob; run_i = oi; }
+    }
+    if (in) { pa[j] = cb; pb[j] = ci; }
+  }
+  sm_b[w][lane] = run_b;
+  sm_i[w][lane] = run_i;
+  __syncthreads();
+  if (w == 0 && lane < rows) {
+    float best = sm_b[0][lane];
+    int bi = sm_i[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float ob = sm_b[k][lane];
+      const int oi = sm_i[k][lane];
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    max0[o0 + r0 + lane] = best;
+    m0[o0 + r0 + lane] = bi;
+  }
+}
+__global__ void __launch_bounds__(256) assign_colarg_merge_kernel(const LgAssign a, const float* __restrict__ part_a,
+                                                                  const float* __restrict__ part_b, int part_ld, int part_bands,
+                                                                  int* __restrict__ m1) {
+  const int pr = blockIdx.y;
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  const int n0 = a.n0[pr], n1 = a.n1[pr];
+  if (j >= n1) return;
+  const int bands = (n0 + kBandRows - 1) / kBandRows;
+  const float* pa = part_a + static_cast<size_t>(pr) * part_bands * part_ld + j;
+  const int* pb = reinterpret_cast<const int*>(part_b) + static_cast<size_t>(pr) * part_bands * part_ld + j;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int b = 0; b < bands; ++b) {                 // ascending bands = ascending rows: strict > keeps the lowest row
+    const float ob = pa[static_cast<size_t>(b) * part_ld];
+    if (ob > best) { best = ob; bi = pb[static_cast<size_t>(b) * part_ld]; }
+  }
+  m1[a.off1[pr] + j] = bi;
+}
+void launch_lg_assign_banded(cudaStream_t s, const LgAssign& a, float* rmax, float* rlog, float* cmax, float* clog,
+                             const float* ls, float* max0, int* m0, int* m1, float filter, float thresh, float* S_dbg,
+                             float* part_a, float* part_b, int part_ld, int part_bands) {
+  if (a.pairs == 0) return;
+  const dim3 gband((a.max_n0 + kBandRows - 1) / kBandRows, a.pairs), gcol((a.max_n1 + 255) / 256, a.pairs);
+  assign_stats_band_kernel<<<gband, 256, 0, s>>>(a, rmax, rlog, part_a, part_b, part_ld, part_bands);
+  assign_col_merge_kernel<<<gcol, 256, 0, s>>>(a, part_a, part_b, part_ld, part_bands, cmax, clog);
+  assign_argmax_band_kernel<<<gband, 256, 0, s>>>(a, rmax, rlog, cmax, clog, ls, max0, m0, part_a, part_b, part_ld, part_bands, S_dbg);
+  assign_colarg_merge_kernel<<<gcol, 256, 0, s>>>(a, part_a, part_b, part_ld, part_bands, m1);
+  match_compact_batch_kernel<<<a.pairs, 1024, 0, s>>>(a, max0, m0, m1, filter, thresh);
+}
+
 void launch_lg_assign(cudaStream_t s, const LgAssign& a, float* rmax, float* rlog, float* cmax, float* clog,
                       const float* ls, float* max0, int* m0, int* m1, float filter, float thresh, float* S_dbg) {
   if (a.pairs == 0) return;

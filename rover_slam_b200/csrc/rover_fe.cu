@@ -119,6 +119,7 @@ struct rfe_ctx {
   float* sim = nullptr;                           // [cap][lg_ld]
   float *rmax = nullptr, *rlog = nullptr, *cmax = nullptr, *clog = nullptr, *ls = nullptr, *max0 = nullptr;
   int *m0 = nullptr, *m1 = nullptr;
+  float *part_a = nullptr, *part_b = nullptr;   // banded assignment: per (pair, 32-row band, column) partials
   float* S_dbg = nullptr;
   const char* prof_tag = nullptr;            // $RFE_PROF_TAG: the launch tag whose UMMA role counters are recorded
   unsigned long long* attn_prof = nullptr;   // armed by rfe_debug_read("lg.attn_prof")
@@ -988,8 +989,14 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
   as.pairs = np;
   {   // dual log-softmax statistics, both arg-maxes, mutual check + compaction of ALL pairs: five launches
     ProfScope ps_(c, "lg.assign");
-    launch_lg_assign(s, as, c->rmax, c->rlog, c->cmax, c->clog, c->ls, c->max0, c->m0, c->m1, kFilterThreshold, thresh,
-                     c->S_dbg);
+    // RFE_ASSIGN=1: the five one-purpose kernels of round 1 (six reads of sim); default: 32-row bands, two reads
+    static const int kAssignMode = getenv("RFE_ASSIGN") ? atoi(getenv("RFE_ASSIGN")) : 2;
+    if (kAssignMode == 2)
+      launch_lg_assign_banded(s, as, c->rmax, c->rlog, c->cmax, c->clog, c->ls, c->max0, c->m0, c->m1, kFilterThreshold, thresh,
+                              c->S_dbg, c->part_a, c->part_b, c->lg_ld, (c->cap + 31) / 32);
+    else
+      launch_lg_assign(s, as, c->rmax, c->rlog, c->cmax, c->clog, c->ls, c->max0, c->m0, c->m1, kFilterThreshold, thresh,
+                       c->S_dbg);
     c->launches += 5;
   }
   RFE_CUDA_CHECK(cudaGetLastError());
@@ -1167,6 +1174,8 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   A_(dev_alloc(c, &c->max0, R));
   A_(dev_alloc(c, &c->m0, R));
   A_(dev_alloc(c, &c->m1, R));
+  A_(dev_alloc(c, &c->part_a, static_cast<size_t>(c->lg_pairs) * ((cap + 31) / 32) * LD));
+  A_(dev_alloc(c, &c->part_b, static_cast<size_t>(c->lg_pairs) * ((cap + 31) / 32) * LD));
   }
   A_(dev_alloc(c, &c->res_matches, B * cap * 2));
   A_(dev_alloc(c, &c->res_scores, B * cap));
