@@ -17,8 +17,10 @@ void launch_select(cudaStream_t s, const float* nms, int B, int H, int W, float 
                    int* row_off, int* counts, int* kpts, float* scores, bool have_counts);
 // optional top-K cap on the compacted keypoint lists (K <= 0: off = the reference's behaviour)
 void launch_topk(cudaStream_t s, int B, int cap, int K, int* counts, int* kpts, float* scores);
-void launch_desc_sample(cudaStream_t s, const float* dense, int h, int w, int B, const int* kpts, const int* counts,
-                        int cap, float* desc, uint8_t* desc_bin);
+// rowss != null: `dense` is un-normalised and rowss [B*h*w][4] holds four partial sums of squares per pixel
+void launch_desc_sample(cudaStream_t s, const float* dense, const float* rowss, int h, int w, int B, const int* kpts,
+                        const int* counts, int cap, float* desc, uint8_t* desc_bin);
+void launch_dense_normalize(cudaStream_t s, const float* dense, const float* rowss, size_t npix, float* out);
 void launch_binarize(cudaStream_t s, const float* desc, int n, uint8_t* out, uint32_t* bits);
 void launch_l2_best2(cudaStream_t s, const float* q, int nq, const float* db, const int* cand_off, const int* cand_idx,
                      float init_dist, float* best_dist, int* best_idx, float* second_dist, int* second_idx);

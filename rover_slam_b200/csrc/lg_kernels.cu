@@ -673,18 +673,22 @@ __global__ void __launch_bounds__(1024) match_compact_batch_kernel(const LgAssig
 // The five kernels above read the N0 x N1 similarity matrix six times (row statistics 2, column statistics 2, row arg-max 1,
 // column arg-max 1; 576 MB of DRAM reads per 8 pairs).  Here a block owns a BAND of 32 rows of one pair and walks the
 // columns in chunks of 256 (thread = column, 32 independent coalesced loads per chunk):
-//   pass 1 (assign_stats_band): per-row (max, sum exp) -- a warp reduces its 32 columns with shuffles, lane i keeps row i's
-//           running pair, the 8 warps merge through shared memory -- AND the band's per-column partial (max, sum exp);
+//   pass 1 (assign_stats_band): per-row (max, sum exp) AND the band's per-column partial (max, sum exp), both from one
+//           32 x 256 shared-memory tile per chunk (column view: thread = column; row view: warp = 4 rows);
 //           assign_col_merge folds the bands' partials into cmax / clog;
 //   pass 2 (assign_argmax_band): S = log-assignment score, row arg-max the same way, per-column partial arg-max of the
 //           band; assign_colarg_merge folds them into m1.
 // Ties resolve to the lowest index exactly as TopK(k = 1) does (strict > in ascending index order, explicit index rule in the
 // shuffles).  sim is read twice.
 constexpr int kBandRows = 32;
+constexpr int kBandCols = 256;
+// A 32 x 256 tile of sim goes through shared memory once: the column view (thread = column, 32 conflict-free loads down
+// the column) gives the band's column partials, the row view (warp = 4 rows, lane = 8 strided columns) the row statistics
+// with ONE shuffle reduction per row and chunk.
 __global__ void __launch_bounds__(256) assign_stats_band_kernel(const LgAssign a, float* __restrict__ rmax,
                                                                 float* __restrict__ rlog, float* __restrict__ part_a,
                                                                 float* __restrict__ part_b, int part_ld, int part_bands) {
-  __shared__ float sm_m[8][kBandRows], sm_s[8][kBandRows];
+  __shared__ float tile[kBandRows][kBandCols + 1];
   const int pr = blockIdx.y, band = blockIdx.x;
   const int n0 = a.n0[pr], n1 = a.n1[pr], ld = a.ld[pr];
   const int r0 = band * kBandRows;
@@ -694,46 +698,51 @@ __global__ void __launch_bounds__(256) assign_stats_band_kernel(const LgAssign a
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* pa = part_a + (static_cast<size_t>(pr) * part_bands + band) * part_ld;
   float* pb = part_b + (static_cast<size_t>(pr) * part_bands + band) * part_ld;
-  float run_m = -INFINITY, run_s = 0.0f;            // lane i: running (max, sum) of row r0 + i over this warp's columns
-  for (int c0 = 0; c0 < n1; c0 += 256) {
+  float run_m[4], run_s[4];                         // rows 4w .. 4w+3 of the band, this lane's columns
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { run_m[k] = -INFINITY; run_s[k] = 0.0f; }
+  for (int c0 = 0; c0 < n1; c0 += kBandCols) {
     const int j = c0 + threadIdx.x;
     const bool in = j < n1;
-    float v[kBandRows];
+    __syncthreads();                                // the previous chunk's row view is done with the tile
 #pragma unroll
-    for (int i = 0; i < kBandRows; ++i) v[i] = (in && i < rows) ? sim[static_cast<size_t>(i) * ld + j] : -INFINITY;
-    // column partial of the band
-    float cm = -INFINITY;
+    for (int i = 0; i < kBandRows; ++i) tile[i][threadIdx.x] = (in && i < rows) ? sim[static_cast<size_t>(i) * ld + j] : -INFINITY;
+    __syncthreads();
+    // column view: partial (max, sum exp) of my column over the band's rows
+    {
+      float cm = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < kBandRows; ++i) cm = fmaxf(cm, v[i]);
-    float cs = 0.0f;
+      for (int i = 0; i < kBandRows; ++i) cm = fmaxf(cm, tile[i][threadIdx.x]);
+      float cs = 0.0f;
 #pragma unroll
-    for (int i = 0; i < kBandRows; ++i) cs += (i < rows) ? expf(v[i] - cm) : 0.0f;
-    if (in) { pa[j] = cm; pb[j] = cs; }
-    // row statistics of this warp's 32 columns
+      for (int i = 0; i < kBandRows; ++i) cs += __expf(tile[i][threadIdx.x] - cm);     // rows beyond n0 hold -inf: exp = 0
+      if (in) { pa[j] = cm; pb[j] = cs; }
+    }
+    // row view: online (max, sum exp) of rows 4w .. 4w+3 over columns lane, lane + 32, ...
 #pragma unroll
-    for (int i = 0; i < kBandRows; ++i) {
-      const float wm = warp_max(v[i]);                            // -inf when the whole warp is beyond n1 (or the row beyond n0)
-      const float e = (in && wm > -INFINITY) ? expf(v[i] - wm) : 0.0f;
-      const float ws = warp_sum(e);
-      if (lane == i && wm > -INFINITY) {
-        const float nm = fmaxf(run_m, wm);
-        run_s = run_s * expf(run_m - nm) + ws * expf(wm - nm);    // exp(-inf) = 0 on the first chunk
-        run_m = nm;
+    for (int k = 0; k < 4; ++k) {
+      const float* trow = tile[4 * w + k];
+      float v[8];
+      float m = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { v[q] = trow[lane + 32 * q]; m = fmaxf(m, v[q]); }
+      if (m > run_m[k]) { run_s[k] *= __expf(run_m[k] - m); run_m[k] = m; }       // exp(-inf) = 0 on the first chunk
+      if (run_m[k] > -INFINITY) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) run_s[k] += __expf(v[q] - run_m[k]);
       }
     }
   }
-  sm_m[w][lane] = run_m;
-  sm_s[w][lane] = run_s;
-  __syncthreads();
-  if (w == 0 && lane < rows) {
-    float m = sm_m[0][lane];
+  // merge the 32 lanes of every row (each lane holds its own reference maximum)
 #pragma unroll
-    for (int k = 1; k < 8; ++k) m = fmaxf(m, sm_m[k][lane]);
-    float sacc = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) sacc += sm_m[k][lane] > -INFINITY ? sm_s[k][lane] * expf(sm_m[k][lane] - m) : 0.0f;
-    rmax[a.off0[pr] + r0 + lane] = m;
-    rlog[a.off0[pr] + r0 + lane] = logf(sacc);
+  for (int k = 0; k < 4; ++k) {
+    const float m = warp_max(run_m[k]);
+    const float sacc = warp_sum(run_m[k] > -INFINITY ? run_s[k] * __expf(run_m[k] - m) : 0.0f);
+    const int i = 4 * w + k;
+    if (lane == 0 && i < rows) {
+      rmax[a.off0[pr] + r0 + i] = m;
+      rlog[a.off0[pr] + r0 + i] = logf(sacc);
+    }
   }
 }
 __global__ void __launch_bounds__(256) assign_col_merge_kernel(const LgAssign a, const float* __restrict__ part_a,
@@ -759,8 +768,7 @@ __global__ void __launch_bounds__(256) assign_argmax_band_kernel(const LgAssign 
                                                                  float* __restrict__ max0, int* __restrict__ m0,
                                                                  float* __restrict__ part_a, float* __restrict__ part_b,
                                                                  int part_ld, int part_bands, float* __restrict__ S_dbg) {
-  __shared__ float sm_b[8][kBandRows];
-  __shared__ int sm_i[8][kBandRows];
+  __shared__ float tile[kBandRows][kBandCols + 1];       // log-assignment scores of the chunk
   __shared__ float s_rm[kBandRows], s_rl[kBandRows], s_a0[kBandRows];
   const int pr = blockIdx.y, band = blockIdx.x;
   const int n0 = a.n0[pr], n1 = a.n1[pr], ld = a.ld[pr];
@@ -776,55 +784,58 @@ __global__ void __launch_bounds__(256) assign_argmax_band_kernel(const LgAssign 
     s_rl[threadIdx.x] = ok ? rlog[o0 + r0 + threadIdx.x] : 0.0f;
     s_a0[threadIdx.x] = ok ? ls[o0 + r0 + threadIdx.x] : 0.0f;
   }
-  __syncthreads();
   float* pa = part_a + (static_cast<size_t>(pr) * part_bands + band) * part_ld;
   int* pb = reinterpret_cast<int*>(part_b) + (static_cast<size_t>(pr) * part_bands + band) * part_ld;
-  float run_b = -INFINITY;                        // lane i: running best of row r0 + i over this warp's columns
-  int run_i = 0x7fffffff;
-  for (int c0 = 0; c0 < n1; c0 += 256) {
+  float run_b[4];                                   // rows 4w .. 4w+3: running best over this lane's columns (ascending)
+  int run_i[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { run_b[k] = -INFINITY; run_i[k] = 0x7fffffff; }
+  for (int c0 = 0; c0 < n1; c0 += kBandCols) {
     const int j = c0 + threadIdx.x;
     const bool in = j < n1;
     const float cm = in ? cmax[o1 + j] : 0.0f, cl = in ? clog[o1 + j] : 0.0f, a1 = in ? ls[o1 + j] : 0.0f;
-    float v[kBandRows];
-#pragma unroll
-    for (int i = 0; i < kBandRows; ++i) v[i] = (in && i < rows) ? sim[static_cast<size_t>(i) * ld + j] : 0.0f;
+    __syncthreads();                                // s_rm .. ready (first chunk) / previous row view done
+    // column view while filling the tile: scores of my column, partial arg-max over the band's rows (lowest row on ties)
     float cb = -INFINITY;
     int ci = 0x7fffffff;
 #pragma unroll
     for (int i = 0; i < kBandRows; ++i) {
       float sc = -INFINITY;
       if (in && i < rows) {
-        sc = assign_score(v[i], s_rm[i], s_rl[i], cm, cl, s_a0[i], a1);
+        sc = assign_score(sim[static_cast<size_t>(i) * ld + j], s_rm[i], s_rl[i], cm, cl, s_a0[i], a1);
         if (S_dbg && pr == a.pairs - 1) S_dbg[static_cast<size_t>(r0 + i) * n1 + j] = sc;
-        if (sc > cb) { cb = sc; ci = r0 + i; }      // ascending rows: the first of equal scores stays
+        if (sc > cb) { cb = sc; ci = r0 + i; }
       }
-      // row arg-max over this warp's 32 columns (ties -> lowest column)
-      float ob = sc;
-      int oi = in ? j : 0x7fffffff;
-#pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        const float tb = __shfl_xor_sync(0xffffffffu, ob, o);
-        const int ti = __shfl_xor_sync(0xffffffffu, oi, o);
-        if (tb > ob || (tb == ob && ti < oi)) { ob = tb; oi = ti; }
-      }
-      if (lane == i && (ob > run_b || (ob == run_b && oi < run_i))) { run_b = ob; run_i = oi; }
+      tile[i][threadIdx.x] = sc;
     }
     if (in) { pa[j] = cb; pb[j] = ci; }
-  }
-  sm_b[w][lane] = run_b;
-  sm_i[w][lane] = run_i;
-  __syncthreads();
-  if (w == 0 && lane < rows) {
-    float best = sm_b[0][lane];
-    int bi = sm_i[0][lane];
+    __syncthreads();
+    // row view: columns lane, lane + 32, ... in ascending order: strict > keeps the lowest column among equals
 #pragma unroll
-    for (int k = 1; k < 8; ++k) {
-      const float ob = sm_b[k][lane];
-      const int oi = sm_i[k][lane];
-      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    for (int k = 0; k < 4; ++k) {
+      const float* trow = tile[4 * w + k];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float sc = trow[lane + 32 * q];
+        if (sc > run_b[k]) { run_b[k] = sc; run_i[k] = c0 + lane + 32 * q; }
+      }
     }
-    max0[o0 + r0 + lane] = best;
-    m0[o0 + r0 + lane] = bi;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float ob = run_b[k];
+    int oi = run_i[k];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float tb = __shfl_xor_sync(0xffffffffu, ob, o);
+      const int ti = __shfl_xor_sync(0xffffffffu, oi, o);
+      if (tb > ob || (tb == ob && ti < oi)) { ob = tb; oi = ti; }
+    }
+    const int i = 4 * w + k;
+    if (lane == 0 && i < rows) {
+      max0[o0 + r0 + i] = ob;
+      m0[o0 + r0 + i] = oi;
+    }
   }
 }
 __global__ void __launch_bounds__(256) assign_colarg_merge_kernel(const LgAssign a, const float* __restrict__ part_a,

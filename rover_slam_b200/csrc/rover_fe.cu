@@ -77,6 +77,8 @@ struct rfe_ctx {
   uint8_t* img = nullptr;
   SplitBuf a1a, a1, a2a, a2, a3a, a3, a4a, feat, pa, da;
   float *heat = nullptr, *nmsmap = nullptr, *dense = nullptr;
+  float* dense_ss = nullptr;    // [B*h/8*w/8][4] partial sums of squares of the un-normalised dense descriptors
+  bool dense_deferred = false;  // the last extraction left `dense` un-normalised (rfe_debug_read normalises on the fly)
   int *row_cnt = nullptr, *row_off = nullptr;
   int* kp_counts = nullptr;     // [max_batch]
   int* kpts = nullptr;          // [max_batch][cap][2]
@@ -551,7 +553,20 @@ int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B, i
     p.out_f32 = c->heat;
     if ((r = launch_umma<80, A_GEMM, EPI_DET>(c, "sp.convPb_softmax", ah, al, bh, bl, p, dim3((npix + 127) / 128, 1, 1)))) return r;
   }
-  {   // descriptor head: 1x1 conv 256->256 + L2 norm
+  // descriptor head.  Default: the 1x1 conv is a plain 128-wide double-buffered GEMM that stores d un-normalised plus four
+  // partial sums of squares per pixel, and the sampler divides by the norm (the fused 256-wide epilogue had ONE accumulator
+  // set and read it twice: 13 % tensor-pipe activity, 131 us per 16 frames).  RFE_CONVDB=1: the fused epilogue of round 1.
+  static const int kConvDbMode = getenv("RFE_CONVDB") ? atoi(getenv("RFE_CONVDB")) : 2;
+  if (kConvDbMode == 2) {
+    Operand A{c->da.hi, c->da.lo, npix, 256, 256, 0, 1};
+    Operand Bw{c->cDb.w.hi, c->cDb.w.lo, 256, 256, 256, 0, 1};
+    UmmaParams p = default_params();
+    p.bias = c->cDb.bias;
+    p.out_f32 = c->dense;
+    p.ld_f32 = 256;
+    p.rowss = c->dense_ss;
+    if ((r = gemm_linear(c, "sp.convDb", A, Bw, p, 128))) return r;
+  } else {   // descriptor head: 1x1 conv 256->256 + L2 norm
     Operand A{c->da.hi, c->da.lo, npix, 256, 256, 0, 1};
     Operand Bw{c->cDb.w.hi, c->cDb.w.lo, 256, 256, 256, 0, 1};
     CUtensorMap ah, al, bh, bl;
@@ -584,10 +599,11 @@ int sp_run(rfe_ctx* c, const uint8_t* d_gray, int h, int w, int stride, int B, i
     launch_topk(s, B, c->cap, c->topk, kp_counts, kpts, kp_scores);
     c->launches++;
   }
-  { ProfScope ps_(c, "sp.desc_sample"); launch_desc_sample(s, c->dense, hc, wc, B, kpts, kp_counts, c->cap, desc,
+  { ProfScope ps_(c, "sp.desc_sample"); launch_desc_sample(s, c->dense, kConvDbMode == 2 ? c->dense_ss : nullptr, hc, wc, B, kpts, kp_counts, c->cap, desc,
                                                            c->desc_bin + static_cast<size_t>(slot_base) * c->cap * 256); }
   c->launches += kNmsMode == 2 ? 4 : 5;      // nms, (count), scan, write, desc_sample
   RFE_CUDA_CHECK(cudaGetLastError());
+  c->dense_deferred = kConvDbMode == 2;
   for (int b = 0; b < B; ++b) c->slot_gen[slot_base + b]++;     // cached layer-0 state of these slots is stale now
   c->last_batch = B;
   c->last_h = h;
@@ -1128,6 +1144,7 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   A_(dev_alloc(c, &c->heat, full));
   A_(dev_alloc(c, &c->nmsmap, full));
   A_(dev_alloc(c, &c->dense, coarse * 256));
+  A_(dev_alloc(c, &c->dense_ss, coarse * 4));
   A_(dev_alloc(c, &c->row_cnt, B * H));
   A_(dev_alloc(c, &c->row_off, B * H));
   A_(dev_alloc(c, &c->kp_counts, 2 * B));            // two feature-slot sets (see rfe_pairs_submit)
@@ -2000,7 +2017,17 @@ int rfe_debug_read(rfe_ctx* c, const char* name, void* dst, size_t capacity, siz
   else if (s == "sp.da") { sb = &c->da; n = B * H * W / 64 * 256; }
   else if (s == "sp.heat") { fb = c->heat; n = B * H * W; }
   else if (s == "sp.nms") { fb = c->nmsmap; n = B * H * W; }
-  else if (s == "sp.dense") { fb = c->dense; n = B * H * W / 64 * 256; }
+  else if (s == "sp.dense") {
+    fb = c->dense; n = B * H * W / 64 * 256;
+    if (c->dense_deferred && dst && n) {     // normalise into the debug scratch: the product normalises inside the sampler
+      if (c->dbg_bytes < n * sizeof(float)) {
+        if ((r = dev_alloc(c, &c->dbg, n))) return r;
+        c->dbg_bytes = n * sizeof(float);
+      }
+      launch_dense_normalize(c->stream, c->dense, c->dense_ss, n / 256, c->dbg);
+      fb = c->dbg;
+    }
+  }
   else if (s == "lg.x") { fb = c->x; n = static_cast<size_t>(c->dbg_off1 + c->dbg_n1) * 256; }
   else if (s == "lg.sim") { fb = c->sim + static_cast<size_t>(c->dbg_pair) * c->cap * c->lg_ld; n = static_cast<size_t>(c->dbg_n0) * round_up(c->dbg_n1, 8); }
   else if (s == "lg.S") {

@@ -627,7 +627,8 @@ void launch_topk(cudaStream_t s, int B, int cap, int K, int* counts, int* kpts, 
 // Descriptor sampling: one warp per keypoint, lane = 8 channels.
 // grid = 2 * ((kp - 4 + 0.5) / (8*dim - 4 - 0.5)) - 1 ; grid_sample(bilinear, zeros, align_corners=True) ; L2 norm.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) desc_sample_kernel(const float* __restrict__ dense /*[B][h][w][256]*/, int h,
+__global__ void __launch_bounds__(256) desc_sample_kernel(const float* __restrict__ dense /*[B][h][w][256]*/,
+                                                          const float* __restrict__ rowss /*[B*h*w][4] or null*/, int h,
                                                           int w, int B, const int* __restrict__ kpts,
                                                           const int* __restrict__ counts, int cap,
                                                           float* __restrict__ desc /*[B][cap][256]*/,
@@ -658,8 +659,17 @@ __global__ void __launch_bounds__(256) desc_sample_kernel(const float* __restric
   for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
   auto corner = [&](int yy, int xx, float wt) {
     if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
-      const float4* p = reinterpret_cast<const float4*>(db + (static_cast<size_t>(yy) * w + xx) * 256);
-      const float4 a = __ldg(p), c = __ldg(p + 1);
+      const size_t pix = static_cast<size_t>(yy) * w + xx;
+      const float4* p = reinterpret_cast<const float4*>(db + pix * 256);
+      float4 a = __ldg(p), c = __ldg(p + 1);
+      if (rowss) {
+        // the descriptor head left the per-pixel L2 normalisation (nodes 402-413: d / max(||d||, 1e-12)) to the sampler:
+        // the 1x1 conv stored d and four partial sums of squares per pixel
+        const float4 q = __ldg(reinterpret_cast<const float4*>(rowss + (static_cast<size_t>(b) * h * w + pix) * 4));
+        const float nrm = fmaxf(sqrtf(((q.x + q.y) + q.z) + q.w), 1e-12f);
+        a.x /= nrm; a.y /= nrm; a.z /= nrm; a.w /= nrm;
+        c.x /= nrm; c.y /= nrm; c.z /= nrm; c.w /= nrm;
+      }
       acc[0] += a.x * wt; acc[1] += a.y * wt; acc[2] += a.z * wt; acc[3] += a.w * wt;
       acc[4] += c.x * wt; acc[5] += c.y * wt; acc[6] += c.z * wt; acc[7] += c.w * wt;
     }
@@ -688,10 +698,25 @@ __global__ void __launch_bounds__(256) desc_sample_kernel(const float* __restric
   }
 }
 
-void launch_desc_sample(cudaStream_t s, const float* dense, int h, int w, int B, const int* kpts, const int* counts,
-                        int cap, float* desc, uint8_t* desc_bin) {
+void launch_desc_sample(cudaStream_t s, const float* dense, const float* rowss, int h, int w, int B, const int* kpts,
+                        const int* counts, int cap, float* desc, uint8_t* desc_bin) {
   const int warps = B * cap;
-  desc_sample_kernel<<<(warps * 32 + 255) / 256, 256, 0, s>>>(dense, h, w, B, kpts, counts, cap, desc, desc_bin);
+  desc_sample_kernel<<<(warps * 32 + 255) / 256, 256, 0, s>>>(dense, rowss, h, w, B, kpts, counts, cap, desc, desc_bin);
+}
+
+// debug / tests: the normalised dense descriptor map when the normalisation is deferred to the sampler
+__global__ void __launch_bounds__(256) dense_normalize_kernel(const float* __restrict__ dense, const float* __restrict__ rowss,
+                                                              size_t npix, float* __restrict__ out) {
+  const size_t wid = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= npix) return;
+  const float4 q = __ldg(reinterpret_cast<const float4*>(rowss + wid * 4));
+  const float nrm = fmaxf(sqrtf(((q.x + q.y) + q.z) + q.w), 1e-12f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) out[wid * 256 + j * 32 + lane] = dense[wid * 256 + j * 32 + lane] / nrm;
+}
+void launch_dense_normalize(cudaStream_t s, const float* dense, const float* rowss, size_t npix, float* out) {
+  if (npix) dense_normalize_kernel<<<static_cast<unsigned>((npix * 32 + 255) / 256), 256, 0, s>>>(dense, rowss, npix, out);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -59,6 +59,9 @@ struct UmmaParams {
   __half* vt_lo;
   int ldv;
   unsigned long long* prof;   // optional [8] cycle counters written by CTA 0 (MMA thread: 0-3, epilogue warp 2: 4-7)
+  // EPI_LINEAR, optional: per-row partial sums of squares of the stored values, [M][2 * tiles_n] (slot = 2 * n-tile + the
+  // warp's column phase): SuperPoint's descriptor head defers its per-pixel L2 normalisation to the sampler
+  float* rowss;
 };
 
 // TMA maps used by the LINEAR / QKV epilogues (unused members are never dereferenced).  All are 3-D:
@@ -606,6 +609,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       const int z = tc.z;
       const bool has_res = (EPI == EPI_LINEAR) && p.residual != nullptr;
       uint64_t* rbar = &res_bar[ew];
+      float ss_acc = 0.0f;                       // p.rowss: sum of squares of this thread's values of the tile
       int c_last = -1;
       for (int c = half * 32; c < BLOCK_N && n0 + c < p.N; c += 64) c_last = c;
       if (c_last < 0) {
@@ -670,6 +674,10 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= p.scale;
+          if (p.rowss) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ss_acc = fmaf(v[j], v[j], ss_acc);     // columns beyond N are zero (zero-filled weights)
+          }
         }
         if (has_res) {
           mbar_wait(rbar, res_phase);
@@ -771,6 +779,8 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
           }
         }
       }
+      if (EPI == EPI_LINEAR && p.rowss && valid)
+        p.rowss[static_cast<size_t>(m) * (2 * p.tiles_n) + 2 * (n0 / BLOCK_N) + half] = ss_acc;
     }
     if constexpr (EPI != EPI_LINEAR && EPI != EPI_QKV) {
     tc_fence_before();
