@@ -1005,8 +1005,9 @@ int lg_run(rfe_ctx* c, const PairDesc* pairs_in, int np_in, int norm_h, int norm
   as.pairs = np;
   {   // dual log-softmax statistics, both arg-maxes, mutual check + compaction of ALL pairs: five launches
     ProfScope ps_(c, "lg.assign");
-    // RFE_ASSIGN=1: the five one-purpose kernels of round 1 (six reads of sim); default: 32-row bands, two reads
-    static const int kAssignMode = getenv("RFE_ASSIGN") ? atoi(getenv("RFE_ASSIGN")) : 2;
+    // default: the five one-purpose kernels (six reads of sim, 294 us per 8 pairs).  RFE_ASSIGN=2: 32-row bands through
+    // shared-memory tiles, two reads of sim -- correct (all GPU tests) but measured slower (404 us): kept for A/B only.
+    static const int kAssignMode = getenv("RFE_ASSIGN") ? atoi(getenv("RFE_ASSIGN")) : 1;
     if (kAssignMode == 2)
       launch_lg_assign_banded(s, as, c->rmax, c->rlog, c->cmax, c->clog, c->ls, c->max0, c->m0, c->m1, kFilterThreshold, thresh,
                               c->S_dbg, c->part_a, c->part_b, c->lg_ld, (c->cap + 31) / 32);
