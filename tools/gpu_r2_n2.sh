@@ -7,7 +7,7 @@ timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --mast
 tail -5 gpurun_out/r02_bench_n2.err
 python - <<'PY'
 import json
-d = json.load(open("gpurun_out/r02_bench_n2.json"))
+d = json.loads([l for l in open("gpurun_out/r02_bench_n2.json") if l.startswith("{")][-1])
 print("N=2 value", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "stream", d["stream"]["value"], "coll bytes/step", d["stream"]["collective_bytes_per_step"],
       "ms/step", round(d["ms_per_step"], 3), "clk", d["clocks"]["sm_mhz"], "counts", d["stream"]["match_counts_last_step"])
 PY
