@@ -35,8 +35,8 @@ sys.path.insert(0, ROOT)
 H, W = 480, 640
 WORKLOAD = ("BASELINE config 5 shape: 640x480 synthetic frame pairs, SuperPoint on both frames + one LightGlue match per pair")
 SP_FLOPS_PER_FRAME = 52.10e9
-ATTN_DRAM_BYTES_PER_LAUNCH = 116_912_128                   # dram__bytes_read.sum + dram__bytes_write.sum of ONE attention launch at 8 pairs
-                                                           # (profiles/r01_attn_full.ncu-rep: 101.6 MB + 15.3 MB; algorithmic bytes 131 MB)
+ATTN_DRAM_BYTES_PER_LAUNCH = 118_045_184                   # dram__bytes_read.sum + dram__bytes_write.sum of ONE attention launch at 8 pairs
+                                                           # (profiles/r02_attn2_full.ncu-rep: 103.03 MB + 15.01 MB; algorithmic bytes 131 MB)
 
 
 def peaks():
@@ -408,7 +408,7 @@ def main():
                      "executed_mma_flops_per_launch": 3.5 * attn_flops,
                      "share_of_step": attn_share,
                      "note": "split-fp16: 3 MMAs per algorithmic MAC for QK^T and PV plus a hi-only max pass = 3.5x: frac <= 0.286 by construction; "
-                             "traffic = DRAM bytes of one launch from the ncu --set full capture profiles/r01_attn_full.ncu-rep (8 pairs per step)"},
+                             "traffic = DRAM bytes of one launch from the ncu --set full capture profiles/r02_attn2_full.ncu-rep (8 pairs per step)"},
         "kernel_us_per_step": breakdown,
     }
     if world == 1:

@@ -31,8 +31,15 @@ constexpr int kAttn2SmemBytes = kAttnQBytes + 2 * kAttnPBytes + (kAttnKStages + 
 
 struct AttnItem {
   int z, head, m0, nq, nk, qrow, krow, T, T1;
+  int part, slot;            // part >= 0: this item covers only a sub-range of the keys (AttnParams::split_*)
 };
-__device__ __forceinline__ AttnItem attn_decode(const AttnParams& p, int item) {
+__device__ __forceinline__ AttnItem attn_decode(const AttnParams& p, int vitem) {
+  int item = vitem, part = -1, slot = 0;
+  if (vitem >= p.split_first) {
+    slot = vitem - p.split_first;
+    item = p.split_first + slot / p.split_s;
+    part = slot - (item - p.split_first) * p.split_s;
+  }
   int z = 0;
   while (z + 1 < p.nprob && item >= p.item_prefix[z + 1]) ++z;
   AttnItem a;
@@ -45,6 +52,14 @@ __device__ __forceinline__ AttnItem attn_decode(const AttnParams& p, int item) {
   a.m0 = (local - a.head * qtiles) * 128;
   a.qrow = p.q_row0[z] + a.m0;
   a.krow = p.k_row0[z];
+  a.part = part;
+  a.slot = slot;
+  if (part >= 0) {           // keys [part * per, min(nk, (part + 1) * per)), per a multiple of 128
+    const int per = ((((a.nk + 127) >> 7) + p.split_s - 1) / p.split_s) * 128;
+    const int kb = part * per;
+    a.krow += kb;
+    a.nk = (a.nk - kb < per) ? a.nk - kb : per;
+  }
   a.T = (a.nk + kAttnKeyTile - 1) / kAttnKeyTile;
   a.T1 = (a.nk + 127) >> 7;
   return a;
@@ -81,7 +96,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
   auto tick = [&]() -> long long { return PROF ? clock64() : 0; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool prof_cta = PROF && p.prof && static_cast<int>(blockIdx.x) == p.prof_cta;
-  const int n_items = p.item_prefix[p.nprob];
+  const int n_items = p.n_items;
   const long long cta_c0 = PROF ? clock64() : 0;
   if (PROF && p.prof && threadIdx.x == 0 && blockIdx.x < 4096) {
     unsigned long long t;
@@ -440,6 +455,23 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(o_empty);     // O may be overwritten by the next item's first P V product
+        if (a.part >= 0) {                       // a key-range part: raw O, row maximum and row sum for attn2_combine_kernel
+          float4* po = reinterpret_cast<float4*>(p.part_o + (static_cast<size_t>(a.slot) * 128 + row) * 64 + cq * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            po[j] = make_float4(__uint_as_float(a0[4 * j]) + __uint_as_float(x0[4 * j]),
+                                __uint_as_float(a0[4 * j + 1]) + __uint_as_float(x0[4 * j + 1]),
+                                __uint_as_float(a0[4 * j + 2]) + __uint_as_float(x0[4 * j + 2]),
+                                __uint_as_float(a0[4 * j + 3]) + __uint_as_float(x0[4 * j + 3]));
+          if (cq == 0) {
+            p.part_ml[(static_cast<size_t>(a.slot) * 2) * 128 + row] = mx;
+            p.part_ml[(static_cast<size_t>(a.slot) * 2 + 1) * 128 + row] = l;
+          }
+          t_epi += tick() - st_p2;
+          n_base += T1 + T;
+          v_base += T;
+          continue;
+        }
         __align__(16) __half oh[16];
         __align__(16) __half ol[16];
         const float inv_l = 1.0f / (RFE_ATTN_V_SCALE * l);   // l = sum E ; both operand scales cancel here
@@ -489,6 +521,51 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     p.prof[32 + 3 * blockIdx.x + 1] = t;
     p.prof[32 + 3 * blockIdx.x + 2] |= static_cast<unsigned long long>(clock64() - cta_c0) << 16;   // SM cycles of this CTA
+  }
+}
+
+// Merges the key-range parts of the split work items: O = sum_c w_c O_c / (256 sum_c w_c l_c), w_c = exp(max_c - max).
+// One block per split item, thread = (row, 16 output columns) exactly like the attention epilogue.
+__global__ void __launch_bounds__(512) attn2_combine_kernel(const AttnParams p) {
+  const int item = p.split_first + blockIdx.x;
+  int z = 0;
+  while (z + 1 < p.nprob && item >= p.item_prefix[z + 1]) ++z;
+  const int nq = p.nq[z], local = item - p.item_prefix[z], qtiles = (nq + 127) >> 7;
+  const int head = local / qtiles, m0 = (local - head * qtiles) * 128;
+  const int row = threadIdx.x & 127, cq = threadIdx.x >> 7;
+  const int slot0 = blockIdx.x * p.split_s;
+  float M = -INFINITY;
+  for (int c = 0; c < p.split_s; ++c) M = fmaxf(M, p.part_ml[(static_cast<size_t>(slot0 + c) * 2) * 128 + row]);
+  float L = 0.0f, acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+  for (int c = 0; c < p.split_s; ++c) {
+    const size_t s = slot0 + c;
+    const float w = expf(p.part_ml[(s * 2) * 128 + row] - M);
+    L = fmaf(w, p.part_ml[(s * 2 + 1) * 128 + row], L);
+    const float4* po = reinterpret_cast<const float4*>(p.part_o + (s * 128 + row) * 64 + cq * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 v = po[j];
+      acc[4 * j] = fmaf(w, v.x, acc[4 * j]);
+      acc[4 * j + 1] = fmaf(w, v.y, acc[4 * j + 1]);
+      acc[4 * j + 2] = fmaf(w, v.z, acc[4 * j + 2]);
+      acc[4 * j + 3] = fmaf(w, v.w, acc[4 * j + 3]);
+    }
+  }
+  __align__(16) __half oh[16];
+  __align__(16) __half ol[16];
+  const float inv_l = 1.0f / (RFE_ATTN_V_SCALE * L);
+  const bool live = m0 + row < nq;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) split_f32(live ? acc[j] * inv_l : 0.0f, oh[j], ol[j]);
+  if (m0 + row < ((nq + 7) & ~7)) {
+    const size_t o = static_cast<size_t>(p.q_row0[z] + m0 + row) * 256 + head * 64 + cq * 16;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      reinterpret_cast<uint4*>(p.out_hi + o)[ch] = reinterpret_cast<const uint4*>(oh)[ch];
+      reinterpret_cast<uint4*>(p.out_lo + o)[ch] = reinterpret_cast<const uint4*>(ol)[ch];
+    }
   }
 }
 

@@ -125,6 +125,8 @@ struct rfe_ctx {
   float* S_dbg = nullptr;
   const char* prof_tag = nullptr;            // $RFE_PROF_TAG: the launch tag whose UMMA role counters are recorded
   unsigned long long* attn_prof = nullptr;   // armed by rfe_debug_read("lg.attn_prof")
+  float* attn_part_o = nullptr;              // key-range parts of the attention tail items (AttnParams::part_o / part_ml)
+  float* attn_part_ml = nullptr;
   int dbg_n0 = 0, dbg_n1 = 0, dbg_off0 = 0, dbg_off1 = 0, dbg_pair = 0;
   // match results: [max_batch] slots
   int* res_matches = nullptr;   // [slots][cap][2]
@@ -694,8 +696,27 @@ int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitB
   } else if (kAttnMode == 2) {
     const int items = p.item_prefix[nprob];
     const int ctas = items < c->num_sms ? items : c->num_sms;
+    // Tail balancing (RFE_ATTN_SPLIT=0 switches it off): with `items` = 7.35 x CTAs the last round keeps a third of the SMs
+    // busy for a whole item; its items are cut into S = CTAs / tail parts along the keys instead (see AttnParams).
+    static const bool kSplit = !(getenv("RFE_ATTN_SPLIT") && atoi(getenv("RFE_ATTN_SPLIT")) == 0);
+    const int tail = items % ctas;
+    int S = (kSplit && tail > 0) ? ctas / tail : 1;
+    if (S > 4) S = 4;
+    int min_nk = 1 << 30;
+    for (int z = 0; z < nprob; ++z) min_nk = p.nk[z] < min_nk ? p.nk[z] : min_nk;
+    while (S > 1 && min_nk < 256 * S) --S;                  // every part keeps at least two 128-key tiles
+    if (S > 1 && (!c->attn_part_o || tail * S > kAttnPartSlots)) S = 1;
+    p.split_s = S;
+    p.split_first = S > 1 ? items - tail : items;
+    p.n_items = S > 1 ? items - tail + tail * S : items;
+    p.part_o = c->attn_part_o;
+    p.part_ml = c->attn_part_ml;
     if (p.prof) attn2_kernel<true><<<ctas, kAttnThreads, kAttn2SmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
     else attn2_kernel<false><<<ctas, kAttnThreads, kAttn2SmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
+    if (S > 1) {
+      attn2_combine_kernel<<<tail, 512, 0, c->stream>>>(p);
+      c->launches++;
+    }
   } else if (p.prof) attn_kernel<true><<<grid, kAttnThreads, kAttnSmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
   else attn_kernel<false><<<grid, kAttnThreads, kAttnSmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
   c->launches++;
@@ -1180,6 +1201,8 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   A_(split_alloc(c, &c->k, R * 256));
   A_(split_alloc(c, &c->vt, 256 * static_cast<size_t>(c->lg_ldv)));
   A_(split_alloc(c, &c->attn, R * 256));
+  A_(dev_alloc(c, &c->attn_part_o, static_cast<size_t>(kAttnPartSlots) * 128 * 64));
+  A_(dev_alloc(c, &c->attn_part_ml, static_cast<size_t>(kAttnPartSlots) * 2 * 128));
   A_(dev_alloc(c, &c->hid, R * 512));
   A_(split_alloc(c, &c->hs, R * 512));
   A_(split_alloc(c, &c->md, R * 256));

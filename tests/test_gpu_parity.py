@@ -479,6 +479,53 @@ def test_fused_conv1a_is_bit_identical_to_the_two_kernel_path(tmp_path):
     assert len(res["1"]["k00"]) > 100
 
 
+_SPLIT_CHILD = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from oracle import synth
+from rover_slam_b200 import FrontEnd
+fe = FrontEnd(max_batch=6, max_height=480, max_width=640, max_keypoints=1280)
+out = {}
+for tag, n, pairs in (("a", 1250, 2), ("b", 800, 3)):
+    k0, k1, d0, d1, perm = synth.lightglue_inputs(n, 900 + n)
+    for p in range(pairs):
+        fe.write_slot(2 * p, k0, d0)
+        fe.write_slot(2 * p + 1, k1, d1)
+    fe.match_slots_batch(list(range(0, 2 * pairs, 2)), list(range(1, 2 * pairs, 2)), 480, 640)
+    for p in range(pairs):
+        out[f"m{tag}{p}"], out[f"s{tag}{p}"] = fe.read_result(p)
+    out["perm" + tag] = perm
+np.savez(sys.argv[2], **out)
+"""
+
+
+def test_attention_key_split_of_the_tail_items_equals_unsplit(tmp_path):
+    """attn2_kernel cuts the work items of its last, partly filled round into key-range parts merged by
+    attn2_combine_kernel (2 pairs x 1250 keypoints: 160 items on 148 SMs -> 12 items in 4 parts; 3 pairs x 800: 168 items ->
+    20 items in 3 parts).  Same matches as with RFE_ATTN_SPLIT=0, scores within the LightGlue tolerance, and every pair of the
+    batch identical to the first (same inputs, different positions in the item list)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ("0", "1"):
+        out = str(tmp_path / f"split{mode}.npz")
+        subprocess.run([sys.executable, "-c", _SPLIT_CHILD, root, out], check=True, env=dict(os.environ, RFE_ATTN_SPLIT=mode), timeout=600)
+        res[mode] = np.load(out)
+    for tag, pairs in (("a", 2), ("b", 3)):
+        for p in range(pairs):
+            m0, s0 = res["0"][f"m{tag}{p}"], res["0"][f"s{tag}{p}"]
+            m1, s1 = res["1"][f"m{tag}{p}"], res["1"][f"s{tag}{p}"]
+            assert len(m0) > 500
+            rep = parity.compare_matches(m0, s0, m1, s1)
+            assert rep["only_ref"] + rep["only_tst"] <= 1 and rep["mscore_maxabs"] <= 1e-4, rep
+        for p in range(1, pairs):               # same inputs at other positions of the item list (split or not)
+            rep = parity.compare_matches(res["1"][f"m{tag}0"], res["1"][f"s{tag}0"], res["1"][f"m{tag}{p}"], res["1"][f"s{tag}{p}"])
+            assert rep["only_ref"] + rep["only_tst"] <= 1 and rep["mscore_maxabs"] <= 1e-4, rep
+        perm = res["1"]["perm" + tag]
+        m1 = res["1"][f"m{tag}0"]
+        assert (perm[m1[:, 1]] == m1[:, 0]).mean() > 0.99
+
+
 # ---- against an independent runtime: OpenCV DNN executing the reference's ONNX files (tests/golden/cv2dnn_*.npz) ----------
 @pytest.mark.parametrize("name", ["sp_640x480_seed0", "sp_752x480_seed100_a"])
 def test_superpoint_vs_cv2dnn_golden(fe, golden_dir, name):
