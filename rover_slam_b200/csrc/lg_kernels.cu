@@ -537,6 +537,10 @@ __global__ void __launch_bounds__(1024) col_lse_batch_kernel(const LgAssign a, f
     clog[a.off1[pr] + j] = logf(sacc);
   }
 }
+// Both arg-max kernels read sim as float4 (four columns per thread): with scalar loads they ran at 1.4-1.7 TB/s, bound by the
+// number of loads in flight (profiles/r02_step_tail_full.csv).  A thread visits its candidates in ascending index order and
+// replaces only on a strictly larger score, the cross-thread reductions prefer the lower index on equality: TopK's
+// lowest-index tie rule, as before.
 __global__ void __launch_bounds__(256) row_argmax_batch_kernel(const LgAssign a, const float* __restrict__ rmax,
                                                                const float* __restrict__ rlog,
                                                                const float* __restrict__ cmax,
@@ -550,15 +554,30 @@ __global__ void __launch_bounds__(256) row_argmax_batch_kernel(const LgAssign a,
   const float* r = a.sim[pr] + static_cast<size_t>(i) * a.ld[pr];
   const int o0 = a.off0[pr], o1 = a.off1[pr];
   const float rm = rmax[o0 + i], rl = rlog[o0 + i], a0 = ls[o0 + i];
+  // rows of sim and the per-column vectors start 32-byte aligned (ld and off1 are multiples of 8) and are padded to 8 columns
+  const float4* r4 = reinterpret_cast<const float4*>(r);
+  const float4* cm4 = reinterpret_cast<const float4*>(cmax + o1);
+  const float4* cl4 = reinterpret_cast<const float4*>(clog + o1);
+  const float4* ls4 = reinterpret_cast<const float4*>(ls + o1);
+  float* dbg = (S_dbg && pr == a.pairs - 1) ? S_dbg + static_cast<size_t>(i) * n1 : nullptr;
   float best = -INFINITY;
   int bi = 0x7fffffff;
+  const int nv = (n1 + 3) >> 2;
 #pragma unroll 4
-  for (int j = lane; j < n1; j += 32) {
-    const float sc = assign_score(r[j], rm, rl, cmax[o1 + j], clog[o1 + j], a0, ls[o1 + j]);
-    if (S_dbg && pr == a.pairs - 1) S_dbg[static_cast<size_t>(i) * n1 + j] = sc;
-    if (sc > best) {
-      best = sc;
-      bi = j;
+  for (int v = lane; v < nv; v += 32) {
+    const float4 sv = r4[v], cm = cm4[v], cl = cl4[v], l1 = ls4[v];
+    const int j = 4 * v;
+    const float sc[4] = {assign_score(sv.x, rm, rl, cm.x, cl.x, a0, l1.x), assign_score(sv.y, rm, rl, cm.y, cl.y, a0, l1.y),
+                         assign_score(sv.z, rm, rl, cm.z, cl.z, a0, l1.z), assign_score(sv.w, rm, rl, cm.w, cl.w, a0, l1.w)};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (j + e < n1) {
+        if (dbg) dbg[j + e] = sc[e];
+        if (sc[e] > best) {
+          best = sc[e];
+          bi = j + e;
+        }
+      }
     }
   }
 #pragma unroll
@@ -575,46 +594,60 @@ __global__ void __launch_bounds__(256) row_argmax_batch_kernel(const LgAssign a,
     m0[o0 + i] = bi;
   }
 }
+// block = 64 columns (16 threads x float4) x 64 row-lanes
 __global__ void __launch_bounds__(1024) col_argmax_batch_kernel(const LgAssign a, const float* __restrict__ rmax,
                                                                 const float* __restrict__ rlog,
                                                                 const float* __restrict__ cmax,
                                                                 const float* __restrict__ clog, const float* __restrict__ ls,
                                                                 int* __restrict__ m1) {
-  __shared__ float rb[32][33];
-  __shared__ int ri[32][33];
+  __shared__ float rb[64][65];
+  __shared__ int ri[64][65];
   const int pr = blockIdx.y;
   const int n0 = a.n0[pr], n1 = a.n1[pr], ld = a.ld[pr];
-  if (blockIdx.x * 32 >= n1) return;
+  if (blockIdx.x * 64 >= n1) return;
   const float* sim = a.sim[pr];
   const int o0 = a.off0[pr], o1 = a.off1[pr];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int j = blockIdx.x * 32 + tx;
-  float best = -INFINITY;
-  int bi = 0x7fffffff;
-  if (j < n1) {
-    const float cm = cmax[o1 + j], cl = clog[o1 + j], a1 = ls[o1 + j];
-#pragma unroll 8
-    for (int i = ty; i < n0; i += 32) {
-      const float sc = assign_score(sim[static_cast<size_t>(i) * ld + j], rmax[o0 + i], rlog[o0 + i], cm, cl, ls[o0 + i], a1);
-      if (sc > best) {
-        best = sc;
-        bi = i;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int j = blockIdx.x * 64 + 4 * tx;
+  float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int bi[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+  if (j < n1) {                                       // j + 3 < ld: columns beyond n1 are computed and never stored
+    const float4 cm = *reinterpret_cast<const float4*>(cmax + o1 + j), cl = *reinterpret_cast<const float4*>(clog + o1 + j),
+                 a1 = *reinterpret_cast<const float4*>(ls + o1 + j);
+#pragma unroll 4
+    for (int i = ty; i < n0; i += 64) {
+      const float4 sv = *reinterpret_cast<const float4*>(sim + static_cast<size_t>(i) * ld + j);
+      const float rm = rmax[o0 + i], rl = rlog[o0 + i], l0 = ls[o0 + i];
+      const float sc[4] = {assign_score(sv.x, rm, rl, cm.x, cl.x, l0, a1.x), assign_score(sv.y, rm, rl, cm.y, cl.y, l0, a1.y),
+                           assign_score(sv.z, rm, rl, cm.z, cl.z, l0, a1.z), assign_score(sv.w, rm, rl, cm.w, cl.w, l0, a1.w)};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (sc[e] > best[e]) {
+          best[e] = sc[e];
+          bi[e] = i;
+        }
       }
     }
   }
-  rb[ty][tx] = best;
-  ri[ty][tx] = bi;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    rb[ty][4 * tx + e] = best[e];
+    ri[ty][4 * tx + e] = bi[e];
+  }
   __syncthreads();
-  if (ty == 0 && j < n1) {
-    for (int k = 1; k < 32; ++k) {
-      const float ob = rb[k][tx];
-      const int oi = ri[k][tx];
-      if (ob > best || (ob == best && oi < bi)) {
-        best = ob;
-        bi = oi;
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < n1) {
+    const int c = threadIdx.x;
+    float b = rb[0][c];
+    int ix = ri[0][c];
+    for (int k = 1; k < 64; ++k) {
+      const float ob = rb[k][c];
+      const int oi = ri[k][c];
+      if (ob > b || (ob == b && oi < ix)) {
+        b = ob;
+        ix = oi;
       }
     }
-    m1[o1 + j] = bi;
+    m1[o1 + blockIdx.x * 64 + c] = ix;
   }
 }
 __global__ void __launch_bounds__(1024) match_compact_batch_kernel(const LgAssign a, const float* __restrict__ max0,
@@ -871,11 +904,11 @@ void launch_lg_assign_banded(cudaStream_t s, const LgAssign& a, float* rmax, flo
 void launch_lg_assign(cudaStream_t s, const LgAssign& a, float* rmax, float* rlog, float* cmax, float* clog,
                       const float* ls, float* max0, int* m0, int* m1, float filter, float thresh, float* S_dbg) {
   if (a.pairs == 0) return;
-  const dim3 grow((a.max_n0 + 7) / 8, a.pairs), gcol((a.max_n1 + 31) / 32, a.pairs);
+  const dim3 grow((a.max_n0 + 7) / 8, a.pairs), gcol((a.max_n1 + 31) / 32, a.pairs), gcol4((a.max_n1 + 63) / 64, a.pairs);
   row_lse_batch_kernel<<<grow, 256, 0, s>>>(a, rmax, rlog);
   col_lse_batch_kernel<<<gcol, 1024, 0, s>>>(a, cmax, clog);
   row_argmax_batch_kernel<<<grow, 256, 0, s>>>(a, rmax, rlog, cmax, clog, ls, max0, m0, S_dbg);
-  col_argmax_batch_kernel<<<gcol, 1024, 0, s>>>(a, rmax, rlog, cmax, clog, ls, m1);
+  col_argmax_batch_kernel<<<gcol4, 1024, 0, s>>>(a, rmax, rlog, cmax, clog, ls, m1);
   match_compact_batch_kernel<<<a.pairs, 1024, 0, s>>>(a, max0, m0, m1, filter, thresh);
 }
 
