@@ -25,7 +25,10 @@ namespace rfe {
 
 // Q 32 KB + K 4 x 16 KB + P 2 x 32 KB + V 3 x 16 KB + 1 KB alignment slack + tail (barriers 512 B, row statistics 2 x 2 KB)
 constexpr int kAttn2TailBytes = 512 + 2 * 4 * 128 * 4;
-constexpr int kAttn2SmemBytes = kAttnQBytes + 2 * kAttnPBytes + (kAttnKStages + kAttnVStages) * kAttnKVBytes + 1024 + kAttn2TailBytes;
+constexpr int attn2_smem_bytes(int nk, int nv, int np) {
+  return kAttnQBytes + np * kAttnPBytes + (nk + nv) * kAttnKVBytes + 1024 + kAttn2TailBytes;
+}
+constexpr int kAttn2SmemBytes = attn2_smem_bytes(kAttnKStages, kAttnVStages, 2);
 
 #ifdef __CUDACC__
 
@@ -65,7 +68,8 @@ __device__ __forceinline__ AttnItem attn_decode(const AttnParams& p, int vitem) 
   return a;
 }
 
-template <bool PROF>
+// G softmax groups (2 x 8 warps or 4 x 4 warps) on key tiles t = grp (mod G); NK / NV / NP: K stages, V stages, P buffers.
+template <bool PROF, int G = 2, int NK = kAttnKStages, int NV = kAttnVStages, int NP = 2>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ CUtensorMap tmQ_lo,
              const __grid_constant__ CUtensorMap tmK_hi, const __grid_constant__ CUtensorMap tmK_lo,
@@ -74,24 +78,34 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                                   // Q_hi | Q_lo
   uint8_t* sK = smem + kAttnQBytes;                     // K stages: pass 1 K_hi(128 keys), pass 2 K_hi | K_lo (64 keys)
-  uint8_t* sP = sK + kAttnKStages * kAttnKVBytes;       // 2 x (P_hi | P_lo)
-  uint8_t* sV = sP + 2 * kAttnPBytes;                   // V stages: Vt_hi | Vt_lo
-  uint8_t* tail = sV + kAttnVStages * kAttnKVBytes;
+  uint8_t* sP = sK + NK * kAttnKVBytes;                 // NP x (P_hi | P_lo)
+  uint8_t* sV = sP + NP * kAttnPBytes;                  // V stages: Vt_hi | Vt_lo
+  uint8_t* tail = sV + NV * kAttnKVBytes;
+  constexpr int WG = kAttnSoftmaxWarps / G;             // warps per softmax group
   uint64_t* q_full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* q_empty = q_full + 1;
-  uint64_t* k_full = q_empty + 1;                       // [4]
-  uint64_t* k_empty = k_full + kAttnKStages;
-  uint64_t* v_full = k_empty + kAttnKStages;            // [3]
-  uint64_t* v_empty = v_full + kAttnVStages;
-  uint64_t* s_full = v_empty + kAttnVStages;            // [3]
+  uint64_t* k_full = q_empty + 1;                       // [NK]
+  uint64_t* k_empty = k_full + NK;
+  uint64_t* v_full = k_empty + NK;                      // [NV]
+  uint64_t* v_empty = v_full + NV;
+  uint64_t* s_full = v_empty + NV;                      // [3]
   uint64_t* s_empty = s_full + kAttnSBufs;              // [3]
-  uint64_t* p_full = s_empty + kAttnSBufs;              // [2]
-  uint64_t* p_empty = p_full + 2;                       // [2]
-  uint64_t* o_full = p_empty + 2;
+  uint64_t* p_full = s_empty + kAttnSBufs;              // [NP]
+  uint64_t* p_empty = p_full + NP;                      // [NP]
+  uint64_t* o_full = p_empty + NP;
   uint64_t* o_empty = o_full + 1;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_empty + 1);
+  // G = 4 only: score-ready barriers per (group, parity of the group's own tile count).  With four groups a group may be more
+  // than one phase away from a barrier shared by all groups, and a parity wait cannot tell phase k from phase k - 2; a group's
+  // own two barriers alternate over its own consecutive tiles, so it is never more than one phase behind them.
+  uint64_t* sfg = o_empty + 1;                          // [4][2]
+  // ... and P-buffer permissions the same way: when the P V issuer has issued tile u it frees buffer u % NP for tile u + NP
+  // and commits to the barrier of THAT tile's group (ordinal = pass-2 tiles of that group so far).
+  uint64_t* peg = sfg + 8;                              // [4][2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(peg + 8);
   float* stat = reinterpret_cast<float*>(tail + 512);   // [2 (item parity)][4][128] partial row max, then partial row sum
-  static_assert(28 * 8 + 4 <= 512 && kAttn2SmemBytes <= 227 * 1024, "tail region / shared-memory budget");
+  static_assert((4 + 16 + 2 * (NK + NV + kAttnSBufs + NP)) * 8 + 4 <= 512 && attn2_smem_bytes(NK, NV, NP) <= 227 * 1024,
+                "tail region / shared-memory budget");
+  static_assert(G == 2 || G == 4, "softmax groups");
 
   auto tick = [&]() -> long long { return PROF ? clock64() : 0; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -112,11 +126,14 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
     tma_prefetch_desc(&tmK_lo); tma_prefetch_desc(&tmV_hi); tma_prefetch_desc(&tmV_lo);
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    for (int s = 0; s < kAttnKStages; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
-    for (int s = 0; s < kAttnVStages; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-    // both passes: the softmax warps work as two groups of eight on alternate key tiles
-    for (int s = 0; s < kAttnSBufs; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kAttnSoftmaxWarps / 2); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&p_full[s], kAttnSoftmaxWarps / 2); mbar_init(&p_empty[s], 1); }
+    for (int s = 0; s < NK; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+    for (int s = 0; s < NV; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+    // both passes: the softmax warps work as G groups of WG warps on key tiles t = grp (mod G)
+    for (int s = 0; s < kAttnSBufs; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], WG); }
+    for (int s = 0; s < NP; ++s) { mbar_init(&p_full[s], WG); mbar_init(&p_empty[s], 1); }
+    for (int s = 0; s < 8; ++s) { mbar_init(&sfg[s], 1); mbar_init(&peg[s], 1); }
+    if (G == 4)                                         // the NP buffers are free at the start: ordinal 0 of groups 0 .. NP-1
+      for (int s = 0; s < NP; ++s) mbar_arrive(&peg[s * 2]);
     mbar_init(o_full, 1);
     mbar_init(o_empty, kAttnSoftmaxWarps);
     fence_barrier_init();
@@ -138,16 +155,16 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const AttnItem a = attn_decode(p, item);
         for (int g = 0; g < a.T1; ++g, ++n) {        // pass 1: 128 keys of K_hi
-          const int st = n % kAttnKStages;
-          mbar_wait(&k_empty[st], ((n / kAttnKStages) & 1) ^ 1);
+          const int st = n % NK;
+          mbar_wait(&k_empty[st], ((n / NK) & 1) ^ 1);
           uint8_t* sb = sK + st * kAttnKVBytes;
           mbar_expect_tx(&k_full[st], kAttnKVBytes);
           tma_load_3d(sb, &tmK_hi, &k_full[st], 0, a.krow + g * 128, a.head);
           tma_load_3d(sb + 8192, &tmK_hi, &k_full[st], 0, a.krow + g * 128 + 64, a.head);
         }
         for (int t = 0; t < a.T; ++t, ++n) {         // pass 2: 64 keys, both planes
-          const int st = n % kAttnKStages;
-          mbar_wait(&k_empty[st], ((n / kAttnKStages) & 1) ^ 1);
+          const int st = n % NK;
+          mbar_wait(&k_empty[st], ((n / NK) & 1) ^ 1);
           uint8_t* sb = sK + st * kAttnKVBytes;
           mbar_expect_tx(&k_full[st], kAttnKVBytes);
           tma_load_3d(sb, &tmK_hi, &k_full[st], 0, a.krow + t * kAttnKeyTile, a.head);
@@ -166,8 +183,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
         tma_load_3d(sQ, &tmQ_hi, q_full, 0, a.qrow, a.head);
         tma_load_3d(sQ + 16384, &tmQ_lo, q_full, 0, a.qrow, a.head);
         for (int t = 0; t < a.T; ++t, ++v) {
-          const int st = v % kAttnVStages;
-          mbar_wait(&v_empty[st], ((v / kAttnVStages) & 1) ^ 1);
+          const int st = v % NV;
+          mbar_wait(&v_empty[st], ((v / NV) & 1) ^ 1);
           uint8_t* sb = sV + st * kAttnKVBytes;
           mbar_expect_tx(&v_full[st], kAttnKVBytes);
           tma_load_3d(sb, &tmV_hi, &v_full[st], a.krow + t * kAttnKeyTile, 0, a.head);
@@ -183,6 +200,16 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
       const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + 16384;
       long long w_q = 0, w_k = 0, w_se = 0, w_k1 = 0, w_se1 = 0, t_p1 = 0, t_p2 = 0;
       uint32_t n = 0, it = 0;
+      uint32_t gc = 0;                               // G = 4: tiles handed to each group so far, four 8-bit counters
+      auto score_ready = [&](int g, int b) -> uint64_t* {
+        if constexpr (G == 4) {
+          const uint32_t sh = 8u * static_cast<uint32_t>(g), cg = (gc >> sh) & 0xffu;
+          gc = (gc & ~(0xffu << sh)) | (((cg + 1u) & 0xffu) << sh);
+          return &sfg[g * 2 + (cg & 1u)];
+        } else {
+          return &s_full[b];
+        }
+      };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const AttnItem a = attn_decode(p, item);
         const long long t0 = tick();
@@ -190,9 +217,9 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
         const long long t1 = tick();
         w_q += t1 - t0;
         for (int g = 0; g < a.T1; ++g, ++n) {        // pass 1: S_hh of 128 keys, one N=128 MMA per k-step
-          const int st = n % kAttnKStages, b = n % kAttnSBufs;
+          const int st = n % NK, b = n % kAttnSBufs;
           const long long c0 = tick();
-          mbar_wait(&k_full[st], (n / kAttnKStages) & 1);
+          mbar_wait(&k_full[st], (n / NK) & 1);
           const long long c1 = tick();
           mbar_wait(&s_empty[b], ((n / kAttnSBufs) & 1) ^ 1);
           w_k1 += c1 - c0;
@@ -203,15 +230,15 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_f16(s_base, make_sw128_kmajor_desc(q_hi + k * 32), make_sw128_kmajor_desc(k_hi + k * 32), idesc128, k > 0);
-          umma_commit(&s_full[b]);
+          umma_commit(score_ready(g & 3, b));
           umma_commit(&k_empty[st]);
         }
         const long long t2 = tick();
         t_p1 += t2 - t1;
         for (int t = 0; t < a.T; ++t, ++n) {         // pass 2: fp32-equivalent scores of a 64-key tile
-          const int st = n % kAttnKStages, b = n % kAttnSBufs;
+          const int st = n % NK, b = n % kAttnSBufs;
           const long long c0 = tick();
-          mbar_wait(&k_full[st], (n / kAttnKStages) & 1);
+          mbar_wait(&k_full[st], (n / NK) & 1);
           const long long c1 = tick();
           mbar_wait(&s_empty[b], ((n / kAttnSBufs) & 1) ^ 1);
           w_k += c1 - c0;
@@ -225,7 +252,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
             umma_f16(s_base, make_sw128_kmajor_desc(q_hi + k * 32), dk, idesc128, k > 0);        // [S_hh | S_hl]
             umma_f16(s_base + 64, make_sw128_kmajor_desc(q_lo + k * 32), dk, idesc64, 1u);       // S_hl += Q_lo K_hi^T
           }
-          umma_commit(&s_full[b]);
+          umma_commit(score_ready(t & 3, b));
           umma_commit(&k_empty[st]);
         }
         umma_commit(q_empty);                        // the Q tile may be replaced once these MMAs have retired
@@ -249,14 +276,16 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
       const uint32_t o_base = tmem_base + 384;
       long long w_v = 0, w_p = 0, w_o = 0;
       uint32_t v = 0, it = 0, tiles = 0;
+      uint32_t pc = 0;                               // G = 4: P-buffer permissions handed to each group, four 8-bit counters
+      for (int s = 0; s < NP; ++s) pc |= 1u << (8 * s);
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const AttnItem a = attn_decode(p, item);
         for (int t = 0; t < a.T; ++t, ++v) {
-          const int st = v % kAttnVStages, pb = v & 1;
+          const int st = v % NV, pb = v % NP;
           const long long c0 = tick();
-          mbar_wait(&v_full[st], (v / kAttnVStages) & 1);
+          mbar_wait(&v_full[st], (v / NV) & 1);
           const long long c1 = tick();
-          mbar_wait(&p_full[pb], (v >> 1) & 1);
+          mbar_wait(&p_full[pb], (v / NP) & 1);
           const long long c2 = tick();
           if (t == 0) mbar_wait(o_empty, (it & 1) ^ 1);     // the previous item's epilogue has read O out of TMEM
           w_v += c1 - c0;
@@ -272,7 +301,15 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
             umma_f16(o_base + 64, make_sw128_kmajor_desc(p_lo + k * 32), dv, idesc64, 1u);
           }
           umma_commit(&v_empty[st]);
-          umma_commit(&p_empty[pb]);
+          if constexpr (G == 4) {
+            const int tn = t + NP;                   // the next user of this buffer: same item, or tile tn - T of the next one
+            const uint32_t g2 = static_cast<uint32_t>(tn < a.T ? tn : tn - a.T) & 3u;
+            const uint32_t sh = 8u * g2, ord = (pc >> sh) & 0xffu;
+            pc = (pc & ~(0xffu << sh)) | (((ord + 1u) & 0xffu) << sh);
+            umma_commit(&peg[g2 * 2 + (ord & 1u)]);
+          } else {
+            umma_commit(&p_empty[pb]);
+          }
         }
         umma_commit(o_full);
         tiles += a.T;
@@ -290,8 +327,10 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
     const int sw = warp;                     // 0..15
     const int q = warp & 3;                  // TMEM lane quarter
     const int cq = sw >> 2;                  // pass 1 / epilogue: which quarter of the columns
-    const int grp = sw >> 3;                 // the group that owns key tiles t with (t & 1) == grp
-    const int ch2 = (sw >> 2) & 1;           // which half of the group's tile
+    const int grp = sw / WG;                 // the group that owns key tiles t with t % G == grp
+    // G = 2: a warp owns 32 of a tile's 64 columns (half ch2 = bit 2 of the warp index); G = 4: all 64, as two sequential halves
+    constexpr int NCH = (G == 2) ? 1 : 2;
+    const int ch_first = (G == 2) ? ((sw >> 2) & 1) : 0;
     const int row = q * 32 + lane;
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float NEG = -INFINITY;
@@ -301,6 +340,15 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
     long long sw_s1 = 0, sw_s = 0, sw_p = 0, sw_o = 0, t_sm1 = 0, t_sm2 = 0, t_epi = 0;
     long long ph_ld = 0, ph_math = 0, ph_sts = 0, ph_fence = 0;     // pass-2 phases of one warp (PROF build)
     uint32_t n_base = 0, v_base = 0, it = 0;
+    uint32_t mycnt = 0, myp = 0;                     // G = 4: tiles / pass-2 tiles this group has taken so far
+    auto wait_scores = [&](int b, uint32_t n) {
+      if constexpr (G == 4) {
+        mbar_wait(&sfg[grp * 2 + (mycnt & 1u)], (mycnt >> 1) & 1u);
+        ++mycnt;
+      } else {
+        mbar_wait(&s_full[b], (n / kAttnSBufs) & 1);
+      }
+    };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const AttnItem a = attn_decode(p, item);
       const int nk = a.nk, T = a.T, T1 = a.T1;
@@ -309,38 +357,44 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
 
       // ---- pass 1: row maximum of the hi*hi scores (two groups on alternate 128-key tiles, 64 columns per warp) ----
       float mx = NEG;
-      for (int g = grp; g < T1; g += 2) {
+      for (int g = grp; g < T1; g += G) {
         const uint32_t n = n_base + g;
         const int b = n % kAttnSBufs;
         const long long w0 = tick();
-        mbar_wait(&s_full[b], (n / kAttnSBufs) & 1);
+        wait_scores(b, n);
         sw_s1 += tick() - w0;
         tc_fence_after();
-        uint32_t a0[32], a1[32];
-        tmem_ld32(tlane + b * 128 + ch2 * 64, a0);
-        tmem_ld32(tlane + b * 128 + ch2 * 64 + 32, a1);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[b]);
-        const int c0 = g * 128 + ch2 * 64;
-        float m0a = NEG, m1a = NEG, m2a = NEG, m3a = NEG;          // four independent chains
-        if (c0 + 64 <= nk) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            m0a = fmaxf(m0a, __uint_as_float(a0[j]));
-            m1a = fmaxf(m1a, __uint_as_float(a0[j + 1]));
-            m2a = fmaxf(m2a, __uint_as_float(a1[j]));
-            m3a = fmaxf(m3a, __uint_as_float(a1[j + 1]));
+        for (int c = 0; c < NCH; ++c) {              // 64 of the tile's 128 columns per step
+          const int ch2 = ch_first + c;
+          uint32_t a0[32], a1[32];
+          tmem_ld32(tlane + b * 128 + ch2 * 64, a0);
+          tmem_ld32(tlane + b * 128 + ch2 * 64 + 32, a1);
+          tmem_ld_wait();
+          if (c == NCH - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[b]);
           }
-        } else {
+          const int c0 = g * 128 + ch2 * 64;
+          float m0a = NEG, m1a = NEG, m2a = NEG, m3a = NEG;          // four independent chains
+          if (c0 + 64 <= nk) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (c0 + j < nk) m0a = fmaxf(m0a, __uint_as_float(a0[j]));
-            if (c0 + 32 + j < nk) m2a = fmaxf(m2a, __uint_as_float(a1[j]));
+            for (int j = 0; j < 32; j += 2) {
+              m0a = fmaxf(m0a, __uint_as_float(a0[j]));
+              m1a = fmaxf(m1a, __uint_as_float(a0[j + 1]));
+              m2a = fmaxf(m2a, __uint_as_float(a1[j]));
+              m3a = fmaxf(m3a, __uint_as_float(a1[j + 1]));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (c0 + j < nk) m0a = fmaxf(m0a, __uint_as_float(a0[j]));
+              if (c0 + 32 + j < nk) m2a = fmaxf(m2a, __uint_as_float(a1[j]));
+            }
           }
+          mx = fmaxf(mx, fmaxf(fmaxf(m0a, m1a), fmaxf(m2a, m3a)));
         }
-        mx = fmaxf(mx, fmaxf(fmaxf(m0a, m1a), fmaxf(m2a, m3a)));
       }
       st_buf[cq * 128 + row] = mx;
       named_bar_sync(1, kSmThreads);
@@ -357,78 +411,91 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
       auto tile_body = [&](int t, auto masked_tag) {
         constexpr bool kMasked = decltype(masked_tag)::value;
         const uint32_t n = n_base + T1 + t, v = v_base + t;
-        const int b = n % kAttnSBufs, pb = v & 1;
+        const int b = n % kAttnSBufs, pb = v % NP;
         const long long w0 = tick();
-        mbar_wait(&s_full[b], (n / kAttnSBufs) & 1);
+        wait_scores(b, n);
         const long long w0b = tick();
         sw_s += w0b - w0;
         tc_fence_after();
-        uint32_t a0[2][16], x0[2][16];
-        const uint32_t base = tlane + b * 128 + ch2 * 32;
-        tmem_ld16(base, a0[0]);
-        tmem_ld16(base + 64, x0[0]);
-        tmem_ld16(base + 16, a0[1]);
-        tmem_ld16(base + 80, x0[1]);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[b]);
-        const long long w1b = tick();
-        ph_ld += w1b - w0b;
-        uint32_t ph[2][8], pl[2][8];
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const int c0 = t * kAttnKeyTile + ch2 * 32 + hf * 16;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            // E = 2^11 exp(s - max) through the SFU (see attn_kernel.cuh); E - rn16(E) IS the scaled low part
-            f32x2 x = fma2(pk2u(a0[hf][2 * j], a0[hf][2 * j + 1]), kL2, nmx);
-            x = fma2(pk2u(x0[hf][2 * j], x0[hf][2 * j + 1]), kL2s, x);
-            float x_0, x_1;
-            upk2(x, x_0, x_1);
-            float e0 = fast_exp2(x_0), e1 = fast_exp2(x_1);
-            if (kMasked) {
-              if (c0 + 2 * j >= nk) e0 = 0.0f;
-              if (c0 + 2 * j + 1 >= nk) e1 = 0.0f;
-            }
-            lsum = add2(lsum, pk2(e0, e1));
-            uint32_t hE;
-            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hE) : "f"(e1), "f"(e0));       // low half = e0
-            ph[hf][j] = hE;                                                          // P_hi = rn16(E)
-            float d0, d1;
-            asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\t"
-                "fma.rn.f32.f16 %0, l, %5, %3;\n\tfma.rn.f32.f16 %1, h, %5, %4;\n\t}"
-                : "=f"(d0), "=f"(d1)
-                : "r"(hE), "f"(e0), "f"(e1), "h"(static_cast<unsigned short>(0xBC00)));   // E - rn16(E), exact
-            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pl[hf][j]) : "f"(d1), "f"(d0));
-          }
-        }
-        const long long w2 = tick();
-        ph_math += w2 - w1b;
-        mbar_wait(&p_empty[pb], ((v >> 1) & 1) ^ 1);       // the P V product two tiles back has consumed this P buffer
-        const long long w2b = tick();
-        sw_p += w2b - w2;
         uint8_t* prow_hi = sP + pb * kAttnPBytes + row * 128;
         uint8_t* prow_lo = prow_hi + 16384;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int sc = ((ch2 * 4 + ch) ^ (row & 7)) << 4;
-          const int hf = ch >> 1, o = 4 * (ch & 1);
-          *reinterpret_cast<uint4*>(prow_hi + sc) = make_uint4(ph[hf][o], ph[hf][o + 1], ph[hf][o + 2], ph[hf][o + 3]);
-          *reinterpret_cast<uint4*>(prow_lo + sc) = make_uint4(pl[hf][o], pl[hf][o + 1], pl[hf][o + 2], pl[hf][o + 3]);
+        for (int c = 0; c < NCH; ++c) {
+          const int ch2 = ch_first + c;
+          const long long w1a = tick();
+          uint32_t a0[2][16], x0[2][16];
+          const uint32_t base = tlane + b * 128 + ch2 * 32;
+          tmem_ld16(base, a0[0]);
+          tmem_ld16(base + 64, x0[0]);
+          tmem_ld16(base + 16, a0[1]);
+          tmem_ld16(base + 80, x0[1]);
+          tmem_ld_wait();
+          if (c == NCH - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[b]);
+          }
+          const long long w1b = tick();
+          ph_ld += w1b - w1a;
+          uint32_t ph[2][8], pl[2][8];
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int c0 = t * kAttnKeyTile + ch2 * 32 + hf * 16;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              // E = 2^11 exp(s - max) through the SFU (see attn_kernel.cuh); E - rn16(E) IS the scaled low part
+              f32x2 x = fma2(pk2u(a0[hf][2 * j], a0[hf][2 * j + 1]), kL2, nmx);
+              x = fma2(pk2u(x0[hf][2 * j], x0[hf][2 * j + 1]), kL2s, x);
+              float x_0, x_1;
+              upk2(x, x_0, x_1);
+              float e0 = fast_exp2(x_0), e1 = fast_exp2(x_1);
+              if (kMasked) {
+                if (c0 + 2 * j >= nk) e0 = 0.0f;
+                if (c0 + 2 * j + 1 >= nk) e1 = 0.0f;
+              }
+              lsum = add2(lsum, pk2(e0, e1));
+              uint32_t hE;
+              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hE) : "f"(e1), "f"(e0));       // low half = e0
+              ph[hf][j] = hE;                                                          // P_hi = rn16(E)
+              float d0, d1;
+              asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\t"
+                  "fma.rn.f32.f16 %0, l, %5, %3;\n\tfma.rn.f32.f16 %1, h, %5, %4;\n\t}"
+                  : "=f"(d0), "=f"(d1)
+                  : "r"(hE), "f"(e0), "f"(e1), "h"(static_cast<unsigned short>(0xBC00)));   // E - rn16(E), exact
+              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pl[hf][j]) : "f"(d1), "f"(d0));
+            }
+          }
+          const long long w2 = tick();
+          ph_math += w2 - w1b;
+          if (c == 0) {                            // the P V product NP tiles back has consumed this P buffer
+            if constexpr (G == 4) {
+              mbar_wait(&peg[grp * 2 + (myp & 1u)], (myp >> 1) & 1u);
+              ++myp;
+            } else {
+              mbar_wait(&p_empty[pb], ((v / NP) & 1) ^ 1);
+            }
+          }
+          const long long w2b = tick();
+          sw_p += w2b - w2;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const int sc = ((ch2 * 4 + ch) ^ (row & 7)) << 4;
+            const int hf = ch >> 1, o = 4 * (ch & 1);
+            *reinterpret_cast<uint4*>(prow_hi + sc) = make_uint4(ph[hf][o], ph[hf][o + 1], ph[hf][o + 2], ph[hf][o + 3]);
+            *reinterpret_cast<uint4*>(prow_lo + sc) = make_uint4(pl[hf][o], pl[hf][o + 1], pl[hf][o + 2], pl[hf][o + 3]);
+          }
+          ph_sts += tick() - w2b;
         }
         const long long w3b = tick();
         fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[pb]);
-        const long long w4b = tick();
-        ph_sts += w3b - w2b;
-        ph_fence += w4b - w3b;
+        ph_fence += tick() - w3b;
       };
       const int t_full = (nk % kAttnKeyTile) ? T - 1 : T;
 #pragma unroll 1
-      for (int t = grp; t < t_full; t += 2) tile_body(t, cuda::std::false_type{});
-      if (t_full < T && ((T - 1) & 1) == grp) tile_body(T - 1, cuda::std::true_type{});
+      for (int t = grp; t < t_full; t += G) tile_body(t, cuda::std::false_type{});
+      if (t_full < T && ((T - 1) % G) == grp) tile_body(T - 1, cuda::std::true_type{});
       const long long st_p2 = tick();
       t_sm2 += st_p2 - st_p1;
       float l;
@@ -437,7 +504,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
         upk2(lsum, l0, l1);
         l = l0 + l1;
       }
-      st_buf[cq * 128 + row] = l;                // cq = 2 * grp + ch2: four partial sums per row
+      st_buf[cq * 128 + row] = l;                // four partial sums per row (G = 2: cq = 2 * grp + ch2; G = 4: cq = grp)
       named_bar_sync(1, kSmThreads);
       l = (st_buf[row] + st_buf[128 + row]) + (st_buf[256 + row] + st_buf[384 + row]);
 

@@ -711,8 +711,37 @@ int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitB
     p.n_items = S > 1 ? items - tail + tail * S : items;
     p.part_o = c->attn_part_o;
     p.part_ml = c->attn_part_ml;
-    if (p.prof) attn2_kernel<true><<<ctas, kAttnThreads, kAttn2SmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
-    else attn2_kernel<false><<<ctas, kAttnThreads, kAttn2SmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
+    // RFE_ATTN_CFG: softmax groups / ring depths (A/B): 0 = 2 groups of 8 warps, K 4 / V 3 / P 2 buffers; 1 = 2 groups, 3/2/3;
+    // 2 = 4 groups of 4 warps, 3/2/3; 3 = 4 groups, 4/3/2
+    static const int kCfgEnv = getenv("RFE_ATTN_CFG") ? atoi(getenv("RFE_ATTN_CFG")) : 0;
+    // the four-group forms need at least four pass-2 tiles and two pass-1 tiles per item (barrier discipline, attn2_kernel.cuh)
+    const int kCfg = (kCfgEnv >= 2 && min_nk < 256) ? 0 : kCfgEnv;
+    auto launch = [&](auto kern, int smem) -> cudaError_t {
+      static const void* configured_fn[16][8] = {};      // [device][instantiation]: opt-in shared memory set once
+      const void** slot = configured_fn[c->device & 15];
+      int i = 0;
+      while (i < 8 && slot[i] && slot[i] != reinterpret_cast<const void*>(kern)) ++i;
+      if (i == 8 || !slot[i]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        if (i < 8) slot[i] = reinterpret_cast<const void*>(kern);
+      }
+      kern<<<ctas, kAttnThreads, smem, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
+      return cudaSuccess;
+    };
+    cudaError_t le;
+    if (p.prof) {
+      if (kCfg == 1) le = launch(attn2_kernel<true, 2, 3, 2, 3>, attn2_smem_bytes(3, 2, 3));
+      else if (kCfg == 2) le = launch(attn2_kernel<true, 4, 3, 2, 3>, attn2_smem_bytes(3, 2, 3));
+      else if (kCfg == 3) le = launch(attn2_kernel<true, 4, 4, 3, 2>, attn2_smem_bytes(4, 3, 2));
+      else le = launch(attn2_kernel<true>, kAttn2SmemBytes);
+    } else {
+      if (kCfg == 1) le = launch(attn2_kernel<false, 2, 3, 2, 3>, attn2_smem_bytes(3, 2, 3));
+      else if (kCfg == 2) le = launch(attn2_kernel<false, 4, 3, 2, 3>, attn2_smem_bytes(3, 2, 3));
+      else if (kCfg == 3) le = launch(attn2_kernel<false, 4, 4, 3, 2>, attn2_smem_bytes(4, 3, 2));
+      else le = launch(attn2_kernel<false>, kAttn2SmemBytes);
+    }
+    RFE_CUDA_CHECK(le);
     if (S > 1) {
       attn2_combine_kernel<<<tail, 512, 0, c->stream>>>(p);
       c->launches++;
