@@ -68,6 +68,46 @@ __device__ __forceinline__ AttnItem attn_decode(const AttnParams& p, int vitem) 
   return a;
 }
 
+// Merges the key-range parts of a split work item: O = sum_c w_c O_c / (256 sum_c w_c l_c), w_c = exp(max_c - max).  Called by
+// the softmax warps of the CTA whose part arrived LAST (thread = (row, 16 output columns) like the epilogue); the parts are
+// always summed in index order from the scratch buffers, so the result does not depend on which part that was.
+__device__ __forceinline__ void attn2_merge_parts(const AttnParams& p, const AttnItem& a, int row, int cq) {
+  const int slot0 = a.slot - a.part;
+  float M = -INFINITY;
+  for (int c = 0; c < p.split_s; ++c) M = fmaxf(M, __ldcg(p.part_ml + (static_cast<size_t>(slot0 + c) * 2) * 128 + row));
+  float L = 0.0f, acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+  for (int c = 0; c < p.split_s; ++c) {
+    const size_t s = slot0 + c;
+    const float w = expf(__ldcg(p.part_ml + (s * 2) * 128 + row) - M);
+    L = fmaf(w, __ldcg(p.part_ml + (s * 2 + 1) * 128 + row), L);
+    const float4* po = reinterpret_cast<const float4*>(p.part_o + (s * 128 + row) * 64 + cq * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 v = __ldcg(po + j);
+      acc[4 * j] = fmaf(w, v.x, acc[4 * j]);
+      acc[4 * j + 1] = fmaf(w, v.y, acc[4 * j + 1]);
+      acc[4 * j + 2] = fmaf(w, v.z, acc[4 * j + 2]);
+      acc[4 * j + 3] = fmaf(w, v.w, acc[4 * j + 3]);
+    }
+  }
+  __align__(16) __half oh[16];
+  __align__(16) __half ol[16];
+  const float inv_l = 1.0f / (RFE_ATTN_V_SCALE * L);
+  const bool live = a.m0 + row < a.nq;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) split_f32(live ? acc[j] * inv_l : 0.0f, oh[j], ol[j]);
+  if (a.m0 + row < ((a.nq + 7) & ~7)) {
+    const size_t o = static_cast<size_t>(a.qrow + row) * 256 + a.head * 64 + cq * 16;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      reinterpret_cast<uint4*>(p.out_hi + o)[ch] = reinterpret_cast<const uint4*>(oh)[ch];
+      reinterpret_cast<uint4*>(p.out_lo + o)[ch] = reinterpret_cast<const uint4*>(ol)[ch];
+    }
+  }
+}
+
 // G softmax groups (2 x 8 warps or 4 x 4 warps) on key tiles t = grp (mod G); NK / NV / NP: K stages, V stages, P buffers.
 template <bool PROF, int G = 2, int NK = kAttnKStages, int NV = kAttnVStages, int NP = 2>
 __global__ void __launch_bounds__(kAttnThreads, 1)
@@ -102,8 +142,9 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
   // and commits to the barrier of THAT tile's group (ordinal = pass-2 tiles of that group so far).
   uint64_t* peg = sfg + 8;                              // [4][2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(peg + 8);
+  uint32_t* last_part = tmem_ptr_smem + 1;               // 1: this CTA's part of a split item arrived last and merges
   float* stat = reinterpret_cast<float*>(tail + 512);   // [2 (item parity)][4][128] partial row max, then partial row sum
-  static_assert((4 + 16 + 2 * (NK + NV + kAttnSBufs + NP)) * 8 + 4 <= 512 && attn2_smem_bytes(NK, NV, NP) <= 227 * 1024,
+  static_assert((4 + 16 + 2 * (NK + NV + kAttnSBufs + NP)) * 8 + 8 <= 512 && attn2_smem_bytes(NK, NV, NP) <= 227 * 1024,
                 "tail region / shared-memory budget");
   static_assert(G == 2 || G == 4, "softmax groups");
 
@@ -522,7 +563,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(o_empty);     // O may be overwritten by the next item's first P V product
-        if (a.part >= 0) {                       // a key-range part: raw O, row maximum and row sum for attn2_combine_kernel
+        if (a.part >= 0) {                       // a key-range part: raw O, row maximum and row sum; the last part to arrive merges
           float4* po = reinterpret_cast<float4*>(p.part_o + (static_cast<size_t>(a.slot) * 128 + row) * 64 + cq * 16);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -533,6 +574,21 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
           if (cq == 0) {
             p.part_ml[(static_cast<size_t>(a.slot) * 2) * 128 + row] = mx;
             p.part_ml[(static_cast<size_t>(a.slot) * 2 + 1) * 128 + row] = l;
+          }
+          // the part that arrives last merges all of them (no extra launch): writes, fence, CTA barrier, one atomic ticket
+          __threadfence();
+          named_bar_sync(1, kSmThreads);
+          if (threadIdx.x == 0) {
+            unsigned* cnt = p.part_cnt + (a.slot - a.part) / p.split_s;
+            const bool last = atomicAdd(cnt, 1u) == static_cast<unsigned>(p.split_s - 1);
+            if (last) *cnt = 0u;                   // nobody else touches the ticket of this item before the next launch
+            *last_part = last;
+          }
+          named_bar_sync(1, kSmThreads);
+          if (*last_part) {
+            __threadfence();
+            AttnItem whole = a;                    // a.qrow / m0 / nq / head are those of the whole item already
+            attn2_merge_parts(p, whole, row, cq);
           }
           t_epi += tick() - st_p2;
           n_base += T1 + T;
@@ -588,51 +644,6 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     p.prof[32 + 3 * blockIdx.x + 1] = t;
     p.prof[32 + 3 * blockIdx.x + 2] |= static_cast<unsigned long long>(clock64() - cta_c0) << 16;   // SM cycles of this CTA
-  }
-}
-
-// Merges the key-range parts of the split work items: O = sum_c w_c O_c / (256 sum_c w_c l_c), w_c = exp(max_c - max).
-// One block per split item, thread = (row, 16 output columns) exactly like the attention epilogue.
-__global__ void __launch_bounds__(512) attn2_combine_kernel(const AttnParams p) {
-  const int item = p.split_first + blockIdx.x;
-  int z = 0;
-  while (z + 1 < p.nprob && item >= p.item_prefix[z + 1]) ++z;
-  const int nq = p.nq[z], local = item - p.item_prefix[z], qtiles = (nq + 127) >> 7;
-  const int head = local / qtiles, m0 = (local - head * qtiles) * 128;
-  const int row = threadIdx.x & 127, cq = threadIdx.x >> 7;
-  const int slot0 = blockIdx.x * p.split_s;
-  float M = -INFINITY;
-  for (int c = 0; c < p.split_s; ++c) M = fmaxf(M, p.part_ml[(static_cast<size_t>(slot0 + c) * 2) * 128 + row]);
-  float L = 0.0f, acc[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
-  for (int c = 0; c < p.split_s; ++c) {
-    const size_t s = slot0 + c;
-    const float w = expf(p.part_ml[(s * 2) * 128 + row] - M);
-    L = fmaf(w, p.part_ml[(s * 2 + 1) * 128 + row], L);
-    const float4* po = reinterpret_cast<const float4*>(p.part_o + (s * 128 + row) * 64 + cq * 16);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 v = po[j];
-      acc[4 * j] = fmaf(w, v.x, acc[4 * j]);
-      acc[4 * j + 1] = fmaf(w, v.y, acc[4 * j + 1]);
-      acc[4 * j + 2] = fmaf(w, v.z, acc[4 * j + 2]);
-      acc[4 * j + 3] = fmaf(w, v.w, acc[4 * j + 3]);
-    }
-  }
-  __align__(16) __half oh[16];
-  __align__(16) __half ol[16];
-  const float inv_l = 1.0f / (RFE_ATTN_V_SCALE * L);
-  const bool live = m0 + row < nq;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) split_f32(live ? acc[j] * inv_l : 0.0f, oh[j], ol[j]);
-  if (m0 + row < ((nq + 7) & ~7)) {
-    const size_t o = static_cast<size_t>(p.q_row0[z] + m0 + row) * 256 + head * 64 + cq * 16;
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      reinterpret_cast<uint4*>(p.out_hi + o)[ch] = reinterpret_cast<const uint4*>(oh)[ch];
-      reinterpret_cast<uint4*>(p.out_lo + o)[ch] = reinterpret_cast<const uint4*>(ol)[ch];
-    }
   }
 }
 

@@ -54,11 +54,12 @@ struct AttnParams {
   // attn2_kernel, tail balancing: the last `items % CTAs` work items would leave most SMs idle for a whole item, so each of
   // them is cut into split_s parts along the keys (128-key granularity).  Virtual item v >= split_first is part
   // (v - split_first) % split_s of real item split_first + (v - split_first) / split_s; a part writes its un-normalised O, its
-  // row maximum and row sum to part_o / part_ml (slot v - split_first) and attn2_combine_kernel merges them.
+  // row maximum and row sum to part_o / part_ml (slot v - split_first); the part that finishes last merges them.
   int n_items;               // virtual work items (== item_prefix[nprob] when nothing is split)
   int split_first, split_s;
   float* part_o;             // [slots][128][64]
   float* part_ml;            // [slots][2][128]: row maximum (score units), row sum of E
+  unsigned* part_cnt;        // [slots]: arrival tickets per split item (the last arriver resets its ticket to 0)
   __half* out_hi;            // split-fp16 [rows][256]
   __half* out_lo;
   unsigned long long* prof;  // optional cycle counters written by CTA prof_cta: where the MMA / softmax roles wait

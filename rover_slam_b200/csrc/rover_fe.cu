@@ -127,6 +127,7 @@ struct rfe_ctx {
   unsigned long long* attn_prof = nullptr;   // armed by rfe_debug_read("lg.attn_prof")
   float* attn_part_o = nullptr;              // key-range parts of the attention tail items (AttnParams::part_o / part_ml)
   float* attn_part_ml = nullptr;
+  unsigned* attn_part_cnt = nullptr;
   int dbg_n0 = 0, dbg_n1 = 0, dbg_off0 = 0, dbg_off1 = 0, dbg_pair = 0;
   // match results: [max_batch] slots
   int* res_matches = nullptr;   // [slots][cap][2]
@@ -711,6 +712,7 @@ int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitB
     p.n_items = S > 1 ? items - tail + tail * S : items;
     p.part_o = c->attn_part_o;
     p.part_ml = c->attn_part_ml;
+    p.part_cnt = c->attn_part_cnt;
     // RFE_ATTN_CFG: softmax groups / ring depths (A/B): 0 = 2 groups of 8 warps, K 4 / V 3 / P 2 buffers; 1 = 2 groups, 3/2/3;
     // 2 = 4 groups of 4 warps, 3/2/3; 3 = 4 groups, 4/3/2
     static const int kCfgEnv = getenv("RFE_ATTN_CFG") ? atoi(getenv("RFE_ATTN_CFG")) : 0;
@@ -742,10 +744,6 @@ int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitB
       else le = launch(attn2_kernel<false>, kAttn2SmemBytes);
     }
     RFE_CUDA_CHECK(le);
-    if (S > 1) {
-      attn2_combine_kernel<<<tail, 512, 0, c->stream>>>(p);
-      c->launches++;
-    }
   } else if (p.prof) attn_kernel<true><<<grid, kAttnThreads, kAttnSmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
   else attn_kernel<false><<<grid, kAttnThreads, kAttnSmemBytes, c->stream>>>(qh, ql, kh, kl, vh, vl, p);
   c->launches++;
@@ -1232,6 +1230,8 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   A_(split_alloc(c, &c->attn, R * 256));
   A_(dev_alloc(c, &c->attn_part_o, static_cast<size_t>(kAttnPartSlots) * 128 * 64));
   A_(dev_alloc(c, &c->attn_part_ml, static_cast<size_t>(kAttnPartSlots) * 2 * 128));
+  A_(dev_alloc(c, &c->attn_part_cnt, static_cast<size_t>(kAttnPartSlots)));
+  C_(cudaMemset(c->attn_part_cnt, 0, kAttnPartSlots * sizeof(unsigned)));
   A_(dev_alloc(c, &c->hid, R * 512));
   A_(split_alloc(c, &c->hs, R * 512));
   A_(split_alloc(c, &c->md, R * 256));

@@ -486,7 +486,7 @@ from oracle import synth
 from rover_slam_b200 import FrontEnd
 fe = FrontEnd(max_batch=6, max_height=480, max_width=640, max_keypoints=1280)
 out = {}
-for tag, n, pairs in (("a", 1250, 2), ("b", 800, 3)):
+for tag, n, pairs in (("a", 1250, 2), ("b", 800, 3), ("c", 1250, 2)):     # c == a again: after a launch with another S
     k0, k1, d0, d1, perm = synth.lightglue_inputs(n, 900 + n)
     for p in range(pairs):
         fe.write_slot(2 * p, k0, d0)
@@ -500,8 +500,8 @@ np.savez(sys.argv[2], **out)
 
 
 def test_attention_key_split_of_the_tail_items_equals_unsplit(tmp_path):
-    """attn2_kernel cuts the work items of its last, partly filled round into key-range parts merged by
-    attn2_combine_kernel (2 pairs x 1250 keypoints: 160 items on 148 SMs -> 12 items in 4 parts; 3 pairs x 800: 168 items ->
+    """attn2_kernel cuts the work items of its last, partly filled round into key-range parts, merged by whichever part
+    finishes last (2 pairs x 1250 keypoints: 160 items on 148 SMs -> 12 items in 4 parts; 3 pairs x 800: 168 items ->
     20 items in 3 parts).  Same matches as with RFE_ATTN_SPLIT=0, scores within the LightGlue tolerance, and every pair of the
     batch identical to the first (same inputs, different positions in the item list)."""
     import subprocess, sys
@@ -511,6 +511,8 @@ def test_attention_key_split_of_the_tail_items_equals_unsplit(tmp_path):
         out = str(tmp_path / f"split{mode}.npz")
         subprocess.run([sys.executable, "-c", _SPLIT_CHILD, root, out], check=True, env=dict(os.environ, RFE_ATTN_SPLIT=mode), timeout=600)
         res[mode] = np.load(out)
+    for p in range(2):                              # bit-identical whichever part arrived last, and after S changed in between
+        assert np.array_equal(res["1"][f"ma{p}"], res["1"][f"mc{p}"]) and np.array_equal(res["1"][f"sa{p}"], res["1"][f"sc{p}"])
     for tag, pairs in (("a", 2), ("b", 3)):
         for p in range(pairs):
             m0, s0 = res["0"][f"m{tag}{p}"], res["0"][f"s{tag}{p}"]
