@@ -108,8 +108,9 @@ __device__ __forceinline__ void attn2_merge_parts(const AttnParams& p, const Att
   }
 }
 
-// G softmax groups (2 x 8 warps or 4 x 4 warps) on key tiles t = grp (mod G); NK / NV / NP: K stages, V stages, P buffers.
-template <bool PROF, int G = 2, int NK = kAttnKStages, int NV = kAttnVStages, int NP = 2>
+// G softmax groups (2 x 8 warps or 4 x 4 warps) on key tiles t = grp (mod G); NK / NV / NP / NS: K stages, V stages, P buffers,
+// score buffers in TMEM.
+template <bool PROF, int G = 2, int NK = kAttnKStages, int NV = kAttnVStages, int NP = 2, int NS = kAttnSBufs>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ CUtensorMap tmQ_lo,
              const __grid_constant__ CUtensorMap tmK_hi, const __grid_constant__ CUtensorMap tmK_lo,
@@ -129,8 +130,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
   uint64_t* v_full = k_empty + NK;                      // [NV]
   uint64_t* v_empty = v_full + NV;
   uint64_t* s_full = v_empty + NV;                      // [3]
-  uint64_t* s_empty = s_full + kAttnSBufs;              // [3]
-  uint64_t* p_full = s_empty + kAttnSBufs;              // [NP]
+  uint64_t* s_empty = s_full + NS;              // [3]
+  uint64_t* p_full = s_empty + NS;              // [NP]
   uint64_t* p_empty = p_full + NP;                      // [NP]
   uint64_t* o_full = p_empty + NP;
   uint64_t* o_empty = o_full + 1;
@@ -144,7 +145,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(peg + 8);
   uint32_t* last_part = tmem_ptr_smem + 1;               // 1: this CTA's part of a split item arrived last and merges
   float* stat = reinterpret_cast<float*>(tail + 512);   // [2 (item parity)][4][128] partial row max, then partial row sum
-  static_assert((4 + 16 + 2 * (NK + NV + kAttnSBufs + NP)) * 8 + 8 <= 512 && attn2_smem_bytes(NK, NV, NP) <= 227 * 1024,
+  static_assert((4 + 16 + 2 * (NK + NV + NS + NP)) * 8 + 8 <= 512 && attn2_smem_bytes(NK, NV, NP) <= 227 * 1024,
                 "tail region / shared-memory budget");
   static_assert(G == 2 || G == 4, "softmax groups");
 
@@ -170,7 +171,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
     for (int s = 0; s < NK; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
     for (int s = 0; s < NV; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     // both passes: the softmax warps work as G groups of WG warps on key tiles t = grp (mod G)
-    for (int s = 0; s < kAttnSBufs; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], WG); }
+    for (int s = 0; s < NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], WG); }
     for (int s = 0; s < NP; ++s) { mbar_init(&p_full[s], WG); mbar_init(&p_empty[s], 1); }
     for (int s = 0; s < 8; ++s) { mbar_init(&sfg[s], 1); mbar_init(&peg[s], 1); }
     if (G == 4)                                         // the NP buffers are free at the start: ordinal 0 of groups 0 .. NP-1
@@ -258,11 +259,11 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
         const long long t1 = tick();
         w_q += t1 - t0;
         for (int g = 0; g < a.T1; ++g, ++n) {        // pass 1: S_hh of 128 keys, one N=128 MMA per k-step
-          const int st = n % NK, b = n % kAttnSBufs;
+          const int st = n % NK, b = n % NS;
           const long long c0 = tick();
           mbar_wait(&k_full[st], (n / NK) & 1);
           const long long c1 = tick();
-          mbar_wait(&s_empty[b], ((n / kAttnSBufs) & 1) ^ 1);
+          mbar_wait(&s_empty[b], ((n / NS) & 1) ^ 1);
           w_k1 += c1 - c0;
           w_se1 += tick() - c1;
           tc_fence_after();
@@ -277,11 +278,11 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
         const long long t2 = tick();
         t_p1 += t2 - t1;
         for (int t = 0; t < a.T; ++t, ++n) {         // pass 2: fp32-equivalent scores of a 64-key tile
-          const int st = n % NK, b = n % kAttnSBufs;
+          const int st = n % NK, b = n % NS;
           const long long c0 = tick();
           mbar_wait(&k_full[st], (n / NK) & 1);
           const long long c1 = tick();
-          mbar_wait(&s_empty[b], ((n / kAttnSBufs) & 1) ^ 1);
+          mbar_wait(&s_empty[b], ((n / NS) & 1) ^ 1);
           w_k += c1 - c0;
           w_se += tick() - c1;
           tc_fence_after();
@@ -387,7 +388,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
         mbar_wait(&sfg[grp * 2 + (mycnt & 1u)], (mycnt >> 1) & 1u);
         ++mycnt;
       } else {
-        mbar_wait(&s_full[b], (n / kAttnSBufs) & 1);
+        mbar_wait(&s_full[b], (n / NS) & 1);
       }
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -400,7 +401,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
       float mx = NEG;
       for (int g = grp; g < T1; g += G) {
         const uint32_t n = n_base + g;
-        const int b = n % kAttnSBufs;
+        const int b = n % NS;
         const long long w0 = tick();
         wait_scores(b, n);
         sw_s1 += tick() - w0;
@@ -452,7 +453,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__
       auto tile_body = [&](int t, auto masked_tag) {
         constexpr bool kMasked = decltype(masked_tag)::value;
         const uint32_t n = n_base + T1 + t, v = v_base + t;
-        const int b = n % kAttnSBufs, pb = v % NP;
+        const int b = n % NS, pb = v % NP;
         const long long w0 = tick();
         wait_scores(b, n);
         const long long w0b = tick();

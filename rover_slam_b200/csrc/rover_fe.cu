@@ -713,11 +713,12 @@ int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitB
     p.part_o = c->attn_part_o;
     p.part_ml = c->attn_part_ml;
     p.part_cnt = c->attn_part_cnt;
-    // RFE_ATTN_CFG: softmax groups / ring depths (A/B): 0 = 2 groups of 8 warps, K 4 / V 3 / P 2 buffers; 1 = 2 groups, 3/2/3;
-    // 2 = 4 groups of 4 warps, 3/2/3; 3 = 4 groups, 4/3/2
-    static const int kCfgEnv = getenv("RFE_ATTN_CFG") ? atoi(getenv("RFE_ATTN_CFG")) : 0;
+    // RFE_ATTN_CFG: softmax groups / ring depths (A/B; default 4): 0 = 2 groups of 8 warps, K 4 / V 3 / P 2 buffers; 1 = 2 groups, 3/2/3;
+    // 2 = 4 groups of 4 warps, 3/2/3; 3 = 4 groups, 4/3/2; 4 = as 0 with two score buffers instead of three (the tensor pipe is one
+    // queue: a score issuer that cannot run three tiles ahead delays the P V products less; +1.5 %)
+    static const int kCfgEnv = getenv("RFE_ATTN_CFG") ? atoi(getenv("RFE_ATTN_CFG")) : 4;
     // the four-group forms need at least four pass-2 tiles and two pass-1 tiles per item (barrier discipline, attn2_kernel.cuh)
-    const int kCfg = (kCfgEnv >= 2 && min_nk < 256) ? 0 : kCfgEnv;
+    const int kCfg = ((kCfgEnv == 2 || kCfgEnv == 3) && min_nk < 256) ? 0 : kCfgEnv;
     auto launch = [&](auto kern, int smem) -> cudaError_t {
       static const void* configured_fn[16][8] = {};      // [device][instantiation]: opt-in shared memory set once
       const void** slot = configured_fn[c->device & 15];
@@ -736,11 +737,13 @@ int attention_fused(rfe_ctx* c, const char* tag, const SplitBuf& Q, const SplitB
       if (kCfg == 1) le = launch(attn2_kernel<true, 2, 3, 2, 3>, attn2_smem_bytes(3, 2, 3));
       else if (kCfg == 2) le = launch(attn2_kernel<true, 4, 3, 2, 3>, attn2_smem_bytes(3, 2, 3));
       else if (kCfg == 3) le = launch(attn2_kernel<true, 4, 4, 3, 2>, attn2_smem_bytes(4, 3, 2));
+      else if (kCfg == 4) le = launch(attn2_kernel<true, 2, 4, 3, 2, 2>, attn2_smem_bytes(4, 3, 2));
       else le = launch(attn2_kernel<true>, kAttn2SmemBytes);
     } else {
       if (kCfg == 1) le = launch(attn2_kernel<false, 2, 3, 2, 3>, attn2_smem_bytes(3, 2, 3));
       else if (kCfg == 2) le = launch(attn2_kernel<false, 4, 3, 2, 3>, attn2_smem_bytes(3, 2, 3));
       else if (kCfg == 3) le = launch(attn2_kernel<false, 4, 4, 3, 2>, attn2_smem_bytes(4, 3, 2));
+      else if (kCfg == 4) le = launch(attn2_kernel<false, 2, 4, 3, 2, 2>, attn2_smem_bytes(4, 3, 2));
       else le = launch(attn2_kernel<false>, kAttn2SmemBytes);
     }
     RFE_CUDA_CHECK(le);
