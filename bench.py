@@ -223,6 +223,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # SMs left to NCCL's kernels during the config-5 stream (rfe_set_sm_limit).  Measured at N = 2 with 0 / 4 / 8 SMs and NCCL
+    # capped at 4 / 8 CTAs: stream / value = 0.963 / 0.964 / 0.947 -- the collectives do not disturb the persistent kernels, so 0.
+    sm_reserve = int(os.environ.get("RFE_SM_RESERVE", "0")) if world > 1 else 0
     P = args.pairs
     B = 2 * P
     stream = torch.cuda.current_stream()
@@ -321,6 +324,8 @@ def main():
         fe.copy_results_device(P, base, base + 4 * P * cap * 2, base + 4 * P * cap * 3)
 
     ps = sharding.PairStream((B, H, W), words, dev, stream_compute)
+    n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    fe.set_sm_limit(n_sms - sm_reserve if sm_reserve else 0)
     stream_sets = None
     if rank == 0:                                       # [n_sets][world][B][H][W] in pinned host memory
         stream_sets = host_all.reshape(world, n_sets, B, H, W).transpose(0, 1).contiguous().pin_memory()
@@ -338,6 +343,7 @@ def main():
     stream_s = max_over_ranks(time.perf_counter() - t0)
     stream_fps = 2 * P * e_steps * world / stream_s
     s_h2d, s_d2h, s_coll = ((ps.h2d_bytes - b0[0]) // e_steps, (ps.d2h_bytes - b0[1]) // e_steps, (ps.collective_bytes - b0[2]) // e_steps)
+    fe.set_sm_limit(0)
 
     # ---- end to end through the host API ("e2e" at N = 1) ----
     run_host(2)
@@ -397,6 +403,7 @@ def main():
         "stream": {"value": stream_fps, "unit": "frames/s", "steps": e_steps, "h2d_bytes_per_step": s_h2d, "d2h_bytes_per_step": s_d2h,
                    "collective": "NCCL scatter (u8 frames) + gather (fixed-size match records), side stream, double buffered" if world > 1 else "none (one rank)",
                    "collective_bytes_per_step": s_coll, "host_api_e2e": e2e,
+                   "sms_left_to_nccl": sm_reserve, "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS") if world > 1 else None,
                    "match_counts_last_step": last_counts.get("c").tolist() if last_counts.get("c") is not None else None,
                    "variant": "independent pairs (2 extracts + 1 match per pair); the SLAM-shaped stream (pair p = frames p, p+1: one "
                    "extract + one match per frame) needs half the extractions per pair and is not what this number measures"},

@@ -80,6 +80,12 @@ int rfe_sp_extract_u8(rfe_ctx* ctx, const uint8_t* gray, int h, int w, int strid
  * stays); descriptors are sampled for the kept ones only.  k <= 0 (default): every keypoint, i.e. the reference's behaviour. */
 int rfe_sp_set_topk(rfe_ctx* ctx, int k);
 
+/* The tensor-core kernels are persistent: one CTA per SM walks a static list of tiles, so a kernel that finds one SM taken by
+ * somebody else's long-running kernel (an NCCL collective waiting for its peers) runs its last CTA after all the others and
+ * takes twice as long.  A process that overlaps communication with the front end (bench.py's config-5 stream)
+ * limits the front end to max_sms SMs and leaves the rest to the communication kernels.  0 = all SMs (default). */
+int rfe_set_sm_limit(rfe_ctx* ctx, int max_sms);
+
 /* Device in / device-resident out (asynchronous on the ctx stream).  d_gray: device pointer, layout as
  * above.  Features stay in the ctx ("slots" 0..batch-1) for rfe_lg_match_slots / rfe_sp_read_slot. */
 int rfe_sp_extract_device(rfe_ctx* ctx, const uint8_t* d_gray, int h, int w, int stride_bytes, int batch);

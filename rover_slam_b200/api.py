@@ -62,6 +62,7 @@ def load_library():
     lib.rfe_sp_extract_u8.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp, vp, vp, ci]
     lib.rfe_sp_extract_device.argtypes = [vp, vp, ci, ci, ci, ci]
     lib.rfe_sp_set_topk.argtypes = [vp, ci]
+    lib.rfe_set_sm_limit.argtypes = [vp, ci]
     lib.rfe_sp_read_slot.argtypes = [vp, ci, vp, vp, vp, vp, ci]
     lib.rfe_sp_read_slot_bin.argtypes = [vp, ci, vp, vp, ci]
     lib.rfe_sp_write_slot.argtypes = [vp, ci, vp, vp, vp, ci]
@@ -161,6 +162,10 @@ class FrontEnd:
     def set_topk(self, k: int):
         """Keep the k best keypoints per image in later extractions (k <= 0: all of them, the reference's behaviour)."""
         self._check(self.lib.rfe_sp_set_topk(self.ctx, int(k)))
+
+    def set_sm_limit(self, max_sms: int):
+        """Persistent kernels use at most max_sms SMs (0 = all): leaves SMs to communication kernels running beside them."""
+        self._check(self.lib.rfe_set_sm_limit(self.ctx, int(max_sms)))
 
     def extract_device(self, d_ptr: int, h: int, w: int, stride: int, batch: int):
         self._check(self.lib.rfe_sp_extract_device(self.ctx, C.c_void_p(d_ptr), h, w, stride, batch))

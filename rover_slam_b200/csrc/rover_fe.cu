@@ -47,7 +47,8 @@ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 struct rfe_ctx {
   int device = 0;
-  int num_sms = 148;
+  int num_sms = 148;                     // SMs the persistent kernels spread over (rfe_set_sm_limit)
+  int device_sms = 148;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int max_batch = 8, max_h = 480, max_w = 768, cap = 4096;
@@ -1130,7 +1131,7 @@ int rfe_create(const rfe_config* cfg, rfe_ctx** out) {
   RFE_CUDA_CHECK(cudaSetDevice(cfg->device));
   rfe_ctx* c = new rfe_ctx();
   c->device = cfg->device;
-  c->num_sms = prop.multiProcessorCount;
+  c->num_sms = c->device_sms = prop.multiProcessorCount;
   c->max_batch = cfg->max_batch > 0 ? cfg->max_batch : 8;
   c->max_h = cfg->max_height > 0 ? cfg->max_height : 480;
   c->max_w = cfg->max_width > 0 ? cfg->max_width : 768;
@@ -1316,6 +1317,17 @@ int rfe_sp_set_topk(rfe_ctx* c, int k) {
     return RFE_ERR_INVALID;
   }
   c->topk = k > 0 ? k : 0;
+  return RFE_OK;
+}
+
+int rfe_set_sm_limit(rfe_ctx* c, int max_sms) {
+  int r = check_ctx(c);
+  if (r) return r;
+  if (max_sms < 0 || max_sms > c->device_sms) {
+    set_error("rfe_set_sm_limit: %d outside 0..%d", max_sms, c->device_sms);
+    return RFE_ERR_INVALID;
+  }
+  c->num_sms = max_sms > 0 ? max_sms : c->device_sms;
   return RFE_OK;
 }
 

@@ -479,6 +479,24 @@ def test_fused_conv1a_is_bit_identical_to_the_two_kernel_path(tmp_path):
     assert len(res["1"]["k00"]) > 100
 
 
+def test_sm_limit_changes_nothing_but_the_grid(fe):
+    """rfe_set_sm_limit: the persistent kernels on 100 SMs give the same keypoints, descriptors and matches as on all of them
+    (tile -> CTA assignment changes, per-tile arithmetic does not)."""
+    a, b = synth.frame_pair(77, 480, 640)
+    pair = np.stack([a, b])
+    want_k, want_m = fe.match_pairs(pair)
+    fe.set_sm_limit(100)
+    try:
+        got_k, got_m = fe.match_pairs(pair)
+    finally:
+        fe.set_sm_limit(0)
+    assert all(np.array_equal(x, y) for x, y in zip(want_k, got_k))
+    rep = parity.compare_matches(want_m[0][0], want_m[0][1], got_m[0][0], got_m[0][1])
+    assert rep["only_ref"] + rep["only_tst"] <= 1 and rep["mscore_maxabs"] <= 1e-4, rep
+    with pytest.raises(Exception):
+        fe.set_sm_limit(100000)
+
+
 _SPLIT_CHILD = r"""
 import sys, numpy as np
 sys.path.insert(0, sys.argv[1])
