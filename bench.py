@@ -375,6 +375,49 @@ def main():
     fe.profile_read(None, reset=True)
     fe.profile(False)
 
+    # ---- labelled fast mode (rfe_set_fast_mode: hi-only fp16 MMAs in SuperPoint's 3x3 convolutions), N = 1 only.  NOT the
+    # parity path and not part of any number above: the same device-resident step, timed again, with the set overlap of its
+    # keypoints and matches against the exact path on the same frames ----
+    fast_block = None
+    if world == 1:
+        def snapshot():
+            step_device(0)
+            fe.sync()
+            kps = [fe.read_slot(b, want_desc=False)[0] for b in range(B)]
+            mts = [fe.read_result(p)[0] for p in range(P)]
+            return kps, mts
+
+        def coords(k):
+            return set(map(tuple, np.asarray(k).tolist()))
+        ek, em = snapshot()
+        fe.set_fast_mode(True)
+        try:
+            for i in range(3):
+                step_device(i)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            f0.record(stream)
+            for i in range(args.steps):
+                step_device(i)
+            f1.record(stream)
+            torch.cuda.synchronize()
+            fast_ms = f0.elapsed_time(f1) / args.steps
+            fk, fm = snapshot()
+        finally:
+            fe.set_fast_mode(False)
+        kp_ov = [len(coords(a) & coords(b)) / max(len(a), 1) for a, b in zip(ek, fk)]
+        m_ov = []
+        for p_ in range(P):
+            e = {(tuple(ek[2 * p_][i]), tuple(ek[2 * p_ + 1][j])) for i, j in em[p_].tolist()}
+            f = {(tuple(fk[2 * p_][i]), tuple(fk[2 * p_ + 1][j])) for i, j in fm[p_].tolist()}
+            m_ov.append(len(e & f) / max(len(e), 1))
+        fast_block = {"value": 2 * P / (fast_ms / 1e3), "unit": "frames/s", "ms_per_step": fast_ms, "steps": args.steps,
+                      "keypoint_overlap_mean": float(np.mean(kp_ov)), "keypoint_overlap_min": float(np.min(kp_ov)),
+                      "match_overlap_mean": float(np.mean(m_ov)), "match_overlap_min": float(np.min(m_ov)),
+                      "what": "NOT the parity path, not the default, not `value`: hi-only fp16 MMAs (1 instead of 3 per MAC) in SuperPoint's "
+                              "3x3 convolutions, LightGlue unchanged; overlap = share of the exact path's keypoints (by pixel) / matches "
+                              "(by pixel pair) that the fast path also returns, same frames"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -408,6 +451,7 @@ def main():
                    "variant": "independent pairs (2 extracts + 1 match per pair); the SLAM-shaped stream (pair p = frames p, p+1: one "
                    "extract + one match per frame) needs half the extractions per pair and is not what this number measures"},
         "gpu_launches": launches,
+        "fast_mode": fast_block,
         "roofline": {"bound": "tensor", "kernel": "attn2_kernel (lg.attn_self / lg.attn_cross: persistent fused 4-head attention of all pairs, 18 launches per step)",
                      "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak if tf_peak else None,
                      "traffic": ATTN_DRAM_BYTES_PER_LAUNCH if P == 8 else None, "peak_source": peak_src, "launch_ms": per_launch_ms, "launches_timed": attn_n,

@@ -80,6 +80,14 @@ int rfe_sp_extract_u8(rfe_ctx* ctx, const uint8_t* gray, int h, int w, int strid
  * stays); descriptors are sampled for the kept ones only.  k <= 0 (default): every keypoint, i.e. the reference's behaviour. */
 int rfe_sp_set_topk(rfe_ctx* ctx, int k);
 
+/* LABELLED FAST MODE -- not the parity path, never the default.  on != 0: SuperPoint's 3x3 convolutions (conv1b .. convPa/Da,
+ * 98 % of the extractor's FLOPs) issue only the hi*hi product of the split-fp16 scheme, i.e. plain fp16 operands with fp32
+ * accumulation: one tensor-core MMA per MAC instead of three.  Keypoints near the detection threshold and NMS near-ties
+ * change (fp16 inputs lose about 1 % of the keypoints); bench.py reports the mode separately with the
+ * keypoint and match overlap against the exact path.  LightGlue is not affected.  on == 0 (default): the reference's fp32
+ * arithmetic. */
+int rfe_set_fast_mode(rfe_ctx* ctx, int on);
+
 /* The tensor-core kernels are persistent: one CTA per SM walks a static list of tiles, so a kernel that finds one SM taken by
  * somebody else's long-running kernel (an NCCL collective waiting for its peers) runs its last CTA after all the others and
  * takes twice as long.  A process that overlaps communication with the front end (bench.py's config-5 stream)

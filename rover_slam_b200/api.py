@@ -63,6 +63,7 @@ def load_library():
     lib.rfe_sp_extract_device.argtypes = [vp, vp, ci, ci, ci, ci]
     lib.rfe_sp_set_topk.argtypes = [vp, ci]
     lib.rfe_set_sm_limit.argtypes = [vp, ci]
+    lib.rfe_set_fast_mode.argtypes = [vp, ci]
     lib.rfe_sp_read_slot.argtypes = [vp, ci, vp, vp, vp, vp, ci]
     lib.rfe_sp_read_slot_bin.argtypes = [vp, ci, vp, vp, ci]
     lib.rfe_sp_write_slot.argtypes = [vp, ci, vp, vp, vp, ci]
@@ -162,6 +163,10 @@ class FrontEnd:
     def set_topk(self, k: int):
         """Keep the k best keypoints per image in later extractions (k <= 0: all of them, the reference's behaviour)."""
         self._check(self.lib.rfe_sp_set_topk(self.ctx, int(k)))
+
+    def set_fast_mode(self, on: bool):
+        """Labelled fast mode (NOT the parity path): hi-only fp16 MMAs in SuperPoint's 3x3 convolutions."""
+        self._check(self.lib.rfe_set_fast_mode(self.ctx, 1 if on else 0))
 
     def set_sm_limit(self, max_sms: int):
         """Persistent kernels use at most max_sms SMs (0 = all): leaves SMs to communication kernels running beside them."""

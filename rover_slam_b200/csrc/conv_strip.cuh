@@ -41,6 +41,7 @@ struct StripParams {
   __half* out_hi;           // NHWC [B][Ho][Wo][64]
   __half* out_lo;
   unsigned long long* prof;   // optional [8] cycle counters of CTA 0's MMA thread
+  int fast;                   // labelled fast mode: hi*hi products only (rfe_set_fast_mode)
   // FUSE1A (conv1a computed in the kernel): the u8 image and the fp32 conv1a weights replace the activation tensor maps
   const uint8_t* img;       // [B][H][img_stride]
   int img_stride;
@@ -310,6 +311,10 @@ __device__ __forceinline__ void conv64_strip_body(const CUtensorMap& tmA_hi, con
                   const uint64_t da_lo = make_sw128_kmajor_desc(a_lo + k * 32);
                   const uint64_t db_cat = make_sw128_kmajor_desc(w_cat + k * 32);
                   const uint64_t db_hi = make_sw128_kmajor_desc(w_hi + k * 32);
+                  if (p.fast) {                  // hh_a (dy 0, 2) / hh_b (dy 1) += A_hi W_hi, nothing else
+                    umma_f16(row_base + (dy == 1 ? 128 : 0), da_hi, db_hi, idesc64, (dy < 2 && dx == 0 && k == 0) ? 0u : 1u);
+                    continue;
+                  }
                   if (dy == 1 && dx == 0 && k == 0) {
                     // first touch of hh_b while hl already holds dy = 0: two N=64 MMAs with different accumulate flags
                     umma_f16(row_base + 128, da_hi, db_hi, idesc64, 0u);                                  // hh_b  = A_hi W_hi
@@ -375,7 +380,7 @@ __device__ __forceinline__ void conv64_strip_body(const CUtensorMap& tmA_hi, con
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              v[r][c + j] = (__uint_as_float(a0[j]) + __uint_as_float(a1[j])) + __uint_as_float(xl[j]) * RFE_SPLIT_INV;
+              v[r][c + j] = (__uint_as_float(a0[j]) + __uint_as_float(a1[j])) + (p.fast ? 0.0f : __uint_as_float(xl[j]) * RFE_SPLIT_INV);
           }
         }
         tc_fence_before();

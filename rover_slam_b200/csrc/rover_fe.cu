@@ -60,6 +60,7 @@ struct rfe_ctx {
   std::vector<long long> slot_gen, cache_gen;   // contents generation of every slot / generation its cache entry was built from
   std::vector<int> cache_nh, cache_nw;          // normalisation size the entry was built with
   long long cache_hits = 0, cache_builds = 0;
+  int fast = 0;                          // rfe_set_fast_mode: hi-only MMAs in SuperPoint's 3x3 convolutions (labelled, not parity)
   int topk = 0;                          // rfe_sp_set_topk: keep the K best keypoints per image (0 = all, the reference)
   std::vector<void*> allocs;
   long long launches = 0;
@@ -456,6 +457,7 @@ int conv3x3(rfe_ctx* c, const char* tag, const SplitBuf& in, int B, int H, int W
   p.out_hi = out.hi;
   p.out_lo = out.lo;
   p.pool = pool ? 1 : 0;
+  p.fast = c->fast;
   dim3 grid(p.tiles_x * p.tiles_y * B, w.n / block_n, 1);
   if (block_n == 64) return launch_umma<64, A_CONV3, EPI_CONV>(c, tag, ah, al, bh, bl, p, grid);
   return launch_umma<128, A_CONV3, EPI_CONV>(c, tag, ah, al, bh, bl, p, grid);
@@ -492,6 +494,7 @@ int conv64_strip(rfe_ctx* c, const char* tag, const SplitBuf& in, int B, int H, 
   p.bias = w.bias;
   p.out_hi = out.hi;
   p.out_lo = out.lo;
+  p.fast = c->fast;
   p.prof = (c->attn_prof && !strcmp(tag, "sp.conv1b")) ? c->attn_prof + 8 : nullptr;
   const int ctas = p.num_items < c->num_sms ? p.num_items : c->num_sms;
   ProfScope ps(c, tag);
@@ -1317,6 +1320,13 @@ int rfe_sp_set_topk(rfe_ctx* c, int k) {
     return RFE_ERR_INVALID;
   }
   c->topk = k > 0 ? k : 0;
+  return RFE_OK;
+}
+
+int rfe_set_fast_mode(rfe_ctx* c, int on) {
+  int r = check_ctx(c);
+  if (r) return r;
+  c->fast = on ? 1 : 0;
   return RFE_OK;
 }
 

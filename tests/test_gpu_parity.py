@@ -479,6 +479,29 @@ def test_fused_conv1a_is_bit_identical_to_the_two_kernel_path(tmp_path):
     assert len(res["1"]["k00"]) > 100
 
 
+def test_fast_mode_is_labelled_close_and_reversible(fe, sp):
+    """rfe_set_fast_mode (hi-only fp16 MMAs in the backbone convolutions) is NOT the parity path: it must stay close to the
+    exact path -- heat-map within 2e-3, at least 97 % of the keypoints in common, their descriptors within 2e-2 -- and
+    switching it off must give back the exact result bit for bit."""
+    img = synth.frame(5, 480, 640)
+    exact = fe.extract(img)[0]
+    heat_exact = fe.debug_read("sp.heat").copy()
+    fe.set_fast_mode(True)
+    try:
+        fast = fe.extract(img)[0]
+        heat_fast = fe.debug_read("sp.heat").copy()
+    finally:
+        fe.set_fast_mode(False)
+    again = fe.extract(img)[0]
+    assert all(np.array_equal(a, b) for a, b in zip(exact, again))
+    assert 0 < np.abs(heat_fast - heat_exact).max() <= 2e-3          # it really is another arithmetic, and a close one
+    ke = {(int(x), int(y)): i for i, (x, y) in enumerate(exact[0])}
+    common = [(ke[(int(x), int(y))], j) for j, (x, y) in enumerate(fast[0]) if (int(x), int(y)) in ke]
+    assert len(common) >= 0.97 * len(exact[0]) and len(common) >= 0.97 * len(fast[0])
+    ie, jf = np.array(common).T
+    assert np.abs(exact[2][ie] - fast[2][jf]).max() <= 2e-2
+
+
 def test_sm_limit_changes_nothing_but_the_grid(fe):
     """rfe_set_sm_limit: the persistent kernels on 100 SMs give the same keypoints, descriptors and matches as on all of them
     (tile -> CTA assignment changes, per-tile arithmetic does not)."""
