@@ -57,3 +57,9 @@ $(CSRC)/dbg_%.o: $(CSRC)/%.cc $(wildcard $(CSRC)/*.h)
 	$(NVCC) $(NVCCFLAGS) -DRFE_DEBUG_WAIT -x cu -c $< -o $@
 dbg: $(DBGOBJ)
 	$(NVCC) $(ARCH) -shared -o rover_slam_b200/librover_fe_dbg.so $(DBGOBJ) -lcudart
+
+# ---- A/B build WITH the strip kernel's issuer clock reads (conv_strip.cuh, RFE_STRIP_PACE): ROVER_FE_LIB=.../librover_fe_pace.so
+$(CSRC)/pace_rover_fe.o: $(CSRC)/rover_fe.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/rover_fe.h
+	$(NVCC) $(NVCCFLAGS) -DRFE_STRIP_PACE=1 -c $< -o $@
+pace: $(CSRC)/pace_rover_fe.o $(OBJ)
+	$(NVCC) $(ARCH) -shared -o rover_slam_b200/librover_fe_pace.so $(CSRC)/pace_rover_fe.o $(filter-out $(CSRC)/rover_fe.o,$(OBJ)) -lcudart

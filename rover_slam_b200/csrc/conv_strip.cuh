@@ -41,7 +41,6 @@ struct StripParams {
   __half* out_hi;           // NHWC [B][Ho][Wo][64]
   __half* out_lo;
   unsigned long long* prof;   // optional [8] cycle counters of CTA 0's MMA thread
-  int fast;                   // labelled fast mode: hi*hi products only (rfe_set_fast_mode)
   // FUSE1A (conv1a computed in the kernel): the u8 image and the fp32 conv1a weights replace the activation tensor maps
   const uint8_t* img;       // [B][H][img_stride]
   int img_stride;
@@ -75,7 +74,7 @@ constexpr int kStripSmemBytes =
 // into the row slot in the 128-byte-swizzled layout the TMA box would have produced (pixel p = one 128-byte row, 16-byte
 // chunk c at (c ^ (p & 7)); pixels outside the image are zeros = conv1b's padding), then fence.proxy.async + arrive.
 // tmA_*: 4-D (C=64, W, H, B) box (64, 130, 1, 1);  tmW_*: 3-D (K=576, 64, 1) box (64, 64, 1)
-template <bool FUSE1A>
+template <bool FUSE1A, bool FAST = false>
 __device__ __forceinline__ void conv64_strip_body(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo,
                                                   const CUtensorMap& tmW_hi, const CUtensorMap& tmW_lo,
                                                   const StripParams& p) {
@@ -94,10 +93,16 @@ __device__ __forceinline__ void conv64_strip_body(const CUtensorMap& tmA_hi, con
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // The cycle-counter reads around the MMA issuer's waits stay in the production build ON PURPOSE: an A/B on the same
-  // B200 (profiles/r01_strip_clock_ab.txt) measured conv1b at 485 us with them and 560 us without (conv2a 169 vs 196):
-  // the reads pace the issuing thread; bounding its run-ahead with an mbarrier instead did not reproduce the gain.
+  // Cycle-counter reads around the MMA issuer's waits (role counters for tools/gpu_probe.py): compiled in only with
+  // -DRFE_STRIP_PACE=1 (make pace) or in the debug library.  Round 1 measured conv1b 15 % FASTER with them in
+  // (profiles/r01_strip_clock_ab.txt) and shipped them; with round 2's kernel the effect is gone -- 932 us with, 910 us
+  // without under ncu, tensor pipe 59.6 % vs 61.3 % (profiles/r02_strip_pace_ab.txt) -- so production no longer depends on it.
+  // (A RUN-TIME switch here instead of the macro changed the kernel's register allocation, 160 -> 126, and cost 40 %.)
+#if defined(RFE_STRIP_PACE) ? RFE_STRIP_PACE : defined(RFE_DEBUG_WAIT)
   auto tick = [&]() -> long long { return clock64(); };
+#else
+  auto tick = [&]() -> long long { return 0; };
+#endif
 
   if (warp == kStripWarpRows && lane == 0) {
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmW_hi); tma_prefetch_desc(&tmW_lo);
@@ -311,7 +316,7 @@ __device__ __forceinline__ void conv64_strip_body(const CUtensorMap& tmA_hi, con
                   const uint64_t da_lo = make_sw128_kmajor_desc(a_lo + k * 32);
                   const uint64_t db_cat = make_sw128_kmajor_desc(w_cat + k * 32);
                   const uint64_t db_hi = make_sw128_kmajor_desc(w_hi + k * 32);
-                  if (p.fast) {                  // hh_a (dy 0, 2) / hh_b (dy 1) += A_hi W_hi, nothing else
+                  if constexpr (FAST) {          // hh_a (dy 0, 2) / hh_b (dy 1) += A_hi W_hi, nothing else
                     umma_f16(row_base + (dy == 1 ? 128 : 0), da_hi, db_hi, idesc64, (dy < 2 && dx == 0 && k == 0) ? 0u : 1u);
                     continue;
                   }
@@ -380,7 +385,7 @@ __device__ __forceinline__ void conv64_strip_body(const CUtensorMap& tmA_hi, con
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              v[r][c + j] = (__uint_as_float(a0[j]) + __uint_as_float(a1[j])) + (p.fast ? 0.0f : __uint_as_float(xl[j]) * RFE_SPLIT_INV);
+              v[r][c + j] = (__uint_as_float(a0[j]) + __uint_as_float(a1[j])) + (FAST ? 0.0f : __uint_as_float(xl[j]) * RFE_SPLIT_INV);
           }
         }
         tc_fence_before();
@@ -442,6 +447,13 @@ conv64_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                     const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                     const __grid_constant__ StripParams p) {
   conv64_strip_body<false>(tmA_hi, tmA_lo, tmW_hi, tmW_lo, p);
+}
+// labelled fast mode (rfe_set_fast_mode): hi*hi products only -- a separate instantiation, the exact kernel's code is untouched
+__global__ void __launch_bounds__(kStripThreads, 1)
+conv64_strip_fast_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                         const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                         const __grid_constant__ StripParams p) {
+  conv64_strip_body<false, true>(tmA_hi, tmA_lo, tmW_hi, tmW_lo, p);
 }
 __global__ void __launch_bounds__(kStripThreadsFused, 1)
 conv64_strip_fused_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,

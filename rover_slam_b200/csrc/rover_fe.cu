@@ -298,11 +298,11 @@ struct ProfScope {   // records a CUDA event pair around one launch when profili
   }
 };
 
-template <int BLOCK_N, int AMODE, int EPI, bool BRES = false>
+template <int BLOCK_N, int AMODE, int EPI, bool BRES = false, bool FAST = false>
 int launch_umma(rfe_ctx* c, const char* tag, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                 const CUtensorMap& b_lo, const UmmaParams& p, dim3 grid, const EpiMaps* em = nullptr) {
   static bool configured[64] = {};
-  auto kern = umma_kernel<BLOCK_N, AMODE, EPI, BRES>;
+  auto kern = umma_kernel<BLOCK_N, AMODE, EPI, BRES, FAST>;
   if (!configured[c->device & 63]) {
     RFE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, umma_smem_bytes(BLOCK_N, BRES)));
     configured[c->device & 63] = true;
@@ -457,8 +457,11 @@ int conv3x3(rfe_ctx* c, const char* tag, const SplitBuf& in, int B, int H, int W
   p.out_hi = out.hi;
   p.out_lo = out.lo;
   p.pool = pool ? 1 : 0;
-  p.fast = c->fast;
   dim3 grid(p.tiles_x * p.tiles_y * B, w.n / block_n, 1);
+  if (c->fast) {          // labelled fast mode: separate instantiations, the exact kernels are not touched by it
+    if (block_n == 64) return launch_umma<64, A_CONV3, EPI_CONV, false, true>(c, tag, ah, al, bh, bl, p, grid);
+    return launch_umma<128, A_CONV3, EPI_CONV, false, true>(c, tag, ah, al, bh, bl, p, grid);
+  }
   if (block_n == 64) return launch_umma<64, A_CONV3, EPI_CONV>(c, tag, ah, al, bh, bl, p, grid);
   return launch_umma<128, A_CONV3, EPI_CONV>(c, tag, ah, al, bh, bl, p, grid);
 }
@@ -471,6 +474,7 @@ int conv64_strip(rfe_ctx* c, const char* tag, const SplitBuf& in, int B, int H, 
   if (!configured[c->device & 63]) {
     RFE_CUDA_CHECK(cudaFuncSetAttribute(conv64_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStripSmemBytes));
     RFE_CUDA_CHECK(cudaFuncSetAttribute(conv64_strip_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStripSmemBytes));
+    RFE_CUDA_CHECK(cudaFuncSetAttribute(conv64_strip_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStripSmemBytes));
     configured[c->device & 63] = true;
   }
   const uint64_t dims[4] = {64, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
@@ -494,7 +498,6 @@ int conv64_strip(rfe_ctx* c, const char* tag, const SplitBuf& in, int B, int H, 
   p.bias = w.bias;
   p.out_hi = out.hi;
   p.out_lo = out.lo;
-  p.fast = c->fast;
   p.prof = (c->attn_prof && !strcmp(tag, "sp.conv1b")) ? c->attn_prof + 8 : nullptr;
   const int ctas = p.num_items < c->num_sms ? p.num_items : c->num_sms;
   ProfScope ps(c, tag);
@@ -503,6 +506,7 @@ int conv64_strip(rfe_ctx* c, const char* tag, const SplitBuf& in, int B, int H, 
   p.w1a = c->conv1a_w;
   p.b1a = c->conv1a_b;
   if (img) conv64_strip_fused_kernel<<<ctas, kStripThreadsFused, kStripSmemBytes, c->stream>>>(ah, al, wh, wl, p);
+  else if (c->fast) conv64_strip_fast_kernel<<<ctas, kStripThreads, kStripSmemBytes, c->stream>>>(ah, al, wh, wl, p);
   else conv64_strip_kernel<<<ctas, kStripThreads, kStripSmemBytes, c->stream>>>(ah, al, wh, wl, p);
   c->launches++;
   RFE_CUDA_CHECK(cudaGetLastError());

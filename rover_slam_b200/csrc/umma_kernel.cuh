@@ -59,7 +59,6 @@ struct UmmaParams {
   __half* vt_lo;
   int ldv;
   unsigned long long* prof;   // optional [8] cycle counters written by CTA 0 (MMA thread: 0-3, epilogue warp 2: 4-7)
-  int fast;                   // labelled fast mode (rfe_set_fast_mode): hi*hi products only, the cross accumulator is not read
   // EPI_LINEAR, optional: per-row partial sums of squares of the stored values, [M][2 * tiles_n] (slot = 2 * n-tile + the
   // warp's column phase): SuperPoint's descriptor head defers its per-pixel L2 normalisation to the sampler
   float* rowss;
@@ -117,7 +116,7 @@ __host__ __device__ constexpr int umma_tmem_cols(int block_n, int amode) {
 
 #ifdef __CUDACC__
 
-template <int BLOCK_N, int AMODE, int EPI, bool BRES = false>
+template <int BLOCK_N, int AMODE, int EPI, bool BRES = false, bool FAST = false>
 __global__ void __launch_bounds__(umma_threads(BLOCK_N, EPI), 1)
 umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
             const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -356,7 +355,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
           const uint64_t db_hi = make_sw128_kmajor_desc(b_hi + k * 32);
           const uint64_t db_lo = make_sw128_kmajor_desc(b_lo + k * 32);
           const uint32_t acc = (ks > 0 || k > 0) ? 1u : 0u;
-          if (p.fast) {                            // fp16 operands, fp32 accumulate: one product instead of three
+          if constexpr (FAST) {                    // labelled fast mode: fp16 operands, fp32 accumulate, one product of three
             umma_f16(acc0, da_hi, db_hi, idesc, (first0 && k == 0) ? 0u : 1u);
           } else if constexpr (kConcatB) {
             // [acc0 | acc1] (+)= A_hi [B_hi;B_lo]^T in ONE N = 2*BLOCK_N MMA (B_lo follows B_hi in the stage and acc1
@@ -418,11 +417,11 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           v[j] = ((__uint_as_float(r0[j]) + __uint_as_float(ra[j])) + __uint_as_float(rb[j])) +
-                 (p.fast ? 0.0f : __uint_as_float(r1[j]) * RFE_SPLIT_INV);      // fast mode: acc1 was never written
+                 (FAST ? 0.0f : __uint_as_float(r1[j]) * RFE_SPLIT_INV);        // fast mode: acc1 was never written
       } else {
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]) + (p.fast ? 0.0f : __uint_as_float(r1[j]) * RFE_SPLIT_INV);
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]) + (FAST ? 0.0f : __uint_as_float(r1[j]) * RFE_SPLIT_INV);
       }
     };
 
