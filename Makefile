@@ -63,3 +63,9 @@ $(CSRC)/pace_rover_fe.o: $(CSRC)/rover_fe.cu $(wildcard $(CSRC)/*.cuh) $(wildcar
 	$(NVCC) $(NVCCFLAGS) -DRFE_STRIP_PACE=1 -c $< -o $@
 pace: $(CSRC)/pace_rover_fe.o $(OBJ)
 	$(NVCC) $(ARCH) -shared -o rover_slam_b200/librover_fe_pace.so $(CSRC)/pace_rover_fe.o $(filter-out $(CSRC)/rover_fe.o,$(OBJ)) -lcudart
+
+# ---- LINEAR-epilogue phase counters (umma_kernel.cuh, RFE_EPI_PROF): ROVER_FE_LIB=.../librover_fe_epiprof.so, tools/gpu_umma_prof.py
+$(CSRC)/epiprof_rover_fe.o: $(CSRC)/rover_fe.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/rover_fe.h
+	$(NVCC) $(NVCCFLAGS) -DRFE_EPI_PROF -c $< -o $@
+epiprof: $(CSRC)/epiprof_rover_fe.o $(OBJ)
+	$(NVCC) $(ARCH) -shared -o rover_slam_b200/librover_fe_epiprof.so $(CSRC)/epiprof_rover_fe.o $(filter-out $(CSRC)/rover_fe.o,$(OBJ)) -lcudart

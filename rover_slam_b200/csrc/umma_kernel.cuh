@@ -393,6 +393,9 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     uint32_t res_phase = 0;
     long long w_tf = 0;
     const long long e_begin = tick();
+#ifdef RFE_EPI_PROF
+    long long ep_other = 0, ep_ld = 0, ep_math = 0, ep_res = 0, ep_f32 = 0, ep_split = 0, ep_wait = 0, ep_store = 0;
+#endif
     for (int tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
     const Tile tc = decode(tile);
     const int m0 = tc.m0, n0 = tc.n0, img = tc.img, x0 = tc.x0, y0 = tc.y0;
@@ -612,6 +615,12 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       const bool has_res = (EPI == EPI_LINEAR) && p.residual != nullptr;
       uint64_t* rbar = &res_bar[ew];
       float ss_acc = 0.0f;                       // p.rowss: sum of squares of this thread's values of the tile
+#ifdef RFE_EPI_PROF
+#define EPI_T(var) var += clock64() - ep_t; ep_t = clock64();
+      long long ep_t = clock64();
+#else
+#define EPI_T(var)
+#endif
       int c_last = -1;
       for (int c = half * 32; c < BLOCK_N && n0 + c < p.N; c += 64) c_last = c;
       if (c_last < 0) {
@@ -627,6 +636,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
           mbar_expect_tx(rbar, 4096);
           tma_load_3d(wst, &em.res, rbar, nb, row0, z);
         }
+        EPI_T(ep_other)
         float v[32];
         {
           uint32_t r0[32], r1[32];
@@ -641,6 +651,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]) * RFE_SPLIT_INV;
         }
+        EPI_T(ep_ld)
         if (p.bias) {
           if (nb + 32 <= p.N) {
 #pragma unroll
@@ -681,6 +692,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) ss_acc = fmaf(v[j], v[j], ss_acc);     // columns beyond N are zero (zero-filled weights)
           }
         }
+        EPI_T(ep_math)
         if (has_res) {
           mbar_wait(rbar, res_phase);
           res_phase ^= 1;
@@ -690,6 +702,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
             v[4 * ch] += t.x; v[4 * ch + 1] += t.y; v[4 * ch + 2] += t.z; v[4 * ch + 3] += t.w;
           }
         }
+        EPI_T(ep_res)
         if (EPI == EPI_LINEAR && p.out_f32) {
           if (!has_res && lane == 0) bulk_wait_read<0>();
           __syncwarp();                                // everyone has read the residual / the old tile has been fetched
@@ -704,6 +717,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
             bulk_commit();
           }
         }
+        EPI_T(ep_f32)
         const bool is_v = (EPI == EPI_QKV) && (n0 >> 8) == 2;
         if (EPI == EPI_QKV || p.out_hi) {
           uint32_t ph[16], pl[16];
@@ -759,8 +773,10 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
               bulk_commit();
             }
           } else {
+            EPI_T(ep_split)
             if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
+            EPI_T(ep_wait)
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
               const int so = lane * 64 + ((ch ^ ((lane >> 1) & 3)) << 4);
@@ -778,6 +794,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
               tma_store_3d(to_k ? &em.k_lo : &em.h_lo, wst + 2048, c0, row0, c2);
               bulk_commit();
             }
+            EPI_T(ep_store)
           }
         }
       }
@@ -795,6 +812,10 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     }
     if (p.prof && blockIdx.x == 0 && warp == 0 && lane == 0) {
       p.prof[4] = tick() - e_begin;     // epilogue-warp loop
+#ifdef RFE_EPI_PROF
+      p.prof[8] = ep_other; p.prof[9] = ep_ld; p.prof[10] = ep_math; p.prof[11] = ep_res; p.prof[12] = ep_f32;
+      p.prof[13] = ep_split; p.prof[14] = ep_wait; p.prof[15] = ep_store;
+#endif
       p.prof[5] = w_tf;                    // waiting for accumulators
     }
   }

@@ -14,3 +14,10 @@ fe.sync()
 pr = fe.debug_read("lg.attn_prof").view(np.uint64)
 print("tag", os.environ.get("RFE_PROF_TAG"), ": MMA thread total %d, wait TMEM drain %d, wait TMA %d, tiles %d | epilogue warp total %d, wait accum %d"
       % tuple(int(v) for v in pr[16:22]))
+names = ["other", "tmem ld", "bias/scale/rotary", "residual wait+add", "f32 stage+store", "split", "wait staging free", "stage+fence+TMA store"]
+ph = [int(v) for v in pr[24:32]]
+if any(ph):
+    tiles = max(int(pr[19]), 1)
+    print("  LINEAR epilogue phases of warp 0 (cycles, all tiles of CTA 0; per chunk = / (2 chunks x tiles)):")
+    for n, v in zip(names, ph):
+        print(f"    {n:26s} {v:9d}  ({v / (2 * tiles):7.0f} per chunk)")
