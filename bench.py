@@ -35,8 +35,8 @@ sys.path.insert(0, ROOT)
 H, W = 480, 640
 WORKLOAD = ("BASELINE config 5 shape: 640x480 synthetic frame pairs, SuperPoint on both frames + one LightGlue match per pair")
 SP_FLOPS_PER_FRAME = 52.10e9
-ATTN_DRAM_BYTES_PER_LAUNCH = 118_045_184                   # dram__bytes_read.sum + dram__bytes_write.sum of ONE attention launch at 8 pairs
-                                                           # (profiles/r02_attn2_full.ncu-rep: 103.03 MB + 15.01 MB; algorithmic bytes 131 MB)
+ATTN_DRAM_BYTES_PER_LAUNCH = 119_588_352                   # dram__bytes_read.sum + dram__bytes_write.sum of ONE attention launch at 8 pairs
+                                                           # (profiles/r02_attn2_full.ncu-rep, final build: 103.18 MB + 16.41 MB; algorithmic bytes 131 MB)
 
 
 def peaks():
