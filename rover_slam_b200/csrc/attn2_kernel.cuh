@@ -12,9 +12,13 @@
 //   * the score issuer starts the next item's pass 1 as soon as its Q tile has landed (Q is reloaded by the V producer the
 //     moment the last score MMA of the current item retires, i.e. under the last P V products and the epilogue);
 //   * TMEM is allocated once per CTA; O is handed back to the P V issuer through an o_empty barrier.
-// Ring counters: n = number of score tiles (pass 1 + pass 2) issued so far by this CTA: K stage n % 4, score buffer n % 3;
-// v = number of pass-2 tiles so far: V stage v % 3, P buffer v & 1.  Every role walks the same item list and derives the
-// same counters.
+// Ring counters: n = number of score tiles (pass 1 + pass 2) issued so far by this CTA: K stage n % NK, score buffer n % NS;
+// v = number of pass-2 tiles so far: V stage v % NV, P buffer v % NP.  Every role walks the same item list and derives the
+// same counters.  Default instantiation (rover_fe.cu, RFE_ATTN_CFG): two softmax groups of eight warps, NK 4, NV 3, NP 2 and
+// NS 2 score buffers -- the tensor pipe is ONE queue, and a score issuer that can run three tiles ahead delays the P V
+// products that free the P buffers (three buffers measured 1.5 % slower).
+//   * tail balancing: the items of the last, partly filled round are cut into key-range parts (AttnParams::split_*); every
+//     part writes un-normalised O, row maximum and row sum, and the part that arrives last merges them in its epilogue.
 // Replaces (reference): the attention MatMul / Softmax / MatMul nodes of lightglue_sim.onnx (layer 0 self: nodes 50-54,
 // cross: 141-151) executed by ONNXRuntime at src/Matchers/lightglue_onnx.cpp:210-214.
 #pragma once
